@@ -1,0 +1,249 @@
+// fp32 parity path: backward of get_model + get_loss (what optimizer.minimize differentiates,
+// train.py:217).  Every activation needed was materialised by forward_f32 in the workspace.
+#include <algorithm>
+
+#include "kernels_f32.cuh"
+#include "loss.cuh"
+
+namespace an3d {
+
+namespace {
+
+struct BnRef {
+  const float *scale, *shift, *mean, *inv;
+  double *acc0, *acc1;
+  float *dgamma, *dbeta;
+  int ch;
+};
+
+BnRef bn_ref(const Model& m, const PlanF32& p, float* grads, bool head, int br, int bn) {
+  BnRef v;
+  const int ch = head ? m.bn_head[bn].ch : m.bn_branch[bn].ch;
+  const int64_t po = m.bn_param_off(head, br, bn), sl = m.bn_slot_off(head, br, bn);
+  v.scale = p.bn.scale + sl;
+  v.shift = p.bn.shift + sl;
+  v.mean = p.bn.mean + sl;
+  v.inv = p.bn.inv + sl;
+  v.acc0 = p.bn.acc0 + sl;
+  v.acc1 = p.bn.acc1 + sl;
+  v.dgamma = grads + po;
+  v.dbeta = grads + po + ch;
+  v.ch = ch;
+  return v;
+}
+
+// dA (grad wrt post-activation, post-dropout) -> dZ (grad wrt pre-BN), written to dZ (may alias dA).
+int bn_relu_backward(const BnRef& v, const float* Z, int R, const float* dA, int64_t ldd, const float* mask,
+                     float mask_scale, float* dZ, int64_t ldo, cudaStream_t st) {
+  ColArgs a;
+  a.Z = Z; a.ldz = v.ch; a.R = R; a.C = v.ch; a.mean = v.mean; a.inv = v.inv; a.scale = v.scale; a.shift = v.shift;
+  a.dA = dA; a.ldd = ldd; a.mask = mask; a.mask_scale = mask_scale; a.acc0 = v.acc0; a.acc1 = v.acc1;
+  AN3D_TRY(launch_col_reduce(a, COL_DY, st));
+  const int64_t total = (int64_t)R * v.ch;
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, dZ, ldo, 1.0 / R);
+  AN3D_LAUNCH_CHECK();
+  bn_bwd_params_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, v.dgamma, v.dbeta, v.ch);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+// Z = pro(X) W + b.  Given dZ [R,cout] (dense, ld = cout):
+//   grads.W += pro(X)^T dZ ; grads.b += colsum(dZ) ; dX = dZ W^T (if dX != nullptr).
+int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
+                    float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
+                    int64_t lddx, double* bias_acc, cudaStream_t st) {
+  {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
+    GemmArgs g;
+    g.A = X; g.lda = ldx; g.B = dZ; g.ldb = L.cout; g.C = grads + L.w; g.ldc = L.cout;
+    g.M = L.cin; g.N = L.cout; g.K = R; g.pro_scale = psc; g.pro_shift = psh; g.pro_mask = pmask;
+    g.pro_mask_scale = pmask_scale; g.accumulate = 1;
+    const int tiles = ((L.cin + 63) / 64) * ((L.cout + 63) / 64);
+    g.ksplit = std::max(1, std::min((R + 255) / 256, (592 + tiles - 1) / tiles));
+    AN3D_TRY(launch_gemm(g, true, false, st));
+  }
+  {  // bias grad
+    AN3D_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * L.cout, st));
+    ColArgs a;
+    a.Z = dZ; a.ldz = L.cout; a.R = R; a.C = L.cout; a.acc0 = bias_acc;
+    AN3D_TRY(launch_col_reduce(a, COL_SUM, st));
+    add_double_to_float_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(bias_acc, grads + L.b, L.cout);
+    AN3D_LAUNCH_CHECK();
+  }
+  if (dX) {  // dgrad: [R, cin] = dZ [R, cout] * W^T
+    GemmArgs g;
+    g.A = dZ; g.lda = L.cout; g.B = params + L.w; g.ldb = L.cout; g.C = dX; g.ldc = lddx;
+    g.M = R; g.N = L.cin; g.K = L.cout;
+    AN3D_TRY(launch_gemm(g, false, true, st));
+  }
+  return AN3D_OK;
+}
+
+// Backward through a conv stack + max-pool.  dG: [B, C_last] with leading dim ldg.
+// Leaves d(stage input) in p.dpin when want_input_grad.
+int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const float* dG, int64_t ldg,
+                        const float* params, float* grads, bool want_input_grad, cudaStream_t st) {
+  const int64_t M = p.M;
+  const int nl = (int)m.conv[s].size();
+  int cur = 0;
+  {
+    const int C = m.conv[s].back().cout;
+    AN3D_CUDA_CHECK(cudaMemsetAsync(p.dbuf[cur], 0, sizeof(float) * M * C, st));
+    const int64_t total = (int64_t)p.B * C;
+    pool_bwd_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dG, ldg, p.gidx[s][br], p.dbuf[cur], p.N,
+                                                                             C, p.B);
+    AN3D_LAUNCH_CHECK();
+  }
+  for (int l = nl - 1; l >= 0; --l) {
+    const Lin& L = m.conv[s][l];
+    BnRef v = bn_ref(m, p, grads, false, br, L.bn);
+    AN3D_TRY(bn_relu_backward(v, p.z[s][l][br], (int)M, p.dbuf[cur], L.cout, nullptr, 1.f, p.dbuf[cur], L.cout, st));
+    const float *X, *psc = nullptr, *psh = nullptr;
+    float* dX = nullptr;
+    int64_t lddx = 0;
+    if (l > 0) {
+      const Lin& P = m.conv[s][l - 1];
+      X = p.z[s][l - 1][br];
+      const int64_t sl = m.bn_slot_off(false, br, P.bn);
+      psc = p.bn.scale + sl;
+      psh = p.bn.shift + sl;
+      dX = p.dbuf[cur ^ 1];
+      lddx = L.cin;
+    } else {
+      X = p.pin[s][br];
+      if (want_input_grad) { dX = p.dpin; lddx = 3; }
+    }
+    AN3D_TRY(linear_backward(L, X, L.cin, psc, psh, nullptr, 1.f, p.dbuf[cur], (int)M, params, grads, dX, lddx,
+                             p.dbias_acc, st));
+    cur ^= 1;
+  }
+  return AN3D_OK;
+}
+
+// Backward through get_mlp.  dOut: [B, out] dense.  x/ldx: the MLP input (already activated).
+// Writes d(input) to dIn (leading dim lddin).
+int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x, int64_t ldx, const float* dOut,
+                 const float* params, float* grads, float* dIn, int64_t lddin, const float* mask, cudaStream_t st) {
+  const bool head = s == HEAD;
+  const int nl = (int)m.fc[s].size();
+  const float* dZ = dOut;
+  int cur = 0;
+  const float mask_scale = mask ? 1.0f / m.arch.keep_prob[s] : 1.f;
+  for (int l = nl - 1; l >= 0; --l) {
+    const Lin& L = m.fc[s][l];
+    if (L.bn >= 0) {
+      BnRef v = bn_ref(m, p, grads, head, br, L.bn);
+      // dZ currently holds dA (grad wrt this layer's post-activation); dropout only after the last hidden layer
+      const bool dropped = (l == nl - 2) && mask;
+      float* buf = const_cast<float*>(dZ);
+      AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], p.B, dZ, L.cout, dropped ? mask : nullptr, mask_scale, buf, L.cout, st));
+    }
+    const float *X, *psc = nullptr, *psh = nullptr, *pm = nullptr;
+    int64_t lx;
+    float* dX;
+    int64_t lddx;
+    if (l > 0) {
+      const Lin& P = m.fc[s][l - 1];
+      X = p.fz[s][l - 1][br];
+      lx = P.cout;
+      const int64_t sl = m.bn_slot_off(head, br, P.bn);
+      psc = p.bn.scale + sl;
+      psh = p.bn.shift + sl;
+      if (l == nl - 1) pm = mask;
+      dX = p.dfc[cur];
+      lddx = L.cin;
+    } else {
+      X = x;
+      lx = ldx;
+      dX = dIn;
+      lddx = lddin;
+    }
+    AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st));
+    dZ = dX;
+    cur ^= 1;
+  }
+  return AN3D_OK;
+}
+
+// dOh[:, :3] = dpred_t ; dOh[:, 3:] = drem ; dc2[0] = ds2c1 - dpred_t ; dc2[1] = ds2c2 + dpred_t  (tp8.py:155)
+__global__ void assemble_head_grad_kernel(const float* dend, float* dOh, float* dc2a, float* dc2b, int B, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* ds2c1 = dend + (int64_t)2 * B * 3;
+  const float* ds2c2 = dend + (int64_t)3 * B * 3;
+  const float* dpt = dend + (int64_t)4 * B * 3;
+  const float* drem = dend + (int64_t)5 * B * 3 + (int64_t)2 * B * 2 * nb;
+  float* o = dOh + (int64_t)b * (3 + 2 * nb);
+  for (int d = 0; d < 3; ++d) {
+    const float g = dpt[b * 3 + d];
+    o[d] = g;
+    dc2a[b * 3 + d] = ds2c1[b * 3 + d] - g;
+    dc2b[b * 3 + d] = ds2c2[b * 3 + d] + g;
+  }
+  for (int j = 0; j < 2 * nb; ++j) o[3 + j] = drem[(int64_t)b * 2 * nb + j];
+}
+
+// dO2[:, :3] = dc2 ; dO2[:, 3:] = dlg (+ dang*pi/nb at nb+k, tp8.py:298) ; dc1 = ds1c + dc2  (tp8.py:109,117)
+__global__ void assemble_s2_grad_kernel(const float* dlg, const float* dc2, const float* dang, const int32_t* angk,
+                                        const float* ds1c, float* dO2, float* dc1, int B, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* o = dO2 + (int64_t)b * (3 + 2 * nb);
+  for (int d = 0; d < 3; ++d) {
+    o[d] = dc2[b * 3 + d];
+    dc1[b * 3 + d] = ds1c[b * 3 + d] + dc2[b * 3 + d];
+  }
+  for (int j = 0; j < 2 * nb; ++j) o[3 + j] = dlg[(int64_t)b * 2 * nb + j];
+  o[3 + nb + angk[b]] += dang[b] * (3.14159265358979323846f / (float)nb);
+}
+
+}  // namespace
+
+int backward_f32(const Model& m, const float* params, const an3d_labels* labels, const an3d_outputs* out, int B, int N,
+                 int flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  PlanF32 p;
+  AN3D_TRY(plan_f32(m, B, N, flags | AN3D_TRAINING, workspace, &p));
+  if (p.bytes > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes, got %lld", (long long)p.bytes, (long long)workspace_bytes);
+    return AN3D_ERR_WORKSPACE;
+  }
+  const int nb = m.nb;
+  AN3D_TRY(run_loss(m, labels, out, B, loss_out, p.loss_scratch, p.dend, st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(grads, 0, sizeof(float) * m.n_trainable, st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));
+  const unsigned b_blocks = (unsigned)((B + 127) / 128);
+  const float* masks[5];
+  for (int i = 0; i < 5; ++i) {
+    const int s = i < 2 ? S1 : (i < 4 ? S2 : HEAD);
+    masks[i] = m.arch.keep_prob[s] < 1.f ? p.mask[i] : nullptr;
+  }
+  const int c_emb = m.conv[EMB].back().cout;
+  // head
+  assemble_head_grad_kernel<<<b_blocks, 128, 0, st>>>(p.dend, p.dout, p.dc2[0], p.dc2[1], B, nb);
+  AN3D_LAUNCH_CHECK();
+  AN3D_TRY(mlp_backward(m, p, HEAD, 0, p.feat, 2 * c_emb, p.dout, params, grads, p.dfeat, 2 * c_emb, masks[4], st));
+  const float* dlg[2] = {p.dend + (int64_t)5 * B * 3, p.dend + (int64_t)5 * B * 3 + (int64_t)B * 2 * nb};
+  const float* ds1c[2] = {p.dend, p.dend + (int64_t)B * 3};
+  for (int br = 0; br < 2; ++br) {
+    // final embedding stack: input q = Rz(a)(p - c2)
+    AN3D_TRY(conv_stack_backward(m, p, EMB, br, p.dfeat + (int64_t)br * c_emb, 2 * c_emb, params, grads, true, st));
+    input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[EMB][br], p.ang[br], p.dc2[br], p.dang[br], N, B);
+    AN3D_LAUNCH_CHECK();
+    // stage 2
+    assemble_s2_grad_kernel<<<b_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], p.dout,
+                                                      p.dc1[br], B, nb);
+    AN3D_LAUNCH_CHECK();
+    const int c2w = m.conv[S2].back().cout;
+    AN3D_TRY(mlp_backward(m, p, S2, br, p.g[S2][br], c2w, p.dout, params, grads, p.dg, c2w, masks[2 + br], st));
+    AN3D_TRY(conv_stack_backward(m, p, S2, br, p.dg, c2w, params, grads, true, st));
+    input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[S2][br], nullptr, p.dc1[br], nullptr, N, B);
+    AN3D_LAUNCH_CHECK();
+    // stage 1: d(delta1) = dc1 (tp8.py:109); its input p - mean(p) carries no parameter gradient
+    const int c1w = m.conv[S1].back().cout;
+    AN3D_TRY(mlp_backward(m, p, S1, br, p.g[S1][br], c1w, p.dc1[br], params, grads, p.dg, c1w, masks[br], st));
+    AN3D_TRY(conv_stack_backward(m, p, S1, br, p.dg, c1w, params, grads, false, st));
+  }
+  return AN3D_OK;
+}
+
+}  // namespace an3d

@@ -1,0 +1,156 @@
+// Internal declarations shared by the translation units of libalignnet_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/alignnet_b200.h"
+
+namespace an3d {
+
+constexpr float kBnEps = 1e-3f;  // utils/tf_util.py:491
+
+void set_error(const char* fmt, ...);
+
+#define AN3D_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      an3d::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return AN3D_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+#define AN3D_TRY(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != AN3D_OK) return _r; \
+  } while (0)
+
+#define AN3D_LAUNCH_CHECK() AN3D_CUDA_CHECK(cudaGetLastError())
+
+// One linear layer (1x1 conv or FC).  Weights are stored as the reference stores them:
+// [Cin, Cout] row-major (conv kernels [1,1,Cin,Cout] / [1,3,1,Cout], FC [Cin,Cout]).
+struct Lin {
+  int cin = 0, cout = 0;
+  int64_t w = 0, b = 0;  // offsets into the flat parameter buffer
+  int bn = -1;           // index into the per-branch (or head) BN table, -1 = no BN
+  std::string scope;     // TF scope below the branch prefix
+};
+
+// One BN layer of a branch (or of the head).
+struct BnLayer {
+  int ch = 0;
+  int64_t choff = 0;  // channel offset inside the per-branch BN block
+  std::string scope;
+};
+
+enum StageId { S1 = 0, S2 = 1, EMB = 2, HEAD = 2 };
+
+struct TensorInfo {
+  std::string name;
+  int64_t offset;
+  int ndim;
+  int64_t shape[4];
+};
+
+struct Model {
+  an3d_arch arch;
+  int nb = 0;
+  std::vector<Lin> conv[3];  // S1, S2, EMB
+  std::vector<Lin> fc[3];    // S1, S2, HEAD
+  std::vector<BnLayer> bn_branch;  // BN layers of one siamese branch, execution order
+  std::vector<BnLayer> bn_head;
+  int64_t bn_branch_ch = 0, bn_head_ch = 0;
+  int64_t bn_base = 0;        // offset of the BN gamma/beta block inside params
+  int64_t n_trainable = 0, n_state = 0;
+  std::vector<TensorInfo> trainable, state;
+
+  // gamma at returned offset, beta at offset + ch (params); mean at offset, var at + ch (state)
+  int64_t bn_param_off(bool head, int branch, int bn) const {
+    if (head) return bn_base + 2 * 2 * bn_branch_ch + 2 * bn_head[bn].choff;
+    return bn_base + (int64_t)branch * 2 * bn_branch_ch + 2 * bn_branch[bn].choff;
+  }
+  int64_t bn_state_off(bool head, int branch, int bn) const {
+    if (head) return 2 * 2 * bn_branch_ch + 2 * bn_head[bn].choff;
+    return (int64_t)branch * 2 * bn_branch_ch + 2 * bn_branch[bn].choff;
+  }
+  // running slot index for per-step BN scratch (scale/shift/mean/inv): channels before this layer
+  int64_t bn_slot_off(bool head, int branch, int bn) const {
+    if (head) return 2 * bn_branch_ch + bn_head[bn].choff;
+    return (int64_t)branch * bn_branch_ch + bn_branch[bn].choff;
+  }
+  int64_t bn_total_ch() const { return 2 * bn_branch_ch + bn_head_ch; }
+};
+
+int build_model(const an3d_arch* arch, Model* m);
+
+// Bump allocator over the caller's workspace; the same code path sizes it and carves it.
+struct Arena {
+  char* base = nullptr;
+  int64_t off = 0;
+  template <typename T>
+  T* take(int64_t count) {
+    off = (off + 255) & ~int64_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+// Per-step BN scratch, one float per BN channel in each array (indexed by Model::bn_slot_off).
+struct BnScratch {
+  float* scale = nullptr;   // gamma * rsqrt(var + eps)
+  float* shift = nullptr;   // beta - mean * scale
+  float* mean = nullptr;    // batch (or moving) mean
+  float* inv = nullptr;     // rsqrt(var + eps)
+  double* acc0 = nullptr;   // reduction scratch (sum / sum dy)
+  double* acc1 = nullptr;   // reduction scratch (sum sq diff / sum dy*xhat)
+};
+
+// Workspace plan of the fp32 (parity) path: everything the backward needs is materialised.
+struct PlanF32 {
+  int B = 0, N = 0;
+  int64_t M = 0;  // rows per branch = B*N
+  float* pin[3][2];                         // stage input points [M,3]
+  float* z[3][AN3D_MAX_LAYERS][2];          // pre-BN conv outputs [M,C]
+  float* g[3][2];                           // pooled features [B,C3] (EMB: both point into feat)
+  int32_t* gidx[3][2];                      // arg rows of the pool [B,C3]
+  float* feat = nullptr;                    // [B, 2*C_emb] head input
+  float* fz[3][AN3D_MAX_LAYERS + 1][2];     // FC pre-BN outputs [B,C] (head uses branch 0)
+  float* mask[5];                           // dropout keep masks [B, width]
+  float* mu[2];                             // centroids [B,3]
+  float* ang[2];                            // decoded stage-2 yaw [B]
+  int32_t* angk[2];                         // argmax bin [B]
+  BnScratch bn;
+  // backward scratch
+  float* dbuf[2];                           // ping-pong activation gradients [max rows * max ch]
+  float* dfc[2];                            // FC-sized gradients [2B * max fc width]
+  float* dfeat = nullptr;                   // [B, 2*C_emb]
+  float* dpin = nullptr;                    // [M,3]
+  float* dg = nullptr;                      // [B, max C3] pooled-feature gradient
+  float* dout = nullptr;                    // [B, 3+2nb] MLP output gradient
+  double* dbias_acc = nullptr;              // [max ch] bias-gradient reduction scratch
+  float* dend = nullptr;                    // gradients of the 8 end_points, packed (see loss.cu)
+  float* dc1[2];                            // [B,3] accumulated centre gradients
+  float* dc2[2];
+  float* dang[2];                           // [B]
+  float* loss_scratch = nullptr;            // loss partial sums
+  int64_t bytes = 0;
+};
+
+int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* p);
+
+struct Ctx {
+  Model model;
+};
+
+int check_device();
+
+}  // namespace an3d
+
+struct an3d_ctx {
+  an3d::Ctx impl;
+};

@@ -1,0 +1,175 @@
+// fp32 parity path: forward pass of get_model (models/tp8.py:135-158) with CUDA-core kernels.
+#include "kernels_f32.cuh"
+
+namespace an3d {
+
+struct BnView {
+  const float *gamma, *beta;
+  float *state_mean, *state_var;
+  float *scale, *shift, *mean, *inv;
+  double *acc0, *acc1;
+  int ch;
+};
+
+static BnView bn_view(const Model& m, const PlanF32& p, const float* params, float* state, bool head, int br, int bn) {
+  BnView v;
+  const int ch = head ? m.bn_head[bn].ch : m.bn_branch[bn].ch;
+  const int64_t po = m.bn_param_off(head, br, bn), so = m.bn_state_off(head, br, bn), sl = m.bn_slot_off(head, br, bn);
+  v.gamma = params + po;
+  v.beta = params + po + ch;
+  v.state_mean = state ? state + so : nullptr;
+  v.state_var = state ? state + so + ch : nullptr;
+  v.scale = p.bn.scale + sl;
+  v.shift = p.bn.shift + sl;
+  v.mean = p.bn.mean + sl;
+  v.inv = p.bn.inv + sl;
+  v.acc0 = p.bn.acc0 + sl;
+  v.acc1 = p.bn.acc1 + sl;
+  v.ch = ch;
+  return v;
+}
+
+// batch statistics of Z[R,C] (two-pass, tf.nn.moments) or shadows -> scale/shift; EMA update
+static int bn_forward(const BnView& v, const float* Z, int R, bool training, float decay, cudaStream_t st) {
+  const int C = v.ch;
+  const int tb = 128, nb = (C + tb - 1) / tb;
+  if (training) {
+    ColArgs a;
+    a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1; a.mean = v.mean;
+    AN3D_TRY(launch_col_reduce(a, COL_SUM, st));
+    bn_mean_kernel<<<nb, tb, 0, st>>>(v.acc0, v.mean, C, 1.0 / R);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(launch_col_reduce(a, COL_SQDIFF, st));
+  }
+  bn_finalize_kernel<<<nb, tb, 0, st>>>(v.acc1, 1.0 / R, v.gamma, v.beta, v.state_mean, v.state_var, v.mean, v.inv,
+                                          v.scale, v.shift, C, training ? 1 : 0, decay);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, const float* params, float* state,
+                              bool training, float decay, cudaStream_t st) {
+  const int64_t M = p.M;
+  const float* x = p.pin[s][br];
+  const float *psc = nullptr, *psh = nullptr;
+  for (size_t l = 0; l < m.conv[s].size(); ++l) {
+    const Lin& L = m.conv[s][l];
+    GemmArgs g;
+    g.A = x; g.lda = L.cin; g.B = params + L.w; g.ldb = L.cout; g.C = p.z[s][l][br]; g.ldc = L.cout;
+    g.M = (int)M; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
+    AN3D_TRY(launch_gemm(g, false, false, st));
+    BnView v = bn_view(m, p, params, state, false, br, L.bn);
+    AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st));
+    x = p.z[s][l][br];
+    psc = v.scale;
+    psh = v.shift;
+  }
+  const Lin& L = m.conv[s].back();
+  const int64_t ldg = s == EMB ? 2 * L.cout : L.cout;
+  dim3 grid(p.B, (L.cout + 127) / 128);
+  pool_kernel<<<grid, 128, 0, st>>>(x, L.cout, p.N, L.cout, psc, psh, p.g[s][br], ldg, p.gidx[s][br]);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+// get_mlp (models/tp8.py:75-82).  x: [B, cin] with leading dim ldx, already activated.
+static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const float* x, int64_t ldx, const float* params,
+                       float* state, bool training, float decay, const float* mask, cudaStream_t st) {
+  const bool head = s == HEAD;
+  const float *psc = nullptr, *psh = nullptr;
+  const size_t nl = m.fc[s].size();
+  for (size_t l = 0; l < nl; ++l) {
+    const Lin& L = m.fc[s][l];
+    GemmArgs g;
+    g.A = x; g.lda = ldx; g.B = params + L.w; g.ldb = L.cout; g.C = p.fz[s][l][br]; g.ldc = L.cout;
+    g.M = p.B; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
+    if (l == nl - 1 && training && mask) {
+      g.pro_mask = mask;
+      g.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
+    }
+    AN3D_TRY(launch_gemm(g, false, false, st));
+    if (L.bn >= 0) {
+      BnView v = bn_view(m, p, params, state, head, br, L.bn);
+      AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
+      psc = v.scale;
+      psh = v.shift;
+    }
+    x = p.fz[s][l][br];
+    ldx = L.cout;
+  }
+  return AN3D_OK;
+}
+
+int forward_f32(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
+                int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
+                int64_t workspace_bytes, cudaStream_t st) {
+  PlanF32 p;
+  AN3D_TRY(plan_f32(m, B, N, flags, workspace, &p));
+  if (p.bytes > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes, got %lld", (long long)p.bytes, (long long)workspace_bytes);
+    return AN3D_ERR_WORKSPACE;
+  }
+  const bool training = (flags & AN3D_TRAINING) != 0;
+  const int nb = m.nb;
+  const int64_t M = p.M;
+  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));
+  const float* masks[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (training) {
+    for (int i = 0; i < 5; ++i) {
+      const int s = i < 2 ? S1 : (i < 4 ? S2 : HEAD);
+      if (m.arch.keep_prob[s] >= 1.f) continue;
+      const int width = m.fc[s][m.fc[s].size() - 2].cout;
+      const int64_t cnt = (int64_t)B * width;
+      if (dropout && dropout->masks[i]) {
+        AN3D_CUDA_CHECK(cudaMemcpyAsync(p.mask[i], dropout->masks[i], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      } else {
+        const uint64_t seed = dropout ? dropout->seed : 0;
+        dropout_mask_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(p.mask[i], cnt, seed, (uint32_t)i,
+                                                                          m.arch.keep_prob[s]);
+        AN3D_LAUNCH_CHECK();
+      }
+      masks[i] = p.mask[i];
+    }
+  }
+  const float* pcs[2] = {pcs1, pcs2};
+  float* c1[2] = {out->pred_s1_pc1centers, out->pred_s1_pc2centers};
+  float* c2[2] = {out->pred_s2_pc1centers, out->pred_s2_pc2centers};
+  float* lg[2] = {out->pred_pc1angle_logits, out->pred_pc2angle_logits};
+  const unsigned pt_blocks = (unsigned)((M + 255) / 256);
+  const unsigned b_blocks = (unsigned)((B + 127) / 128);
+  for (int br = 0; br < 2; ++br) {
+    centroid_kernel<<<(B + 3) / 4, 128, 0, st>>>(pcs[br], N, p.mu[br], B);
+    AN3D_LAUNCH_CHECK();
+    // stage 1 (tp8.py:106-109)
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], p.mu[br], nullptr, p.pin[S1][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, S1, br, params, state, training, bn_decay, st));
+    AN3D_TRY(mlp_forward(m, p, S1, br, p.g[S1][br], m.conv[S1].back().cout, params, state, training, bn_decay,
+                         masks[br], st));
+    post_s1_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(p.fz[S1][m.fc[S1].size() - 1][br], p.mu[br], c1[br], B);
+    AN3D_LAUNCH_CHECK();
+    // stage 2 (tp8.py:113-118)
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c1[br], nullptr, p.pin[S2][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, S2, br, params, state, training, bn_decay, st));
+    AN3D_TRY(mlp_forward(m, p, S2, br, p.g[S2][br], m.conv[S2].back().cout, params, state, training, bn_decay,
+                         masks[2 + br], st));
+    post_s2_kernel<<<b_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
+                                             p.angk[br], B, nb);
+    AN3D_LAUNCH_CHECK();
+    // canonicalise + final embedding (tp8.py:122-130)
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c2[br], p.ang[br], p.pin[EMB][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, EMB, br, params, state, training, bn_decay, st));
+  }
+  // head (tp8.py:144-156)
+  AN3D_TRY(mlp_forward(m, p, HEAD, 0, p.feat, 2 * m.conv[EMB].back().cout, params, state, training, bn_decay, masks[4],
+                       st));
+  post_head_kernel<<<b_blocks, 128, 0, st>>>(p.fz[HEAD][m.fc[HEAD].size() - 1][0], c2[0], c2[1], out->pred_translations,
+                                             out->pred_remaining_angle_logits, B, nb);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+}  // namespace an3d

@@ -1,0 +1,171 @@
+// Flat-buffer TF-Adam, host-decode of angle logits, batched z-axis rigid transforms.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace an3d {
+namespace {
+
+constexpr float kPi = 3.14159265358979323846f;
+
+// tf.train.AdamOptimizer [TF-sem]: m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
+// p <- p - lr_t m / (sqrt(v) + eps),  lr_t = lr sqrt(1-b2^t)/(1-b1^t)  (train.py:212-217)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float grad_scale, float b1, float b2,
+                            float eps) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4),
+           pp = *reinterpret_cast<float4*>(p + i4);
+    const float ga[4] = {gg.x * grad_scale, gg.y * grad_scale, gg.z * grad_scale, gg.w * grad_scale};
+    float* ma = &mm.x; float* va = &vv.x; float* pa = &pp.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
+      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
+      pa[k] = pa[k] - lr_t * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+    *reinterpret_cast<float4*>(p + i4) = pp;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float gi = g[i] * grad_scale;
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    }
+  }
+}
+
+__device__ __forceinline__ float floor_modf(float x, float y) {
+  float r = fmodf(x, y);
+  if (r != 0.f && ((y < 0.f) != (r < 0.f))) r += y;
+  return r;
+}
+
+__global__ void decode_angles_kernel(const float* logits, float* angles, int B, int nb, int scaled) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* lg = logits + (int64_t)b * 2 * nb;
+  int k = 0;
+  float best = lg[0];
+  for (int j = 1; j < nb; ++j)
+    if (lg[j] > best) { best = lg[j]; k = j; }
+  const float apc = 2.0f * kPi / (float)nb;
+  if (scaled) {  // tf_get_angles, models/tp8.py:294-301
+    const float a = (float)k * apc + lg[nb + k] * (kPi / (float)nb);
+    angles[b] = floor_modf(a + kPi, 2.0f * kPi) - kPi;
+  } else {       // classLogits2angle, models/tp8.py:229-244 (quirk Q1: unscaled residual)
+    float a = (float)k * apc + lg[nb + k];
+    if (a > kPi) a -= 2.0f * kPi;
+    angles[b] = a;
+  }
+}
+
+// p' = Rz(theta)(p - c) + c + t  (tp_utils/pointcloud.py:279-298)
+__global__ void rigid_apply_kernel(const float* __restrict__ pts, const float* __restrict__ t,
+                                   const float* __restrict__ ang, const float* __restrict__ ctr,
+                                   float* __restrict__ out, int N, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / N);
+  float cx = 0.f, cy = 0.f, cz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f, s = 0.f, c = 1.f;
+  if (ctr) { cx = ctr[b * 3]; cy = ctr[b * 3 + 1]; cz = ctr[b * 3 + 2]; }
+  if (t) { tx = t[b * 3]; ty = t[b * 3 + 1]; tz = t[b * 3 + 2]; }
+  if (ang) sincosf(ang[b], &s, &c);
+  const float x = pts[i * 3] - cx, y = pts[i * 3 + 1] - cy, z = pts[i * 3 + 2] - cz;
+  out[i * 3] = (c * x - s * y) + cx + tx;
+  out[i * 3 + 1] = (s * x + c * y) + cy + ty;
+  out[i * 3 + 2] = z + cz + tz;
+}
+
+// t' = -d + Rz(theta) d + t, d = c_new - c_old  (tp_utils/pointcloud.py:309-318)
+__global__ void recenter_kernel(const float* t, const float* ang, const float* c_old, const float* c_new, float* out,
+                                int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dx = c_new[i * 3] - c_old[i * 3], dy = c_new[i * 3 + 1] - c_old[i * 3 + 1],
+              dz = c_new[i * 3 + 2] - c_old[i * 3 + 2];
+  float s, c;
+  sincosf(ang[i], &s, &c);
+  out[i * 3] = -dx + (c * dx - s * dy) + t[i * 3];
+  out[i * 3 + 1] = -dy + (s * dx + c * dy) + t[i * 3 + 1];
+  out[i * 3 + 2] = -dz + dz + t[i * 3 + 2];
+}
+
+}  // namespace
+}  // namespace an3d
+
+using namespace an3d;
+
+extern "C" {
+
+int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float lr, int64_t step,
+                   float grad_scale, float beta1, float beta2, float eps, void* stream) {
+  if (!params || !grads || !m || !v || count < 0 || step < 1) {
+    set_error("an3d_adam_step: bad argument (step must be >= 1)");
+    return AN3D_ERR_INVALID;
+  }
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) {
+    set_error("an3d_adam_step: buffers must be 16-byte aligned");
+    return AN3D_ERR_ALIGN;
+  }
+  AN3D_TRY(check_device());
+  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                      (1.0 - std::pow((double)beta1, (double)step));
+  const int64_t nthreads = (count + 3) / 4;
+  if (nthreads == 0) return AN3D_OK;
+  adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, count,
+                                                                                   (float)lr_t, grad_scale, beta1,
+                                                                                   beta2, eps);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_t num_bins, int32_t scaled,
+                       void* stream) {
+  if (!logits || !angles || batch < 0 || num_bins < 1) {
+    set_error("an3d_decode_angles: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  if (batch == 0) return AN3D_OK;
+  decode_angles_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, angles, batch, num_bins, scaled);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_rigid_apply(const float* pts, const float* translation, const float* angle, const float* center, float* out,
+                     int32_t batch, int32_t num_points, void* stream) {
+  if (!pts || !out || batch < 0 || num_points < 0) {
+    set_error("an3d_rigid_apply: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  const int64_t total = (int64_t)batch * num_points;
+  if (total == 0) return AN3D_OK;
+  rigid_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pts, translation, angle, center,
+                                                                                       out, num_points, total);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_recenter_translations(const float* translations, const float* angles, const float* old_centers,
+                               const float* new_centers, float* out, int32_t count, void* stream) {
+  if (!translations || !angles || !old_centers || !new_centers || !out || count < 0) {
+    set_error("an3d_recenter_translations: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  if (count == 0) return AN3D_OK;
+  recenter_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(translations, angles, old_centers, new_centers,
+                                                                         out, count);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+}  // extern "C"

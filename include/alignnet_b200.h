@@ -1,0 +1,170 @@
+/*
+ * alignnet_b200.h -- C ABI of libalignnet_b200.so: the B200 (sm_100a) engine for the AlignNet-3D
+ * `tp8` hot path (siamese 3-stage PointNet pose regressor: forward, loss, backward, TF-Adam, rigid
+ * apply).
+ *
+ * The reference (grossjohannes/AlignNet-3D) is pure Python on TensorFlow 1.8 and has NO FFI; this
+ * header is the boundary a maintainer would bind from `models/tp8.py` with ctypes (see
+ * INTEGRATION.md).  Each entry point cites the reference interface it replaces (file:line into
+ * the reference tree).
+ *
+ * Conventions
+ *   - every function returns int: 0 = AN3D_OK, negative = AN3D_ERR_*; an3d_last_error() returns
+ *     a thread-local message for the last failure.  No exceptions cross the boundary.
+ *   - NO CPU FALLBACK: compute entry points fail with AN3D_ERR_NO_DEVICE / AN3D_ERR_ARCH when no
+ *     sm_100 device is current.  Host-only queries (create, layout, workspace size) work anywhere.
+ *   - the caller owns every buffer (device pointers unless stated otherwise): inputs, outputs,
+ *     flat parameter / gradient / Adam buffers, BN shadow state, workspace.  All device pointers
+ *     must be 16-byte aligned and contiguous (checked, AN3D_ERR_ALIGN).
+ *   - calls are stream-ordered and asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - a ctx is host-only immutable model metadata; it is thread-compatible (no internal state is
+ *     mutated by compute calls), one workspace per in-flight step.
+ */
+#ifndef ALIGNNET_B200_H_
+#define ALIGNNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AN3D_VERSION 100
+
+enum {
+  AN3D_OK = 0,
+  AN3D_ERR_INVALID = -1,      /* bad argument / shape / NULL pointer                       */
+  AN3D_ERR_UNSUPPORTED = -2,  /* config the engine rejects (never a silent fallback)       */
+  AN3D_ERR_NO_DEVICE = -3,    /* no CUDA device                                            */
+  AN3D_ERR_ARCH = -4,         /* device is not sm_100 (B200)                               */
+  AN3D_ERR_CUDA = -5,         /* CUDA runtime error (message in an3d_last_error)           */
+  AN3D_ERR_ALIGN = -6,        /* pointer not 16-byte aligned                               */
+  AN3D_ERR_WORKSPACE = -7     /* workspace too small                                       */
+};
+
+#define AN3D_MAX_LAYERS 8
+
+/* Architecture = the `model` block of the reference's config JSON (configs/default.json:7-23;
+ * read at models/tp8.py:98,108,115,130,154,307-308,318). */
+typedef struct an3d_arch {
+  int32_t num_bins;                       /* cfg.model.angles.num_bins                      */
+  int32_t accept_inverted_angle;          /* cfg.model.angles.accept_inverted_angle         */
+  float angle_factor;                     /* cfg.model.options.angle_factor                 */
+  float early_stage_factor;               /* cfg.model.options.early_stage_factor           */
+  int32_t n_conv[3];                      /* #conv layers of s1transformer / s2transformer / embedding */
+  int32_t conv[3][AN3D_MAX_LAYERS];       /* their widths                                   */
+  int32_t n_fc[3];                        /* #hidden FC layers of s1 / s2 / remaining_transform_prediction */
+  int32_t fc[3][AN3D_MAX_LAYERS];         /* their widths (output layer is implied: 3 or 3+2*num_bins) */
+  float keep_prob[3];                     /* dropout KEEP probability after the last hidden FC (tp8.py:81,86) */
+} an3d_arch;
+
+typedef struct an3d_ctx an3d_ctx;
+
+/* Flags for an3d_forward / an3d_workspace_bytes. */
+enum {
+  AN3D_TRAINING = 1,        /* is_training=True: batch statistics, EMA update, dropout (tf_util.py:476-488,572) */
+  AN3D_PRECISION_FP32 = 0,  /* CUDA-core fp32 everywhere: the <=1e-4 parity mode               */
+  AN3D_PRECISION_BF16 = 2   /* bf16 tcgen05 tensor-core GEMMs with fp32 accumulation (fast mode) */
+};
+
+/* The eight tensors of end_points (models/tp8.py:146-156).  Centers/translations [B,3],
+ * logits [B, 2*num_bins], fp32, row-major. */
+typedef struct an3d_outputs {
+  float* pred_s1_pc1centers;
+  float* pred_s1_pc2centers;
+  float* pred_s2_pc1centers;
+  float* pred_s2_pc2centers;
+  float* pred_pc1angle_logits;
+  float* pred_pc2angle_logits;
+  float* pred_translations;
+  float* pred_remaining_angle_logits;
+} an3d_outputs;
+
+/* Labels = placeholders 3..8 of models/tp8.py:13-23 (translations [B,3], *_angles [B,1], ...). */
+typedef struct an3d_labels {
+  const float* translations;
+  const float* rel_angles;    /* unused by the 'separate' loss, kept for signature parity */
+  const float* pc1_centers;
+  const float* pc2_centers;
+  const float* pc1_angles;
+  const float* pc2_angles;
+} an3d_labels;
+
+/* Dropout control.  masks[i] (optional, device, fp32 0/1 keep-masks [B, last hidden width]) for
+ * i = s1/branch1, s1/branch2, s2/branch1, s2/branch2, head; NULL -> Philox-style counter RNG
+ * keyed by `seed` (tf.nn.dropout at utils/tf_util.py:572-574). */
+typedef struct an3d_dropout {
+  uint64_t seed;
+  const float* masks[5];
+} an3d_dropout;
+
+/* ---- host-only ------------------------------------------------------------------------ */
+int an3d_version(void);
+const char* an3d_last_error(void);
+
+/* Validates the architecture (rejects what v1 does not implement with AN3D_ERR_UNSUPPORTED) and
+ * builds the flat parameter layout.  Replaces graph construction in get_model, models/tp8.py:135. */
+int an3d_create(const an3d_arch* arch, an3d_ctx** out_ctx);
+int an3d_destroy(an3d_ctx* ctx);
+
+/* Flat-buffer layout.  which = 0: trainable parameters (fp32 buffer `params`, same layout for
+ * `grads`, Adam `m`, `v`); which = 1: BN shadow state (`bn_state`).  Names are the TF variable
+ * names of the reference graph (utils/tf_util.py:148-160,333-339,470-479). */
+int an3d_num_elements(const an3d_ctx* ctx, int which, int64_t* out_count);
+int an3d_num_tensors(const an3d_ctx* ctx, int which, int32_t* out_count);
+int an3d_tensor_info(const an3d_ctx* ctx, int which, int32_t index, char* name, int32_t name_capacity,
+                     int64_t* offset, int32_t* ndim, int64_t shape[4]);
+
+/* Bytes of caller-owned scratch needed for one step at (B, N) with the given flags. */
+int an3d_workspace_bytes(const an3d_ctx* ctx, int32_t batch, int32_t num_points, int32_t flags, int64_t* out_bytes);
+
+/* ---- device --------------------------------------------------------------------------- */
+
+/* get_model (models/tp8.py:135-158) for both siamese branches + head.
+ *   params    [num_elements(0)] fp32          bn_state [num_elements(1)] fp32 (updated in training)
+ *   pcs1,pcs2 [B,N,3] fp32                    bn_decay: value of train.py:159-174 at this step
+ *   dropout   may be NULL when !AN3D_TRAINING
+ * In training mode the workspace keeps what an3d_loss_backward needs. */
+int an3d_forward(const an3d_ctx* ctx, const float* params, float* bn_state, const float* pcs1, const float* pcs2,
+                 int32_t batch, int32_t num_points, int32_t flags, float bn_decay, const an3d_dropout* dropout,
+                 const an3d_outputs* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* get_loss -> _get_loss_separate (models/tp8.py:304-354, 401-407).  loss_out: device float[20]:
+ * [0] per_transform_loss, [1] losses/translation, [2] losses/angle, [3..] the stage scalars of
+ * tp8.py:339-353 in that order ([3..16]), rest zero. */
+int an3d_loss(const an3d_ctx* ctx, const an3d_labels* labels, const an3d_outputs* out, int32_t batch,
+              float* loss_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Loss + full backward of the step last run by an3d_forward(AN3D_TRAINING) on `workspace`:
+ * what optimizer.minimize(loss) differentiates (train.py:217).  grads: flat fp32, overwritten. */
+int an3d_loss_backward(const an3d_ctx* ctx, const float* params, const float* pcs1, const float* pcs2,
+                       const an3d_labels* labels, const an3d_outputs* out, int32_t batch, int32_t num_points,
+                       int32_t flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* tf.train.AdamOptimizer.apply_gradients (train.py:212-217) over the flat buffers:
+ * g = grads*grad_scale; m,v EMAs; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
+ * step = t >= 1. */
+int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float lr, int64_t step,
+                   float grad_scale, float beta1, float beta2, float eps, void* stream);
+
+/* tf_get_angles (models/tp8.py:294-301; scaled=1: residual * pi/nb, floor-mod wrap) or
+ * classLogits2angle (tp8.py:229-244; scaled=0: unscaled residual, `if a > pi: a -= 2pi`). */
+int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_t num_bins, int32_t scaled,
+                       void* stream);
+
+/* get_mat_angle + transform_points (tp_utils/pointcloud.py:279-298), batched:
+ * out[b,n,:] = Rz(angle[b]) (pts[b,n,:] - center[b]) + center[b] + translation[b].
+ * translation / angle / center may be NULL (identity), as in the reference's defaults. */
+int an3d_rigid_apply(const float* pts, const float* translation, const float* angle, const float* center,
+                     float* out, int32_t batch, int32_t num_points, void* stream);
+
+/* translate_transform_to_new_center_of_rotation (tp_utils/pointcloud.py:309-318):
+ * out[i] = -d + Rz(angle[i]) d + t[i],  d = new_center[i] - old_center[i]. */
+int an3d_recenter_translations(const float* translations, const float* angles, const float* old_centers,
+                               const float* new_centers, float* out, int32_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNNET_B200_H_ */
