@@ -44,6 +44,8 @@ def case(name, arch, B, N, seed, grads=True):
     if grads:
         loss, ep64, g, st64 = TR.loss_and_grads(batch, arch, params, state, 0.5, masks)
         out["train/loss"] = np.float64(loss)
+        for k, v in ep64.items():
+            out["train64/" + k] = v
         for k, v in g.items():
             out["gradnorm/" + k] = np.float64(np.sqrt((v ** 2).sum()))
             if v.size <= 2048:
