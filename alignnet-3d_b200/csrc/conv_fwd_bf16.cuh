@@ -1,0 +1,384 @@
+// Fused PointNet conv stack (3 -> 64 -> 128 -> C3, BN + ReLU folded, max-pool) for sm_100a.
+//
+// One persistent CTA per SM walks a contiguous range of work items (item = one cloud, or one
+// <=256-point chunk of a cloud).  Per item:
+//   front-end warps : recentre/rotate the points, layer 1 (K = 3, CUDA-core FFMA) -> bf16 A1 tile in
+//                     shared memory; after the layer-2 MMA, TMEM -> BN affine + ReLU -> bf16 A2 tile
+//   MMA thread      : tcgen05.mma  D2[128 ch, pts] = W2^T A1^T   (K = 64)
+//                     tcgen05.mma  D3[128 ch, pts] = W3^T[chunk] A2^T  (K = 128) per 128-channel chunk,
+//                     accumulators in TMEM, two point-halves double-buffered against the epilogue
+//   back-end warps  : TMEM -> per-channel running max over the cloud's points (one thread owns one
+//                     channel, so the max-pool and the BN statistics need no cross-thread reduction)
+//   loader thread   : bulk async copies (TMA unit) of the pre-packed W2^T / W3^T images
+// Accumulators are channel-major (TMEM lane = output channel, column = point): the weights are the
+// MMA "A" operand, the activations the "B" operand.  W3 is sign-folded with sign(gamma) at pack time
+// so that the pooled extreme of the raw accumulator is always a max (BN + ReLU are monotone).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace an3d {
+namespace convfwd {
+
+using namespace umma;
+
+constexpr int kThreads = 320;          // 4 back-end + 4 front-end warps, MMA warp, loader warp
+constexpr int kMaxPC = 256;            // points per item
+constexpr uint32_t kW2Bytes = 128 * 64 * 2;
+constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
+constexpr uint32_t kPlaneW2 = 128 * 16;   // plane stride of the weight images (rows = 128 channels)
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;
+
+enum Mode { MODE_STATS2 = 0, MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
+
+struct Params {
+  const float* pcs;       // [B, N, 3] raw points of this branch
+  const float* center;    // [B, 3] subtracted from the points
+  const float* angle;     // [B] rotation about z applied after recentring, or nullptr
+  int B, N;
+  int PC, npc;            // points per item (multiple of 16, <= 256) and items per cloud
+  int item_begin_stride;  // items per CTA
+  int n_items;
+  const float* w1f;       // [3][64] layer-1 weights with the BN scale folded in
+  const float* c1f;       // [64]    folded bias
+  const __nv_bfloat16* w2t_img;  // plane image of W2^T [128 ch][64 k]
+  const float* s2;        // [128] BN scale of layer 2
+  const float* t2f;       // [128] folded shift (includes the conv bias)
+  const __nv_bfloat16* w3t_img;  // nchunk plane images of (sign-folded) W3^T [128 ch][128 k]
+  int nchunk;             // C3 / 128
+  int nstages;            // W3 ring depth (2 or 3)
+  uint32_t* zext;         // [B][C3] ordered-uint packed max of the raw layer-3 accumulator
+  double* stats2;         // [128][2]  sum, sum of squares of the raw layer-2 accumulator
+  double* stats3;         // [C3][2]   same for layer 3 (sign-folded)
+  __nv_bfloat16* a1_out;  // optional [B*N, 64]  saved activations for the backward pass
+  __nv_bfloat16* a2_out;  // optional [B*N, 128]
+  uint32_t idx_mask;      // low mantissa bits that carry the arg-max point index (training)
+};
+
+__host__ __device__ inline uint32_t plane_stride(int rows) { return (uint32_t)rows * 16u + 16u; }
+
+inline size_t smem_bytes(int PC, int nstages) {
+  const size_t a2 = 16 * (size_t)plane_stride(PC);
+  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,s2,t2f*/ + 256 /*barriers*/ + 128;
+}
+
+__device__ __forceinline__ uint32_t to_ordered(uint32_t bits) {
+  return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct Barriers {
+  uint64_t w2_full;
+  uint64_t w3_full[3];
+  uint64_t w3_empty[3];
+  uint64_t a1_full;
+  uint64_t d2_full;
+  uint64_t a2_full[2];
+  uint64_t a2_empty[2];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  float xf[8];   // per-item transform: cx, cy, cz, cos, sin
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
+  const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
+  const uint32_t a2_bytes = 16 * plane2;
+  uint8_t* sA2[2] = {smem, smem + a2_bytes};
+  uint8_t* sW2 = smem + 2 * a2_bytes;
+  uint8_t* sW3 = sW2 + kW2Bytes;
+  float* sW1f = reinterpret_cast<float*>(sW3 + (size_t)P.nstages * kW3ChunkBytes);  // [3][64]
+  float* sC1f = sW1f + 192;
+  float* sS2 = sC1f + 64;
+  float* sT2f = sS2 + 128;
+  Barriers* bars = reinterpret_cast<Barriers*>(sT2f + 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
+  const int it_end = min(P.n_items, it_begin + P.item_begin_stride);
+  const int n_local = it_end - it_begin;
+
+  if (tid == 0) {
+    mbar_init(&bars->w2_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars->w3_full[i], 1); mbar_init(&bars->w3_empty[i], 1); }
+    mbar_init(&bars->a1_full, 128);
+    mbar_init(&bars->d2_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a2_full[i], 128);
+      mbar_init(&bars->a2_empty[i], 1);
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->acc_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 192; i += kThreads) sW1f[i] = P.w1f[i];
+  for (int i = tid; i < 64; i += kThreads) sC1f[i] = P.c1f[i];
+  if (MODE != MODE_STATS2)
+    for (int i = tid; i < 128; i += kThreads) { sS2[i] = P.s2[i]; sT2f[i] = P.t2f[i]; }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp >= 4 && warp < 8) {
+    // ================================ front-end ================================
+    const int f = tid - 128;                       // 0..127: point slot (layer 1) / channel (layer-2 epilogue)
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
+    double st_s = 0.0, st_ss = 0.0;
+    for (int li = 0; li < n_local; ++li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      const int NT = (nvalid + 15) & ~15;
+      const int64_t row0 = (int64_t)cloud * P.N + p0;
+      const int b = li & 1;
+      if (MODE != MODE_STATS2 && li >= 2) { mbar_wait(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
+      // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
+      uint8_t* sA1 = sA2[b];
+      if (f == 0) {
+        float sn = 0.f, cs = 1.f;
+        if (P.angle) sincosf(P.angle[cloud], &sn, &cs);
+        bars->xf[0] = P.center[cloud * 3]; bars->xf[1] = P.center[cloud * 3 + 1]; bars->xf[2] = P.center[cloud * 3 + 2];
+        bars->xf[3] = cs; bars->xf[4] = sn;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float cx = bars->xf[0], cy = bars->xf[1], cz = bars->xf[2], cs = bars->xf[3], sn = bars->xf[4];
+      // ---- layer 1: y = relu(W1f^T p' + c1f), one thread per point, 8 channels per 16-byte chunk
+      for (int p = f; p < NT; p += 128) {
+        if (p < nvalid) {
+          const float* src = P.pcs + (row0 + p) * 3;
+          const float x0 = src[0] - cx, y0 = src[1] - cy, z = src[2] - cz;
+          const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c8 * 8 + j;
+              v[j] = fmaxf(fmaf(x, sW1f[c], fmaf(y, sW1f[64 + c], fmaf(z, sW1f[128 + c], sC1f[c]))), 0.f);
+            }
+            uint4 q;
+            q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+            q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = q;
+            if (MODE == MODE_FULL_TRAIN && P.a1_out)
+              *reinterpret_cast<uint4*>(P.a1_out + (row0 + p) * 64 + c8 * 8) = q;
+          }
+        } else {
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->a1_full);
+      // ---- layer-2 epilogue: channel k = f
+      mbar_wait(&bars->d2_full, ph_d2); ph_d2 ^= 1;
+      tc_fence_after();
+      const int k = f;
+      const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
+      uint8_t* dst = sA2[b] + (k >> 3) * plane2 + (k & 7) * 2;
+      float ts = 0.f, tss = 0.f;
+      for (int g16 = 0; g16 < NT; g16 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int p = g16 + j;
+          const float acc = __uint_as_float(r[j]);
+          if (MODE == MODE_STATS2) {
+            if (p < nvalid) { ts += acc; tss = fmaf(acc, acc, tss); }
+          } else {
+            const float v = p < nvalid ? fmaxf(fmaf(acc, sc, sh), 0.f) : 0.f;
+            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+            *reinterpret_cast<__nv_bfloat16*>(dst + p * 16) = hb;
+            if (MODE == MODE_FULL_TRAIN && P.a2_out && p < nvalid) P.a2_out[(row0 + p) * 128 + k] = hb;
+          }
+        }
+      }
+      tc_fence_before();
+      if (MODE == MODE_STATS2) {
+        st_s += (double)ts; st_ss += (double)tss;
+      } else {
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->a2_full[b]);
+      }
+    }
+    if (MODE == MODE_STATS2 && n_local > 0) {
+      atomicAdd(P.stats2 + 2 * f, st_s);
+      atomicAdd(P.stats2 + 2 * f + 1, st_ss);
+    }
+  } else if (warp < 4) {
+    // ================================ back-end =================================
+    if (MODE != MODE_STATS2) {
+      const int e = tid;                             // channel within the 128-channel chunk
+      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+      uint32_t ph_full[2] = {0, 0};
+      double s3[8], ss3[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s3[j] = 0.0; ss3[j] = 0.0; }
+      const int C3 = P.nchunk * 128;
+      for (int li = 0; li < n_local; ++li) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int p0 = pchunk * P.PC;
+        const int nvalid = min(P.PC, P.N - p0);
+        const int NT = (nvalid + 15) & ~15;
+        int N0 = ((NT >> 1) + 15) & ~15;
+        if (N0 > NT) N0 = NT;
+        const int Nh[2] = {N0, NT - N0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j >= P.nchunk) break;
+          float m = -INFINITY, ts = 0.f, tss = 0.f;
+          for (int h = 0; h < 2; ++h) {
+            if (Nh[h] == 0) continue;
+            mbar_wait(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+            tc_fence_after();
+            const int off = h ? N0 : 0;
+            for (int g16 = 0; g16 < Nh[h]; g16 += 16) {
+              uint32_t r[16];
+              tmem_ld16(tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0) + g16, r);
+              tmem_ld_wait();
+              if (off + g16 + 16 <= nvalid) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  if (MODE == MODE_FULL_TRAIN) {
+                    const float v = __uint_as_float(r[q]);
+                    ts += v; tss = fmaf(v, v, tss);
+                    m = fmaxf(m, __uint_as_float((r[q] & ~P.idx_mask) | (uint32_t)(p0 + off + g16 + q)));
+                  } else {
+                    m = fmaxf(m, __uint_as_float(r[q]));
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  if (off + g16 + q < nvalid) {
+                    if (MODE == MODE_FULL_TRAIN) {
+                      const float v = __uint_as_float(r[q]);
+                      ts += v; tss = fmaf(v, v, tss);
+                      m = fmaxf(m, __uint_as_float((r[q] & ~P.idx_mask) | (uint32_t)(p0 + off + g16 + q)));
+                    } else {
+                      m = fmaxf(m, __uint_as_float(r[q]));
+                    }
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->acc_empty[h]);
+          }
+          const uint32_t key = to_ordered(__float_as_uint(m));
+          uint32_t* zp = P.zext + (size_t)cloud * C3 + j * 128 + e;
+          if (P.npc == 1) *zp = key; else atomicMax(zp, key);
+          if (MODE == MODE_FULL_TRAIN) { s3[j] += (double)ts; ss3[j] += (double)tss; }
+        }
+      }
+      if (MODE == MODE_FULL_TRAIN && n_local > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j >= P.nchunk) break;
+          atomicAdd(P.stats3 + 2 * (j * 128 + e), s3[j]);
+          atomicAdd(P.stats3 + 2 * (j * 128 + e) + 1, ss3[j]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================================ MMA issuer ===============================
+    if (lane == 0 && n_local > 0) {
+      uint32_t ph_a1 = 0, ph_a2f[2] = {0, 0}, ph_w3f[3] = {0, 0, 0}, ph_acce[2] = {1, 1};
+      uint32_t wcount = 0;
+      mbar_wait(&bars->w2_full, 0);
+      auto issue_l2 = [&](int li) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+        const int NT = (nvalid + 15) & ~15;
+        mbar_wait(&bars->a1_full, ph_a1); ph_a1 ^= 1;
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        const uint32_t a_base = smem_u32(sW2), b_base = smem_u32(sA2[li & 1]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_bf16(tmem + kTmemD2, make_desc(a_base + ks * 2 * kPlaneW2, kPlaneW2, 128),
+                   make_desc(b_base + ks * 2 * plane1, plane1, 128), idesc, ks > 0);
+        mma_commit(&bars->d2_full);
+      };
+      issue_l2(0);
+      for (int li = 0; li < n_local; ++li) {
+        if (MODE == MODE_STATS2) {
+          if (li + 1 < n_local) issue_l2(li + 1);
+          continue;
+        }
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+        const int NT = (nvalid + 15) & ~15;
+        int N0 = ((NT >> 1) + 15) & ~15;
+        if (N0 > NT) N0 = NT;
+        const int Nh[2] = {N0, NT - N0};
+        const int b = li & 1;
+        mbar_wait(&bars->a2_full[b], ph_a2f[b]); ph_a2f[b] ^= 1;
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(sA2[b]);
+        for (int j = 0; j < P.nchunk; ++j) {
+          const int stage = wcount % P.nstages;
+          mbar_wait(&bars->w3_full[stage], ph_w3f[stage]); ph_w3f[stage] ^= 1;
+          const uint32_t a_base = smem_u32(sW3 + (size_t)stage * kW3ChunkBytes);
+          for (int h = 0; h < 2; ++h) {
+            if (Nh[h] == 0) continue;
+            mbar_wait(&bars->acc_empty[h], ph_acce[h]); ph_acce[h] ^= 1;
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(128, Nh[h], 0, 0);
+            const uint32_t bh = b_base + (h ? N0 : 0) * 16;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_bf16(tmem + (h ? kTmemAcc1 : kTmemAcc0), make_desc(a_base + ks * 2 * kPlaneW2, kPlaneW2, 128),
+                       make_desc(bh + ks * 2 * plane2, plane2, 128), idesc, ks > 0);
+            mma_commit(&bars->acc_full[h]);
+          }
+          mma_commit(&bars->w3_empty[stage]);
+          ++wcount;
+          if (j == 0 && li + 1 < n_local) issue_l2(li + 1);
+        }
+        mma_commit(&bars->a2_empty[b]);
+      }
+    }
+  } else {
+    // ================================ weight loader ============================
+    if (lane == 0 && n_local > 0) {
+      mbar_arrive_expect_tx(&bars->w2_full, kW2Bytes);
+      bulk_copy_g2s(sW2, P.w2t_img, kW2Bytes, &bars->w2_full);
+      if (MODE != MODE_STATS2) {
+        uint32_t ph_e[3] = {1, 1, 1};
+        const int total = n_local * P.nchunk;
+        for (int q = 0; q < total; ++q) {
+          const int stage = q % P.nstages;
+          mbar_wait(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
+          mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
+          bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
+                        P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,
+                        &bars->w3_full[stage]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace convfwd
+}  // namespace an3d

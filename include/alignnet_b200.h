@@ -164,6 +164,13 @@ int an3d_rigid_apply(const float* pts, const float* translation, const float* an
 int an3d_recenter_translations(const float* translations, const float* angles, const float* old_centers,
                                const float* new_centers, float* out, int32_t count, void* stream);
 
+/* Diagnostic (used by the test-suite, not by the hot path): one-CTA tcgen05 GEMM
+ * d[128, n] = A * B^T over bf16 operands staged exactly like the production kernels stage them.
+ * a_mn / b_mn = 0: operand given K-major (A [128,k], B [n,k] row-major); 1: MN-major (A [k,128],
+ * B [k,n] row-major).  Pins the shared-memory / instruction descriptor conventions on hardware. */
+int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn,
+                       int32_t b_mn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

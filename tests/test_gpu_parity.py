@@ -30,6 +30,7 @@ TOL_TRAIN = 2.5e-4
 # zero, e.g. biases / betas that feed a batch-statistics BN) and 5e-3 on per-tensor norms.
 GRAD_REL = 1e-2
 GRAD_ABS = 2e-6
+GRAD_ABS_GLOBAL = 5e-5   # x (largest |grad| of any tensor): cancellation noise of sums that are exactly zero
 NORM_REL = 5e-3
 
 
@@ -118,13 +119,14 @@ def test_loss_and_gradients_fp32(name):
         if n.endswith("/biases") and "/bn" not in n and ref_norm < 1e-6:
             continue   # bias feeding a BN: gradient is exactly zero up to rounding noise
         assert abs(got_norm - ref_norm) <= NORM_REL * ref_norm + 1e-5, (n, got_norm, ref_norm)
+    gmax = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith("grad/"))
     for k in [k for k in g.files if k.startswith("grad/")]:
         n = k[5:]
         ref = g[k]
         scale = float(np.abs(ref).max())
         err = float(np.abs(grads[n].reshape(ref.shape) - ref).max())
         worst = max(worst, err / max(scale, 1e-12))
-        assert err <= GRAD_REL * scale + GRAD_ABS, (n, err, scale)
+        assert err <= GRAD_REL * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (n, err, scale)
 
 
 def test_loss_forward_only_and_parts():
@@ -161,10 +163,11 @@ def test_full_gradient_vs_autograd_small(accept_inverted):
     torch.cuda.synchronize()
     assert abs(float(loss[0].cpu()) - loss_ref) < 1e-4 * max(1.0, abs(loss_ref))
     grads = e.get_grads()
+    gmax = max(float(np.abs(v).max()) for v in grads_ref.values())
     for n, ref in grads_ref.items():
         scale = float(np.abs(ref).max())
         err = float(np.abs(grads[n].reshape(ref.shape) - ref).max())
-        assert err <= GRAD_REL * scale + GRAD_ABS, (n, err, scale)
+        assert err <= GRAD_REL * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (n, err, scale)
     st = e.get_state()
     for k, v in st_ref.items():
         np.testing.assert_allclose(st[k], v, atol=1e-4, rtol=1e-4, err_msg=k)
