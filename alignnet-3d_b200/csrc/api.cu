@@ -4,15 +4,11 @@
 #include "loss.cuh"
 
 namespace an3d {
-int forward_f32(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
-                int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
-                int64_t workspace_bytes, cudaStream_t st);
-int backward_f32(const Model& m, const float* params, const an3d_labels* labels, const an3d_outputs* out, int B, int N,
-                 int flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
-int plan_bf16_bytes(const Model& m, int B, int N, int flags, int64_t* bytes);
-int forward_bf16(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
+int forward_impl(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
                  int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
                  int64_t workspace_bytes, cudaStream_t st);
+int backward_f32(const Model& m, const float* params, const an3d_labels* labels, const an3d_outputs* out, int B, int N,
+                 int flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int backward_bf16(const Model& m, const float* params, const float* pcs1, const float* pcs2, const an3d_labels* labels,
                   const an3d_outputs* out, int B, int N, int flags, float* grads, float* loss_out, void* workspace,
                   int64_t workspace_bytes, cudaStream_t st);
@@ -58,7 +54,6 @@ int an3d_workspace_bytes(const an3d_ctx* ctx, int32_t batch, int32_t num_points,
     set_error("an3d_workspace_bytes: NULL argument");
     return AN3D_ERR_INVALID;
   }
-  if (flags & AN3D_PRECISION_BF16) return plan_bf16_bytes(ctx->impl.model, batch, num_points, flags, out_bytes);
   PlanF32 p;
   AN3D_TRY(plan_f32(ctx->impl.model, batch, num_points, flags, nullptr, &p));
   *out_bytes = p.bytes;
@@ -83,10 +78,7 @@ int an3d_forward(const an3d_ctx* ctx, const float* params, float* bn_state, cons
   AN3D_TRY(check_outputs(out));
   AN3D_TRY(check_device());
   cudaStream_t st = (cudaStream_t)stream;
-  if (flags & AN3D_PRECISION_BF16)
-    return forward_bf16(ctx->impl.model, params, bn_state, pcs1, pcs2, batch, num_points, flags, bn_decay, dropout, out,
-                        workspace, workspace_bytes, st);
-  return forward_f32(ctx->impl.model, params, bn_state, pcs1, pcs2, batch, num_points, flags, bn_decay, dropout, out,
+  return forward_impl(ctx->impl.model, params, bn_state, pcs1, pcs2, batch, num_points, flags, bn_decay, dropout, out,
                      workspace, workspace_bytes, st);
 }
 

@@ -1,0 +1,305 @@
+// bf16 fast path: host orchestration and the small fold / pack / finalize kernels around the
+// fused tcgen05 conv-stack kernel (conv_fwd_bf16.cuh).
+#include <algorithm>
+
+#include "bf16_path.cuh"
+#include "conv_fwd_bf16.cuh"
+
+namespace an3d {
+
+namespace {
+
+constexpr int kMaxSmem = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: bf16 plane images  (element (row r, k) -> (k/8)*rows*8 + r*8 + k%8)
+// ---------------------------------------------------------------------------------------------
+// W2 [64][128] (TF [Cin][Cout]) -> W2^T image [128 ch][64 k]
+__global__ void pack_w2t_kernel(const float* W2, __nv_bfloat16* img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 64) return;
+  const int c = i / 64, k = i % 64;
+  img[(k >> 3) * 1024 + c * 8 + (k & 7)] = __float2bfloat16_rn(W2[k * 128 + c]);
+}
+
+// W3 [128][C3] -> nchunk images of W3^T [128 ch][128 k], column c multiplied by sign(gamma3[c])
+__global__ void pack_w3t_kernel(const float* W3, const float* gamma3, __nv_bfloat16* img, int C3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C3 * 128) return;
+  const int c = i / 128, k = i % 128;
+  const float sg = gamma3[c] < 0.f ? -1.f : 1.f;
+  const int j = c >> 7, r = c & 127;
+  img[(size_t)j * 16384 + (k >> 3) * 1024 + r * 8 + (k & 7)] = __float2bfloat16_rn(sg * W3[(size_t)k * C3 + c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layer-1 batch statistics in closed form: first and second moments of the transformed points
+// ---------------------------------------------------------------------------------------------
+__global__ void moments_kernel(const float* pcs, const float* center, const float* angle, int N, int64_t total,
+                               double* mom /*[9]*/) {
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / N);
+    const float x0 = pcs[i * 3] - center[b * 3], y0 = pcs[i * 3 + 1] - center[b * 3 + 1],
+                z = pcs[i * 3 + 2] - center[b * 3 + 2];
+    float x = x0, y = y0;
+    if (angle) {
+      float sn, cs;
+      sincosf(angle[b], &sn, &cs);
+      x = x0 * cs - y0 * sn;
+      y = x0 * sn + y0 * cs;
+    }
+    s[0] += x; s[1] += y; s[2] += z;
+    s[3] += (double)x * x; s[4] += (double)x * y; s[5] += (double)x * z;
+    s[6] += (double)y * y; s[7] += (double)y * z; s[8] += (double)z * z;
+  }
+  __shared__ double sm[8][9];
+  for (int q = 0; q < 9; ++q)
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0)
+    for (int q = 0; q < 9; ++q) sm[w][q] = s[q];
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i][threadIdx.x];
+    atomicAdd(mom + threadIdx.x, t);
+  }
+}
+
+struct BnIo {
+  const float *gamma, *beta;
+  float *state_mean, *state_var;
+  float *scale, *shift, *mean, *inv;
+};
+
+__device__ __forceinline__ void bn_fold(const BnIo& io, int c, float mu, float var, int training, float decay,
+                                        float* sc_out, float* sh_out) {
+  if (training) {
+    const float om = 1.f - decay;
+    io.state_mean[c] = io.state_mean[c] - om * (io.state_mean[c] - mu);
+    io.state_var[c] = io.state_var[c] - om * (io.state_var[c] - var);
+  } else {
+    mu = io.state_mean[c];
+    var = io.state_var[c];
+  }
+  const float rs = 1.0f / sqrtf(var + kBnEps);
+  const float sc = io.gamma[c] * rs;
+  io.mean[c] = mu;
+  io.inv[c] = rs;
+  io.scale[c] = sc;
+  io.shift[c] = io.beta[c] - mu * sc;
+  *sc_out = sc;
+  *sh_out = io.beta[c] - mu * sc;
+}
+
+// layer 1: z = W1^T p + b1 ; mean_z = W1^T mean_p + b1 ; var_z = w^T Cov w  (exact, fp64)
+__global__ void fold_l1_kernel(const double* mom, double count, const float* W1 /*[3][64]*/, const float* b1, BnIo io,
+                               int training, float decay, float* w1f, float* c1f) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  float mu = 0.f, var = 1.f;
+  if (training) {
+    const double mx = mom[0] / count, my = mom[1] / count, mz = mom[2] / count;
+    const double cxx = mom[3] / count - mx * mx, cxy = mom[4] / count - mx * my, cxz = mom[5] / count - mx * mz,
+                 cyy = mom[6] / count - my * my, cyz = mom[7] / count - my * mz, czz = mom[8] / count - mz * mz;
+    const double wx = W1[c], wy = W1[64 + c], wz = W1[128 + c];
+    mu = (float)(wx * mx + wy * my + wz * mz + (double)b1[c]);
+    const double v = wx * wx * cxx + wy * wy * cyy + wz * wz * czz + 2.0 * (wx * wy * cxy + wx * wz * cxz + wy * wz * cyz);
+    var = (float)fmax(v, 0.0);
+  }
+  float sc, sh;
+  bn_fold(io, c, mu, var, training, decay, &sc, &sh);
+  w1f[c] = sc * W1[c];
+  w1f[64 + c] = sc * W1[64 + c];
+  w1f[128 + c] = sc * W1[128 + c];
+  c1f[c] = sc * b1[c] + sh;
+}
+
+// layers 2/3: statistics of the raw accumulator (bias excluded; layer 3 sign-folded by sign(gamma))
+__global__ void fold_acc_kernel(const double* stats, double count, const float* bias, BnIo io, int C, int training,
+                                float decay, int sign_folded, float* shift_folded) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mu = 0.f, var = 1.f;
+  if (training) {
+    const double sg = (sign_folded && io.gamma[c] < 0.f) ? -1.0 : 1.0;
+    const double m = stats[2 * c] / count;
+    const double v = stats[2 * c + 1] / count - m * m;
+    mu = (float)(sg * m + (double)bias[c]);
+    var = (float)fmax(v, 0.0);
+  }
+  float sc, sh;
+  bn_fold(io, c, mu, var, training, decay, &sc, &sh);
+  if (shift_folded) shift_folded[c] = sc * bias[c] + sh;
+}
+
+// pooled feature from the packed extreme of the sign-folded raw accumulator:
+//   z_ext = sign(gamma) * unpack(key) + b3 ;  g = relu(scale * z_ext + shift)   (BN + ReLU are monotone)
+__global__ void pool_finalize_kernel(const uint32_t* zext, int B, int C3, const float* gamma, const float* bias,
+                                     const float* scale, const float* shift, uint32_t idx_mask, float* G, int64_t ldg,
+                                     int32_t* gidx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * C3) return;
+  const int b = (int)(i / C3), c = (int)(i % C3);
+  const uint32_t key = zext[i];
+  const uint32_t bits = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  const float v = __uint_as_float(bits & ~idx_mask);
+  const float sg = gamma[c] < 0.f ? -1.f : 1.f;
+  const float z = sg * v + bias[c];
+  G[(int64_t)b * ldg + c] = fmaxf(fmaf(z, scale[c], shift[c]), 0.f);
+  if (gidx) gidx[i] = (int32_t)(bits & idx_mask);
+}
+
+BnIo bn_io(const Model& m, const PlanF32& p, const float* params, float* state, int br, int bn) {
+  BnIo io;
+  const int ch = m.bn_branch[bn].ch;
+  const int64_t po = m.bn_param_off(false, br, bn), so = m.bn_state_off(false, br, bn), sl = m.bn_slot_off(false, br, bn);
+  io.gamma = params + po;
+  io.beta = params + po + ch;
+  io.state_mean = state + so;
+  io.state_var = state + so + ch;
+  io.scale = p.bn.scale + sl;
+  io.shift = p.bn.shift + sl;
+  io.mean = p.bn.mean + sl;
+  io.inv = p.bn.inv + sl;
+  return io;
+}
+
+template <int MODE>
+int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  const int tag = MODE == convfwd::MODE_STATS2 ? PROF_CONV_STATS2 : PROF_CONV_FULL;
+  prof_mark(tag, true, st);
+  convfwd::conv_stack_fwd_kernel<MODE><<<grid, convfwd::kThreads, smem, st>>>(P);
+  prof_mark(tag, false, st);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+}  // namespace
+
+int bf16_supported(const Model& m) {
+  for (int s = 0; s < 3; ++s) {
+    if (m.conv[s].size() != 3 || m.conv[s][0].cout != 64 || m.conv[s][1].cout != 128 || m.conv[s][2].cout % 128 != 0 ||
+        m.conv[s][2].cout > 1024) {
+      set_error("bf16 path implements conv stacks of the form [64, 128, C] with C a multiple of 128 (<= 1024); stage %d "
+                "differs -- use AN3D_PRECISION_FP32 for this architecture", s);
+      return AN3D_ERR_UNSUPPORTED;
+    }
+  }
+  return AN3D_OK;
+}
+
+void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
+  const bool training = (flags & AN3D_TRAINING) != 0;
+  const int64_t M = (int64_t)B * N;
+  q->npc = (N + convfwd::kMaxPC - 1) / convfwd::kMaxPC;
+  q->PC = (((N + q->npc - 1) / q->npc) + 15) & ~15;
+  int bits = 0;
+  while ((1 << bits) < N) ++bits;
+  q->idx_mask = (1u << bits) - 1u;
+  for (int s = 0; s < 3; ++s) {
+    const int C3 = m.conv[s].back().cout;
+    q->w2t[s] = a.take<__nv_bfloat16>(128 * 64);
+    for (int br = 0; br < 2; ++br) {
+      q->w3t[s][br] = a.take<__nv_bfloat16>((int64_t)C3 * 128);
+      q->w1f[s][br] = a.take<float>(192);
+      q->c1f[s][br] = a.take<float>(64);
+      q->t2f[s][br] = a.take<float>(128);
+      q->moments[s][br] = a.take<double>(16);
+      q->stats2[s][br] = a.take<double>(256);
+      q->stats3[s][br] = a.take<double>(2 * (int64_t)C3);
+      q->zext[s][br] = a.take<uint32_t>((int64_t)B * C3);
+      q->a1[s][br] = training ? a.take<__nv_bfloat16>(M * 64) : nullptr;
+      q->a2[s][br] = training ? a.take<__nv_bfloat16>(M * 128) : nullptr;
+    }
+  }
+}
+
+int pack_weights_bf16(const Model& m, const PlanF32& p, const float* params, cudaStream_t st) {
+  for (int s = 0; s < 3; ++s) {
+    const int C3 = m.conv[s].back().cout;
+    pack_w2t_kernel<<<(128 * 64 + 255) / 256, 256, 0, st>>>(params + m.conv[s][1].w, p.bf.w2t[s]);
+    AN3D_LAUNCH_CHECK();
+    for (int br = 0; br < 2; ++br) {
+      const float* gamma3 = params + m.bn_param_off(false, br, m.conv[s][2].bn);
+      pack_w3t_kernel<<<(C3 * 128 + 255) / 256, 256, 0, st>>>(params + m.conv[s][2].w, gamma3, p.bf.w3t[s][br], C3);
+      AN3D_LAUNCH_CHECK();
+    }
+  }
+  return AN3D_OK;
+}
+
+int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, const float* pcs, const float* center,
+                            const float* angle, const float* params, float* state, bool training, float decay,
+                            cudaStream_t st) {
+  const PlanBf16& q = p.bf;
+  const int B = p.B, N = p.N;
+  const int64_t M = p.M;
+  const Lin &L1 = m.conv[s][0], &L2 = m.conv[s][1], &L3 = m.conv[s][2];
+  const int C3 = L3.cout;
+  int dev = 0, sms = 148;
+  AN3D_CUDA_CHECK(cudaGetDevice(&dev));
+  AN3D_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  BnIo io1 = bn_io(m, p, params, state, br, L1.bn), io2 = bn_io(m, p, params, state, br, L2.bn),
+       io3 = bn_io(m, p, params, state, br, L3.bn);
+
+  convfwd::Params P;
+  P.pcs = pcs; P.center = center; P.angle = angle; P.B = B; P.N = N; P.PC = q.PC; P.npc = q.npc;
+  P.n_items = B * q.npc;
+  const int grid = std::min(P.n_items, sms);
+  P.item_begin_stride = (P.n_items + grid - 1) / grid;
+  P.w1f = q.w1f[s][br]; P.c1f = q.c1f[s][br]; P.w2t_img = q.w2t[s]; P.s2 = io2.scale; P.t2f = q.t2f[s][br];
+  P.w3t_img = q.w3t[s][br]; P.nchunk = C3 / 128;
+  P.nstages = convfwd::smem_bytes(q.PC, 3) <= (size_t)kMaxSmem ? 3 : 2;
+  P.zext = q.zext[s][br]; P.stats2 = q.stats2[s][br]; P.stats3 = q.stats3[s][br];
+  P.a1_out = training ? q.a1[s][br] : nullptr; P.a2_out = training ? q.a2[s][br] : nullptr;
+  P.idx_mask = q.idx_mask;
+  const size_t smem = convfwd::smem_bytes(q.PC, P.nstages);
+  if (smem > (size_t)kMaxSmem) {
+    set_error("conv_stack_forward_bf16: tile needs %zu bytes of shared memory", smem);
+    return AN3D_ERR_UNSUPPORTED;
+  }
+
+  if (training) {
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.moments[s][br], 0, 16 * sizeof(double), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats2[s][br], 0, 256 * sizeof(double), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats3[s][br], 0, 2 * (size_t)C3 * sizeof(double), st));
+    const int mb = (int)std::min<int64_t>((M + 255) / 256, 4 * sms);
+    moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
+    AN3D_LAUNCH_CHECK();
+  }
+  fold_l1_kernel<<<1, 64, 0, st>>>(q.moments[s][br], (double)M, params + L1.w, params + L1.b, io1, training ? 1 : 0, decay,
+                                   q.w1f[s][br], q.c1f[s][br]);
+  AN3D_LAUNCH_CHECK();
+  if (training) AN3D_TRY(launch_fused<convfwd::MODE_STATS2>(P, grid, smem, st));
+  fold_acc_kernel<<<1, 128, 0, st>>>(q.stats2[s][br], (double)M, params + L2.b, io2, 128, training ? 1 : 0, decay, 0,
+                                     q.t2f[s][br]);
+  AN3D_LAUNCH_CHECK();
+  if (q.npc > 1) AN3D_CUDA_CHECK(cudaMemsetAsync(q.zext[s][br], 0, (size_t)B * C3 * sizeof(uint32_t), st));
+  if (training) AN3D_TRY(launch_fused<convfwd::MODE_FULL_TRAIN>(P, grid, smem, st));
+  else AN3D_TRY(launch_fused<convfwd::MODE_FULL_EVAL>(P, grid, smem, st));
+  fold_acc_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.stats3[s][br], (double)M, params + L3.b, io3, C3, training ? 1 : 0,
+                                                    decay, 1, nullptr);
+  AN3D_LAUNCH_CHECK();
+  const int64_t ldg = s == EMB ? 2 * C3 : C3;
+  const int64_t tot = (int64_t)B * C3;
+  pool_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q.zext[s][br], B, C3, io3.gamma, params + L3.b,
+                                                                      io3.scale, io3.shift, training ? q.idx_mask : 0u,
+                                                                      p.g[s][br], ldg, training ? p.gidx[s][br] : nullptr);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+}  // namespace an3d
+
+namespace an3d {
+int backward_bf16(const Model&, const float*, const float*, const float*, const an3d_labels*, const an3d_outputs*, int,
+                  int, int, float*, float*, void*, int64_t, cudaStream_t) {
+  set_error("bf16 backward not built yet");
+  return AN3D_ERR_UNSUPPORTED;
+}
+}  // namespace an3d

@@ -29,7 +29,18 @@ void set_error(const char* fmt, ...);
     if (_r != AN3D_OK) return _r; \
   } while (0)
 
-#define AN3D_LAUNCH_CHECK() AN3D_CUDA_CHECK(cudaGetLastError())
+extern unsigned long long g_launch_count;   // kernels launched by this library (an3d_launch_count)
+#define AN3D_LAUNCH_CHECK()                  \
+  do {                                       \
+    ++an3d::g_launch_count;                  \
+    AN3D_CUDA_CHECK(cudaGetLastError());     \
+  } while (0)
+
+// Optional per-kernel timing (an3d_profile_begin/end): CUDA events recorded on the launch stream
+// around the tagged heavy kernels.
+enum ProfTag { PROF_CONV_STATS2 = 0, PROF_CONV_FULL = 1, PROF_BWD_T1 = 2, PROF_BWD_DGRAD3 = 3, PROF_BWD_L2 = 4,
+               PROF_FC = 5, PROF_NTAGS = 8 };
+void prof_mark(int tag, bool begin, cudaStream_t st);
 
 // One linear layer (1x1 conv or FC).  Weights are stored as the reference stores them:
 // [Cin, Cout] row-major (conv kernels [1,1,Cin,Cout] / [1,3,1,Cout], FC [Cin,Cout]).
@@ -110,6 +121,24 @@ struct BnScratch {
   double* acc1 = nullptr;   // reduction scratch (sum sq diff / sum dy*xhat)
 };
 
+// Extra buffers of the bf16 tcgen05 path (conv stacks); FC layers, loss and the inter-stage
+// glue reuse the PlanF32 buffers.
+struct PlanBf16 {
+  int PC = 0, npc = 0;                      // points per work item (multiple of 16) and items per cloud
+  uint32_t idx_mask = 0;                    // low mantissa bits carrying the arg-max point index
+  __nv_bfloat16* w2t[3];                    // W2^T plane image [128 ch][64 k]
+  __nv_bfloat16* w3t[3][2];                 // sign-folded W3^T plane images, per branch (BN gamma is per branch)
+  float* w1f[3][2];                         // layer-1 weights with BN scale folded [3][64]
+  float* c1f[3][2];                         // folded layer-1 bias [64]
+  float* t2f[3][2];                         // folded layer-2 shift [128]
+  double* moments[3][2];                    // first/second moments of the stage input points
+  double* stats2[3][2];                     // sum / sum-of-squares of the raw layer-2 accumulator [128][2]
+  double* stats3[3][2];                     // same for layer 3 [C3][2]
+  uint32_t* zext[3][2];                     // packed pooled extreme [B][C3]
+  __nv_bfloat16* a1[3][2];                  // saved activations (training) [M,64]
+  __nv_bfloat16* a2[3][2];                  // [M,128]
+};
+
 // Workspace plan of the fp32 (parity) path: everything the backward needs is materialised.
 struct PlanF32 {
   int B = 0, N = 0;
@@ -138,6 +167,7 @@ struct PlanF32 {
   float* dc2[2];
   float* dang[2];                           // [B]
   float* loss_scratch = nullptr;            // loss partial sums
+  PlanBf16 bf;                              // only carved when AN3D_PRECISION_BF16 is set
   int64_t bytes = 0;
 };
 

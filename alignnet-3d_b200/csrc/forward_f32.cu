@@ -1,5 +1,6 @@
 // fp32 parity path: forward pass of get_model (models/tp8.py:135-158) with CUDA-core kernels.
 #include "kernels_f32.cuh"
+#include "bf16_path.cuh"
 
 namespace an3d {
 
@@ -100,7 +101,7 @@ static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const fl
   return AN3D_OK;
 }
 
-int forward_f32(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
+int forward_impl(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
                 int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
                 int64_t workspace_bytes, cudaStream_t st) {
   PlanF32 p;
@@ -110,6 +111,8 @@ int forward_f32(const Model& m, const float* params, float* state, const float* 
     return AN3D_ERR_WORKSPACE;
   }
   const bool training = (flags & AN3D_TRAINING) != 0;
+  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
+  if (bf16) AN3D_TRY(pack_weights_bf16(m, p, params, st));
   const int nb = m.nb;
   const int64_t M = p.M;
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
@@ -142,26 +145,38 @@ int forward_f32(const Model& m, const float* params, float* state, const float* 
     centroid_kernel<<<(B + 3) / 4, 128, 0, st>>>(pcs[br], N, p.mu[br], B);
     AN3D_LAUNCH_CHECK();
     // stage 1 (tp8.py:106-109)
-    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], p.mu[br], nullptr, p.pin[S1][br], N, M);
-    AN3D_LAUNCH_CHECK();
-    AN3D_TRY(conv_stack_forward(m, p, S1, br, params, state, training, bn_decay, st));
+    if (bf16) {
+      AN3D_TRY(conv_stack_forward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, params, state, training, bn_decay, st));
+    } else {
+      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], p.mu[br], nullptr, p.pin[S1][br], N, M);
+      AN3D_LAUNCH_CHECK();
+      AN3D_TRY(conv_stack_forward(m, p, S1, br, params, state, training, bn_decay, st));
+    }
     AN3D_TRY(mlp_forward(m, p, S1, br, p.g[S1][br], m.conv[S1].back().cout, params, state, training, bn_decay,
                          masks[br], st));
     post_s1_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(p.fz[S1][m.fc[S1].size() - 1][br], p.mu[br], c1[br], B);
     AN3D_LAUNCH_CHECK();
     // stage 2 (tp8.py:113-118)
-    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c1[br], nullptr, p.pin[S2][br], N, M);
-    AN3D_LAUNCH_CHECK();
-    AN3D_TRY(conv_stack_forward(m, p, S2, br, params, state, training, bn_decay, st));
+    if (bf16) {
+      AN3D_TRY(conv_stack_forward_bf16(m, p, S2, br, pcs[br], c1[br], nullptr, params, state, training, bn_decay, st));
+    } else {
+      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c1[br], nullptr, p.pin[S2][br], N, M);
+      AN3D_LAUNCH_CHECK();
+      AN3D_TRY(conv_stack_forward(m, p, S2, br, params, state, training, bn_decay, st));
+    }
     AN3D_TRY(mlp_forward(m, p, S2, br, p.g[S2][br], m.conv[S2].back().cout, params, state, training, bn_decay,
                          masks[2 + br], st));
     post_s2_kernel<<<b_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
                                              p.angk[br], B, nb);
     AN3D_LAUNCH_CHECK();
     // canonicalise + final embedding (tp8.py:122-130)
-    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c2[br], p.ang[br], p.pin[EMB][br], N, M);
-    AN3D_LAUNCH_CHECK();
-    AN3D_TRY(conv_stack_forward(m, p, EMB, br, params, state, training, bn_decay, st));
+    if (bf16) {
+      AN3D_TRY(conv_stack_forward_bf16(m, p, EMB, br, pcs[br], c2[br], p.ang[br], params, state, training, bn_decay, st));
+    } else {
+      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c2[br], p.ang[br], p.pin[EMB][br], N, M);
+      AN3D_LAUNCH_CHECK();
+      AN3D_TRY(conv_stack_forward(m, p, EMB, br, params, state, training, bn_decay, st));
+    }
   }
   // head (tp8.py:144-156)
   AN3D_TRY(mlp_forward(m, p, HEAD, 0, p.feat, 2 * m.conv[EMB].back().cout, params, state, training, bn_decay, masks[4],

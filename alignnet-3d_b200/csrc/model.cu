@@ -8,6 +8,45 @@
 namespace an3d {
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_launch_count = 0;
+
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs: begin, end
+  std::vector<int> tag;
+};
+static ProfState g_prof;
+
+void prof_mark(int tag, bool begin, cudaStream_t st) {
+  if (!g_prof.on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof.ev.push_back(e);
+  if (begin) g_prof.tag.push_back(tag);
+}
+void prof_begin() {
+  for (auto e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.tag.clear();
+  g_prof.on = true;
+}
+void prof_end(float* ms, int* count) {
+  g_prof.on = false;
+  for (int i = 0; i < PROF_NTAGS; ++i) { ms[i] = 0.f; count[i] = 0; }
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    float t = 0.f;
+    cudaEventSynchronize(g_prof.ev[i + 1]);
+    if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) == cudaSuccess) {
+      const int tag = g_prof.tag[i / 2];
+      ms[tag] += t;
+      count[tag] += 1;
+    }
+  }
+  for (auto e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.tag.clear();
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -191,11 +230,29 @@ int build_model(const an3d_arch* a, Model* m) {
 
 namespace an3d {
 const char* last_error();
+void prof_begin();
+void prof_end(float* ms, int* count);
 }
 
 extern "C" {
 
 int an3d_version(void) { return AN3D_VERSION; }
+
+uint64_t an3d_launch_count(void) { return an3d::g_launch_count; }
+
+int an3d_profile_begin(void) {
+  an3d::prof_begin();
+  return AN3D_OK;
+}
+
+int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag) {
+  if (!ms_by_tag || !launches_by_tag) {
+    an3d::set_error("an3d_profile_end: NULL argument");
+    return AN3D_ERR_INVALID;
+  }
+  an3d::prof_end(ms_by_tag, launches_by_tag);
+  return AN3D_OK;
+}
 
 const char* an3d_last_error(void) { return an3d::last_error(); }
 

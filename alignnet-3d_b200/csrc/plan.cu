@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "loss.cuh"
+#include "bf16_path.cuh"
 
 namespace an3d {
 
@@ -12,6 +13,8 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     return AN3D_ERR_INVALID;
   }
   const bool training = (flags & AN3D_TRAINING) != 0;
+  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
+  if (bf16) AN3D_TRY(bf16_supported(m));
   Arena a;
   a.base = static_cast<char*>(workspace);
   p->B = B;
@@ -23,9 +26,9 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
   int64_t max_conv_ch = 0, max_fc_ch = 0;
   for (int s = 0; s < 3; ++s) {
     for (int br = 0; br < 2; ++br) {
-      p->pin[s][br] = a.take<float>(M * 3);
+      p->pin[s][br] = bf16 ? nullptr : a.take<float>(M * 3);
       for (size_t l = 0; l < m.conv[s].size(); ++l) {
-        p->z[s][l][br] = a.take<float>(M * m.conv[s][l].cout);
+        p->z[s][l][br] = bf16 ? nullptr : a.take<float>(M * m.conv[s][l].cout);
         max_conv_ch = std::max<int64_t>(max_conv_ch, m.conv[s][l].cout);
       }
       const int c3 = m.conv[s].back().cout;
@@ -67,7 +70,7 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
   p->loss_scratch = a.take<float>(loss_scratch_floats(B));
   p->dend = a.take<float>((int64_t)B * (5 * 3 + 3 * 2 * m.nb));
   if (training) {
-    const int64_t big = M * max_conv_ch;
+    const int64_t big = bf16 ? 0 : M * max_conv_ch;
     p->dbuf[0] = a.take<float>(big);
     p->dbuf[1] = a.take<float>(big);
     p->dfc[0] = a.take<float>((int64_t)B * max_fc_ch);
@@ -89,6 +92,7 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     p->dbias_acc = nullptr;
     for (int br = 0; br < 2; ++br) p->dc1[br] = p->dc2[br] = p->dang[br] = nullptr;
   }
+  if (bf16) plan_bf16(m, B, N, flags, a, &p->bf);
   p->bytes = (a.off + 255) & ~int64_t(255);
   return AN3D_OK;
 }

@@ -164,6 +164,15 @@ int an3d_rigid_apply(const float* pts, const float* translation, const float* an
 int an3d_recenter_translations(const float* translations, const float* angles, const float* old_centers,
                                const float* new_centers, float* out, int32_t count, void* stream);
 
+/* Instrumentation for bench.py.  an3d_launch_count: kernels launched by this library since load.
+ * an3d_profile_begin/end: while enabled, CUDA events are recorded on the launch stream around the
+ * heavy kernels; _end synchronises and returns, per tag (host arrays of 8: 0 conv-stack layer-2
+ * statistics pass, 1 conv-stack full pass, 2..4 backward kernels, 5 FC), the summed device
+ * milliseconds and the number of launches. */
+uint64_t an3d_launch_count(void);
+int an3d_profile_begin(void);
+int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag);
+
 /* Diagnostic (used by the test-suite, not by the hot path): one-CTA tcgen05 GEMM
  * d[128, n] = A * B^T over bf16 operands staged exactly like the production kernels stage them.
  * a_mn / b_mn = 0: operand given K-major (A [128,k], B [n,k] row-major); 1: MN-major (A [k,128],
