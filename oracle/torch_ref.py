@@ -46,12 +46,23 @@ def _bn(z, spec, branch, params, state, new_state, training, bn_decay, axes):
     return z * inv + (beta - mean * inv)
 
 
+SIM_BF16 = False   # model the rounding points of the engine's bf16 fast mode (tests only)
+
+
+def _r16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
 def _conv_stack(p, specs, branch, params, state, new_state, training, bn_decay):
-    """models/tp8.py:49-59."""
+    """models/tp8.py:49-59.  With SIM_BF16 the inputs of every conv after the first (activations and
+    weights) are rounded to bf16, which is where the engine's tensor-core path rounds."""
     x = p
-    for s in specs:
+    for i, s in enumerate(specs):
         n = weight_names(s)
-        z = x @ params[n["weights"]] + params[n["biases"]]
+        w = params[n["weights"]]
+        if SIM_BF16 and i > 0:
+            x, w = _r16(x), _r16(w)
+        z = x @ w + params[n["biases"]]
         x = torch.relu(_bn(z, s, branch, params, state, new_state, training, bn_decay, (0, 1)))
     return x.max(dim=1).values
 
