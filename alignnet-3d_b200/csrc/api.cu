@@ -7,9 +7,7 @@ namespace an3d {
 int forward_impl(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
                  int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
                  int64_t workspace_bytes, cudaStream_t st);
-int backward_f32(const Model& m, const float* params, const an3d_labels* labels, const an3d_outputs* out, int B, int N,
-                 int flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
-int backward_bf16(const Model& m, const float* params, const float* pcs1, const float* pcs2, const an3d_labels* labels,
+int backward_impl(const Model& m, const float* params, const float* pcs1, const float* pcs2, const an3d_labels* labels,
                   const an3d_outputs* out, int B, int N, int flags, float* grads, float* loss_out, void* workspace,
                   int64_t workspace_bytes, cudaStream_t st);
 }  // namespace an3d
@@ -116,11 +114,8 @@ int an3d_loss_backward(const an3d_ctx* ctx, const float* params, const float* pc
   AN3D_TRY(check_outputs(out));
   AN3D_TRY(check_device());
   cudaStream_t st = (cudaStream_t)stream;
-  if (flags & AN3D_PRECISION_BF16)
-    return backward_bf16(ctx->impl.model, params, pcs1, pcs2, labels, out, batch, num_points, flags, grads, loss_out,
-                         workspace, workspace_bytes, st);
-  return backward_f32(ctx->impl.model, params, labels, out, batch, num_points, flags, grads, loss_out, workspace,
-                      workspace_bytes, st);
+  return backward_impl(ctx->impl.model, params, pcs1, pcs2, labels, out, batch, num_points, flags, grads, loss_out,
+                       workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

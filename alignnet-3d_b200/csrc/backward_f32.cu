@@ -4,6 +4,7 @@
 
 #include "kernels_f32.cuh"
 #include "loss.cuh"
+#include "bf16_path.cuh"
 
 namespace an3d {
 
@@ -198,8 +199,9 @@ __global__ void assemble_s2_grad_kernel(const float* dlg, const float* dc2, cons
 
 }  // namespace
 
-int backward_f32(const Model& m, const float* params, const an3d_labels* labels, const an3d_outputs* out, int B, int N,
-                 int flags, float* grads, float* loss_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+int backward_impl(const Model& m, const float* params, const float* pcs1, const float* pcs2, const an3d_labels* labels,
+                  const an3d_outputs* out, int B, int N, int flags, float* grads, float* loss_out, void* workspace,
+                  int64_t workspace_bytes, cudaStream_t st) {
   PlanF32 p;
   AN3D_TRY(plan_f32(m, B, N, flags | AN3D_TRAINING, workspace, &p));
   if (p.bytes > workspace_bytes) {
@@ -207,6 +209,11 @@ int backward_f32(const Model& m, const float* params, const an3d_labels* labels,
     return AN3D_ERR_WORKSPACE;
   }
   const int nb = m.nb;
+  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
+  const float* pcs[2] = {pcs1, pcs2};
+  const float* c1o[2] = {out->pred_s1_pc1centers, out->pred_s1_pc2centers};
+  const float* c2o[2] = {out->pred_s2_pc1centers, out->pred_s2_pc2centers};
+  if (bf16) AN3D_TRY(pack_weights_bf16_bwd(m, p, params, st));
   AN3D_TRY(run_loss(m, labels, out, B, loss_out, p.loss_scratch, p.dend, st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(grads, 0, sizeof(float) * m.n_trainable, st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
@@ -226,22 +233,38 @@ int backward_f32(const Model& m, const float* params, const an3d_labels* labels,
   const float* ds1c[2] = {p.dend, p.dend + (int64_t)B * 3};
   for (int br = 0; br < 2; ++br) {
     // final embedding stack: input q = Rz(a)(p - c2)
-    AN3D_TRY(conv_stack_backward(m, p, EMB, br, p.dfeat + (int64_t)br * c_emb, 2 * c_emb, params, grads, true, st));
-    input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[EMB][br], p.ang[br], p.dc2[br], p.dang[br], N, B);
-    AN3D_LAUNCH_CHECK();
+    if (bf16) {
+      AN3D_CUDA_CHECK(cudaMemsetAsync(p.dang[br], 0, sizeof(float) * B, st));
+      AN3D_TRY(conv_stack_backward_bf16(m, p, EMB, br, pcs[br], c2o[br], p.ang[br], p.dfeat + (int64_t)br * c_emb,
+                                        2 * c_emb, params, grads, true, p.dc2[br], p.dang[br], st));
+    } else {
+      AN3D_TRY(conv_stack_backward(m, p, EMB, br, p.dfeat + (int64_t)br * c_emb, 2 * c_emb, params, grads, true, st));
+      input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[EMB][br], p.ang[br], p.dc2[br], p.dang[br], N, B);
+      AN3D_LAUNCH_CHECK();
+    }
     // stage 2
     assemble_s2_grad_kernel<<<b_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], p.dout,
                                                       p.dc1[br], B, nb);
     AN3D_LAUNCH_CHECK();
     const int c2w = m.conv[S2].back().cout;
     AN3D_TRY(mlp_backward(m, p, S2, br, p.g[S2][br], c2w, p.dout, params, grads, p.dg, c2w, masks[2 + br], st));
-    AN3D_TRY(conv_stack_backward(m, p, S2, br, p.dg, c2w, params, grads, true, st));
-    input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[S2][br], nullptr, p.dc1[br], nullptr, N, B);
-    AN3D_LAUNCH_CHECK();
+    if (bf16) {
+      AN3D_TRY(conv_stack_backward_bf16(m, p, S2, br, pcs[br], c1o[br], nullptr, p.dg, c2w, params, grads, true,
+                                        p.dc1[br], nullptr, st));
+    } else {
+      AN3D_TRY(conv_stack_backward(m, p, S2, br, p.dg, c2w, params, grads, true, st));
+      input_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(p.dpin, p.pin[S2][br], nullptr, p.dc1[br], nullptr, N, B);
+      AN3D_LAUNCH_CHECK();
+    }
     // stage 1: d(delta1) = dc1 (tp8.py:109); its input p - mean(p) carries no parameter gradient
     const int c1w = m.conv[S1].back().cout;
     AN3D_TRY(mlp_backward(m, p, S1, br, p.g[S1][br], c1w, p.dc1[br], params, grads, p.dg, c1w, masks[br], st));
-    AN3D_TRY(conv_stack_backward(m, p, S1, br, p.dg, c1w, params, grads, false, st));
+    if (bf16) {
+      AN3D_TRY(conv_stack_backward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, p.dg, c1w, params, grads, false,
+                                        nullptr, nullptr, st));
+    } else {
+      AN3D_TRY(conv_stack_backward(m, p, S1, br, p.dg, c1w, params, grads, false, st));
+    }
   }
   return AN3D_OK;
 }

@@ -1,0 +1,308 @@
+// bf16 fast path, backward: small coefficient / packing kernels and the host orchestration around
+// the tcgen05 backward kernels of conv_bwd_bf16.cuh.  FC layers, loss and the inter-stage glue are
+// shared with the fp32 path (backward_f32.cu).
+#include <algorithm>
+
+#include "bf16_path.cuh"
+#include "conv_bwd_bf16.cuh"
+
+namespace an3d {
+
+namespace {
+
+constexpr int kMaxSmem = 227 * 1024;
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// W3 [128][C3] -> C3/64 half-chunk images [128 rows k][64 c] (K-major in c), unfolded
+__global__ void pack_w3n_kernel(const float* W3, __nv_bfloat16* img, int C3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C3 * 128) return;
+  const int k = i / C3, c = i % C3;
+  const int hc = c >> 6, cc = c & 63;
+  img[(size_t)hc * 8192 + (cc >> 3) * 1024 + k * 8 + (cc & 7)] = __float2bfloat16_rn(W3[i]);
+}
+
+// W2 [64][128] -> image [128 rows k1 (rows >= 64 zero)][128 k2]
+__global__ void pack_w2p_kernel(const float* W2, __nv_bfloat16* img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128) return;
+  const int k1 = i / 128, k2 = i % 128;
+  img[(k2 >> 3) * 1024 + k1 * 8 + (k2 & 7)] = __float2bfloat16_rn(k1 < 64 ? W2[k1 * 128 + k2] : 0.f);
+}
+
+// dyext = dG * [g > 0]; per-channel sums of dyext and dyext * xhat_ext (BN3 backward)
+__global__ void pool_bwd_prep_kernel(const float* dG, int64_t lddg, const float* G, int64_t ldg, const uint32_t* zext,
+                                     int B, int C3, const float* gamma, const float* bias, const float* mean,
+                                     const float* inv, uint32_t idx_mask, float* dyext, double* red3, int bchunk) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C3) return;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  const float sg = gamma[c] < 0.f ? -1.f : 1.f;
+  const float bi = bias[c], mu = mean[c], iv = inv[c];
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = b0; b < b1; ++b) {
+    const float g = G[(int64_t)b * ldg + c];
+    const float d = g > 0.f ? dG[(int64_t)b * lddg + c] : 0.f;
+    dyext[(int64_t)b * C3 + c] = d;
+    const uint32_t key = zext[(int64_t)b * C3 + c];
+    const uint32_t bits = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    const float z = sg * __uint_as_float(bits & ~idx_mask) + bi;
+    s0 += (double)d;
+    s1 += (double)d * (double)((z - mu) * iv);
+  }
+  atomicAdd(red3 + c, s0);
+  atomicAdd(red3 + C3 + c, s1);
+}
+
+// BN3 backward coefficients: dgamma, dbeta; q = -s3 inv3 dgamma / M ; p' = -s3 dbeta / M - q mu3 + q b3
+__global__ void bwd3_coeff_kernel(const double* red3, int C3, double count, const float* scale, const float* inv,
+                                  const float* mean, const float* bias, float* dgamma, float* dbeta, float* coef3) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C3) return;
+  const double db = red3[c], dg = red3[C3 + c];
+  dbeta[c] = (float)db;
+  dgamma[c] = (float)dg;
+  const double s3 = scale[c];
+  const double q = -s3 * (double)inv[c] * dg / count;
+  const double pp = -s3 * db / count - q * (double)mean[c] + q * (double)bias[c];
+  coef3[c] = (float)q;
+  coef3[C3 + c] = (float)pp;
+}
+
+// Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights), written as the two K-half images
+// of the A operand (rows k, contraction k'); block 0 also writes u[k] = sum_c p'[c] W3b[k,c].
+__global__ void gq_kernel(const float* W3, const float* coef3, int C3, __nv_bfloat16* gq_img, float* uvec) {
+  const int kp = blockIdx.x, k = threadIdx.x;
+  const float* rk = W3 + (size_t)k * C3;
+  const float* rkp = W3 + (size_t)kp * C3;
+  float acc = 0.f, uacc = 0.f;
+  for (int c = 0; c < C3; ++c) {
+    const float wk = bf16r(rk[c]);
+    acc = fmaf(bf16r(rkp[c]) * coef3[c], wk, acc);
+    uacc = fmaf(coef3[C3 + c], wk, uacc);
+  }
+  const int h = kp >> 6, kk = kp & 63;
+  gq_img[(size_t)h * 8192 + (kk >> 3) * 1024 + k * 8 + (kk & 7)] = __float2bfloat16_rn(acc);
+  if (kp == 0) uvec[k] = uacc;
+}
+
+// grads.W3[k,c] += T1[k,c] + sa2[k] p'[c] + q[c] * sum_k' G2[k,k'] W3b[k',c]
+__global__ void wgrad3_dense_kernel(const float* W3, const float* t1, const float* gram, const double* sa2,
+                                    const float* coef3, int C3, float* gW3) {
+  __shared__ float sw[128][33];
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 32 channels x 8 row groups
+  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
+    const int kp = i >> 5, cc = i & 31;
+    sw[kp][cc] = bf16r(W3[(size_t)kp * C3 + c0 + cc]);
+  }
+  __syncthreads();
+  const int c = c0 + tx;
+  const float q = coef3[c], pp = coef3[C3 + c];
+  for (int k = ty; k < 128; k += 8) {
+    const float* grow = gram + (size_t)k * 128;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int kp = 0; kp < 128; ++kp) acc = fmaf(grow[kp], sw[kp][tx], acc);
+    gW3[(size_t)k * C3 + c] += t1[(size_t)k * C3 + c] + (float)sa2[k] * pp + q * acc;
+  }
+}
+
+// BN backward coefficients of layers 2 / 1 from (sum dy, sum dy*xhat)
+__global__ void bn_bwd_coeff_kernel(const double* red, int C, double count, float* dgamma, float* dbeta, float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = (float)red[2 * c];
+  dgamma[c] = (float)red[2 * c + 1];
+  coef[2 * c] = (float)(red[2 * c] / count);
+  coef[2 * c + 1] = (float)(red[2 * c + 1] / count);
+}
+
+// layer-1 backward on CUDA cores: dz1 = s1 (dy1 - m0 - xhat1 m1); wgrad1; gradient of the stage input
+// reduced per cloud to d(center) and d(angle).  One block per item, 256 threads = 64 channels x 4.
+__global__ void __launch_bounds__(256) bwd_l1_kernel(const float* pcs, const float* center, const float* angle,
+                                                     const __nv_bfloat16* dy1, int N, int PC, int npc, const float* W1,
+                                                     const float* b1, const float* mean1, const float* inv1,
+                                                     const float* scale1, const float* coef1, float* gW1,
+                                                     float* dcenter, float* dangle, int want_input_grad) {
+  __shared__ float sp[256 * 3];
+  __shared__ float red[4][64][4];
+  __shared__ float fin[64][4];
+  const int it = blockIdx.x;
+  const int cloud = it / npc, pchunk = it - cloud * npc;
+  const int p0 = pchunk * PC;
+  const int nvalid = min(PC, N - p0);
+  const int64_t row0 = (int64_t)cloud * N + p0;
+  float sn = 0.f, cs = 1.f;
+  if (angle) sincosf(angle[cloud], &sn, &cs);
+  const float cx = center[cloud * 3], cy = center[cloud * 3 + 1], cz = center[cloud * 3 + 2];
+  for (int p = threadIdx.x; p < nvalid; p += 256) {
+    const float* src = pcs + (row0 + p) * 3;
+    const float x0 = src[0] - cx, y0 = src[1] - cy;
+    sp[p * 3] = x0 * cs - y0 * sn;
+    sp[p * 3 + 1] = x0 * sn + y0 * cs;
+    sp[p * 3 + 2] = src[2] - cz;
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63, gq = threadIdx.x >> 6;
+  const float wx = W1[c], wy = W1[64 + c], wz = W1[128 + c], bb = b1[c], mu = mean1[c], iv = inv1[c], s1 = scale1[c];
+  const float m0 = coef1[2 * c], m1 = coef1[2 * c + 1];
+  float a = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+  for (int p = gq; p < nvalid; p += 4) {
+    const float x = sp[p * 3], y = sp[p * 3 + 1], z = sp[p * 3 + 2];
+    const float xh = (fmaf(x, wx, fmaf(y, wy, fmaf(z, wz, bb))) - mu) * iv;
+    const float dz = s1 * (__bfloat162float(dy1[(row0 + p) * 64 + c]) - m0 - xh * m1);
+    a += dz; bx = fmaf(dz, x, bx); by = fmaf(dz, y, by); bz = fmaf(dz, z, bz);
+  }
+  red[gq][c][0] = a; red[gq][c][1] = bx; red[gq][c][2] = by; red[gq][c][3] = bz;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float v[4];
+    for (int j = 0; j < 4; ++j) v[j] = red[0][c][j] + red[1][c][j] + red[2][c][j] + red[3][c][j];
+    atomicAdd(gW1 + c, v[1]);
+    atomicAdd(gW1 + 64 + c, v[2]);
+    atomicAdd(gW1 + 128 + c, v[3]);
+    // d(sum_p dq_d) = sum_c W1[d,c] A_c ; d(angle) = sum_c (-W1[x,c] By_c + W1[y,c] Bx_c)
+    fin[c][0] = wx * v[0]; fin[c][1] = wy * v[0]; fin[c][2] = wz * v[0]; fin[c][3] = -wx * v[2] + wy * v[1];
+  }
+  __syncthreads();
+  if (want_input_grad && threadIdx.x < 4) {
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += fin[i][threadIdx.x];
+    fin[0][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (want_input_grad && threadIdx.x == 0) {
+    const float gx = fin[0][0], gy = fin[0][1], gz = fin[0][2];
+    atomicAdd(dcenter + cloud * 3, -(gx * cs + gy * sn));
+    atomicAdd(dcenter + cloud * 3 + 1, -(-gx * sn + gy * cs));
+    atomicAdd(dcenter + cloud * 3 + 2, -gz);
+    if (dangle) atomicAdd(dangle + cloud, fin[0][3]);
+  }
+}
+
+}  // namespace
+
+int pack_weights_bf16_bwd(const Model& m, const PlanF32& p, const float* params, cudaStream_t st) {
+  for (int s = 0; s < 3; ++s) {
+    const int C3 = m.conv[s].back().cout;
+    pack_w3n_kernel<<<(C3 * 128 + 255) / 256, 256, 0, st>>>(params + m.conv[s][2].w, p.bf.w3n[s], C3);
+    AN3D_LAUNCH_CHECK();
+    pack_w2p_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(params + m.conv[s][1].w, p.bf.w2p[s]);
+    AN3D_LAUNCH_CHECK();
+  }
+  return AN3D_OK;
+}
+
+// dG: gradient w.r.t. the pooled feature [B, C3] (leading dim lddg).  Accumulates parameter gradients
+// into `grads`; with want_input_grad adds -R^T sum dq into dcenter [B,3] and sum(...) into dangle [B]
+// (dangle must be zero on entry).
+int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, const float* pcs, const float* center,
+                             const float* angle, const float* dG, int64_t lddg, const float* params, float* grads,
+                             bool want_input_grad, float* dcenter, float* dangle, cudaStream_t st) {
+  const PlanBf16& q = p.bf;
+  const int B = p.B, N = p.N;
+  const int64_t M = p.M;
+  const Lin &L1 = m.conv[s][0], &L2 = m.conv[s][1], &L3 = m.conv[s][2];
+  const int C3 = L3.cout;
+  int dev = 0, sms = 148;
+  AN3D_CUDA_CHECK(cudaGetDevice(&dev));
+  AN3D_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  auto slot = [&](int bn) { return m.bn_slot_off(false, br, bn); };
+  auto poff = [&](int bn) { return m.bn_param_off(false, br, bn); };
+  const float *sc1 = p.bn.scale + slot(L1.bn), *mean1 = p.bn.mean + slot(L1.bn), *inv1 = p.bn.inv + slot(L1.bn);
+  const float *sc2 = p.bn.scale + slot(L2.bn), *mean2 = p.bn.mean + slot(L2.bn), *inv2 = p.bn.inv + slot(L2.bn);
+  const float *sc3 = p.bn.scale + slot(L3.bn), *mean3 = p.bn.mean + slot(L3.bn), *inv3 = p.bn.inv + slot(L3.bn);
+  const float *gamma1 = params + poff(L1.bn), *beta1 = gamma1 + 64;
+  const float *gamma2 = params + poff(L2.bn), *beta2 = gamma2 + 128;
+  const float* gamma3 = params + poff(L3.bn);
+  const int n_items = B * q.npc;
+  const int64_t ldg = s == EMB ? 2 * C3 : C3;
+
+  // ---- layer 3: pooled gradient -> BN3 coefficients ----
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red3, 0, 2 * (size_t)C3 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram, 0, 128 * 128 * sizeof(float), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.t1, 0, 128 * (size_t)C3 * sizeof(float), st));
+  {
+    const int bchunk = 64;
+    dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
+    pool_bwd_prep_kernel<<<grid, 128, 0, st>>>(dG, lddg, p.g[s][br], ldg, q.zext[s][br], B, C3, gamma3, params + L3.b, mean3,
+                                               inv3, q.idx_mask, q.dyext, q.red3, bchunk);
+    AN3D_LAUNCH_CHECK();
+    bwd3_coeff_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.red3, C3, (double)M, sc3, inv3, mean3, params + L3.b,
+                                                        grads + poff(L3.bn), grads + poff(L3.bn) + C3, q.coef3);
+    AN3D_LAUNCH_CHECK();
+    gq_kernel<<<128, 128, 0, st>>>(params + L3.w, q.coef3, C3, q.gq, q.uvec);
+    AN3D_LAUNCH_CHECK();
+  }
+  // ---- wgrad3: sparse part + Gram on the tensor cores, dense correction on CUDA cores ----
+  {
+    convbwd::Wg3Params W;
+    W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
+    W.gidx = p.gidx[s][br]; W.dyext = q.dyext; W.s3 = sc3; W.B = B; W.N = N; W.PC = q.PC; W.npc = q.npc; W.C3 = C3;
+    W.n_items = n_items; W.gW3 = q.t1; W.gram = q.gram;
+    const int npass = (C3 / 64 + convbwd::kWg3SlotsPerPass - 1) / convbwd::kWg3SlotsPerPass;
+    const int nranges = std::max(1, std::min(n_items, sms / npass));
+    W.items_per_cta = (n_items + nranges - 1) / nranges;
+    const size_t smem = convbwd::wg3_smem_bytes(q.PC);
+    if (smem > (size_t)kMaxSmem) { set_error("wgrad3 tile too large"); return AN3D_ERR_UNSUPPORTED; }
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_mark(PROF_BWD_T1, true, st);
+    convbwd::wgrad3_kernel<<<dim3(nranges, npass), convbwd::kWg3Threads, smem, st>>>(W);
+    prof_mark(PROF_BWD_T1, false, st);
+    AN3D_LAUNCH_CHECK();
+    wgrad3_dense_kernel<<<C3 / 32, 256, 0, st>>>(params + L3.w, q.t1, q.gram, q.sa2[s][br], q.coef3, C3, grads + L3.w);
+    AN3D_LAUNCH_CHECK();
+  }
+  // ---- dgrad3 -> dy2 images + BN2 backward sums ----
+  {
+    convbwd::Dg3Params D;
+    D.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); D.dy2_img = reinterpret_cast<uint8_t*>(q.dy2img);
+    D.img_bytes = (uint32_t)q.img_bytes; D.gidx = p.gidx[s][br]; D.dyext = q.dyext; D.s3 = sc3; D.gq_img = q.gq;
+    D.w3n_img = q.w3n[s]; D.uvec = q.uvec; D.gamma2 = gamma2; D.beta2 = beta2; D.B = B; D.N = N; D.PC = q.PC; D.npc = q.npc;
+    D.C3 = C3; D.n_items = n_items; D.red2 = q.red2;
+    const int grid = std::min(n_items, sms);
+    D.items_per_cta = (n_items + grid - 1) / grid;
+    const size_t smem = convbwd::dg3_smem_bytes(q.PC);
+    if (smem > (size_t)kMaxSmem) { set_error("dgrad3 tile too large"); return AN3D_ERR_UNSUPPORTED; }
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_mark(PROF_BWD_DGRAD3, true, st);
+    convbwd::dgrad3_kernel<<<grid, convbwd::kDg3Threads, smem, st>>>(D);
+    prof_mark(PROF_BWD_DGRAD3, false, st);
+    AN3D_LAUNCH_CHECK();
+    bn_bwd_coeff_kernel<<<1, 128, 0, st>>>(q.red2, 128, (double)M, grads + poff(L2.bn), grads + poff(L2.bn) + 128, q.coef2);
+    AN3D_LAUNCH_CHECK();
+  }
+  // ---- layer 2 backward -> wgrad2, dy1 + BN1 backward sums ----
+  {
+    convbwd::L2Params P2;
+    P2.pcs = pcs; P2.center = center; P2.angle = angle; P2.dy2_img = reinterpret_cast<const uint8_t*>(q.dy2img);
+    P2.img_bytes = (uint32_t)q.img_bytes; P2.B = B; P2.N = N; P2.PC = q.PC; P2.npc = q.npc; P2.n_items = n_items;
+    const int grid = std::min(n_items, sms);
+    P2.items_per_cta = (n_items + grid - 1) / grid;
+    P2.w1f = q.w1f[s][br]; P2.c1f = q.c1f[s][br]; P2.W1 = params + L1.w; P2.b1 = params + L1.b; P2.mean1 = mean1;
+    P2.inv1 = inv1; P2.gamma1 = gamma1; P2.beta1 = beta1; P2.w2t_img = q.w2t[s]; P2.w2p_img = q.w2p[s];
+    P2.b2 = params + L2.b; P2.mean2 = mean2; P2.inv2 = inv2; P2.s2 = sc2; P2.coef2 = q.coef2; P2.gW2 = grads + L2.w;
+    P2.dy1 = q.dy1; P2.red1 = q.red1;
+    const size_t smem = convbwd::l2_smem_bytes(q.PC);
+    if (smem > (size_t)kMaxSmem) { set_error("bwd_l2 tile too large"); return AN3D_ERR_UNSUPPORTED; }
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::bwd_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_mark(PROF_BWD_L2, true, st);
+    convbwd::bwd_l2_kernel<<<grid, convbwd::kL2Threads, smem, st>>>(P2);
+    prof_mark(PROF_BWD_L2, false, st);
+    AN3D_LAUNCH_CHECK();
+    bn_bwd_coeff_kernel<<<1, 64, 0, st>>>(q.red1, 64, (double)M, grads + poff(L1.bn), grads + poff(L1.bn) + 64, q.coef1);
+    AN3D_LAUNCH_CHECK();
+  }
+  // ---- layer 1 backward (CUDA cores) ----
+  bwd_l1_kernel<<<n_items, 256, 0, st>>>(pcs, center, angle, q.dy1, N, q.PC, q.npc, params + L1.w, params + L1.b, mean1,
+                                         inv1, sc1, q.coef1, grads + L1.w, dcenter, dangle, want_input_grad ? 1 : 0);
+  AN3D_LAUNCH_CHECK();
+  // biases of conv layers feed a batch-statistics BN: their gradient is identically zero (left at 0).
+  return AN3D_OK;
+}
+
+}  // namespace an3d

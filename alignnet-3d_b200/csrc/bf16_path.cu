@@ -195,11 +195,15 @@ int bf16_supported(const Model& m) {
 void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
   const bool training = (flags & AN3D_TRAINING) != 0;
   const int64_t M = (int64_t)B * N;
-  q->npc = (N + convfwd::kMaxPC - 1) / convfwd::kMaxPC;
+  // training tiles are capped at 208 points so that the backward kernels (two tile images, two
+  // scatter tiles and a weight ring in shared memory) fit; inference uses up to 256
+  const int maxpc = training ? 208 : convfwd::kMaxPC;
+  q->npc = (N + maxpc - 1) / maxpc;
   q->PC = (((N + q->npc - 1) / q->npc) + 15) & ~15;
   int bits = 0;
   while ((1 << bits) < N) ++bits;
   q->idx_mask = (1u << bits) - 1u;
+  q->img_bytes = 16 * (int64_t)convfwd::plane_stride(q->PC);
   for (int s = 0; s < 3; ++s) {
     const int C3 = m.conv[s].back().cout;
     q->w2t[s] = a.take<__nv_bfloat16>(128 * 64);
@@ -212,9 +216,31 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
       q->stats2[s][br] = a.take<double>(256);
       q->stats3[s][br] = a.take<double>(2 * (int64_t)C3);
       q->zext[s][br] = a.take<uint32_t>((int64_t)B * C3);
-      q->a1[s][br] = training ? a.take<__nv_bfloat16>(M * 64) : nullptr;
-      q->a2[s][br] = training ? a.take<__nv_bfloat16>(M * 128) : nullptr;
+      q->a2img[s][br] = training ? a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2)) : nullptr;
+      q->sa2[s][br] = a.take<double>(128);
     }
+  }
+  if (training) {
+    int64_t c3max = 0;
+    for (int s = 0; s < 3; ++s) {
+      const int C3 = m.conv[s].back().cout;
+      c3max = std::max<int64_t>(c3max, C3);
+      q->w3n[s] = a.take<__nv_bfloat16>((int64_t)C3 * 128);
+      q->w2p[s] = a.take<__nv_bfloat16>(128 * 128);
+    }
+    q->dyext = a.take<float>((int64_t)B * c3max);
+    q->red3 = a.take<double>(2 * c3max);
+    q->coef3 = a.take<float>(4 * c3max);
+    q->gq = a.take<__nv_bfloat16>(128 * 128);
+    q->uvec = a.take<float>(128);
+    q->gram = a.take<float>(128 * 128);
+    q->t1 = a.take<float>(128 * c3max);
+    q->dy2img = a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2));
+    q->red2 = a.take<double>(256);
+    q->coef2 = a.take<float>(256);
+    q->dy1 = a.take<__nv_bfloat16>(M * 64);
+    q->red1 = a.take<double>(128);
+    q->coef1 = a.take<float>(128);
   }
 }
 
@@ -256,7 +282,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   P.w3t_img = q.w3t[s][br]; P.nchunk = C3 / 128;
   P.nstages = convfwd::smem_bytes(q.PC, 3) <= (size_t)kMaxSmem ? 3 : 2;
   P.zext = q.zext[s][br]; P.stats2 = q.stats2[s][br]; P.stats3 = q.stats3[s][br];
-  P.a1_out = training ? q.a1[s][br] : nullptr; P.a2_out = training ? q.a2[s][br] : nullptr;
+  P.a2_img = training ? q.a2img[s][br] : nullptr; P.sa2 = training ? q.sa2[s][br] : nullptr;
   P.idx_mask = q.idx_mask;
   const size_t smem = convfwd::smem_bytes(q.PC, P.nstages);
   if (smem > (size_t)kMaxSmem) {
@@ -268,6 +294,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.moments[s][br], 0, 16 * sizeof(double), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats2[s][br], 0, 256 * sizeof(double), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats3[s][br], 0, 2 * (size_t)C3 * sizeof(double), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.sa2[s][br], 0, 128 * sizeof(double), st));
     const int mb = (int)std::min<int64_t>((M + 255) / 256, 4 * sms);
     moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
     AN3D_LAUNCH_CHECK();
@@ -296,10 +323,3 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
 
 }  // namespace an3d
 
-namespace an3d {
-int backward_bf16(const Model&, const float*, const float*, const float*, const an3d_labels*, const an3d_outputs*, int,
-                  int, int, float*, float*, void*, int64_t, cudaStream_t) {
-  set_error("bf16 backward not built yet");
-  return AN3D_ERR_UNSUPPORTED;
-}
-}  // namespace an3d

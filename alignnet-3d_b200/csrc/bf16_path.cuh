@@ -12,4 +12,9 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
                             const float* angle, const float* params, float* state, bool training, float decay,
                             cudaStream_t st);
 
+int pack_weights_bf16_bwd(const Model& m, const PlanF32& p, const float* params, cudaStream_t st);
+int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, const float* pcs, const float* center,
+                             const float* angle, const float* dG, int64_t lddg, const float* params, float* grads,
+                             bool want_input_grad, float* dcenter, float* dangle, cudaStream_t st);
+
 }  // namespace an3d

@@ -135,8 +135,25 @@ struct PlanBf16 {
   double* stats2[3][2];                     // sum / sum-of-squares of the raw layer-2 accumulator [128][2]
   double* stats3[3][2];                     // same for layer 3 [C3][2]
   uint32_t* zext[3][2];                     // packed pooled extreme [B][C3]
-  __nv_bfloat16* a1[3][2];                  // saved activations (training) [M,64]
-  __nv_bfloat16* a2[3][2];                  // [M,128]
+  __nv_bfloat16* a2img[3][2];               // saved layer-2 activations (training): per item the A2 smem tile image
+  int64_t img_bytes = 0;                    // bytes of one item image (16 planes)
+  double* sa2[3][2];                        // column sums of a2 [128]
+  // ---- backward scratch (training) ----
+  __nv_bfloat16* w3n[3];                    // W3 (unfolded) half-chunk images [C3/64][128 k][64 c], K-major in c
+  __nv_bfloat16* w2p[3];                    // W2 padded to 128 rows, image [128 k1][128 k2]
+  float* dyext = nullptr;                   // [B, C3max] gradient at the pooled arg rows (after the ReLU mask)
+  double* red3 = nullptr;                   // [2][C3max] sum dy, sum dy*xhat of layer 3
+  float* coef3 = nullptr;                   // [4][C3max]: q, p', (unused), (unused)
+  __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
+  float* uvec = nullptr;                    // [128]
+  float* gram = nullptr;                    // [128][128] a2^T a2
+  float* t1 = nullptr;                      // [128][C3max] sparse part of wgrad3 (16-byte aligned scratch)
+  __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
+  double* red2 = nullptr;                   // [128][2]
+  float* coef2 = nullptr;                   // [128][2]  m0, m1
+  __nv_bfloat16* dy1 = nullptr;             // [M, 64] row-major
+  double* red1 = nullptr;                   // [64][2]
+  float* coef1 = nullptr;                   // [64][2]
 };
 
 // Workspace plan of the fp32 (parity) path: everything the backward needs is materialised.

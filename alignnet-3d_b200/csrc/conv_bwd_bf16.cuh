@@ -1,0 +1,672 @@
+// Backward of the fused conv stack on the tensor cores (sm_100a, tcgen05).
+//
+// The max-pool makes the gradient w.r.t. the widest activation sparse (one row per cloud and
+// channel) and training-mode BN makes it "sparse + affine in z3":
+//     dz3[m,c] = s3[c] dy3[m,c] + p'[c] + q[c] r3[m,c],      r3 = a2 W3 (raw accumulator)
+// so neither z3 nor dz3 ([M, C3], gigabytes) is ever materialised:
+//     wgrad3 = A2^T S + sa2 (x) p' + (G2 W3) diag(q)          S = sparse s3*dy3, G2 = A2^T A2 (Gram)
+//     da2    = S (W3)^T + u + A2 Gq                           Gq = W3 diag(q) W3^T, u = W3 p'
+// Kernels here:
+//   wgrad3_kernel : T1 = A2^T S and the Gram matrix, contraction over points (MN-major operands)
+//   dgrad3_kernel : da2 -> dy2 (ReLU mask) + BN2 backward sums, per cloud
+//   bwd_l2_kernel : dz2 -> wgrad2, da1 -> dy1 + BN1 backward sums
+// A2 / dy2 tiles travel between kernels as the exact shared-memory plane images (bulk copies).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+#include "conv_fwd_bf16.cuh"
+
+namespace an3d {
+namespace convbwd {
+
+using namespace umma;
+using convfwd::plane_stride;
+
+constexpr uint32_t kWHalfBytes = 128 * 64 * 2;   // one [128 rows][64 k] weight image
+constexpr uint32_t kPlaneW = 2048;
+
+// =============================================================================================
+// wgrad3: T1[k, c] = sum_pt a2[pt, k] * S[pt, c]   (+ Gram[k, k'] = sum_pt a2[pt,k] a2[pt,k'])
+// =============================================================================================
+struct Wg3Params {
+  const uint8_t* a2_img;
+  uint32_t img_bytes;
+  const int32_t* gidx;   // [B][C3] arg row (index within the cloud)
+  const float* dyext;    // [B][C3] gradient at the arg row (ReLU-masked)
+  const float* s3;       // [C3] BN scale
+  int B, N, PC, npc, C3, n_items, items_per_cta;
+  float* gW3;            // [128][C3]
+  float* gram;           // [128][128]
+};
+constexpr int kWg3Threads = 192;
+constexpr int kWg3SlotsPerPass = 6;      // 6 x 64 channels + 128 Gram columns = 512 TMEM columns
+
+inline size_t wg3_smem_bytes(int PC) { return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 256; }
+
+struct Wg3Bars {
+  uint64_t a2_full[2], a2_empty[2], sd_full[2], sd_empty[2], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane = plane_stride(P.PC);
+  const uint32_t sd_bytes = 8 * plane;
+  uint8_t* sA2[2] = {smem, smem + P.img_bytes};
+  uint8_t* sSd[2] = {smem + 2 * P.img_bytes, smem + 2 * P.img_bytes + sd_bytes};
+  Wg3Bars* bars = reinterpret_cast<Wg3Bars*>(smem + 2 * P.img_bytes + 2 * sd_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
+  const int it_end = min(P.n_items, it_begin + P.items_per_cta);
+  const int n_local = it_end - it_begin;
+  const int pass = blockIdx.y;
+  const int c0 = pass * kWg3SlotsPerPass * 64;
+  const int nslots = min(kWg3SlotsPerPass, (P.C3 - c0) / 64);
+  const bool do_gram = pass == 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_empty[i], 1);
+      mbar_init(&bars->sd_full[i], 64); mbar_init(&bars->sd_empty[i], 1);
+    }
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kWg3Threads * 16) *reinterpret_cast<uint4*>(sSd[0] + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 4) tmem_alloc(&bars->tmem_base, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < 2) {
+    // ---- scatter threads: one channel of the current 64-channel slot each ----
+    const int t = tid;
+    int prev_off[2] = {-1, -1};
+    uint32_t ph_e[2] = {1, 1};
+    int g = 0;
+    for (int li = 0; li < n_local; ++li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      for (int s = 0; s < nslots; ++s, ++g) {
+        const int c = c0 + s * 64 + t;
+        const int idx = P.gidx[(size_t)cloud * P.C3 + c];
+        const float w = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+        const int sb = g & 1;
+        mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
+        if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
+        const int row = idx - p0;
+        if (row >= 0 && row < nvalid && w != 0.f) {
+          const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
+          prev_off[sb] = off;
+        } else {
+          prev_off[sb] = -1;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->sd_full[sb]);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0 && n_local > 0) {
+      uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0};
+      int g = 0;
+      for (int li = 0; li < n_local; ++li) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+        const int NT = (nvalid + 15) & ~15;
+        const int b = li & 1;
+        mbar_wait(&bars->a2_full[b], ph_a2[b]); ph_a2[b] ^= 1;
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA2[b]);
+        if (do_gram) {
+          const uint32_t idesc = make_idesc(128, 128, 1, 1);
+          for (int ks = 0; ks < NT / 16; ++ks) {
+            const uint64_t d = make_desc(a_base + ks * 256, 128, plane);
+            mma_bf16(tmem + 384, d, d, idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        const uint32_t idesc = make_idesc(128, 64, 1, 1);
+        for (int s = 0; s < nslots; ++s, ++g) {
+          const int sb = g & 1;
+          mbar_wait(&bars->sd_full[sb], ph_sd[sb]); ph_sd[sb] ^= 1;
+          tc_fence_after();
+          const uint32_t s_base = smem_u32(sSd[sb]);
+          for (int ks = 0; ks < NT / 16; ++ks)
+            mma_bf16(tmem + s * 64, make_desc(a_base + ks * 256, 128, plane), make_desc(s_base + ks * 256, 128, plane),
+                     idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          mma_commit(&bars->sd_empty[sb]);
+        }
+        mma_commit(&bars->a2_empty[b]);
+      }
+      mma_commit(&bars->done);
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t ph_e[2] = {1, 1};
+      for (int li = 0; li < n_local; ++li) {
+        const int b = li & 1;
+        mbar_wait(&bars->a2_empty[b], ph_e[b]); ph_e[b] ^= 1;
+        mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
+        bulk_copy_g2s(sA2[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
+      }
+    }
+  }
+  // ---- epilogue: TMEM -> vector reductions into the gradient buffers (lanes = k) ----
+  if (warp < 4 && n_local > 0) {
+    mbar_wait(&bars->done, 0);
+    tc_fence_after();
+    const int k = tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int s = 0; s < nslots; ++s) {
+      for (int g16 = 0; g16 < 64; g16 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + s * 64 + g16, r);
+        tmem_ld_wait();
+        float* dst = P.gW3 + (size_t)k * P.C3 + c0 + s * 64 + g16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                     __uint_as_float(r[j + 3]));
+      }
+    }
+    if (do_gram) {
+      for (int g16 = 0; g16 < 128; g16 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + 384 + g16, r);
+        tmem_ld_wait();
+        float* dst = P.gram + (size_t)k * 128 + g16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                     __uint_as_float(r[j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// dgrad3: da2^T[k, pt] = Gq a2^T + u + W3 S^T ; dy2 = da2 * [a2 > 0] ; sums for the BN2 backward
+// =============================================================================================
+struct Dg3Params {
+  const uint8_t* a2_img;
+  uint8_t* dy2_img;
+  uint32_t img_bytes;
+  const int32_t* gidx;
+  const float* dyext;
+  const float* s3;
+  const __nv_bfloat16* gq_img;   // 2 halves [128 k][64 k']
+  const __nv_bfloat16* w3n_img;  // C3/64 half-chunks [128 k][64 c]
+  const float* uvec;             // [128]
+  const float* gamma2;           // [128]
+  const float* beta2;            // [128]
+  int B, N, PC, npc, C3, n_items, items_per_cta;
+  double* red2;                  // [128][2] sum dy2, sum dy2 * xhat2
+};
+constexpr int kDg3Threads = 288;   // 4 epilogue warps, 2 scatter warps, MMA, weight loader, tile loader
+
+inline size_t dg3_smem_bytes(int PC) {
+  return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 3 * kWHalfBytes + 3 * 128 * 4 + 256;
+}
+
+struct Dg3Bars {
+  uint64_t a2_full[2], a2_free[2], w_full[3], w_empty[3], sd_full[2], sd_empty[2], d_full[2], d_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane = plane_stride(P.PC);
+  const uint32_t sd_bytes = 8 * plane;
+  uint8_t* sA2[2] = {smem, smem + P.img_bytes};
+  uint8_t* sSd[2] = {smem + 2 * P.img_bytes, smem + 2 * P.img_bytes + sd_bytes};
+  uint8_t* sW = smem + 2 * P.img_bytes + 2 * sd_bytes;
+  float* sU = reinterpret_cast<float*>(sW + 3 * kWHalfBytes);
+  float* sBeta = sU + 128;
+  float* sIg = sBeta + 128;
+  Dg3Bars* bars = reinterpret_cast<Dg3Bars*>(sIg + 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
+  const int it_end = min(P.n_items, it_begin + P.items_per_cta);
+  const int n_local = it_end - it_begin;
+  const int nhc = P.C3 / 64;
+  const int nring = 2 + nhc;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_free[i], 1);
+      mbar_init(&bars->sd_full[i], 64); mbar_init(&bars->sd_empty[i], 1);
+      mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 128);
+    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    fence_barrier_init();
+  }
+  for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kDg3Threads * 16) *reinterpret_cast<uint4*>(sSd[0] + i) = make_uint4(0, 0, 0, 0);
+  if (tid < 128) {
+    sU[tid] = P.uvec[tid];
+    sBeta[tid] = P.beta2[tid];
+    const float gm = P.gamma2[tid];
+    sIg[tid] = gm != 0.f ? 1.0f / gm : 0.f;
+  }
+  if (warp == 6) tmem_alloc(&bars->tmem_base, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < 4) {
+    // ---- epilogue: lane = channel k of a2 ----
+    const int k = tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t ph_d[2] = {0, 0};
+    double acc0 = 0.0, acc1 = 0.0;
+    const float u = sU[k], beta = sBeta[k], ig = sIg[k];
+    for (int li = 0; li < n_local; ++li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+      const int NT = (nvalid + 15) & ~15;
+      const int b = li & 1;
+      mbar_wait(&bars->d_full[b], ph_d[b]); ph_d[b] ^= 1;
+      tc_fence_after();
+      uint8_t* col = sA2[b] + (k >> 3) * plane + (k & 7) * 2;
+      float s0 = 0.f, s1 = 0.f;
+      for (int g16 = 0; g16 < NT; g16 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + b * 256 + g16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int p = g16 + j;
+          __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
+          const float a = __bfloat162float(*ptr);
+          float dy = 0.f;
+          if (p < nvalid && a > 0.f) dy = __uint_as_float(r[j]) + u;
+          const __nv_bfloat16 hb = __float2bfloat16_rn(dy);
+          const float dyr = __bfloat162float(hb);
+          s0 += dyr;
+          s1 = fmaf(dyr, (a - beta) * ig, s1);
+          *ptr = hb;
+        }
+      }
+      acc0 += (double)s0; acc1 += (double)s1;
+      tc_fence_before();
+      mbar_arrive(&bars->d_empty[b]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, sA2[b], P.img_bytes);
+        bulk_wait_read_all();
+        mbar_arrive(&bars->a2_free[b]);
+      }
+    }
+    if (n_local > 0) {
+      atomicAdd(P.red2 + 2 * k, acc0);
+      atomicAdd(P.red2 + 2 * k + 1, acc1);
+    }
+  } else if (warp < 6) {
+    // ---- scatter threads ----
+    const int t = tid - 128;
+    int prev_off[2] = {-1, -1};
+    uint32_t ph_e[2] = {1, 1};
+    int g = 0;
+    for (int li = 0; li < n_local; ++li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      for (int hc = 0; hc < nhc; ++hc, ++g) {
+        const int c = hc * 64 + t;
+        const int idx = P.gidx[(size_t)cloud * P.C3 + c];
+        const float w = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+        const int sb = g & 1;
+        mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
+        if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
+        const int row = idx - p0;
+        if (row >= 0 && row < nvalid && w != 0.f) {
+          const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
+          prev_off[sb] = off;
+        } else {
+          prev_off[sb] = -1;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->sd_full[sb]);
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0 && n_local > 0) {
+      uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0}, ph_w[3] = {0, 0, 0}, ph_de[2] = {1, 1};
+      int g = 0, wq = 0;
+      for (int li = 0; li < n_local; ++li) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+        const int NT = (nvalid + 15) & ~15;
+        const int b = li & 1;
+        mbar_wait(&bars->a2_full[b], ph_a2[b]); ph_a2[b] ^= 1;
+        mbar_wait(&bars->d_empty[b], ph_de[b]); ph_de[b] ^= 1;
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        const uint32_t d_tmem = tmem + b * 256;
+        for (int r = 0; r < nring; ++r, ++wq) {
+          const int st = wq % 3;
+          mbar_wait(&bars->w_full[st], ph_w[st]); ph_w[st] ^= 1;
+          const uint32_t a_base = smem_u32(sW + (size_t)st * kWHalfBytes);
+          uint32_t b_base;
+          int sb = 0;
+          if (r < 2) {
+            b_base = smem_u32(sA2[b]) + r * 8 * plane;
+          } else {
+            sb = g & 1;
+            mbar_wait(&bars->sd_full[sb], ph_sd[sb]); ph_sd[sb] ^= 1;
+            b_base = smem_u32(sSd[sb]);
+          }
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16(d_tmem, make_desc(a_base + ks * 2 * kPlaneW, kPlaneW, 128), make_desc(b_base + ks * 2 * plane, plane, 128),
+                     idesc, (r > 0 || ks > 0) ? 1u : 0u);
+          if (r >= 2) { mma_commit(&bars->sd_empty[sb]); ++g; }
+          mma_commit(&bars->w_empty[st]);
+        }
+        mma_commit(&bars->d_full[b]);
+      }
+    }
+  } else if (warp == 7) {
+    if (lane == 0 && n_local > 0) {
+      uint32_t ph_e[3] = {1, 1, 1};
+      int wq = 0;
+      for (int li = 0; li < n_local; ++li) {
+        for (int r = 0; r < nring; ++r, ++wq) {
+          const int st = wq % 3;
+          mbar_wait(&bars->w_empty[st], ph_e[st]); ph_e[st] ^= 1;
+          mbar_arrive_expect_tx(&bars->w_full[st], kWHalfBytes);
+          const __nv_bfloat16* src = r < 2 ? P.gq_img + (size_t)r * 8192 : P.w3n_img + (size_t)(r - 2) * 8192;
+          bulk_copy_g2s(sW + (size_t)st * kWHalfBytes, src, kWHalfBytes, &bars->w_full[st]);
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t ph_f[2] = {1, 1};
+      for (int li = 0; li < n_local; ++li) {
+        const int b = li & 1;
+        mbar_wait(&bars->a2_free[b], ph_f[b]); ph_f[b] ^= 1;
+        mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
+        bulk_copy_g2s(sA2[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// layer-2 backward: dz2 = s2 (dy2 - m0 - xhat2 m1) ; wgrad2 += a1^T dz2 ; da1 = dz2 W2^T ;
+//                   dy1 = da1 * [a1 > 0] (+ BN1 backward sums), dy1 stored row-major bf16
+// =============================================================================================
+struct L2Params {
+  const float* pcs;
+  const float* center;
+  const float* angle;
+  const uint8_t* dy2_img;
+  uint32_t img_bytes;
+  int B, N, PC, npc, n_items, items_per_cta;
+  const float* w1f;  const float* c1f;      // folded layer 1 (forward recompute of a1)
+  const float* W1;   const float* b1;       // raw layer-1 weights [3][64], bias
+  const float* mean1; const float* inv1; const float* gamma1; const float* beta1;
+  const __nv_bfloat16* w2t_img;             // forward image [128 k2][64 k1]
+  const __nv_bfloat16* w2p_img;             // [128 k1 (zero padded)][128 k2]
+  const float* b2; const float* mean2; const float* inv2; const float* s2;
+  const float* coef2;                       // [128][2] m0, m1
+  float* gW2;                               // [64][128]
+  __nv_bfloat16* dy1;                       // [B*N][64]
+  double* red1;                             // [64][2]
+};
+constexpr int kL2Threads = 320;
+
+inline size_t l2_smem_bytes(int PC) {
+  return 8 * (size_t)plane_stride(PC) + 16 * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
+         256 * 3 * 4 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
+}
+
+struct L2Bars {
+  uint64_t w_full, dz_full, dz_free, a1_full, d2_full, dz_ready, da_full, done;
+  uint32_t tmem_base;
+  float xf[8];
+};
+
+__global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane = plane_stride(P.PC);
+  uint8_t* sA1 = smem;
+  uint8_t* sDZ = sA1 + 8 * plane;
+  uint8_t* sW2T = sDZ + 16 * plane;
+  uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
+  float* sPts = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [256][3] transformed points
+  float* sW1f = sPts + 768;      // 192
+  float* sC1f = sW1f + 192;      // 64
+  float* sW1 = sC1f + 64;        // 192
+  float* sL1 = sW1 + 192;        // b1, mean1, inv1, gamma1, beta1 : 5 x 64
+  float* sL2 = sL1 + 320;        // cx2 (= (b2-mean2)*inv2), inv2, s2, m0, m1, spare : 6 x 128
+  L2Bars* bars = reinterpret_cast<L2Bars*>(sL2 + 768);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
+  const int it_end = min(P.n_items, it_begin + P.items_per_cta);
+  const int n_local = it_end - it_begin;
+
+  if (tid == 0) {
+    mbar_init(&bars->w_full, 1); mbar_init(&bars->dz_full, 1); mbar_init(&bars->dz_free, 1);
+    mbar_init(&bars->a1_full, 256); mbar_init(&bars->d2_full, 1); mbar_init(&bars->dz_ready, 256);
+    mbar_init(&bars->da_full, 1); mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 192; i += kL2Threads) { sW1f[i] = P.w1f[i]; sW1[i] = P.W1[i]; }
+  for (int i = tid; i < 64; i += kL2Threads) {
+    sC1f[i] = P.c1f[i];
+    sL1[i] = P.b1[i]; sL1[64 + i] = P.mean1[i]; sL1[128 + i] = P.inv1[i]; sL1[192 + i] = P.gamma1[i]; sL1[256 + i] = P.beta1[i];
+  }
+  for (int i = tid; i < 128; i += kL2Threads) {
+    sL2[i] = (P.b2[i] - P.mean2[i]) * P.inv2[i];
+    sL2[128 + i] = P.inv2[i]; sL2[256 + i] = P.s2[i]; sL2[384 + i] = P.coef2[2 * i]; sL2[512 + i] = P.coef2[2 * i + 1];
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  constexpr uint32_t kD = 0, kWG = 256;   // D2 / DA share columns [0,256); wgrad2 accumulator at [256,320)
+
+  if (warp < 8) {
+    const int t = tid;                     // 0..255
+    const int k = t & 127, half = t >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph = 0;                       // all per-item barriers flip once per item
+    double r0 = 0.0, r1 = 0.0;
+    for (int li = 0; li < n_local; ++li, ph ^= 1) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      const int NT = (nvalid + 15) & ~15;
+      const int64_t row0 = (int64_t)cloud * P.N + p0;
+      if (t == 0) {
+        float sn = 0.f, cs = 1.f;
+        if (P.angle) sincosf(P.angle[cloud], &sn, &cs);
+        bars->xf[0] = P.center[cloud * 3]; bars->xf[1] = P.center[cloud * 3 + 1]; bars->xf[2] = P.center[cloud * 3 + 2];
+        bars->xf[3] = cs; bars->xf[4] = sn;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // ---- recompute a1 (layer 1), one thread per point ----
+      if (t < NT) {
+        const int p = t;
+        if (p < nvalid) {
+          const float* src = P.pcs + (row0 + p) * 3;
+          const float x0 = src[0] - bars->xf[0], y0 = src[1] - bars->xf[1], z = src[2] - bars->xf[2];
+          const float x = x0 * bars->xf[3] - y0 * bars->xf[4], y = x0 * bars->xf[4] + y0 * bars->xf[3];
+          sPts[p * 3] = x; sPts[p * 3 + 1] = y; sPts[p * 3 + 2] = z;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c8 * 8 + j;
+              v[j] = fmaxf(fmaf(x, sW1f[c], fmaf(y, sW1f[64 + c], fmaf(z, sW1f[128 + c], sC1f[c]))), 0.f);
+            }
+            uint4 q;
+            q.x = convfwd::pack_bf16x2(v[0], v[1]); q.y = convfwd::pack_bf16x2(v[2], v[3]);
+            q.z = convfwd::pack_bf16x2(v[4], v[5]); q.w = convfwd::pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = q;
+          }
+        } else {
+          sPts[p * 3] = 0.f; sPts[p * 3 + 1] = 0.f; sPts[p * 3 + 2] = 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->a1_full);
+      // ---- dz2 from the raw layer-2 accumulator (xhat2) and dy2 ----
+      mbar_wait(&bars->d2_full, ph);
+      mbar_wait(&bars->dz_full, ph);
+      tc_fence_after();
+      {
+        const float cx = sL2[k], inv2 = sL2[128 + k], s2 = sL2[256 + k], m0 = sL2[384 + k], m1 = sL2[512 + k];
+        uint8_t* col = sDZ + (k >> 3) * plane + (k & 7) * 2;
+        const int nh = ((NT >> 1) + 15) & ~15;
+        const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
+        for (int g16 = pbeg; g16 < pend; g16 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + kD + g16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int p = g16 + j;
+            __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
+            float dz = 0.f;
+            if (p < nvalid) {
+              const float xh = fmaf(__uint_as_float(r[j]), inv2, cx);
+              dz = s2 * (__bfloat162float(*ptr) - m0 - xh * m1);
+            }
+            *ptr = __float2bfloat16_rn(dz);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->dz_ready);
+      // ---- dy1 = da1 * [a1 > 0], BN1 backward sums (channels k1 < 64 only) ----
+      mbar_wait(&bars->da_full, ph);
+      tc_fence_after();
+      if (k < 64) {
+        const float wx = sW1[k], wy = sW1[64 + k], wz = sW1[128 + k];
+        const float b1 = sL1[k], mu1 = sL1[64 + k], inv1 = sL1[128 + k], g1 = sL1[192 + k], be1 = sL1[256 + k];
+        const int nh = ((NT >> 1) + 15) & ~15;
+        const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
+        float s0 = 0.f, s1 = 0.f;
+        for (int g16 = pbeg; g16 < pend; g16 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + kD + g16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int p = g16 + j;
+            if (p < nvalid) {
+              const float z1 = fmaf(sPts[p * 3], wx, fmaf(sPts[p * 3 + 1], wy, fmaf(sPts[p * 3 + 2], wz, b1)));
+              const float xh = (z1 - mu1) * inv1;
+              const float dy = fmaf(g1, xh, be1) > 0.f ? __uint_as_float(r[j]) : 0.f;
+              const __nv_bfloat16 hb = __float2bfloat16_rn(dy);
+              const float dyr = __bfloat162float(hb);
+              s0 += dyr;
+              s1 = fmaf(dyr, xh, s1);
+              P.dy1[(row0 + p) * 64 + k] = hb;
+            }
+          }
+        }
+        r0 += (double)s0; r1 += (double)s1;
+      }
+      tc_fence_before();
+    }
+    if (n_local > 0) {
+      if (k < 64) { atomicAdd(P.red1 + 2 * k, r0); atomicAdd(P.red1 + 2 * k + 1, r1); }
+      // ---- wgrad2 accumulator: lane = k2, 64 columns = k1 ----
+      mbar_wait(&bars->done, 0);
+      tc_fence_after();
+      if (half == 0) {
+        for (int g16 = 0; g16 < 64; g16 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + kWG + g16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(P.gW2 + (size_t)(g16 + j) * 128 + k, __uint_as_float(r[j]));
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && n_local > 0) {
+      uint32_t ph = 0;
+      mbar_wait(&bars->w_full, 0);
+      for (int li = 0; li < n_local; ++li, ph ^= 1) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+        const int NT = (nvalid + 15) & ~15;
+        mbar_wait(&bars->a1_full, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = make_idesc(128, NT, 0, 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16(tmem + kD, make_desc(smem_u32(sW2T) + ks * 2 * kPlaneW, kPlaneW, 128),
+                     make_desc(smem_u32(sA1) + ks * 2 * plane, plane, 128), idesc, ks > 0);
+          mma_commit(&bars->d2_full);
+        }
+        mbar_wait(&bars->dz_ready, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
+          for (int ks = 0; ks < NT / 16; ++ks)
+            mma_bf16(tmem + kWG, make_desc(smem_u32(sDZ) + ks * 256, 128, plane), make_desc(smem_u32(sA1) + ks * 256, 128, plane),
+                     idesc_w, (li > 0 || ks > 0) ? 1u : 0u);
+          const uint32_t idesc = make_idesc(128, NT, 0, 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16(tmem + kD, make_desc(smem_u32(sW2P) + ks * 2 * kPlaneW, kPlaneW, 128),
+                     make_desc(smem_u32(sDZ) + ks * 2 * plane, plane, 128), idesc, ks > 0);
+          mma_commit(&bars->da_full);
+          mma_commit(&bars->dz_free);
+        }
+      }
+      mma_commit(&bars->done);
+    }
+  } else {
+    if (lane == 0 && n_local > 0) {
+      mbar_arrive_expect_tx(&bars->w_full, convfwd::kW2Bytes + 128 * 128 * 2);
+      bulk_copy_g2s(sW2T, P.w2t_img, convfwd::kW2Bytes, &bars->w_full);
+      bulk_copy_g2s(sW2P, P.w2p_img, 128 * 128 * 2, &bars->w_full);
+      uint32_t ph_f = 1;
+      for (int li = 0; li < n_local; ++li, ph_f ^= 1) {
+        mbar_wait(&bars->dz_free, ph_f);
+        mbar_arrive_expect_tx(&bars->dz_full, P.img_bytes);
+        bulk_copy_g2s(sDZ, P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace convbwd
+}  // namespace an3d

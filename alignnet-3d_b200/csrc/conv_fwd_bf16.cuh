@@ -51,8 +51,9 @@ struct Params {
   uint32_t* zext;         // [B][C3] ordered-uint packed max of the raw layer-3 accumulator
   double* stats2;         // [128][2]  sum, sum of squares of the raw layer-2 accumulator
   double* stats3;         // [C3][2]   same for layer 3 (sign-folded)
-  __nv_bfloat16* a1_out;  // optional [B*N, 64]  saved activations for the backward pass
-  __nv_bfloat16* a2_out;  // optional [B*N, 128]
+  __nv_bfloat16* a2_img;  // optional: per item, the A2 tile exactly as staged in shared memory (16 planes),
+                          // saved for the backward kernels (bulk store, TMA unit)
+  double* sa2;            // optional [128]: column sums of the (bf16-rounded) layer-2 activations
   uint32_t idx_mask;      // low mantissa bits that carry the arg-max point index (training)
 };
 
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     const int f = tid - 128;                       // 0..127: point slot (layer 1) / channel (layer-2 epilogue)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
-    double st_s = 0.0, st_ss = 0.0;
+    double st_s = 0.0, st_ss = 0.0, st_a2 = 0.0;
+    const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int64_t row0 = (int64_t)cloud * P.N + p0;
       const int b = li & 1;
       if (MODE != MODE_STATS2 && li >= 2) { mbar_wait(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
+      if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
       uint8_t* sA1 = sA2[b];
       if (f == 0) {
@@ -172,8 +175,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
             q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
             q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
             *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = q;
-            if (MODE == MODE_FULL_TRAIN && P.a1_out)
-              *reinterpret_cast<uint4*>(P.a1_out + (row0 + p) * 64 + c8 * 8) = q;
           }
         } else {
 #pragma unroll
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int k = f;
       const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
       uint8_t* dst = sA2[b] + (k >> 3) * plane2 + (k & 7) * 2;
-      float ts = 0.f, tss = 0.f;
+      float ts = 0.f, tss = 0.f, ta2 = 0.f;
       for (int g16 = 0; g16 < NT; g16 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
             const float v = p < nvalid ? fmaxf(fmaf(acc, sc, sh), 0.f) : 0.f;
             const __nv_bfloat16 hb = __float2bfloat16_rn(v);
             *reinterpret_cast<__nv_bfloat16*>(dst + p * 16) = hb;
-            if (MODE == MODE_FULL_TRAIN && P.a2_out && p < nvalid) P.a2_out[(row0 + p) * 128 + k] = hb;
+            if (MODE == MODE_FULL_TRAIN) ta2 += __bfloat162float(hb);
           }
         }
       }
@@ -211,10 +212,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       if (MODE == MODE_STATS2) {
         st_s += (double)ts; st_ss += (double)tss;
       } else {
+        st_a2 += (double)ta2;
         fence_proxy_async_smem();
         mbar_arrive(&bars->a2_full[b]);
+        if (save_a2) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");      // every front-end thread has written + fenced
+          if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, sA2[b], a2_bytes);
+        }
       }
     }
+    if (save_a2 && f == 0) bulk_wait_read_all();
+    if (MODE == MODE_FULL_TRAIN && P.sa2 && n_local > 0) atomicAdd(P.sa2 + f, st_a2);
     if (MODE == MODE_STATS2 && n_local > 0) {
       atomicAdd(P.stats2 + 2 * f, st_s);
       atomicAdd(P.stats2 + 2 * f + 1, st_ss);

@@ -51,6 +51,23 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                : "memory");
 }
 
+// bulk async copy shared -> global (TMA store); completion tracked with bulk groups
+__device__ __forceinline__ void bulk_copy_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk stores issued by this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void bulk_wait_read_but1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// 16-byte vector reduction to global memory (sm_90+)
+__device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------------------------
 // One full warp allocates `cols` (power of two >= 32) columns; the base address lands in *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
