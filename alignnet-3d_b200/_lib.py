@@ -74,6 +74,9 @@ SIGNATURES = {
     "an3d_launch_count": (C.c_uint64, []),
     "an3d_profile_begin": (C.c_int, []),
     "an3d_profile_end": (C.c_int, [C.POINTER(C.c_float * 8), C.POINTER(C.c_int32 * 8)]),
+    "an3d_selftest_conv_stack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "an3d_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p]),
     "an3d_recenter_translations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

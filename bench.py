@@ -33,7 +33,7 @@ WORKLOADS = {
     "c3": dict(name="c3: SynthCarsPersons-shaped synthetic B=4096 N=200 bf16 fwd+bwd+Adam training step", B=4096,
                N=200, train=True, persons=0.2),
 }
-DEFAULT_WORKLOAD = "c2"
+DEFAULT_WORKLOAD = "c3"
 
 
 def flops_per_pair(N: int, train: bool) -> float:

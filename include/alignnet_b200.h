@@ -180,6 +180,15 @@ int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag);
 int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn,
                        int32_t b_mn, void* stream);
 
+/* Diagnostic (test-suite only): training-mode forward + backward of ONE conv stack (stage 0..2) of
+ * ONE branch on the bf16 tensor-core path with a caller-supplied upstream gradient dG [B, C3].
+ * g_out [B, C3] receives the pooled feature, grads (flat, zeroed first) the parameter gradients of
+ * that stack, dcenter [B,3] / dangle [B] the gradient w.r.t. the recentring / canonicalisation. */
+int an3d_selftest_conv_stack(const an3d_ctx* ctx, const float* params, float* bn_state, int32_t stage, int32_t branch,
+                             const float* pcs, const float* center, const float* angle, int32_t batch,
+                             int32_t num_points, const float* dG, float* g_out, float* grads, float* dcenter,
+                             float* dangle, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
