@@ -5,6 +5,7 @@
 #include "kernels_f32.cuh"
 #include "loss.cuh"
 #include "bf16_path.cuh"
+#include "fc_gemm_bf16.cuh"
 
 namespace an3d {
 
@@ -52,8 +53,25 @@ int bn_relu_backward(const BnRef& v, const float* Z, int R, const float* dA, int
 //   grads.W += pro(X)^T dZ ; grads.b += colsum(dZ) ; dX = dZ W^T (if dX != nullptr).
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
                     float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
-                    int64_t lddx, double* bias_acc, cudaStream_t st) {
-  {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
+                    int64_t lddx, double* bias_acc, cudaStream_t st, bool bf16 = false) {
+  bool wgrad_done = false, dgrad_done = false;
+  if (bf16) {
+    fcgemm::Params f;
+    f.A = X; f.lda = ldx; f.a_mn = 1; f.B = dZ; f.ldb = L.cout; f.b_mn = 1; f.C = grads + L.w; f.ldc = L.cout;
+    f.M = L.cin; f.N = L.cout; f.K = R; f.bias = nullptr; f.pro_scale = psc; f.pro_shift = psh; f.pro_mask = pmask;
+    f.pro_mask_scale = pmask_scale; f.accumulate = 1;
+    const int tiles = ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
+    f.ksplit = std::max(1, std::min((R + 511) / 512, (296 + tiles - 1) / tiles));
+    if (fcgemm::usable(f)) { AN3D_TRY(fcgemm::launch(f, st)); wgrad_done = true; }
+    if (dX) {
+      fcgemm::Params d;
+      d.A = dZ; d.lda = L.cout; d.a_mn = 0; d.B = params + L.w; d.ldb = L.cout; d.b_mn = 0; d.C = dX; d.ldc = lddx;
+      d.M = R; d.N = L.cin; d.K = L.cout; d.bias = nullptr; d.pro_scale = nullptr; d.pro_shift = nullptr; d.pro_mask = nullptr;
+      d.pro_mask_scale = 1.f; d.ksplit = 1; d.accumulate = 0;
+      if (fcgemm::usable(d)) { AN3D_TRY(fcgemm::launch(d, st)); dgrad_done = true; }
+    }
+  }
+  if (!wgrad_done) {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
     GemmArgs g;
     g.A = X; g.lda = ldx; g.B = dZ; g.ldb = L.cout; g.C = grads + L.w; g.ldc = L.cout;
     g.M = L.cin; g.N = L.cout; g.K = R; g.pro_scale = psc; g.pro_shift = psh; g.pro_mask = pmask;
@@ -70,7 +88,7 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     add_double_to_float_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(bias_acc, grads + L.b, L.cout);
     AN3D_LAUNCH_CHECK();
   }
-  if (dX) {  // dgrad: [R, cin] = dZ [R, cout] * W^T
+  if (dX && !dgrad_done) {  // dgrad: [R, cin] = dZ [R, cout] * W^T
     GemmArgs g;
     g.A = dZ; g.lda = L.cout; g.B = params + L.w; g.ldb = L.cout; g.C = dX; g.ldc = lddx;
     g.M = R; g.N = L.cin; g.K = L.cout;
@@ -158,7 +176,8 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
       dX = dIn;
       lddx = lddin;
     }
-    AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st));
+    AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st,
+                             p.bf16));
     dZ = dX;
     cur ^= 1;
   }

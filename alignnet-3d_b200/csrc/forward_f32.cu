@@ -1,6 +1,7 @@
 // fp32 parity path: forward pass of get_model (models/tp8.py:135-158) with CUDA-core kernels.
 #include "kernels_f32.cuh"
 #include "bf16_path.cuh"
+#include "fc_gemm_bf16.cuh"
 
 namespace an3d {
 
@@ -88,7 +89,12 @@ static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const fl
       g.pro_mask = mask;
       g.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
     }
-    AN3D_TRY(launch_gemm(g, false, false, st));
+    fcgemm::Params f;
+    f.A = g.A; f.lda = g.lda; f.a_mn = 0; f.B = g.B; f.ldb = g.ldb; f.b_mn = 1; f.C = g.C; f.ldc = g.ldc;
+    f.M = g.M; f.N = g.N; f.K = g.K; f.bias = g.bias; f.pro_scale = g.pro_scale; f.pro_shift = g.pro_shift;
+    f.pro_mask = g.pro_mask; f.pro_mask_scale = g.pro_mask_scale; f.ksplit = 1; f.accumulate = 0;
+    if (p.bf16 && fcgemm::usable(f)) AN3D_TRY(fcgemm::launch(f, st));
+    else AN3D_TRY(launch_gemm(g, false, false, st));
     if (L.bn >= 0) {
       BnView v = bn_view(m, p, params, state, head, br, L.bn);
       AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));

@@ -150,12 +150,14 @@ int build_model(const an3d_arch* a, Model* m) {
     l.cin = cin;
     l.cout = cout;
     l.scope = scope;
+    off = (off + 3) & ~int64_t(3);   // every tensor starts 16-byte aligned (vector loads / reductions)
     l.w = off;
     if (first_conv)
       add_tensor(m->trainable, prefix + scope + "/weights", off, {1, 3, 1, cout});
     else
       add_tensor(m->trainable, prefix + scope + "/weights", off, {cin, cout});
     off += (int64_t)cin * cout;
+    off = (off + 3) & ~int64_t(3);
     l.b = off;
     add_tensor(m->trainable, prefix + scope + "/biases", off, {cout});
     off += cout;
@@ -196,6 +198,7 @@ int build_model(const an3d_arch* a, Model* m) {
     add_lin(m->fc[2], "", "fc" + std::to_string(a->n_fc[2] + 1), fin, out_dim[2], false, true, false);
   }
   // BN gamma/beta: branch 0 ("siamese/"), branch 1 ("siamese_1/", quirk Q0), head
+  off = (off + 3) & ~int64_t(3);
   m->bn_base = off;
   int64_t soff = 0;
   for (int br = 0; br < 2; ++br) {
@@ -221,7 +224,7 @@ int build_model(const an3d_arch* a, Model* m) {
     add_tensor(m->state, b.scope + "/bn/moments/Squeeze_1/ExponentialMovingAverage", soff, {b.ch});
     soff += b.ch;
   }
-  m->n_trainable = off;
+  m->n_trainable = (off + 3) & ~int64_t(3);
   m->n_state = soff;
   return AN3D_OK;
 }

@@ -19,6 +19,7 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
   a.base = static_cast<char*>(workspace);
   p->B = B;
   p->N = N;
+  p->bf16 = bf16;
   p->M = (int64_t)B * N;
   const int64_t M = p->M;
   const int c_emb = m.conv[EMB].back().cout;

@@ -109,7 +109,9 @@ int an3d_destroy(an3d_ctx* ctx);
 
 /* Flat-buffer layout.  which = 0: trainable parameters (fp32 buffer `params`, same layout for
  * `grads`, Adam `m`, `v`); which = 1: BN shadow state (`bn_state`).  Names are the TF variable
- * names of the reference graph (utils/tf_util.py:148-160,333-339,470-479). */
+ * names of the reference graph (utils/tf_util.py:148-160,333-339,470-479).
+ * Every tensor starts on a 16-byte boundary, so an3d_num_elements() may exceed the sum of the
+ * tensor sizes by a few padding floats (which stay zero). */
 int an3d_num_elements(const an3d_ctx* ctx, int which, int64_t* out_count);
 int an3d_num_tensors(const an3d_ctx* ctx, int which, int32_t* out_count);
 int an3d_tensor_info(const an3d_ctx* ctx, int which, int32_t index, char* name, int32_t name_capacity,

@@ -68,11 +68,16 @@ def _conv_stack(p, specs, branch, params, state, new_state, training, bn_decay):
 
 
 def _mlp(g, specs, branch, params, state, new_state, training, bn_decay, keep, mask):
-    """models/tp8.py:75-82."""
+    """models/tp8.py:75-82.  With SIM_BF16 and a batch of at least 64 rows the hidden FC layers round
+    their inputs and weights to bf16 (the engine runs those GEMMs on the tensor cores; smaller
+    batches and the narrow output layer stay in fp32)."""
     x = g
     for s in specs[:-1]:
         n = weight_names(s)
-        z = x @ params[n["weights"]] + params[n["biases"]]
+        w = params[n["weights"]]
+        if SIM_BF16 and x.shape[0] >= 64:
+            x, w = _r16(x), _r16(w)
+        z = x @ w + params[n["biases"]]
         x = torch.relu(_bn(z, s, branch, params, state, new_state, training, bn_decay, (0,)))
     if training and keep is not None and mask is not None:
         x = x / keep * mask
