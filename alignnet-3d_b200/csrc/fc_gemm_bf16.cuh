@@ -190,7 +190,7 @@ inline bool usable(const Params& p) {
          (!p.pro_mask || al(p.pro_mask)) && (!p.bias || true) && p.K >= 64 && p.M >= 64 && p.N >= 64;
 }
 
-inline int launch(const Params& p, cudaStream_t st) {
+static int launch(const Params& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
