@@ -134,7 +134,7 @@ def test_bf16_fc_tensor_core_path_matches_rounding_model():
         dev = to_dev(batch)
         ep = e.forward(dev["pcs1"], dev["pcs2"], training, 0.5, {k: torch.ones(B, 256, device="cuda") for k in MASK_KEYS})
         torch.cuda.synchronize()
-        compare(ep, {k: v.numpy() for k, v in ep_ref.items()}, arch, 8e-2, 1.5e-2)
+        compare(ep, {k: v.numpy() for k, v in ep_ref.items()}, arch, 1.5e-1, 1.5e-2)
 
 
 @pytest.mark.parametrize("name,training", [("shipped_B32_N200", True), ("shipped_B32_N200", False)])
