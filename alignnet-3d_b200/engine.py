@@ -254,13 +254,11 @@ class Engine:
     def loss(self, labels: Dict[str, torch.Tensor], end_points: Dict[str, torch.Tensor]) -> torch.Tensor:
         """get_loss forward only (models/tp8.py:401-407).  Returns the 20-float loss vector."""
         B = int(end_points["pred_translations"].shape[0])
-        ws = self._workspace(*getattr(self, "_last", (B, 1, self.pflag)))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ls, os_ = self._label_struct(labels), self._out_struct(end_points)
         scratch = torch.empty(64 * B + 1024, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.an3d_loss(self.ctx, C.byref(ls), C.byref(os_), B, self.loss_buf.data_ptr(),
                                       scratch.data_ptr(), scratch.numel() * 4, stream), "an3d_loss")
-        del ws
         return self.loss_buf
 
     def backward(self, pcs1, pcs2, labels: Dict[str, torch.Tensor], end_points: Dict[str, torch.Tensor]) -> torch.Tensor:
