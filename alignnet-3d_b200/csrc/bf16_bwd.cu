@@ -72,15 +72,27 @@ __global__ void bwd3_coeff_kernel(const double* red3, int C3, double count, cons
 
 // Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights), written as the two K-half images
 // of the A operand (rows k, contraction k'); block 0 also writes u[k] = sum_c p'[c] W3b[k,c].
-__global__ void gq_kernel(const float* W3, const float* coef3, int C3, __nv_bfloat16* gq_img, float* uvec) {
+// One block per k'; W3 is streamed through shared memory in [128 x 32] tiles (coalesced loads).
+__global__ void __launch_bounds__(128) gq_kernel(const float* W3, const float* coef3, int C3, __nv_bfloat16* gq_img,
+                                                 float* uvec) {
+  __shared__ float sw[128][33];
+  __shared__ float sq[32], sp[32];
   const int kp = blockIdx.x, k = threadIdx.x;
-  const float* rk = W3 + (size_t)k * C3;
-  const float* rkp = W3 + (size_t)kp * C3;
   float acc = 0.f, uacc = 0.f;
-  for (int c = 0; c < C3; ++c) {
-    const float wk = bf16r(rk[c]);
-    acc = fmaf(bf16r(rkp[c]) * coef3[c], wk, acc);
-    uacc = fmaf(coef3[C3 + c], wk, uacc);
+  for (int c0 = 0; c0 < C3; c0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 32; i += 128) {
+      const int r = i >> 5, cc = i & 31;
+      sw[r][cc] = bf16r(W3[(size_t)r * C3 + c0 + cc]);
+    }
+    if (threadIdx.x < 32) { sq[threadIdx.x] = coef3[c0 + threadIdx.x]; sp[threadIdx.x] = coef3[C3 + c0 + threadIdx.x]; }
+    __syncthreads();
+#pragma unroll 8
+    for (int cc = 0; cc < 32; ++cc) {
+      const float wk = sw[k][cc];
+      acc = fmaf(sw[kp][cc] * sq[cc], wk, acc);
+      uacc = fmaf(sp[cc], wk, uacc);
+    }
   }
   const int h = kp >> 6, kk = kp & 63;
   gq_img[(size_t)h * 8192 + (kk >> 3) * 1024 + k * 8 + (kk & 7)] = __float2bfloat16_rn(acc);
@@ -100,7 +112,8 @@ __global__ void wgrad3_dense_kernel(const float* W3, const float* t1, const floa
   __syncthreads();
   const int c = c0 + tx;
   const float q = coef3[c], pp = coef3[C3 + c];
-  for (int k = ty; k < 128; k += 8) {
+  const int kbeg = blockIdx.y * 32;
+  for (int k = kbeg + ty; k < kbeg + 32; k += 8) {
     const float* grow = gram + (size_t)k * 128;
     float acc = 0.f;
 #pragma unroll 8
@@ -227,7 +240,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram, 0, 128 * 128 * sizeof(float), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.t1, 0, 128 * (size_t)C3 * sizeof(float), st));
   {
-    const int bchunk = 64;
+    const int bchunk = 16;
     dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
     pool_bwd_prep_kernel<<<grid, 128, 0, st>>>(dG, lddg, p.g[s][br], ldg, q.zext[s][br], B, C3, gamma3, params + L3.b, mean3,
                                                inv3, q.idx_mask, q.dyext, q.red3, bchunk);
@@ -254,7 +267,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     convbwd::wgrad3_kernel<<<dim3(nranges, npass), convbwd::kWg3Threads, smem, st>>>(W);
     prof_mark(PROF_BWD_T1, false, st);
     AN3D_LAUNCH_CHECK();
-    wgrad3_dense_kernel<<<C3 / 32, 256, 0, st>>>(params + L3.w, q.t1, q.gram, q.sa2[s][br], q.coef3, C3, grads + L3.w);
+    wgrad3_dense_kernel<<<dim3(C3 / 32, 4), 256, 0, st>>>(params + L3.w, q.t1, q.gram, q.sa2[s][br], q.coef3, C3, grads + L3.w);
     AN3D_LAUNCH_CHECK();
   }
   // ---- dgrad3 -> dy2 images + BN2 backward sums ----

@@ -81,24 +81,41 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params 
   const uint32_t tmem = bars->tmem_base;
 
   if (warp < 2) {
-    // ---- scatter threads: one channel of the current 64-channel slot each ----
+    // ---- scatter threads: one channel of the current 64-channel slot each.  The (arg row, weight) pairs of
+    // the NEXT item are loaded into registers while the current item is scattered, so the global-load
+    // latency never sits between two MMAs.
     const int t = tid;
     int prev_off[2] = {-1, -1};
     uint32_t ph_e[2] = {1, 1};
     int g = 0;
+    int cur_idx[kWg3SlotsPerPass], nxt_idx[kWg3SlotsPerPass];
+    float cur_w[kWg3SlotsPerPass], nxt_w[kWg3SlotsPerPass];
+    auto fetch = [&](int li, int (&ix)[kWg3SlotsPerPass], float (&wv)[kWg3SlotsPerPass]) {
+      const int cloud = (it_begin + li) / P.npc;
+#pragma unroll
+      for (int s = 0; s < kWg3SlotsPerPass; ++s) {
+        if (s < nslots) {
+          const int c = c0 + s * 64 + t;
+          ix[s] = P.gidx[(size_t)cloud * P.C3 + c];
+          wv[s] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+        }
+      }
+    };
+    if (n_local > 0) fetch(0, cur_idx, cur_w);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
       const int p0 = pchunk * P.PC;
       const int nvalid = min(P.PC, P.N - p0);
-      for (int s = 0; s < nslots; ++s, ++g) {
-        const int c = c0 + s * 64 + t;
-        const int idx = P.gidx[(size_t)cloud * P.C3 + c];
-        const float w = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+      if (li + 1 < n_local) fetch(li + 1, nxt_idx, nxt_w);
+#pragma unroll
+      for (int s = 0; s < kWg3SlotsPerPass; ++s) {
+        if (s >= nslots) break;
         const int sb = g & 1;
         mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
         if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
-        const int row = idx - p0;
+        const int row = cur_idx[s] - p0;
+        const float w = cur_w[s];
         if (row >= 0 && row < nvalid && w != 0.f) {
           const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
@@ -108,7 +125,10 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params 
         }
         fence_proxy_async_smem();
         mbar_arrive(&bars->sd_full[sb]);
+        ++g;
       }
+#pragma unroll
+      for (int s = 0; s < kWg3SlotsPerPass; ++s) { cur_idx[s] = nxt_idx[s]; cur_w[s] = nxt_w[s]; }
     }
   } else if (warp == 4) {
     if (lane == 0 && n_local > 0) {
@@ -313,24 +333,40 @@ __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3Params 
       atomicAdd(P.red2 + 2 * k + 1, acc1);
     }
   } else if (warp < 6) {
-    // ---- scatter threads ----
+    // ---- scatter threads (next item's arg rows / weights prefetched into registers) ----
     const int t = tid - 128;
     int prev_off[2] = {-1, -1};
     uint32_t ph_e[2] = {1, 1};
     int g = 0;
+    constexpr int kMaxHc = 16;   // C3 <= 1024
+    int cur_idx[kMaxHc], nxt_idx[kMaxHc];
+    float cur_w[kMaxHc], nxt_w[kMaxHc];
+    auto fetch = [&](int li, int (&ix)[kMaxHc], float (&wv)[kMaxHc]) {
+      const int cloud = (it_begin + li) / P.npc;
+#pragma unroll
+      for (int hc = 0; hc < kMaxHc; ++hc) {
+        if (hc < nhc) {
+          const int c = hc * 64 + t;
+          ix[hc] = P.gidx[(size_t)cloud * P.C3 + c];
+          wv[hc] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+        }
+      }
+    };
+    if (n_local > 0) fetch(0, cur_idx, cur_w);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
       const int p0 = pchunk * P.PC;
       const int nvalid = min(P.PC, P.N - p0);
-      for (int hc = 0; hc < nhc; ++hc, ++g) {
-        const int c = hc * 64 + t;
-        const int idx = P.gidx[(size_t)cloud * P.C3 + c];
-        const float w = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+      if (li + 1 < n_local) fetch(li + 1, nxt_idx, nxt_w);
+#pragma unroll
+      for (int hc = 0; hc < kMaxHc; ++hc) {
+        if (hc >= nhc) break;
         const int sb = g & 1;
         mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
         if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
-        const int row = idx - p0;
+        const int row = cur_idx[hc] - p0;
+        const float w = cur_w[hc];
         if (row >= 0 && row < nvalid && w != 0.f) {
           const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
@@ -340,7 +376,10 @@ __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3Params 
         }
         fence_proxy_async_smem();
         mbar_arrive(&bars->sd_full[sb]);
+        ++g;
       }
+#pragma unroll
+      for (int hc = 0; hc < kMaxHc; ++hc) { cur_idx[hc] = nxt_idx[hc]; cur_w[hc] = nxt_w[hc]; }
     }
   } else if (warp == 6) {
     if (lane == 0 && n_local > 0) {
@@ -436,12 +475,12 @@ struct L2Params {
 constexpr int kL2Threads = 320;
 
 inline size_t l2_smem_bytes(int PC) {
-  return 8 * (size_t)plane_stride(PC) + 16 * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
+  return 8 * (size_t)plane_stride(PC) + 2 * 16 * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
          256 * 3 * 4 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
 }
 
 struct L2Bars {
-  uint64_t w_full, dz_full, dz_free, a1_full, d2_full, dz_ready, da_full, done;
+  uint64_t w_full, dz_full[2], dz_free[2], a1_full, d2_full, dz_ready, da_full, done;
   uint32_t tmem_base;
   float xf[8];
 };
@@ -450,8 +489,8 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   uint8_t* sA1 = smem;
-  uint8_t* sDZ = sA1 + 8 * plane;
-  uint8_t* sW2T = sDZ + 16 * plane;
+  uint8_t* sDZb[2] = {sA1 + 8 * plane, sA1 + 24 * plane};   // dy2 tile of the next item is prefetched
+  uint8_t* sW2T = sA1 + 40 * plane;
   uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
   float* sPts = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [256][3] transformed points
   float* sW1f = sPts + 768;      // 192
@@ -466,7 +505,8 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
   const int n_local = it_end - it_begin;
 
   if (tid == 0) {
-    mbar_init(&bars->w_full, 1); mbar_init(&bars->dz_full, 1); mbar_init(&bars->dz_free, 1);
+    mbar_init(&bars->w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->dz_full[i], 1); mbar_init(&bars->dz_free[i], 1); }
     mbar_init(&bars->a1_full, 256); mbar_init(&bars->d2_full, 1); mbar_init(&bars->dz_ready, 256);
     mbar_init(&bars->da_full, 1); mbar_init(&bars->done, 1);
     fence_barrier_init();
@@ -500,6 +540,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       const int nvalid = min(P.PC, P.N - p0);
       const int NT = (nvalid + 15) & ~15;
       const int64_t row0 = (int64_t)cloud * P.N + p0;
+      uint8_t* sDZ = sDZb[li & 1];
       if (t == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(P.angle[cloud], &sn, &cs);
@@ -538,7 +579,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       mbar_arrive(&bars->a1_full);
       // ---- dz2 from the raw layer-2 accumulator (xhat2) and dy2 ----
       mbar_wait(&bars->d2_full, ph);
-      mbar_wait(&bars->dz_full, ph);
+      mbar_wait(&bars->dz_full[li & 1], (uint32_t)((li >> 1) & 1));
       tc_fence_after();
       {
         const float cx = sL2[k], inv2 = sL2[128 + k], s2 = sL2[256 + k], m0 = sL2[384 + k], m1 = sL2[512 + k];
@@ -634,6 +675,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
         }
         mbar_wait(&bars->dz_ready, ph);
         tc_fence_after();
+        uint8_t* sDZ = sDZb[li & 1];
         {
           const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
           for (int ks = 0; ks < NT / 16; ++ks)
@@ -645,7 +687,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
             mma_bf16(tmem + kD, make_desc(smem_u32(sW2P) + ks * 2 * kPlaneW, kPlaneW, 128),
                      make_desc(smem_u32(sDZ) + ks * 2 * plane, plane, 128), idesc, ks > 0);
           mma_commit(&bars->da_full);
-          mma_commit(&bars->dz_free);
+          mma_commit(&bars->dz_free[li & 1]);
         }
       }
       mma_commit(&bars->done);
@@ -655,11 +697,11 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       mbar_arrive_expect_tx(&bars->w_full, convfwd::kW2Bytes + 128 * 128 * 2);
       bulk_copy_g2s(sW2T, P.w2t_img, convfwd::kW2Bytes, &bars->w_full);
       bulk_copy_g2s(sW2P, P.w2p_img, 128 * 128 * 2, &bars->w_full);
-      uint32_t ph_f = 1;
-      for (int li = 0; li < n_local; ++li, ph_f ^= 1) {
-        mbar_wait(&bars->dz_free, ph_f);
-        mbar_arrive_expect_tx(&bars->dz_full, P.img_bytes);
-        bulk_copy_g2s(sDZ, P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full);
+      for (int li = 0; li < n_local; ++li) {
+        const int b = li & 1;
+        mbar_wait(&bars->dz_free[b], (uint32_t)(((li >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&bars->dz_full[b], P.img_bytes);
+        bulk_copy_g2s(sDZb[b], P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[b]);
       }
     }
   }

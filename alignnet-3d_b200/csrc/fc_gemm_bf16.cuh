@@ -33,7 +33,7 @@ struct Params {
 };
 
 constexpr int kThreads = 288;               // 4 epilogue warps, 4 loader warps, 1 MMA warp
-constexpr int kStages = 4;
+constexpr int kStages = 3;                   // 100 KB of tiles -> two CTAs per SM
 constexpr uint32_t kPlaneK = 128 * 16 + 16;   // K-major tile: 8 planes x 128 rows
 constexpr uint32_t kPlaneMN = 64 * 16 + 16;   // MN-major tile: 16 planes x 64 rows
 constexpr uint32_t kTileBytes = 16 * kPlaneMN > 8 * kPlaneK ? 16 * kPlaneMN : 8 * kPlaneK;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const float* src, int64_
   }
 }
 
-static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Params P) {
+static __global__ void __launch_bounds__(kThreads, 2) fc_gemm_kernel(const Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kTileStride;
