@@ -257,14 +257,25 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
     W.gidx = p.gidx[s][br]; W.dyext = q.dyext; W.s3 = sc3; W.B = B; W.N = N; W.PC = q.PC; W.npc = q.npc; W.C3 = C3;
     W.n_items = n_items; W.gW3 = q.t1; W.gram = q.gram;
-    const int npass = (C3 / 64 + convbwd::kWg3SlotsPerPass - 1) / convbwd::kWg3SlotsPerPass;
-    const int nranges = std::max(1, std::min(n_items, sms / npass));
+    // Gram matrix A2^T A2 on the tensor cores (the kernel's sparse slots are unused: C3 = 0)
+    W.C3 = 0;
+    const int nranges = std::max(1, std::min(n_items, sms));
     W.items_per_cta = (n_items + nranges - 1) / nranges;
     const size_t smem = convbwd::wg3_smem_bytes(q.PC);
     if (smem > (size_t)kMaxSmem) { set_error("wgrad3 tile too large"); return AN3D_ERR_UNSUPPORTED; }
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_mark(PROF_BWD_T1, true, st);
-    convbwd::wgrad3_kernel<<<dim3(nranges, npass), convbwd::kWg3Threads, smem, st>>>(W);
+    convbwd::wgrad3_kernel<<<dim3(nranges, 1), convbwd::kWg3Threads, smem, st>>>(W);
+    AN3D_LAUNCH_CHECK();
+    // sparse part T1 = A2^T S: gather-scale-accumulate on CUDA cores (1/N of the dense FLOPs)
+    convbwd::T1Params T;
+    T.a2_img = W.a2_img; T.img_bytes = W.img_bytes; T.gidx = W.gidx; T.dyext = W.dyext; T.s3 = W.s3; T.B = B; T.N = N;
+    T.PC = q.PC; T.npc = q.npc; T.C3 = C3; T.n_items = n_items; T.t1 = q.t1;
+    const int tr = std::max(1, std::min(n_items, sms / 4));
+    T.items_per_cta = (n_items + tr - 1) / tr;
+    const size_t tsmem = convbwd::t1_smem_bytes(q.PC, C3);
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::t1_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    convbwd::t1_sparse_kernel<<<dim3(tr, 4), convbwd::kT1Threads, tsmem, st>>>(T);
     prof_mark(PROF_BWD_T1, false, st);
     AN3D_LAUNCH_CHECK();
     wgrad3_dense_kernel<<<dim3(C3 / 32, 4), 256, 0, st>>>(params + L3.w, q.t1, q.gram, q.sa2[s][br], q.coef3, C3, grads + L3.w);

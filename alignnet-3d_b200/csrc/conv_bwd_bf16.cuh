@@ -213,6 +213,95 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params 
 }
 
 // =============================================================================================
+// t1_sparse: T1[k, c] = sum over clouds of w[b,c] * a2[b, r*(b,c), k] on CUDA cores.
+// S has exactly one non-zero per (cloud, channel), so the "GEMM" A2^T S is a gather-scale-accumulate
+// with 1/N of the dense FLOPs.  CTA = (cloud range, quarter of the 128 k rows): it only needs 4 of
+// the 16 planes of each saved A2 image (one bulk copy), keeps T1[32 k][C3] in registers
+// (warp = channel group, lane = k) and flushes once with vector reductions.
+// =============================================================================================
+struct T1Params {
+  const uint8_t* a2_img;
+  uint32_t img_bytes;
+  const int32_t* gidx;
+  const float* dyext;
+  const float* s3;
+  int B, N, PC, npc, C3, n_items, items_per_cta;
+  float* t1;             // [128][C3], 16-byte aligned, accumulated with reductions
+};
+constexpr int kT1Threads = 1024;
+inline size_t t1_smem_bytes(int PC, int C3) { return 2 * 4 * (size_t)plane_stride(PC) + 2 * (size_t)C3 * 8 + 64; }
+
+__global__ void __launch_bounds__(kT1Threads, 1) t1_sparse_kernel(const T1Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane = plane_stride(P.PC);
+  const uint32_t qbytes = 4 * plane;
+  uint8_t* sA[2] = {smem, smem + qbytes};
+  float* sWv = reinterpret_cast<float*>(smem + 2 * qbytes);      // [2][C3]
+  int* sRow = reinterpret_cast<int*>(sWv + 2 * P.C3);            // [2][C3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * P.C3); // a_full[2]
+  const int tid = threadIdx.x, cg = tid >> 5, kk = tid & 31;
+  const int kq = blockIdx.y;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
+  const int it_end = min(P.n_items, it_begin + P.items_per_cta);
+  const int n_local = it_end - it_begin;
+  const int CH = P.C3 / 32;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  if (n_local == 0) return;
+
+  auto fetch = [&](int li, float& w, int& row) {   // channel c = tid of item li
+    w = 0.f; row = -1;
+    if (tid < P.C3) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
+      const float wv = P.s3[tid] * P.dyext[(size_t)cloud * P.C3 + tid];
+      const int r = P.gidx[(size_t)cloud * P.C3 + tid] - p0;
+      if (r >= 0 && r < nvalid && wv != 0.f) { w = wv; row = r; }
+    }
+  };
+  auto load_img = [&](int li) {
+    const int b = li & 1;
+    mbar_arrive_expect_tx(&bars[b], qbytes);
+    bulk_copy_g2s(sA[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes + (size_t)kq * qbytes, qbytes, &bars[b]);
+  };
+  if (tid == 0) { load_img(0); if (n_local > 1) load_img(1); }
+  {
+    float w; int row;
+    fetch(0, w, row);
+    if (tid < P.C3) { sWv[tid] = w; sRow[tid] = row; }
+  }
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  const uint32_t lane_off = (kk >> 3) * plane + (kk & 7) * 2;
+  for (int li = 0; li < n_local; ++li) {
+    const int b = li & 1;
+    float nw = 0.f; int nrow = -1;
+    if (li + 1 < n_local) fetch(li + 1, nw, nrow);
+    mbar_wait(&bars[b], (uint32_t)((li >> 1) & 1));
+    const float* wv = sWv + b * P.C3 + cg * CH;
+    const int* rv = sRow + b * P.C3 + cg * CH;
+    const uint8_t* img = sA[b] + lane_off;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < CH) {
+        const int r = rv[j];
+        if (r >= 0) acc[j] = fmaf(wv[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + r * 16)), acc[j]);
+      }
+    }
+    if (li + 1 < n_local && tid < P.C3) { sWv[(b ^ 1) * P.C3 + tid] = nw; sRow[(b ^ 1) * P.C3 + tid] = nrow; }
+    __syncthreads();
+    if (tid == 0 && li + 2 < n_local) load_img(li + 2);
+  }
+  float* dst = P.t1 + (size_t)(kq * 32 + kk) * P.C3 + cg * CH;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    if (j < CH) red_add_v4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+// =============================================================================================
 // dgrad3: da2^T[k, pt] = Gq a2^T + u + W3 S^T ; dy2 = da2 * [a2 > 0] ; sums for the BN2 backward
 // =============================================================================================
 struct Dg3Params {
