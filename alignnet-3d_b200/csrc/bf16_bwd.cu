@@ -70,16 +70,16 @@ __global__ void bwd3_coeff_kernel(const double* red3, int C3, double count, cons
   coef3[C3 + c] = (float)pp;
 }
 
-// Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights), written as the two K-half images
-// of the A operand (rows k, contraction k'); block 0 also writes u[k] = sum_c p'[c] W3b[k,c].
-// One block per k'; W3 is streamed through shared memory in [128 x 32] tiles (coalesced loads).
-__global__ void __launch_bounds__(128) gq_kernel(const float* W3, const float* coef3, int C3, __nv_bfloat16* gq_img,
-                                                 float* uvec) {
+// Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights) and u[k] = sum_c p'[c] W3b[k,c]:
+// partial sums over 128-channel slices (grid = 128 k' x C3/128), accumulated in fp32 ...
+__global__ void __launch_bounds__(128) gq_partial_kernel(const float* W3, const float* coef3, int C3, float* gq_f32,
+                                                         float* uvec) {
   __shared__ float sw[128][33];
   __shared__ float sq[32], sp[32];
   const int kp = blockIdx.x, k = threadIdx.x;
+  const int cbeg = blockIdx.y * 128;
   float acc = 0.f, uacc = 0.f;
-  for (int c0 = 0; c0 < C3; c0 += 32) {
+  for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
     __syncthreads();
     for (int i = threadIdx.x; i < 128 * 32; i += 128) {
       const int r = i >> 5, cc = i & 31;
@@ -94,9 +94,17 @@ __global__ void __launch_bounds__(128) gq_kernel(const float* W3, const float* c
       uacc = fmaf(sp[cc], wk, uacc);
     }
   }
+  atomicAdd(gq_f32 + kp * 128 + k, acc);
+  if (kp == 0) atomicAdd(uvec + k, uacc);
+}
+
+// ... then packed as the two K-half bf16 images of the A operand (rows k, contraction k')
+__global__ void gq_pack_kernel(const float* gq_f32, __nv_bfloat16* gq_img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128) return;
+  const int kp = i >> 7, k = i & 127;
   const int h = kp >> 6, kk = kp & 63;
-  gq_img[(size_t)h * 8192 + (kk >> 3) * 1024 + k * 8 + (kk & 7)] = __float2bfloat16_rn(acc);
-  if (kp == 0) uvec[k] = uacc;
+  gq_img[(size_t)h * 8192 + (kk >> 3) * 1024 + k * 8 + (kk & 7)] = __float2bfloat16_rn(gq_f32[i]);
 }
 
 // grads.W3[k,c] += T1[k,c] + sa2[k] p'[c] + q[c] * sum_k' G2[k,k'] W3b[k',c]
@@ -248,7 +256,11 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     bwd3_coeff_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.red3, C3, (double)M, sc3, inv3, mean3, params + L3.b,
                                                         grads + poff(L3.bn), grads + poff(L3.bn) + C3, q.coef3);
     AN3D_LAUNCH_CHECK();
-    gq_kernel<<<128, 128, 0, st>>>(params + L3.w, q.coef3, C3, q.gq, q.uvec);
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gq_f32, 0, 128 * 128 * sizeof(float), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.uvec, 0, 128 * sizeof(float), st));
+    gq_partial_kernel<<<dim3(128, C3 / 128), 128, 0, st>>>(params + L3.w, q.coef3, C3, q.gq_f32, q.uvec);
+    AN3D_LAUNCH_CHECK();
+    gq_pack_kernel<<<64, 256, 0, st>>>(q.gq_f32, q.gq);
     AN3D_LAUNCH_CHECK();
   }
   // ---- wgrad3: sparse part + Gram on the tensor cores, dense correction on CUDA cores ----

@@ -232,6 +232,7 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
     q->red3 = a.take<double>(2 * c3max);
     q->coef3 = a.take<float>(4 * c3max);
     q->gq = a.take<__nv_bfloat16>(128 * 128);
+    q->gq_f32 = a.take<float>(128 * 128);
     q->uvec = a.take<float>(128);
     q->gram = a.take<float>(128 * 128);
     q->t1 = a.take<float>(128 * c3max);

@@ -145,6 +145,7 @@ struct PlanBf16 {
   double* red3 = nullptr;                   // [2][C3max] sum dy, sum dy*xhat of layer 3
   float* coef3 = nullptr;                   // [4][C3max]: q, p', (unused), (unused)
   __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
+  float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
   float* uvec = nullptr;                    // [128]
   float* gram = nullptr;                    // [128][128] a2^T a2
   float* t1 = nullptr;                      // [128][C3max] sparse part of wgrad3 (16-byte aligned scratch)

@@ -229,71 +229,94 @@ struct T1Params {
   float* t1;             // [128][C3], 16-byte aligned, accumulated with reductions
 };
 constexpr int kT1Threads = 1024;
-inline size_t t1_smem_bytes(int PC, int C3) { return 2 * 4 * (size_t)plane_stride(PC) + 2 * (size_t)C3 * 8 + 64; }
+constexpr int kT1Batch = 4;              // items processed per block-wide synchronisation
+inline size_t t1_smem_bytes(int PC, int C3) {
+  return 2 * kT1Batch * 4 * (size_t)plane_stride(PC) + 2 * kT1Batch * (size_t)C3 * 8 + 64;
+}
 
 __global__ void __launch_bounds__(kT1Threads, 1) t1_sparse_kernel(const T1Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t qbytes = 4 * plane;
-  uint8_t* sA[2] = {smem, smem + qbytes};
-  float* sWv = reinterpret_cast<float*>(smem + 2 * qbytes);      // [2][C3]
-  int* sRow = reinterpret_cast<int*>(sWv + 2 * P.C3);            // [2][C3]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * P.C3); // a_full[2]
+  uint8_t* sA = smem;                                                        // [2][kT1Batch][qbytes]
+  float* sWv = reinterpret_cast<float*>(smem + 2 * kT1Batch * qbytes);       // [2][kT1Batch][C3]
+  int* sRow = reinterpret_cast<int*>(sWv + 2 * kT1Batch * P.C3);             // [2][kT1Batch][C3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * kT1Batch * P.C3);  // a_full[2]
   const int tid = threadIdx.x, cg = tid >> 5, kk = tid & 31;
   const int kq = blockIdx.y;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
+  const int n_batches = (n_local + kT1Batch - 1) / kT1Batch;
   const int CH = P.C3 / 32;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
   __syncthreads();
   if (n_local == 0) return;
 
-  auto fetch = [&](int li, float& w, int& row) {   // channel c = tid of item li
-    w = 0.f; row = -1;
-    if (tid < P.C3) {
-      const int it = it_begin + li;
-      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-      const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
-      const float wv = P.s3[tid] * P.dyext[(size_t)cloud * P.C3 + tid];
-      const int r = P.gidx[(size_t)cloud * P.C3 + tid] - p0;
-      if (r >= 0 && r < nvalid && wv != 0.f) { w = wv; row = r; }
+  auto fetch = [&](int bi, float (&w)[kT1Batch], int (&row)[kT1Batch]) {   // channel c = tid of the items of batch bi
+#pragma unroll
+    for (int i = 0; i < kT1Batch; ++i) {
+      w[i] = 0.f; row[i] = -1;
+      const int li = bi * kT1Batch + i;
+      if (tid < P.C3 && li < n_local) {
+        const int it = it_begin + li;
+        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+        const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
+        const float wv = P.s3[tid] * P.dyext[(size_t)cloud * P.C3 + tid];
+        const int r = P.gidx[(size_t)cloud * P.C3 + tid] - p0;
+        if (r >= 0 && r < nvalid && wv != 0.f) { w[i] = wv; row[i] = r; }
+      }
     }
   };
-  auto load_img = [&](int li) {
-    const int b = li & 1;
-    mbar_arrive_expect_tx(&bars[b], qbytes);
-    bulk_copy_g2s(sA[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes + (size_t)kq * qbytes, qbytes, &bars[b]);
+  auto store = [&](int slot, const float (&w)[kT1Batch], const int (&row)[kT1Batch]) {
+    if (tid < P.C3) {
+#pragma unroll
+      for (int i = 0; i < kT1Batch; ++i) {
+        sWv[(slot * kT1Batch + i) * P.C3 + tid] = w[i];
+        sRow[(slot * kT1Batch + i) * P.C3 + tid] = row[i];
+      }
+    }
   };
-  if (tid == 0) { load_img(0); if (n_local > 1) load_img(1); }
+  auto load_imgs = [&](int bi) {
+    const int b = bi & 1;
+    const int cnt = min(kT1Batch, n_local - bi * kT1Batch);
+    mbar_arrive_expect_tx(&bars[b], cnt * qbytes);
+    for (int i = 0; i < cnt; ++i)
+      bulk_copy_g2s(sA + (size_t)(b * kT1Batch + i) * qbytes,
+                    P.a2_img + (size_t)(it_begin + bi * kT1Batch + i) * P.img_bytes + (size_t)kq * qbytes, qbytes, &bars[b]);
+  };
+  if (tid == 0) { load_imgs(0); if (n_batches > 1) load_imgs(1); }
   {
-    float w; int row;
+    float w[kT1Batch]; int row[kT1Batch];
     fetch(0, w, row);
-    if (tid < P.C3) { sWv[tid] = w; sRow[tid] = row; }
+    store(0, w, row);
   }
   __syncthreads();
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
   const uint32_t lane_off = (kk >> 3) * plane + (kk & 7) * 2;
-  for (int li = 0; li < n_local; ++li) {
-    const int b = li & 1;
-    float nw = 0.f; int nrow = -1;
-    if (li + 1 < n_local) fetch(li + 1, nw, nrow);
-    mbar_wait(&bars[b], (uint32_t)((li >> 1) & 1));
-    const float* wv = sWv + b * P.C3 + cg * CH;
-    const int* rv = sRow + b * P.C3 + cg * CH;
-    const uint8_t* img = sA[b] + lane_off;
+  for (int bi = 0; bi < n_batches; ++bi) {
+    const int b = bi & 1;
+    float nw[kT1Batch]; int nrow[kT1Batch];
+    if (bi + 1 < n_batches) fetch(bi + 1, nw, nrow);
+    mbar_wait(&bars[b], (uint32_t)((bi >> 1) & 1));
+    const int cnt = min(kT1Batch, n_local - bi * kT1Batch);
+    for (int i = 0; i < cnt; ++i) {
+      const float* wv = sWv + (b * kT1Batch + i) * P.C3 + cg * CH;
+      const int* rv = sRow + (b * kT1Batch + i) * P.C3 + cg * CH;
+      const uint8_t* img = sA + (size_t)(b * kT1Batch + i) * qbytes + lane_off;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < CH) {
-        const int r = rv[j];
-        if (r >= 0) acc[j] = fmaf(wv[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + r * 16)), acc[j]);
+      for (int j = 0; j < 32; ++j) {
+        if (j < CH) {
+          const int r = rv[j];
+          if (r >= 0) acc[j] = fmaf(wv[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + r * 16)), acc[j]);
+        }
       }
     }
-    if (li + 1 < n_local && tid < P.C3) { sWv[(b ^ 1) * P.C3 + tid] = nw; sRow[(b ^ 1) * P.C3 + tid] = nrow; }
+    if (bi + 1 < n_batches) store(b ^ 1, nw, nrow);
     __syncthreads();
-    if (tid == 0 && li + 2 < n_local) load_img(li + 2);
+    if (tid == 0 && bi + 2 < n_batches) load_imgs(bi + 2);
   }
   float* dst = P.t1 + (size_t)(kq * 32 + kk) * P.C3 + cg * CH;
 #pragma unroll
@@ -571,7 +594,7 @@ inline size_t l2_smem_bytes(int PC) {
 struct L2Bars {
   uint64_t w_full, dz_full[2], dz_free[2], a1_full, d2_full, dz_ready, da_full, done;
   uint32_t tmem_base;
-  float xf[8];
+  float xf[16];
 };
 
 __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
@@ -622,6 +645,24 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph = 0;                       // all per-item barriers flip once per item
     double r0 = 0.0, r1 = 0.0;
+    // register prefetch of the next item's transform (thread 0) and point (thread t): keeps the global
+    // latency out of the barrier at the top of each item
+    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
+    auto prefetch = [&](int li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      if (t == 0) {
+        pf_c[0] = P.center[cloud * 3]; pf_c[1] = P.center[cloud * 3 + 1]; pf_c[2] = P.center[cloud * 3 + 2];
+        pf_ang = P.angle ? P.angle[cloud] : 0.f;
+      }
+      if (t < nvalid) {
+        const float* src = P.pcs + ((int64_t)cloud * P.N + p0 + t) * 3;
+        pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
+      }
+    };
+    if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li, ph ^= 1) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -630,20 +671,21 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       const int NT = (nvalid + 15) & ~15;
       const int64_t row0 = (int64_t)cloud * P.N + p0;
       uint8_t* sDZ = sDZb[li & 1];
+      float* xf = bars->xf + (li & 1) * 8;
       if (t == 0) {
         float sn = 0.f, cs = 1.f;
-        if (P.angle) sincosf(P.angle[cloud], &sn, &cs);
-        bars->xf[0] = P.center[cloud * 3]; bars->xf[1] = P.center[cloud * 3 + 1]; bars->xf[2] = P.center[cloud * 3 + 2];
-        bars->xf[3] = cs; bars->xf[4] = sn;
+        if (P.angle) sincosf(pf_ang, &sn, &cs);
+        xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
+      if (li + 1 < n_local) prefetch(li + 1);
       // ---- recompute a1 (layer 1), one thread per point ----
       if (t < NT) {
         const int p = t;
         if (p < nvalid) {
-          const float* src = P.pcs + (row0 + p) * 3;
-          const float x0 = src[0] - bars->xf[0], y0 = src[1] - bars->xf[1], z = src[2] - bars->xf[2];
-          const float x = x0 * bars->xf[3] - y0 * bars->xf[4], y = x0 * bars->xf[4] + y0 * bars->xf[3];
+          const float x0 = cur_p[0] - xf[0], y0 = cur_p[1] - xf[1], z = cur_p[2] - xf[2];
+          const float x = x0 * xf[3] - y0 * xf[4], y = x0 * xf[4] + y0 * xf[3];
           sPts[p * 3] = x; sPts[p * 3 + 1] = y; sPts[p * 3 + 2] = z;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {

@@ -84,7 +84,7 @@ struct Barriers {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  float xf[8];   // per-item transform: cx, cy, cz, cos, sin
+  float xf[16];  // per-item transform (double-buffered): cx, cy, cz, cos, sin
 };
 
 template <int MODE>
@@ -137,6 +137,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
     double st_s = 0.0, st_ss = 0.0, st_a2 = 0.0;
     const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
+    // register prefetch of the next item's transform (thread 0) and points (threads own points f, f+128):
+    // the global-load latency is paid behind the current item's work instead of in front of a barrier
+    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[2][3];
+    auto prefetch = [&](int li) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC;
+      const int nvalid = min(P.PC, P.N - p0);
+      const int64_t row0 = (int64_t)cloud * P.N + p0;
+      if (f == 0) {
+        pf_c[0] = P.center[cloud * 3]; pf_c[1] = P.center[cloud * 3 + 1]; pf_c[2] = P.center[cloud * 3 + 2];
+        pf_ang = P.angle ? P.angle[cloud] : 0.f;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = f + 128 * h;
+        if (p < nvalid) {
+          const float* src = P.pcs + (row0 + p) * 3;
+          pf_p[h][0] = src[0]; pf_p[h][1] = src[1]; pf_p[h][2] = src[2];
+        }
+      }
+    };
+    if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -151,17 +174,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       uint8_t* sA1 = sA2[b];
       if (f == 0) {
         float sn = 0.f, cs = 1.f;
-        if (P.angle) sincosf(P.angle[cloud], &sn, &cs);
-        bars->xf[0] = P.center[cloud * 3]; bars->xf[1] = P.center[cloud * 3 + 1]; bars->xf[2] = P.center[cloud * 3 + 2];
-        bars->xf[3] = cs; bars->xf[4] = sn;
+        if (P.angle) sincosf(pf_ang, &sn, &cs);
+        float* xf = bars->xf + (li & 1) * 8;
+        xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float cx = bars->xf[0], cy = bars->xf[1], cz = bars->xf[2], cs = bars->xf[3], sn = bars->xf[4];
+      const float* xfr = bars->xf + (li & 1) * 8;
+      const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
+      float cur_p[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { cur_p[h][0] = pf_p[h][0]; cur_p[h][1] = pf_p[h][1]; cur_p[h][2] = pf_p[h][2]; }
+      if (li + 1 < n_local) prefetch(li + 1);
+      (void)row0;
       // ---- layer 1: y = relu(W1f^T p' + c1f), one thread per point, 8 channels per 16-byte chunk
-      for (int p = f; p < NT; p += 128) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int p = f + 128 * hh;
+        if (p >= NT) continue;
         if (p < nvalid) {
-          const float* src = P.pcs + (row0 + p) * 3;
-          const float x0 = src[0] - cx, y0 = src[1] - cy, z = src[2] - cz;
+          const float x0 = cur_p[hh][0] - cx, y0 = cur_p[hh][1] - cy, z = cur_p[hh][2] - cz;
           const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
