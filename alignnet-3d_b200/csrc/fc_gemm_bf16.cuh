@@ -10,6 +10,8 @@
 // descriptors differ -- which covers forward (X W), wgrad (X^T dZ, split-K with reductions) and
 // dgrad (dZ W^T) without any transposed copies.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -181,13 +183,21 @@ static __global__ void __launch_bounds__(kThreads, 2) fc_gemm_kernel(const Param
   if (warp == 8) tmem_dealloc(tmem, 128);
 }
 
+inline double min_flop() {
+  const char* e = getenv("AN3D_FC_TENSOR_MIN_FLOP");
+  return e ? atof(e) : 2.0e9;
+}
+
 // usable when every 16-byte access of the kernel is aligned and the extents are chunkable
 inline bool usable(const Params& p) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int a_contig = p.a_mn ? p.M : p.K, b_contig = p.b_mn ? p.N : p.K;
   return al(p.A) && al(p.B) && al(p.C) && (p.lda % 4 == 0) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0) && (a_contig % 8 == 0) &&
          (b_contig % 8 == 0) && (p.N % 4 == 0) && (!p.pro_scale || (al(p.pro_scale) && al(p.pro_shift))) &&
-         (!p.pro_mask || al(p.pro_mask)) && (!p.bias || true) && p.K >= 64 && p.M >= 64 && p.N >= 64;
+         (!p.pro_mask || al(p.pro_mask)) && p.K >= 64 && p.M >= 64 && p.N >= 64 &&
+         // below ~2 GFLOP the launch is latency-bound and the SIMT fp32 GEMM (more, smaller tiles) is faster;
+         // AN3D_FC_TENSOR_MIN_FLOP overrides the threshold (the test-suite sets 0 to exercise this kernel)
+         2.0 * p.M * p.N * p.K >= min_flop();
 }
 
 static int launch(const Params& p, cudaStream_t st) {
