@@ -23,12 +23,13 @@ __global__ void pack_w3n_kernel(const float* W3, __nv_bfloat16* img, int C3) {
   img[(size_t)hc * 8192 + (cc >> 3) * 1024 + k * 8 + (cc & 7)] = __float2bfloat16_rn(W3[i]);
 }
 
-// W2 [64][128] -> image [128 rows k1 (rows >= 64 zero)][128 k2]
+// W2 [64][128] -> image [128 rows][128 k2]; rows 64..127 repeat rows 0..63 so that all four TMEM lane
+// quarters of the da1 accumulator carry real data (each warp pair then handles a quarter of the points)
 __global__ void pack_w2p_kernel(const float* W2, __nv_bfloat16* img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128 * 128) return;
   const int k1 = i / 128, k2 = i % 128;
-  img[(k2 >> 3) * 1024 + k1 * 8 + (k2 & 7)] = __float2bfloat16_rn(k1 < 64 ? W2[k1 * 128 + k2] : 0.f);
+  img[(k2 >> 3) * 1024 + k1 * 8 + (k2 & 7)] = __float2bfloat16_rn(W2[(k1 & 63) * 128 + k2]);
 }
 
 // dyext = dG * [g > 0]; per-channel sums of dyext and dyext * xhat_ext (BN3 backward)

@@ -713,7 +713,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       mbar_wait(&bars->dz_full[li & 1], (uint32_t)((li >> 1) & 1));
       tc_fence_after();
       {
-        const float cx = sL2[k], inv2 = sL2[128 + k], s2 = sL2[256 + k], m0 = sL2[384 + k], m1 = sL2[512 + k];
+        // dz = s2 (dy - m0 - xhat m1), xhat = acc*inv2 + cx   ==   dy*cA + cB + acc*cC
+        const float cA = sL2[256 + k];
+        const float cB = -sL2[256 + k] * (sL2[384 + k] + sL2[512 + k] * sL2[k]);
+        const float cC = -sL2[256 + k] * sL2[512 + k] * sL2[128 + k];
         uint8_t* col = sDZ + (k >> 3) * plane + (k & 7) * 2;
         const int nh = ((NT >> 1) + 15) & ~15;
         const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
@@ -725,11 +728,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
           for (int j = 0; j < 16; ++j) {
             const int p = g16 + j;
             __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
-            float dz = 0.f;
-            if (p < nvalid) {
-              const float xh = fmaf(__uint_as_float(r[j]), inv2, cx);
-              dz = s2 * (__bfloat162float(*ptr) - m0 - xh * m1);
-            }
+            const float dz = p < nvalid ? fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)) : 0.f;
             *ptr = __float2bfloat16_rn(dz);
           }
         }
@@ -740,11 +739,15 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       // ---- dy1 = da1 * [a1 > 0], BN1 backward sums (channels k1 < 64 only) ----
       mbar_wait(&bars->da_full, ph);
       tc_fence_after();
-      if (k < 64) {
-        const float wx = sW1[k], wy = sW1[64 + k], wz = sW1[128 + k];
-        const float b1 = sL1[k], mu1 = sL1[64 + k], inv1 = sL1[128 + k], g1 = sL1[192 + k], be1 = sL1[256 + k];
-        const int nh = ((NT >> 1) + 15) & ~15;
-        const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
+      {
+        // accumulator rows 64..127 duplicate rows 0..63: channel k1 = k & 63, and the four (lane half, warp
+        // group) combinations each take a quarter of the point columns
+        const int k1 = k & 63;
+        const float wx = sW1[k1], wy = sW1[64 + k1], wz = sW1[128 + k1];
+        const float b1 = sL1[k1], mu1 = sL1[64 + k1], inv1 = sL1[128 + k1], g1 = sL1[192 + k1], be1 = sL1[256 + k1];
+        const int nq = ((NT >> 2) + 15) & ~15;
+        const int part = (k >> 6) + 2 * half;
+        const int pbeg = min(NT, part * nq), pend = part == 3 ? NT : min(NT, (part + 1) * nq);
         float s0 = 0.f, s1 = 0.f;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
               const float dyr = __bfloat162float(hb);
               s0 += dyr;
               s1 = fmaf(dyr, xh, s1);
-              P.dy1[(row0 + p) * 64 + k] = hb;
+              P.dy1[(row0 + p) * 64 + k1] = hb;
             }
           }
         }
@@ -770,7 +773,8 @@ __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P)
       tc_fence_before();
     }
     if (n_local > 0) {
-      if (k < 64) { atomicAdd(P.red1 + 2 * k, r0); atomicAdd(P.red1 + 2 * k + 1, r1); }
+      atomicAdd(P.red1 + 2 * (k & 63), r0);
+      atomicAdd(P.red1 + 2 * (k & 63) + 1, r1);
       // ---- wgrad2 accumulator: lane = k2, 64 columns = k1 ----
       mbar_wait(&bars->done, 0);
       tc_fence_after();

@@ -35,7 +35,7 @@ struct Params {
 };
 
 constexpr int kThreads = 288;               // 4 epilogue warps, 4 loader warps, 1 MMA warp
-constexpr int kStages = 3;                   // 100 KB of tiles -> two CTAs per SM
+constexpr int kStages = 4;
 constexpr uint32_t kPlaneK = 128 * 16 + 16;   // K-major tile: 8 planes x 128 rows
 constexpr uint32_t kPlaneMN = 64 * 16 + 16;   // MN-major tile: 16 planes x 64 rows
 constexpr uint32_t kTileBytes = 16 * kPlaneMN > 8 * kPlaneK ? 16 * kPlaneMN : 8 * kPlaneK;
@@ -47,51 +47,70 @@ struct Bars {
   uint32_t tmem_base;
 };
 
-// Stage one 64-K-block of an operand.  chan_* describe the optional prologue.
-__device__ __forceinline__ void load_tile(uint8_t* dst, const float* src, int64_t ld, int mn_major, int mn0, int mn_ext,
-                                          int k0, int k_end, const float* pro_scale, const float* pro_shift,
-                                          const float* pro_mask, float mask_scale, int t) {
-  // K-major: rows = 128 mn, 8 chunk columns (k);  MN-major: rows = 64 k, 16 chunk columns (mn)
+// Staging of one 64-K-block of an operand, split in two phases so that the global loads of BOTH
+// operands are in flight together (one latency period per K block instead of two).
+struct TileRegs { float4 v[16]; };
+
+__device__ __forceinline__ void tile_issue(TileRegs& R, const float* src, int64_t ld, int mn_major, int mn0, int mn_ext,
+                                           int k0, int k_end, int t) {
+  const int ncc = mn_major ? 16 : 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = t + 128 * i;
+    const int row = q / ncc, cc = q - row * ncc;
+    const int g_row = mn_major ? k0 + row : mn0 + row;
+    const int g_col = mn_major ? mn0 + cc * 8 : k0 + cc * 8;
+    const bool ok = mn_major ? (g_row < k_end && g_col < mn_ext) : (g_row < mn_ext && g_col < k_end);
+    if (ok) {
+      const float* p = src + (int64_t)g_row * ld + g_col;
+      R.v[2 * i] = *reinterpret_cast<const float4*>(p);
+      R.v[2 * i + 1] = *reinterpret_cast<const float4*>(p + 4);
+    } else {
+      R.v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      R.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+__device__ __forceinline__ void tile_finish(const TileRegs& R, uint8_t* dst, int64_t ld, int mn_major, int mn0, int mn_ext,
+                                            int k0, int k_end, const float* pro_scale, const float* pro_shift,
+                                            const float* pro_mask, float mask_scale, int t) {
   const int ncc = mn_major ? 16 : 8;
   const uint32_t plane = mn_major ? kPlaneMN : kPlaneK;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int q = t + 128 * i;
     const int row = q / ncc, cc = q - row * ncc;
-    const int g_row = mn_major ? k0 + row : mn0 + row;          // global row index
-    const int g_col = mn_major ? mn0 + cc * 8 : k0 + cc * 8;    // global column of the chunk start
-    const bool row_ok = mn_major ? g_row < k_end : g_row < mn_ext;
-    const bool col_ok = mn_major ? g_col < mn_ext : g_col < k_end;
-    uint4 out = make_uint4(0, 0, 0, 0);
-    if (row_ok && col_ok) {
-      const float* p = src + (int64_t)g_row * ld + g_col;
-      float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
-      float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      if (pro_scale) {
-        const float4 s0 = *reinterpret_cast<const float4*>(pro_scale + g_col), s1 = *reinterpret_cast<const float4*>(pro_scale + g_col + 4);
-        const float4 h0 = *reinterpret_cast<const float4*>(pro_shift + g_col), h1 = *reinterpret_cast<const float4*>(pro_shift + g_col + 4);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const int g_row = mn_major ? k0 + row : mn0 + row;
+    const int g_col = mn_major ? mn0 + cc * 8 : k0 + cc * 8;
+    const bool ok = mn_major ? (g_row < k_end && g_col < mn_ext) : (g_row < mn_ext && g_col < k_end);
+    float v[8] = {R.v[2 * i].x, R.v[2 * i].y, R.v[2 * i].z, R.v[2 * i].w,
+                  R.v[2 * i + 1].x, R.v[2 * i + 1].y, R.v[2 * i + 1].z, R.v[2 * i + 1].w};
+    if (ok && pro_scale) {
+      const float4 s0 = *reinterpret_cast<const float4*>(pro_scale + g_col), s1 = *reinterpret_cast<const float4*>(pro_scale + g_col + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(pro_shift + g_col), h1 = *reinterpret_cast<const float4*>(pro_shift + g_col + 4);
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.f);
-      }
-      if (pro_mask) {
-        const float* mp = pro_mask + (int64_t)g_row * ld + g_col;
-        const float4 m0 = *reinterpret_cast<const float4*>(mp), m1 = *reinterpret_cast<const float4*>(mp + 4);
-        const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= mk[e] * mask_scale;
-      }
-      __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]),
-                     b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
-      out.x = *reinterpret_cast<uint32_t*>(&b0); out.y = *reinterpret_cast<uint32_t*>(&b1);
-      out.z = *reinterpret_cast<uint32_t*>(&b2); out.w = *reinterpret_cast<uint32_t*>(&b3);
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.f);
     }
+    if (ok && pro_mask) {
+      const float* mp = pro_mask + (int64_t)g_row * ld + g_col;
+      const float4 m0 = *reinterpret_cast<const float4*>(mp), m1 = *reinterpret_cast<const float4*>(mp + 4);
+      const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= mk[e] * mask_scale;
+    }
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]),
+                   b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 out;
+    out.x = *reinterpret_cast<uint32_t*>(&b0); out.y = *reinterpret_cast<uint32_t*>(&b1);
+    out.z = *reinterpret_cast<uint32_t*>(&b2); out.w = *reinterpret_cast<uint32_t*>(&b3);
     *reinterpret_cast<uint4*>(dst + cc * plane + row * 16) = out;
   }
 }
 
-static __global__ void __launch_bounds__(kThreads, 2) fc_gemm_kernel(const Params P) {
+static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kTileStride;
@@ -119,13 +138,22 @@ static __global__ void __launch_bounds__(kThreads, 2) fc_gemm_kernel(const Param
     uint32_t ph_e[kStages];
 #pragma unroll
     for (int i = 0; i < kStages; ++i) ph_e[i] = 1;
+    TileRegs ra, rb;
+    if (nkb > 0) {
+      tile_issue(ra, P.A, P.lda, P.a_mn, i0, P.M, kbeg, kend, t);
+      tile_issue(rb, P.B, P.ldb, P.b_mn, j0, P.N, kbeg, kend, t);
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int st = kb % kStages;
       mbar_wait(&bars->empty[st], ph_e[st]); ph_e[st] ^= 1;
       const int k0 = kbeg + kb * 64;
-      load_tile(sA + st * kTileStride, P.A, P.lda, P.a_mn, i0, P.M, k0, kend, P.pro_scale, P.pro_shift, P.pro_mask,
-                P.pro_mask_scale, t);
-      load_tile(sB + st * kTileStride, P.B, P.ldb, P.b_mn, j0, P.N, k0, kend, nullptr, nullptr, nullptr, 1.f, t);
+      tile_finish(ra, sA + st * kTileStride, P.lda, P.a_mn, i0, P.M, k0, kend, P.pro_scale, P.pro_shift, P.pro_mask,
+                  P.pro_mask_scale, t);
+      tile_finish(rb, sB + st * kTileStride, P.ldb, P.b_mn, j0, P.N, k0, kend, nullptr, nullptr, nullptr, 1.f, t);
+      if (kb + 1 < nkb) {   // next block's loads are issued before this block is handed to the MMA thread
+        tile_issue(ra, P.A, P.lda, P.a_mn, i0, P.M, k0 + 64, kend, t);
+        tile_issue(rb, P.B, P.ldb, P.b_mn, j0, P.N, k0 + 64, kend, t);
+      }
       fence_proxy_async_smem();
       mbar_arrive(&bars->full[st]);
     }
