@@ -213,7 +213,7 @@ static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Param
 
 inline double min_flop() {
   const char* e = getenv("AN3D_FC_TENSOR_MIN_FLOP");
-  return e ? atof(e) : 2.0e9;
+  return e ? atof(e) : 1.0e9;
 }
 
 // usable when every 16-byte access of the kernel is aligned and the extents are chunkable
@@ -223,7 +223,7 @@ inline bool usable(const Params& p) {
   return al(p.A) && al(p.B) && al(p.C) && (p.lda % 4 == 0) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0) && (a_contig % 8 == 0) &&
          (b_contig % 8 == 0) && (p.N % 4 == 0) && (!p.pro_scale || (al(p.pro_scale) && al(p.pro_shift))) &&
          (!p.pro_mask || al(p.pro_mask)) && p.K >= 64 && p.M >= 64 && p.N >= 64 &&
-         // below ~2 GFLOP the launch is latency-bound and the SIMT fp32 GEMM (more, smaller tiles) is faster;
+         // below ~1 GFLOP the launch is latency-bound and the SIMT fp32 GEMM (more, smaller tiles) is faster;
          // AN3D_FC_TENSOR_MIN_FLOP overrides the threshold (the test-suite sets 0 to exercise this kernel)
          2.0 * p.M * p.N * p.K >= min_flop();
 }
