@@ -246,7 +246,6 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red3, 0, 2 * (size_t)C3 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
-  AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram, 0, 128 * 128 * sizeof(float), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.t1, 0, 128 * (size_t)C3 * sizeof(float), st));
   {
     const int bchunk = 16;
@@ -268,18 +267,9 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   {
     convbwd::Wg3Params W;
     W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
-    W.gidx = p.gidx[s][br]; W.dyext = q.dyext; W.s3 = sc3; W.B = B; W.N = N; W.PC = q.PC; W.npc = q.npc; W.C3 = C3;
-    W.n_items = n_items; W.gW3 = q.t1; W.gram = q.gram;
-    // Gram matrix A2^T A2 on the tensor cores (the kernel's sparse slots are unused: C3 = 0)
-    W.C3 = 0;
-    const int nranges = std::max(1, std::min(n_items, sms));
-    W.items_per_cta = (n_items + nranges - 1) / nranges;
-    const size_t smem = convbwd::wg3_smem_bytes(q.PC);
-    if (smem > (size_t)kMaxSmem) { set_error("wgrad3 tile too large"); return AN3D_ERR_UNSUPPORTED; }
-    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    W.gidx = p.gidx[s][br]; W.dyext = q.dyext; W.s3 = sc3;
+    // (the Gram matrix A2^T A2 was computed on the tensor cores by the forward pass)
     prof_mark(PROF_BWD_T1, true, st);
-    convbwd::wgrad3_kernel<<<dim3(nranges, 1), convbwd::kWg3Threads, smem, st>>>(W);
-    AN3D_LAUNCH_CHECK();
     // sparse part T1 = A2^T S: gather-scale-accumulate on CUDA cores (1/N of the dense FLOPs)
     convbwd::T1Params T;
     T.a2_img = W.a2_img; T.img_bytes = W.img_bytes; T.gidx = W.gidx; T.dyext = W.dyext; T.s3 = W.s3; T.B = B; T.N = N;
@@ -291,7 +281,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     convbwd::t1_sparse_kernel<<<dim3(tr, 4), convbwd::kT1Threads, tsmem, st>>>(T);
     prof_mark(PROF_BWD_T1, false, st);
     AN3D_LAUNCH_CHECK();
-    wgrad3_dense_kernel<<<dim3(C3 / 32, 4), 256, 0, st>>>(params + L3.w, q.t1, q.gram, q.sa2[s][br], q.coef3, C3, grads + L3.w);
+    wgrad3_dense_kernel<<<dim3(C3 / 32, 4), 256, 0, st>>>(params + L3.w, q.t1, q.gram[s][br], q.sa2[s][br], q.coef3, C3, grads + L3.w);
     AN3D_LAUNCH_CHECK();
   }
   // ---- dgrad3 -> dy2 images + BN2 backward sums ----

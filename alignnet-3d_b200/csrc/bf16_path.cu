@@ -4,6 +4,7 @@
 
 #include "bf16_path.cuh"
 #include "conv_fwd_bf16.cuh"
+#include "conv_bwd_bf16.cuh"
 
 namespace an3d {
 
@@ -134,6 +135,38 @@ __global__ void fold_acc_kernel(const double* stats, double count, const float* 
   if (shift_folded) shift_folded[c] = sc * bias[c] + sh;
 }
 
+// Layer-3 batch statistics without touching the [M, C3] accumulator: with r3 = a2 W3b,
+//   sum_m r3[m,c]   = sa2 . w_c              sum_m r3[m,c]^2 = w_c^T (A2^T A2) w_c
+// (bf16-rounded weights, Gram matrix from the tensor-core pass).  256 threads = 32 channels x 8 row groups.
+__global__ void stats3_from_gram_kernel(const float* W3, const float* gram, const double* sa2, int C3, double* stats3) {
+  __shared__ float sw[128][33];
+  __shared__ double red[2][8][32];
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
+    const int kp = i >> 5, cc = i & 31;
+    sw[kp][cc] = __bfloat162float(__float2bfloat16_rn(W3[(size_t)kp * C3 + c0 + cc]));
+  }
+  __syncthreads();
+  double m = 0.0, qd = 0.0;
+  for (int k = ty; k < 128; k += 8) {
+    const float* grow = gram + (size_t)k * 128;
+    float t = 0.f;
+#pragma unroll 8
+    for (int kp = 0; kp < 128; ++kp) t = fmaf(grow[kp], sw[kp][tx], t);
+    qd += (double)sw[k][tx] * (double)t;
+    m += sa2[k] * (double)sw[k][tx];
+  }
+  red[0][ty][tx] = m;
+  red[1][ty][tx] = qd;
+  __syncthreads();
+  if (ty == 0) {
+    for (int i = 1; i < 8; ++i) { m += red[0][i][tx]; qd += red[1][i][tx]; }
+    stats3[2 * (c0 + tx)] = m;
+    stats3[2 * (c0 + tx) + 1] = qd;
+  }
+}
+
 // pooled feature from the packed extreme of the sign-folded raw accumulator:
 //   z_ext = sign(gamma) * unpack(key) + b3 ;  g = relu(scale * z_ext + shift)   (BN + ReLU are monotone)
 __global__ void pool_finalize_kernel(const uint32_t* zext, int B, int C3, const float* gamma, const float* bias,
@@ -218,6 +251,7 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
       q->zext[s][br] = a.take<uint32_t>((int64_t)B * C3);
       q->a2img[s][br] = training ? a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2)) : nullptr;
       q->sa2[s][br] = a.take<double>(128);
+      q->gram[s][br] = a.take<float>(128 * 128);
     }
   }
   if (training) {
@@ -234,7 +268,6 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
     q->gq = a.take<__nv_bfloat16>(128 * 128);
     q->gq_f32 = a.take<float>(128 * 128);
     q->uvec = a.take<float>(128);
-    q->gram = a.take<float>(128 * 128);
     q->t1 = a.take<float>(128 * c3max);
     q->dy2img = a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2));
     q->red2 = a.take<double>(256);
@@ -294,7 +327,6 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   if (training) {
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.moments[s][br], 0, 16 * sizeof(double), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats2[s][br], 0, 256 * sizeof(double), st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats3[s][br], 0, 2 * (size_t)C3 * sizeof(double), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.sa2[s][br], 0, 128 * sizeof(double), st));
     const int mb = (int)std::min<int64_t>((M + 255) / 256, 4 * sms);
     moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
@@ -310,8 +342,24 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   if (q.npc > 1) AN3D_CUDA_CHECK(cudaMemsetAsync(q.zext[s][br], 0, (size_t)B * C3 * sizeof(uint32_t), st));
   if (training) AN3D_TRY(launch_fused<convfwd::MODE_FULL_TRAIN>(P, grid, smem, st));
   else AN3D_TRY(launch_fused<convfwd::MODE_FULL_EVAL>(P, grid, smem, st));
+  if (training) {
+    // Gram matrix of the saved layer-2 activations on the tensor cores -> layer-3 BN statistics
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram[s][br], 0, 128 * 128 * sizeof(float), st));
+    convbwd::Wg3Params W;
+    W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
+    W.gidx = nullptr; W.dyext = nullptr; W.s3 = nullptr; W.B = B; W.N = N; W.PC = q.PC; W.npc = q.npc; W.C3 = 0;
+    W.n_items = P.n_items; W.gW3 = nullptr; W.gram = q.gram[s][br];
+    const int nranges = std::max(1, std::min(P.n_items, sms));
+    W.items_per_cta = (P.n_items + nranges - 1) / nranges;
+    const size_t gsmem = convbwd::wg3_smem_bytes(q.PC);
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    convbwd::wgrad3_kernel<<<dim3(nranges, 1), convbwd::kWg3Threads, gsmem, st>>>(W);
+    AN3D_LAUNCH_CHECK();
+    stats3_from_gram_kernel<<<C3 / 32, 256, 0, st>>>(params + L3.w, q.gram[s][br], q.sa2[s][br], C3, q.stats3[s][br]);
+    AN3D_LAUNCH_CHECK();
+  }
   fold_acc_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.stats3[s][br], (double)M, params + L3.b, io3, C3, training ? 1 : 0,
-                                                    decay, 1, nullptr);
+                                                    decay, 0, nullptr);
   AN3D_LAUNCH_CHECK();
   const int64_t ldg = s == EMB ? 2 * C3 : C3;
   const int64_t tot = (int64_t)B * C3;

@@ -147,7 +147,7 @@ struct PlanBf16 {
   __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
   float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
   float* uvec = nullptr;                    // [128]
-  float* gram = nullptr;                    // [128][128] a2^T a2
+  float* gram[3][2];                        // [128][128] a2^T a2 per (stage, branch): BN3 statistics and wgrad3
   float* t1 = nullptr;                      // [128][C3max] sparse part of wgrad3 (16-byte aligned scratch)
   __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
   double* red2 = nullptr;                   // [128][2]

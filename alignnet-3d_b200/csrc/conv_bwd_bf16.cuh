@@ -48,7 +48,7 @@ struct Wg3Bars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params P) {
+static __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t sd_bytes = 8 * plane;
@@ -234,7 +234,7 @@ inline size_t t1_smem_bytes(int PC, int C3) {
   return 2 * kT1Batch * 4 * (size_t)plane_stride(PC) + 2 * kT1Batch * (size_t)C3 * 8 + 64;
 }
 
-__global__ void __launch_bounds__(kT1Threads, 1) t1_sparse_kernel(const T1Params P) {
+static __global__ void __launch_bounds__(kT1Threads, 1) t1_sparse_kernel(const T1Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t qbytes = 4 * plane;
@@ -353,7 +353,7 @@ struct Dg3Bars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3Params P) {
+static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t sd_bytes = 8 * plane;
@@ -597,7 +597,7 @@ struct L2Bars {
   float xf[16];
 };
 
-__global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
+static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   uint8_t* sA1 = smem;

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int NT = (nvalid + 15) & ~15;
       const int64_t row0 = (int64_t)cloud * P.N + p0;
       const int b = li & 1;
-      if (MODE != MODE_STATS2 && li >= 2) { mbar_wait(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
+      if (MODE != MODE_STATS2 && li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
       uint8_t* sA1 = sA2[b];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
       // ---- layer-2 epilogue: channel k = f
-      mbar_wait(&bars->d2_full, ph_d2); ph_d2 ^= 1;
+      mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
       tc_fence_after();
       const int k = f;
       const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
@@ -264,9 +264,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int e = tid;                             // channel within the 128-channel chunk
       const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
       uint32_t ph_full[2] = {0, 0};
-      double s3[8], ss3[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s3[j] = 0.0; ss3[j] = 0.0; }
       const int C3 = P.nchunk * 128;
       for (int li = 0; li < n_local; ++li) {
         const int it = it_begin + li;
@@ -280,40 +277,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j >= P.nchunk) break;
-          float m = -INFINITY, ts = 0.f, tss = 0.f;
+          float m = -INFINITY;
           for (int h = 0; h < 2; ++h) {
             if (Nh[h] == 0) continue;
-            mbar_wait(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+            mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
             tc_fence_after();
             const int off = h ? N0 : 0;
             for (int g16 = 0; g16 < Nh[h]; g16 += 16) {
               uint32_t r[16];
               tmem_ld16(tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0) + g16, r);
               tmem_ld_wait();
+              // per 16-column group: pack the column-in-group (immediate) into the low 4 bits, take the group
+              // max, then splice the group's base index in only if the group wins (3 instr / 16 elements)
+              float gm = -INFINITY;
               if (off + g16 + 16 <= nvalid) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                  if (MODE == MODE_FULL_TRAIN) {
-                    const float v = __uint_as_float(r[q]);
-                    ts += v; tss = fmaf(v, v, tss);
-                    m = fmaxf(m, __uint_as_float((r[q] & ~P.idx_mask) | (uint32_t)(p0 + off + g16 + q)));
-                  } else {
-                    m = fmaxf(m, __uint_as_float(r[q]));
-                  }
+                  if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
+                  else gm = fmaxf(gm, __uint_as_float(r[q]));
                 }
               } else {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                   if (off + g16 + q < nvalid) {
-                    if (MODE == MODE_FULL_TRAIN) {
-                      const float v = __uint_as_float(r[q]);
-                      ts += v; tss = fmaf(v, v, tss);
-                      m = fmaxf(m, __uint_as_float((r[q] & ~P.idx_mask) | (uint32_t)(p0 + off + g16 + q)));
-                    } else {
-                      m = fmaxf(m, __uint_as_float(r[q]));
-                    }
+                    if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
+                    else gm = fmaxf(gm, __uint_as_float(r[q]));
                   }
                 }
+              }
+              if (MODE == MODE_FULL_TRAIN) {
+                if (gm > m) m = __uint_as_float((__float_as_uint(gm) & ~(P.idx_mask & ~15u)) | (uint32_t)(p0 + off + g16));
+              } else {
+                m = fmaxf(m, gm);
               }
             }
             tc_fence_before();
@@ -322,15 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           const uint32_t key = to_ordered(__float_as_uint(m));
           uint32_t* zp = P.zext + (size_t)cloud * C3 + j * 128 + e;
           if (P.npc == 1) *zp = key; else atomicMax(zp, key);
-          if (MODE == MODE_FULL_TRAIN) { s3[j] += (double)ts; ss3[j] += (double)tss; }
-        }
-      }
-      if (MODE == MODE_FULL_TRAIN && n_local > 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j >= P.nchunk) break;
-          atomicAdd(P.stats3 + 2 * (j * 128 + e), s3[j]);
-          atomicAdd(P.stats3 + 2 * (j * 128 + e) + 1, ss3[j]);
+
         }
       }
     }
@@ -405,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         const int total = n_local * P.nchunk;
         for (int q = 0; q < total; ++q) {
           const int stage = q % P.nstages;
-          mbar_wait(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
+          mbar_wait_relaxed(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
           mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
           bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
                         P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,

@@ -38,6 +38,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for waiters that are not on the critical path (loaders, epilogues): back off between probes so the
+// spinning warp does not steal issue slots from the warps doing the math on the same sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 
 // ---- proxy fences --------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
