@@ -339,7 +339,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   fold_acc_kernel<<<1, 128, 0, st>>>(q.stats2[s][br], (double)M, params + L2.b, io2, 128, training ? 1 : 0, decay, 0,
                                      q.t2f[s][br]);
   AN3D_LAUNCH_CHECK();
-  if (q.npc > 1) AN3D_CUDA_CHECK(cudaMemsetAsync(q.zext[s][br], 0, (size_t)B * C3 * sizeof(uint32_t), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(q.zext[s][br], 0, (size_t)B * C3 * sizeof(uint32_t), st));
   if (training) AN3D_TRY(launch_fused<convfwd::MODE_FULL_TRAIN>(P, grid, smem, st));
   else AN3D_TRY(launch_fused<convfwd::MODE_FULL_EVAL>(P, grid, smem, st));
   if (training) {

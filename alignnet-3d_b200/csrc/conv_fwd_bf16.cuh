@@ -22,7 +22,7 @@ namespace convfwd {
 
 using namespace umma;
 
-constexpr int kThreads = 320;          // 4 back-end + 4 front-end warps, MMA warp, loader warp
+constexpr int kThreads = 448;          // 4 back-end + 4 front-end warps, MMA warp, loader warp, 4 more back-end warps
 constexpr int kMaxPC = 256;            // points per item
 constexpr uint32_t kW2Bytes = 128 * 64 * 2;
 constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
@@ -87,6 +87,35 @@ struct Barriers {
   float xf[16];  // per-item transform (double-buffered): cx, cy, cz, cos, sin
 };
 
+// Running max over one 16-column group of an accumulator row.  Training mode carries the arg-max point
+// index in the low mantissa bits: the column-in-group (an immediate) goes into the low 4 bits of every
+// element, the group's base index is spliced in only if the group wins.
+template <int MODE>
+__device__ __forceinline__ void reduce_group(const uint32_t (&r)[16], int col0, int nvalid, int p0, uint32_t idx_mask,
+                                             float& m) {
+  float gm = -INFINITY;
+  if (col0 + 16 <= nvalid) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
+      else gm = fmaxf(gm, __uint_as_float(r[q]));
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (col0 + q < nvalid) {
+        if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
+        else gm = fmaxf(gm, __uint_as_float(r[q]));
+      }
+    }
+  }
+  if (MODE == MODE_FULL_TRAIN) {
+    if (gm > m) m = __uint_as_float((__float_as_uint(gm) & ~(idx_mask & ~15u)) | (uint32_t)(p0 + col0));
+  } else {
+    m = fmaxf(m, gm);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -116,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_init(&bars->a2_full[i], 128);
       mbar_init(&bars->a2_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1);
-      mbar_init(&bars->acc_empty[i], 128);
+      mbar_init(&bars->acc_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -258,11 +287,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       atomicAdd(P.stats2 + 2 * f, st_s);
       atomicAdd(P.stats2 + 2 * f + 1, st_ss);
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 || warp >= 10) {
     // ================================ back-end =================================
+    // two warps per TMEM lane quarter (warps w and w+10 with equal w%4): the 16-column groups of every
+    // accumulator half are dealt alternately to the two, which halves the latency of draining a half --
+    // the MMA thread can only refill a half once it is drained, so this latency paces the tensor pipe.
     if (MODE != MODE_STATS2) {
-      const int e = tid;                             // channel within the 128-channel chunk
-      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+      const int bgroup = warp < 4 ? 0 : 1;
+      const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       uint32_t ph_full[2] = {0, 0};
       const int C3 = P.nchunk * 128;
       for (int li = 0; li < n_local; ++li) {
@@ -283,40 +316,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
             mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
             tc_fence_after();
             const int off = h ? N0 : 0;
-            for (int g16 = 0; g16 < Nh[h]; g16 += 16) {
-              uint32_t r[16];
-              tmem_ld16(tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0) + g16, r);
+            const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
+            // software pipeline: the load of the next group is in flight while this one is reduced
+            uint32_t ra[16], rb[16];
+            int g16 = bgroup * 16;
+            if (g16 < Nh[h]) tmem_ld16(tbase + g16, ra);
+            for (; g16 < Nh[h]; g16 += 64) {
               tmem_ld_wait();
-              // per 16-column group: pack the column-in-group (immediate) into the low 4 bits, take the group
-              // max, then splice the group's base index in only if the group wins (3 instr / 16 elements)
-              float gm = -INFINITY;
-              if (off + g16 + 16 <= nvalid) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
-                  else gm = fmaxf(gm, __uint_as_float(r[q]));
-                }
-              } else {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  if (off + g16 + q < nvalid) {
-                    if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
-                    else gm = fmaxf(gm, __uint_as_float(r[q]));
-                  }
-                }
-              }
-              if (MODE == MODE_FULL_TRAIN) {
-                if (gm > m) m = __uint_as_float((__float_as_uint(gm) & ~(P.idx_mask & ~15u)) | (uint32_t)(p0 + off + g16));
-              } else {
-                m = fmaxf(m, gm);
+              const int g2 = g16 + 32;
+              if (g2 < Nh[h]) tmem_ld16(tbase + g2, rb);
+              reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, m);
+              if (g2 < Nh[h]) {
+                tmem_ld_wait();
+                if (g2 + 32 < Nh[h]) tmem_ld16(tbase + g2 + 32, ra);
+                reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, m);
               }
             }
             tc_fence_before();
             mbar_arrive(&bars->acc_empty[h]);
           }
-          const uint32_t key = to_ordered(__float_as_uint(m));
-          uint32_t* zp = P.zext + (size_t)cloud * C3 + j * 128 + e;
-          if (P.npc == 1) *zp = key; else atomicMax(zp, key);
+          atomicMax(P.zext + (size_t)cloud * C3 + j * 128 + e, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
 
         }
       }
