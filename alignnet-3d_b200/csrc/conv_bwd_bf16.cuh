@@ -55,7 +55,7 @@ static __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3
   uint8_t* sA2[2] = {smem, smem + P.img_bytes};
   uint8_t* sSd[2] = {smem + 2 * P.img_bytes, smem + 2 * P.img_bytes + sd_bytes};
   Wg3Bars* bars = reinterpret_cast<Wg3Bars*>(smem + 2 * P.img_bytes + 2 * sd_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
@@ -131,7 +131,7 @@ static __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3
       for (int s = 0; s < kWg3SlotsPerPass; ++s) { cur_idx[s] = nxt_idx[s]; cur_w[s] = nxt_w[s]; }
     }
   } else if (warp == 4) {
-    if (lane == 0 && n_local > 0) {
+    if (n_local > 0) {
       uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0};
       int g = 0;
       for (int li = 0; li < n_local; ++li) {
@@ -364,7 +364,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   float* sBeta = sU + 128;
   float* sIg = sBeta + 128;
   Dg3Bars* bars = reinterpret_cast<Dg3Bars*>(sIg + 128);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
@@ -494,7 +494,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       for (int hc = 0; hc < kMaxHc; ++hc) { cur_idx[hc] = nxt_idx[hc]; cur_w[hc] = nxt_w[hc]; }
     }
   } else if (warp == 6) {
-    if (lane == 0 && n_local > 0) {
+    if (n_local > 0) {
       uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0}, ph_w[3] = {0, 0, 0}, ph_de[2] = {1, 1};
       int g = 0, wq = 0;
       for (int li = 0; li < n_local; ++li) {
@@ -611,7 +611,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
   float* sL1 = sW1 + 192;        // b1, mean1, inv1, gamma1, beta1 : 5 x 64
   float* sL2 = sL1 + 320;        // cx2 (= (b2-mean2)*inv2), inv2, s2, m0, m1, spare : 6 x 128
   L2Bars* bars = reinterpret_cast<L2Bars*>(sL2 + 768);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
@@ -790,7 +790,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       tc_fence_before();
     }
   } else if (warp == 8) {
-    if (lane == 0 && n_local > 0) {
+    if (n_local > 0) {
       uint32_t ph = 0;
       mbar_wait(&bars->w_full, 0);
       for (int li = 0; li < n_local; ++li, ph ^= 1) {

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   float* sT2f = sS2 + 128;
   Barriers* bars = reinterpret_cast<Barriers*>(sT2f + 128);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
   const int it_end = min(P.n_items, it_begin + P.item_begin_stride);
   const int n_local = it_end - it_begin;
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       }
     }
   } else if (warp == 8) {
-    // ================================ MMA issuer ===============================
-    if (lane == 0 && n_local > 0) {
+    // ================================ MMA issuer (whole warp, one elected lane issues) ===============
+    if (n_local > 0) {
       uint32_t ph_a1 = 0, ph_a2f[2] = {0, 0}, ph_w3f[3] = {0, 0, 0}, ph_acce[2] = {1, 1};
       uint32_t wcount = 0;
       mbar_wait(&bars->w2_full, 0);

@@ -115,7 +115,7 @@ static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Param
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kTileStride;
   Bars* bars = reinterpret_cast<Bars*>(smem + 2 * kStages * kTileStride);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx();
   const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128;
   int kchunk = (P.K + P.ksplit - 1) / P.ksplit;
   kchunk = (kchunk + 63) & ~63;
@@ -158,7 +158,7 @@ static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Param
       mbar_arrive(&bars->full[st]);
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {
       uint32_t ph_f[kStages];
 #pragma unroll
       for (int i = 0; i < kStages; ++i) ph_f[i] = 0;

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const __nv_bfloat16*
   const uint32_t a_plane = a_rows * 16 + 16, b_plane = b_rows * 16 + 16;  // +16: odd multiple of 16B to spread banks
   uint8_t* sa = smem;
   uint8_t* sb = smem + ((a_planes * a_plane + 127) & ~127u);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = uniform_warp_idx();
   if (tid == 0) {
     mbar_init(&bar_done, 1);
     fence_barrier_init();
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 128) {
+  if (warp == 4) {
     const uint32_t idesc = make_idesc(128, N, a_mn, b_mn);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t ad, bd;
