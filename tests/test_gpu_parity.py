@@ -273,3 +273,81 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         e.forward(x, x, False)
         e.backward(x, x, {}, e._outputs(2))
+
+
+# ------------------------------------------------------------------------------------------------
+# against the reference's own code (tests/golden/reference_*.npz: /root/reference models/tp8.py +
+# utils/tf_util.py executed on the TF1 shim; generator tests/golden/make_reference_golden.py)
+# ------------------------------------------------------------------------------------------------
+def _ref_case(name):
+    import os
+    from helpers import GOLDEN
+    return np.load(os.path.join(GOLDEN, f"reference_{name}.npz"))
+
+
+@pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
+def test_fp32_engine_vs_reference_run_eval(name):
+    """north_star: pred_translations / pred_angles within 1e-4 abs of the reference path, same inputs."""
+    r = _ref_case(name)
+    g, arch, params, state, batch, masks = golden_case(name)
+    e = make_engine(arch, params, state)
+    dev = to_dev(batch)
+    ep = e.forward(dev["pcs1"], dev["pcs2"], False)
+    torch.cuda.synchronize()
+    for k in OUTPUT_KEYS:
+        got = ep[k].cpu().numpy()
+        np.testing.assert_allclose(got, r["f32/eval/" + k], atol=TOL, rtol=0, err_msg=k)
+        np.testing.assert_allclose(got, r["f64/eval/" + k], atol=TOL, rtol=0, err_msg=k)
+    ok = np.ones(len(r["f64/eval/pred_angles"]), bool)
+    for k in ("pred_pc1angle_logits", "pred_pc2angle_logits", "pred_remaining_angle_logits"):
+        ok &= top2_margin(r["f64/eval/" + k], arch.num_bins) > 1e-3
+    assert ok.mean() > 0.8
+    pa = e.pred_angles(ep).cpu().numpy()
+    np.testing.assert_allclose(pa[ok], r["f64/eval/pred_angles"][ok], atol=TOL)
+    # forward-only loss of the eval outputs (reference get_loss on its eval end_points)
+    lv = e.loss(dev, ep).cpu().numpy()
+    assert abs(lv[0] - float(r["f64/eval/loss"])) < 2e-4 * max(1.0, abs(float(r["f64/eval/loss"])))
+
+
+@pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
+def test_fp32_engine_vs_reference_run_train(name):
+    r = _ref_case(name)
+    g, arch, params, state, batch, masks = golden_case(name)
+    e = make_engine(arch, params, state)
+    dev, dm = to_dev(batch), to_dev(masks)
+    ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.5, dm)
+    loss = e.backward(dev["pcs1"], dev["pcs2"], dev, ep)
+    torch.cuda.synchronize()
+    for k in OUTPUT_KEYS:
+        np.testing.assert_allclose(ep[k].cpu().numpy(), r["f64/train/" + k], atol=TOL_TRAIN, rtol=0, err_msg=k)
+    ref_loss = float(r["f64/train/loss"])
+    assert abs(float(loss.cpu().numpy()[0]) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    st = e.get_state()
+    for k in [k for k in r.files if k.startswith("state/")]:
+        np.testing.assert_allclose(st[k[6:]], r[k], atol=TOL, rtol=1e-4, err_msg=k)
+    grads = e.get_grads()
+    gmax = max(float(np.abs(r[k]).max()) for k in r.files if k.startswith("grad/"))
+    for k in [k for k in r.files if k.startswith("gradnorm/")]:
+        n, ref_norm = k[9:], float(r[k])
+        if n.endswith("/biases") and ref_norm < 1e-6:
+            continue
+        got_norm = float(np.sqrt((grads[n].astype(np.float64) ** 2).sum()))
+        assert abs(got_norm - ref_norm) <= NORM_REL * ref_norm + 1e-5, (n, got_norm, ref_norm)
+    for k in [k for k in r.files if k.startswith("grad/")]:
+        ref = r[k]
+        scale = float(np.abs(ref).max())
+        err = float(np.abs(grads[k[5:]].reshape(ref.shape) - ref).max())
+        assert err <= GRAD_REL * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (k, err, scale)
+
+
+def test_rigid_kernels_vs_reference_functions():
+    """a17-a19 on the device against the reference's own pointcloud.py functions (reference_rigid.npz)."""
+    import os
+    from alignnet_b200 import engine
+    from helpers import GOLDEN
+    r = np.load(os.path.join(GOLDEN, "reference_rigid.npz"))
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()   # noqa: E731
+    out = engine.rigid_apply(f(r["pts"]), f(r["t"]), f(r["theta"]), f(r["c"])).cpu().numpy()
+    np.testing.assert_allclose(out, r["moved"][:, :, :3], atol=1e-4)
+    t2 = engine.recenter_translations(f(r["t"]), f(r["theta"]), f(r["c"]), f(r["new_c"])).cpu().numpy()
+    np.testing.assert_allclose(t2, r["t_new"], atol=1e-4)
