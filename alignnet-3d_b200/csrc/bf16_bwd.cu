@@ -108,27 +108,13 @@ __global__ void gq_pack_kernel(const float* gq_f32, __nv_bfloat16* gq_img) {
   gq_img[(size_t)h * 8192 + (kk >> 3) * 1024 + k * 8 + (kk & 7)] = __float2bfloat16_rn(gq_f32[i]);
 }
 
-// grads.W3[k,c] += T1[k,c] + sa2[k] p'[c] + q[c] * sum_k' G2[k,k'] W3b[k',c]
-__global__ void wgrad3_dense_kernel(const float* W3, const float* t1, const float* gram, const double* sa2,
-                                    const float* coef3, int C3, float* gW3) {
-  __shared__ float sw[128][33];
-  const int c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 32 channels x 8 row groups
-  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
-    const int kp = i >> 5, cc = i & 31;
-    sw[kp][cc] = bf16r(W3[(size_t)kp * C3 + c0 + cc]);
-  }
-  __syncthreads();
-  const int c = c0 + tx;
-  const float q = coef3[c], pp = coef3[C3 + c];
-  const int kbeg = blockIdx.y * 32;
-  for (int k = kbeg + ty; k < kbeg + 32; k += 8) {
-    const float* grow = gram + (size_t)k * 128;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int kp = 0; kp < 128; ++kp) acc = fmaf(grow[kp], sw[kp][tx], acc);
-    gW3[(size_t)k * C3 + c] += t1[(size_t)k * C3 + c] + (float)sa2[k] * pp + q * acc;
-  }
+// grads.W3[k,c] += sa2[k] p'[c] + q[c] * GW[k,c]   (GW = G2 W3b from the forward pass; the sparse part T1 is
+// reduced straight into grads.W3 by t1_sparse_kernel)
+__global__ void wgrad3_dense_kernel(const float* gw, const double* sa2, const float* coef3, int C3, float* gW3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * C3) return;
+  const int k = i / C3, c = i - k * C3;
+  gW3[i] += (float)sa2[k] * coef3[C3 + c] + coef3[c] * gw[i];
 }
 
 // BN backward coefficients of layers 2 / 1 from (sum dy, sum dy*xhat)
@@ -246,7 +232,6 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red3, 0, 2 * (size_t)C3 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
-  AN3D_CUDA_CHECK(cudaMemsetAsync(q.t1, 0, 128 * (size_t)C3 * sizeof(float), st));
   {
     const int bchunk = 16;
     dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
@@ -273,15 +258,16 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     // sparse part T1 = A2^T S: gather-scale-accumulate on CUDA cores (1/N of the dense FLOPs)
     convbwd::T1Params T;
     T.a2_img = W.a2_img; T.img_bytes = W.img_bytes; T.gidx = W.gidx; T.dyext = W.dyext; T.s3 = W.s3; T.B = B; T.N = N;
-    T.PC = q.PC; T.npc = q.npc; T.C3 = C3; T.n_items = n_items; T.t1 = q.t1;
-    const int tr = std::max(1, std::min(n_items, sms / 4));
+    T.PC = q.PC; T.npc = q.npc; T.C3 = C3; T.n_items = n_items; T.t1 = grads + L3.w;
+    // 1024 resident threads per SM: one CTA of 1024 channels, or two of <= 512
+    const int tr = std::max(1, std::min(n_items, (sms / 4) * (C3 <= 512 ? 2 : 1)));
     T.items_per_cta = (n_items + tr - 1) / tr;
-    const size_t tsmem = convbwd::t1_smem_bytes(q.PC, C3);
+    const size_t tsmem = convbwd::t1_smem_bytes(q.PC);
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::t1_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-    convbwd::t1_sparse_kernel<<<dim3(tr, 4), convbwd::kT1Threads, tsmem, st>>>(T);
+    convbwd::t1_sparse_kernel<<<dim3(tr, 4), convbwd::t1_threads(C3), tsmem, st>>>(T);
     prof_mark(PROF_BWD_T1, false, st);
     AN3D_LAUNCH_CHECK();
-    wgrad3_dense_kernel<<<dim3(C3 / 32, 4), 256, 0, st>>>(params + L3.w, q.t1, q.gram[s][br], q.sa2[s][br], q.coef3, C3, grads + L3.w);
+    wgrad3_dense_kernel<<<(128 * C3 + 255) / 256, 256, 0, st>>>(q.gw[s][br], q.sa2[s][br], q.coef3, C3, grads + L3.w);
     AN3D_LAUNCH_CHECK();
   }
   // ---- dgrad3 -> dy2 images + BN2 backward sums ----

@@ -137,31 +137,51 @@ __global__ void fold_acc_kernel(const double* stats, double count, const float* 
 
 // Layer-3 batch statistics without touching the [M, C3] accumulator: with r3 = a2 W3b,
 //   sum_m r3[m,c]   = sa2 . w_c              sum_m r3[m,c]^2 = w_c^T (A2^T A2) w_c
-// (bf16-rounded weights, Gram matrix from the tensor-core pass).  256 threads = 32 channels x 8 row groups.
-__global__ void stats3_from_gram_kernel(const float* W3, const float* gram, const double* sa2, int C3, double* stats3) {
-  __shared__ float sw[128][33];
-  __shared__ double red[2][8][32];
+// (bf16-rounded weights, Gram matrix from the tensor-core pass).  The product GW = (A2^T A2) W3b is kept
+// for the backward pass (dense part of wgrad3).  CTA = 32 channels, 512 threads = 32 channels x 16 row
+// groups of 8 rows; Gram matrix and weight tile staged in shared memory.
+constexpr int kGwThreads = 512;
+constexpr size_t kGwSmem = (128 * 128 + 128 * 33) * sizeof(float) + 2 * 16 * 32 * sizeof(double);
+__global__ void __launch_bounds__(kGwThreads) gw3_stats_kernel(const float* W3, const float* gram, const double* sa2, int C3,
+                                                               float* gw, double* stats3) {
+  extern __shared__ __align__(16) uint8_t gw_smem[];
+  float* sg = reinterpret_cast<float*>(gw_smem);          // [128][128]
+  float* sw = sg + 128 * 128;                              // [128][33]
+  double* red = reinterpret_cast<double*>(sw + 128 * 33);  // [2][16][32]
   const int c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
+  for (int i = threadIdx.x; i < 128 * 128 / 4; i += kGwThreads)
+    reinterpret_cast<float4*>(sg)[i] = reinterpret_cast<const float4*>(gram)[i];
+  for (int i = threadIdx.x; i < 128 * 32; i += kGwThreads) {
     const int kp = i >> 5, cc = i & 31;
-    sw[kp][cc] = __bfloat162float(__float2bfloat16_rn(W3[(size_t)kp * C3 + c0 + cc]));
+    sw[kp * 33 + cc] = __bfloat162float(__float2bfloat16_rn(W3[(size_t)kp * C3 + c0 + cc]));
   }
   __syncthreads();
-  double m = 0.0, qd = 0.0;
-  for (int k = ty; k < 128; k += 8) {
-    const float* grow = gram + (size_t)k * 128;
-    float t = 0.f;
-#pragma unroll 8
-    for (int kp = 0; kp < 128; ++kp) t = fmaf(grow[kp], sw[kp][tx], t);
-    qd += (double)sw[k][tx] * (double)t;
-    m += sa2[k] * (double)sw[k][tx];
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  for (int kp = 0; kp < 128; kp += 4) {
+    const float w0 = sw[kp * 33 + tx], w1 = sw[(kp + 1) * 33 + tx], w2 = sw[(kp + 2) * 33 + tx], w3 = sw[(kp + 3) * 33 + tx];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float4 g = *reinterpret_cast<const float4*>(sg + (ty + 16 * r) * 128 + kp);
+      acc[r] = fmaf(g.x, w0, fmaf(g.y, w1, fmaf(g.z, w2, fmaf(g.w, w3, acc[r]))));
+    }
   }
-  red[0][ty][tx] = m;
-  red[1][ty][tx] = qd;
+  double m = 0.0, qd = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = ty + 16 * r;
+    const float w = sw[k * 33 + tx];
+    if (gw) gw[(size_t)k * C3 + c0 + tx] = acc[r];
+    qd += (double)w * (double)acc[r];
+    m += sa2[k] * (double)w;
+  }
+  red[ty * 32 + tx] = m;
+  red[512 + ty * 32 + tx] = qd;
   __syncthreads();
   if (ty == 0) {
-    for (int i = 1; i < 8; ++i) { m += red[0][i][tx]; qd += red[1][i][tx]; }
+    for (int i = 1; i < 16; ++i) { m += red[i * 32 + tx]; qd += red[512 + i * 32 + tx]; }
     stats3[2 * (c0 + tx)] = m;
     stats3[2 * (c0 + tx) + 1] = qd;
   }
@@ -252,6 +272,7 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
       q->a2img[s][br] = training ? a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2)) : nullptr;
       q->sa2[s][br] = a.take<double>(128);
       q->gram[s][br] = a.take<float>(128 * 128);
+      q->gw[s][br] = training ? a.take<float>(128 * (int64_t)C3) : nullptr;
     }
   }
   if (training) {
@@ -355,7 +376,9 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     convbwd::wgrad3_kernel<<<dim3(nranges, 1), convbwd::kWg3Threads, gsmem, st>>>(W);
     AN3D_LAUNCH_CHECK();
-    stats3_from_gram_kernel<<<C3 / 32, 256, 0, st>>>(params + L3.w, q.gram[s][br], q.sa2[s][br], C3, q.stats3[s][br]);
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(gw3_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGwSmem));
+    gw3_stats_kernel<<<C3 / 32, kGwThreads, kGwSmem, st>>>(params + L3.w, q.gram[s][br], q.sa2[s][br], C3, q.gw[s][br],
+                                                           q.stats3[s][br]);
     AN3D_LAUNCH_CHECK();
   }
   fold_acc_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.stats3[s][br], (double)M, params + L3.b, io3, C3, training ? 1 : 0,

@@ -148,6 +148,7 @@ struct PlanBf16 {
   float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
   float* uvec = nullptr;                    // [128]
   float* gram[3][2];                        // [128][128] a2^T a2 per (stage, branch): BN3 statistics and wgrad3
+  float* gw[3][2];                          // [128][C3] gram * W3 (bf16-rounded weights), forward -> backward
   float* t1 = nullptr;                      // [128][C3max] sparse part of wgrad3 (16-byte aligned scratch)
   __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
   double* red2 = nullptr;                   // [128][2]

@@ -215,9 +215,11 @@ static __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3
 // =============================================================================================
 // t1_sparse: T1[k, c] = sum over clouds of w[b,c] * a2[b, r*(b,c), k] on CUDA cores.
 // S has exactly one non-zero per (cloud, channel), so the "GEMM" A2^T S is a gather-scale-accumulate
-// with 1/N of the dense FLOPs.  CTA = (cloud range, quarter of the 128 k rows): it only needs 4 of
-// the 16 planes of each saved A2 image (one bulk copy), keeps T1[32 k][C3] in registers
-// (warp = channel group, lane = k) and flushes once with vector reductions.
+// with 1/N of the dense FLOPs.  CTA = (cloud range, quarter of the 128 k rows); it needs only 4 of the
+// 16 planes of each saved A2 image (one bulk copy per item into a kT1Stages-deep ring).  THREAD = one
+// channel: its (arg row, weight) pair comes straight from global memory into registers (coalesced,
+// prefetched two items ahead), the 32 k-values of the selected row are four 16-byte shared-memory
+// loads, and T1[32 k][c] lives in 32 registers until one flush with reductions at the end.
 // =============================================================================================
 struct T1Params {
   const uint8_t* a2_img;
@@ -226,102 +228,89 @@ struct T1Params {
   const float* dyext;
   const float* s3;
   int B, N, PC, npc, C3, n_items, items_per_cta;
-  float* t1;             // [128][C3], 16-byte aligned, accumulated with reductions
+  float* t1;             // [128][C3], accumulated with reductions
 };
-constexpr int kT1Threads = 1024;
-constexpr int kT1Batch = 4;              // items processed per block-wide synchronisation
-inline size_t t1_smem_bytes(int PC, int C3) {
-  return 2 * kT1Batch * 4 * (size_t)plane_stride(PC) + 2 * kT1Batch * (size_t)C3 * 8 + 64;
-}
+constexpr int kT1Stages = 6;
+inline int t1_threads(int C3) { return C3 < 1024 ? C3 : 1024; }
+inline size_t t1_smem_bytes(int PC) { return (size_t)kT1Stages * 4 * plane_stride(PC) + 2 * kT1Stages * 8 + 64; }
 
-static __global__ void __launch_bounds__(kT1Threads, 1) t1_sparse_kernel(const T1Params P) {
+static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t qbytes = 4 * plane;
-  uint8_t* sA = smem;                                                        // [2][kT1Batch][qbytes]
-  float* sWv = reinterpret_cast<float*>(smem + 2 * kT1Batch * qbytes);       // [2][kT1Batch][C3]
-  int* sRow = reinterpret_cast<int*>(sWv + 2 * kT1Batch * P.C3);             // [2][kT1Batch][C3]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * kT1Batch * P.C3);  // a_full[2]
-  const int tid = threadIdx.x, cg = tid >> 5, kk = tid & 31;
+  uint8_t* sA = smem;                                                               // [kT1Stages][qbytes]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kT1Stages * qbytes);  // [kT1Stages]
+  uint64_t* empty = full + kT1Stages;                                               // [kT1Stages]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
   const int kq = blockIdx.y;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
-  const int n_batches = (n_local + kT1Batch - 1) / kT1Batch;
-  const int CH = P.C3 / 32;
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-  __syncthreads();
-  if (n_local == 0) return;
-
-  auto fetch = [&](int bi, float (&w)[kT1Batch], int (&row)[kT1Batch]) {   // channel c = tid of the items of batch bi
-#pragma unroll
-    for (int i = 0; i < kT1Batch; ++i) {
-      w[i] = 0.f; row[i] = -1;
-      const int li = bi * kT1Batch + i;
-      if (tid < P.C3 && li < n_local) {
-        const int it = it_begin + li;
-        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-        const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
-        const float wv = P.s3[tid] * P.dyext[(size_t)cloud * P.C3 + tid];
-        const int r = P.gidx[(size_t)cloud * P.C3 + tid] - p0;
-        if (r >= 0 && r < nvalid && wv != 0.f) { w[i] = wv; row[i] = r; }
-      }
-    }
-  };
-  auto store = [&](int slot, const float (&w)[kT1Batch], const int (&row)[kT1Batch]) {
-    if (tid < P.C3) {
-#pragma unroll
-      for (int i = 0; i < kT1Batch; ++i) {
-        sWv[(slot * kT1Batch + i) * P.C3 + tid] = w[i];
-        sRow[(slot * kT1Batch + i) * P.C3 + tid] = row[i];
-      }
-    }
-  };
-  auto load_imgs = [&](int bi) {
-    const int b = bi & 1;
-    const int cnt = min(kT1Batch, n_local - bi * kT1Batch);
-    mbar_arrive_expect_tx(&bars[b], cnt * qbytes);
-    for (int i = 0; i < cnt; ++i)
-      bulk_copy_g2s(sA + (size_t)(b * kT1Batch + i) * qbytes,
-                    P.a2_img + (size_t)(it_begin + bi * kT1Batch + i) * P.img_bytes + (size_t)kq * qbytes, qbytes, &bars[b]);
-  };
-  if (tid == 0) { load_imgs(0); if (n_batches > 1) load_imgs(1); }
-  {
-    float w[kT1Batch]; int row[kT1Batch];
-    fetch(0, w, row);
-    store(0, w, row);
+  if (tid == 0) {
+    for (int i = 0; i < kT1Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], nwarps); }
+    fence_barrier_init();
   }
   __syncthreads();
+  if (n_local == 0) return;
+  auto load_img = [&](int li) {
+    const int st = li % kT1Stages;
+    mbar_arrive_expect_tx(&full[st], qbytes);
+    bulk_copy_g2s(sA + (size_t)st * qbytes, P.a2_img + (size_t)(it_begin + li) * P.img_bytes + (size_t)kq * qbytes, qbytes,
+                  &full[st]);
+  };
+  if (tid == 0)
+    for (int li = 0; li < min(n_local, kT1Stages); ++li) load_img(li);
+
+  const int c = tid;                       // blockDim.x == C3 (<= 1024)
+  const float s3c = P.s3[c];
+  auto fetch = [&](int li, float& w, int& row) {
+    w = 0.f; row = -1;
+    if (li < n_local) {
+      const int it = it_begin + li;
+      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
+      const float wv = s3c * P.dyext[(size_t)cloud * P.C3 + c];
+      const int r = P.gidx[(size_t)cloud * P.C3 + c] - p0;
+      if (r >= 0 && r < nvalid && wv != 0.f) { w = wv; row = r; }
+    }
+  };
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  const uint32_t lane_off = (kk >> 3) * plane + (kk & 7) * 2;
-  for (int bi = 0; bi < n_batches; ++bi) {
-    const int b = bi & 1;
-    float nw[kT1Batch]; int nrow[kT1Batch];
-    if (bi + 1 < n_batches) fetch(bi + 1, nw, nrow);
-    mbar_wait(&bars[b], (uint32_t)((bi >> 1) & 1));
-    const int cnt = min(kT1Batch, n_local - bi * kT1Batch);
-    for (int i = 0; i < cnt; ++i) {
-      const float* wv = sWv + (b * kT1Batch + i) * P.C3 + cg * CH;
-      const int* rv = sRow + (b * kT1Batch + i) * P.C3 + cg * CH;
-      const uint8_t* img = sA + (size_t)(b * kT1Batch + i) * qbytes + lane_off;
+  float w0, w1, w2; int r0, r1, r2;
+  fetch(0, w0, r0);
+  fetch(1, w1, r1);
+  for (int li = 0; li < n_local; ++li) {
+    const int st = li % kT1Stages;
+    fetch(li + 2, w2, r2);
+    // refill the stage drained one iteration ago (every warp has arrived on its `empty` barrier by now, or will shortly)
+    if (tid == 0 && li >= 1 && li - 1 + kT1Stages < n_local) {
+      const int sp = (li - 1) % kT1Stages;
+      mbar_wait(&empty[sp], (uint32_t)(((li - 1) / kT1Stages) & 1));
+      load_img(li - 1 + kT1Stages);
+    }
+    mbar_wait(&full[st], (uint32_t)((li / kT1Stages) & 1));
+    if (r0 >= 0) {
+      const uint8_t* src = sA + (size_t)st * qbytes + (uint32_t)r0 * 16u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < CH) {
-          const int r = rv[j];
-          if (r >= 0) acc[j] = fmaf(wv[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + r * 16)), acc[j]);
+      for (int kc = 0; kc < 4; ++kc) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + kc * plane);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          acc[kc * 8 + 2 * h] = fmaf(w0, __uint_as_float(u[h] << 16), acc[kc * 8 + 2 * h]);
+          acc[kc * 8 + 2 * h + 1] = fmaf(w0, __uint_as_float(u[h] & 0xffff0000u), acc[kc * 8 + 2 * h + 1]);
         }
       }
     }
-    if (bi + 1 < n_batches) store(b ^ 1, nw, nrow);
-    __syncthreads();
-    if (tid == 0 && bi + 2 < n_batches) load_imgs(bi + 2);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    w0 = w1; r0 = r1; w1 = w2; r1 = r2;
   }
-  float* dst = P.t1 + (size_t)(kq * 32 + kk) * P.C3 + cg * CH;
+  float* dst = P.t1 + (size_t)(kq * 32) * P.C3 + c;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4)
-    if (j < CH) red_add_v4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * P.C3, acc[j]);
 }
 
 // =============================================================================================
