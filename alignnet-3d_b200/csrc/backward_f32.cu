@@ -80,7 +80,9 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     g.ksplit = std::max(1, std::min((R + 255) / 256, (592 + tiles - 1) / tiles));
     AN3D_TRY(launch_gemm(g, true, false, st));
   }
-  {  // bias grad
+  // bias grad.  A bias that feeds a batch-statistics BN has an identically zero gradient (TF computes rounding
+  // noise there); the bf16 path leaves it at zero, as it does for the conv stacks.
+  if (!(bf16 && L.bn >= 0)) {
     AN3D_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * L.cout, st));
     ColArgs a;
     a.Z = dZ; a.ldz = L.cout; a.R = R; a.C = L.cout; a.acc0 = bias_acc;

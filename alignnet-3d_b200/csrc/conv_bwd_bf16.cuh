@@ -573,28 +573,38 @@ struct L2Params {
   __nv_bfloat16* dy1;                       // [B*N][64]
   double* red1;                             // [64][2]
 };
-constexpr int kL2Threads = 320;
+// Two worker groups of 8 warps walk alternate items (ping-pong): while one group is in a CUDA-core phase
+// (layer-1 recompute, dz2 / dy1 epilogues) the other one's MMAs, TMEM loads and barrier round trips are in
+// flight, so the per-item dependency chain  a1 -> D2 -> dz2 -> (wgrad2, da1) -> dy1  no longer idles the SM.
+constexpr int kL2Groups = 2;
+constexpr int kL2GroupThreads = 256;
+constexpr int kL2Threads = kL2Groups * kL2GroupThreads + 64;   // + MMA warp + loader warp
+constexpr int kL2MmaWarp = kL2Groups * kL2GroupThreads / 32;
+constexpr uint32_t kL2AccStride = 224;                         // TMEM columns per group accumulator (PC <= 208)
+constexpr uint32_t kL2AccWG = 448;                             // wgrad2 accumulator [448, 512)
 
 inline size_t l2_smem_bytes(int PC) {
-  return 8 * (size_t)plane_stride(PC) + 2 * 16 * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
-         256 * 3 * 4 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
+  return kL2Groups * (8 + 16) * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
+         kL2Groups * 256 * 3 * 4 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
 }
 
 struct L2Bars {
-  uint64_t w_full, dz_full[2], dz_free[2], a1_full, d2_full, dz_ready, da_full, done;
+  uint64_t w_full, done;
+  uint64_t dz_full[kL2Groups], dz_free[kL2Groups], a1_full[kL2Groups], d2_full[kL2Groups], dz_ready[kL2Groups],
+      da_full[kL2Groups];
   uint32_t tmem_base;
-  float xf[16];
+  float xf[kL2Groups][8];
 };
 
 static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
-  uint8_t* sA1 = smem;
-  uint8_t* sDZb[2] = {sA1 + 8 * plane, sA1 + 24 * plane};   // dy2 tile of the next item is prefetched
-  uint8_t* sW2T = sA1 + 40 * plane;
+  uint8_t* sA1b[kL2Groups] = {smem, smem + 8 * plane};
+  uint8_t* sDZb[kL2Groups] = {smem + 16 * plane, smem + 32 * plane};
+  uint8_t* sW2T = smem + 48 * plane;
   uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
-  float* sPts = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [256][3] transformed points
-  float* sW1f = sPts + 768;      // 192
+  float* sPtsAll = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [groups][256][3] transformed points
+  float* sW1f = sPtsAll + kL2Groups * 768;   // 192
   float* sC1f = sW1f + 192;      // 64
   float* sW1 = sC1f + 64;        // 192
   float* sL1 = sW1 + 192;        // b1, mean1, inv1, gamma1, beta1 : 5 x 64
@@ -607,9 +617,12 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
 
   if (tid == 0) {
     mbar_init(&bars->w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->dz_full[i], 1); mbar_init(&bars->dz_free[i], 1); }
-    mbar_init(&bars->a1_full, 256); mbar_init(&bars->d2_full, 1); mbar_init(&bars->dz_ready, 256);
-    mbar_init(&bars->da_full, 1); mbar_init(&bars->done, 1);
+    mbar_init(&bars->done, 1);
+    for (int i = 0; i < kL2Groups; ++i) {
+      mbar_init(&bars->dz_full[i], 1); mbar_init(&bars->dz_free[i], 1);
+      mbar_init(&bars->a1_full[i], kL2GroupThreads); mbar_init(&bars->d2_full[i], 1);
+      mbar_init(&bars->dz_ready[i], kL2GroupThreads); mbar_init(&bars->da_full[i], 1);
+    }
     fence_barrier_init();
   }
   for (int i = tid; i < 192; i += kL2Threads) { sW1f[i] = P.w1f[i]; sW1[i] = P.W1[i]; }
@@ -621,18 +634,23 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
     sL2[i] = (P.b2[i] - P.mean2[i]) * P.inv2[i];
     sL2[128 + i] = P.inv2[i]; sL2[256 + i] = P.s2[i]; sL2[384 + i] = P.coef2[2 * i]; sL2[512 + i] = P.coef2[2 * i + 1];
   }
-  if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == kL2MmaWarp) tmem_alloc(&bars->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  constexpr uint32_t kD = 0, kWG = 256;   // D2 / DA share columns [0,256); wgrad2 accumulator at [256,320)
 
-  if (warp < 8) {
-    const int t = tid;                     // 0..255
+  if (warp < kL2MmaWarp) {
+    const int grp = warp >> 3;             // worker group: items grp, grp + 2, ...
+    const int t = tid & (kL2GroupThreads - 1);   // 0..255 within the group
     const int k = t & 127, half = t >> 7;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph = 0;                       // all per-item barriers flip once per item
+    const uint32_t kD = grp * kL2AccStride;
+    uint8_t* sA1 = sA1b[grp];
+    uint8_t* sDZ = sDZb[grp];
+    float* sPts = sPtsAll + grp * 768;
+    float* xf = bars->xf[grp];
+    uint32_t ph = 0;                       // all per-item barriers of the group flip once per item
     double r0 = 0.0, r1 = 0.0;
     // register prefetch of the next item's transform (thread 0) and point (thread t): keeps the global
     // latency out of the barrier at the top of each item
@@ -651,24 +669,28 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
       }
     };
-    if (n_local > 0) prefetch(0);
-    for (int li = 0; li < n_local; ++li, ph ^= 1) {
+    if (grp < n_local) prefetch(grp);
+    for (int li = grp; li < n_local; li += kL2Groups, ph ^= 1) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
       const int p0 = pchunk * P.PC;
       const int nvalid = min(P.PC, P.N - p0);
       const int NT = (nvalid + 15) & ~15;
       const int64_t row0 = (int64_t)cloud * P.N + p0;
-      uint8_t* sDZ = sDZb[li & 1];
-      float* xf = bars->xf + (li & 1) * 8;
+      // the previous item's readers of xf / sPts are past this point only after the barrier below; xf is
+      // written by thread 0 before it, which is safe because every reader of the previous values finished
+      // its dy1 phase before arriving here (same thread order) -- sPts is rewritten after the barrier
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
       if (t == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(pf_ang, &sn, &cs);
         xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
       const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
-      if (li + 1 < n_local) prefetch(li + 1);
+      if (li + kL2Groups < n_local) prefetch(li + kL2Groups);
       // ---- recompute a1 (layer 1), one thread per point ----
       if (t < NT) {
         const int p = t;
@@ -696,10 +718,10 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&bars->a1_full);
+      mbar_arrive(&bars->a1_full[grp]);
       // ---- dz2 from the raw layer-2 accumulator (xhat2) and dy2 ----
-      mbar_wait(&bars->d2_full, ph);
-      mbar_wait(&bars->dz_full[li & 1], (uint32_t)((li >> 1) & 1));
+      mbar_wait_relaxed(&bars->d2_full[grp], ph);
+      mbar_wait_relaxed(&bars->dz_full[grp], ph);
       tc_fence_after();
       {
         // dz = s2 (dy - m0 - xhat m1), xhat = acc*inv2 + cx   ==   dy*cA + cB + acc*cC
@@ -724,9 +746,9 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&bars->dz_ready);
+      mbar_arrive(&bars->dz_ready[grp]);
       // ---- dy1 = da1 * [a1 > 0], BN1 backward sums (channels k1 < 64 only) ----
-      mbar_wait(&bars->da_full, ph);
+      mbar_wait_relaxed(&bars->da_full[grp], ph);
       tc_fence_after();
       {
         // accumulator rows 64..127 duplicate rows 0..63: channel k1 = k & 63, and the four (lane half, warp
@@ -762,57 +784,67 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       tc_fence_before();
     }
     if (n_local > 0) {
-      atomicAdd(P.red1 + 2 * (k & 63), r0);
-      atomicAdd(P.red1 + 2 * (k & 63) + 1, r1);
+      if (grp < n_local) {
+        atomicAdd(P.red1 + 2 * (k & 63), r0);
+        atomicAdd(P.red1 + 2 * (k & 63) + 1, r1);
+      }
       // ---- wgrad2 accumulator: lane = k2, 64 columns = k1 ----
-      mbar_wait(&bars->done, 0);
-      tc_fence_after();
-      if (half == 0) {
+      if (grp == 0 && half == 0) {
+        mbar_wait_relaxed(&bars->done, 0);
+        tc_fence_after();
         for (int g16 = 0; g16 < 64; g16 += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem + lane_base + kWG + g16, r);
+          tmem_ld16(tmem + lane_base + kL2AccWG + g16, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(P.gW2 + (size_t)(g16 + j) * 128 + k, __uint_as_float(r[j]));
         }
+        tc_fence_before();
       }
-      tc_fence_before();
     }
-  } else if (warp == 8) {
+  } else if (warp == kL2MmaWarp) {
     if (n_local > 0) {
-      uint32_t ph = 0;
       mbar_wait(&bars->w_full, 0);
-      for (int li = 0; li < n_local; ++li, ph ^= 1) {
+      auto nt_of = [&](int li) {
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-        const int NT = (nvalid + 15) & ~15;
-        mbar_wait(&bars->a1_full, ph);
+        return (nvalid + 15) & ~15;
+      };
+      auto issue_d2 = [&](int li) {
+        const int g = li & 1;
+        mbar_wait(&bars->a1_full[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
-        {
-          const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        const uint32_t idesc = make_idesc(128, nt_of(li), 0, 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16(tmem + kD, make_desc(smem_u32(sW2T) + ks * 2 * kPlaneW, kPlaneW, 128),
-                     make_desc(smem_u32(sA1) + ks * 2 * plane, plane, 128), idesc, ks > 0);
-          mma_commit(&bars->d2_full);
-        }
-        mbar_wait(&bars->dz_ready, ph);
+        for (int ks = 0; ks < 4; ++ks)
+          mma_bf16(tmem + g * kL2AccStride, make_desc(smem_u32(sW2T) + ks * 2 * kPlaneW, kPlaneW, 128),
+                   make_desc(smem_u32(sA1b[g]) + ks * 2 * plane, plane, 128), idesc, ks > 0);
+        mma_commit(&bars->d2_full[g]);
+      };
+      auto issue_bwd = [&](int li) {
+        const int g = li & 1;
+        const int NT = nt_of(li);
+        mbar_wait(&bars->dz_ready[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
-        uint8_t* sDZ = sDZb[li & 1];
-        {
-          const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
-          for (int ks = 0; ks < NT / 16; ++ks)
-            mma_bf16(tmem + kWG, make_desc(smem_u32(sDZ) + ks * 256, 128, plane), make_desc(smem_u32(sA1) + ks * 256, 128, plane),
-                     idesc_w, (li > 0 || ks > 0) ? 1u : 0u);
-          const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
+        for (int ks = 0; ks < NT / 16; ++ks)
+          mma_bf16(tmem + kL2AccWG, make_desc(smem_u32(sDZb[g]) + ks * 256, 128, plane),
+                   make_desc(smem_u32(sA1b[g]) + ks * 256, 128, plane), idesc_w, (li > 0 || ks > 0) ? 1u : 0u);
+        const uint32_t idesc = make_idesc(128, NT, 0, 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            mma_bf16(tmem + kD, make_desc(smem_u32(sW2P) + ks * 2 * kPlaneW, kPlaneW, 128),
-                     make_desc(smem_u32(sDZ) + ks * 2 * plane, plane, 128), idesc, ks > 0);
-          mma_commit(&bars->da_full);
-          mma_commit(&bars->dz_free[li & 1]);
-        }
+        for (int ks = 0; ks < 8; ++ks)
+          mma_bf16(tmem + g * kL2AccStride, make_desc(smem_u32(sW2P) + ks * 2 * kPlaneW, kPlaneW, 128),
+                   make_desc(smem_u32(sDZb[g]) + ks * 2 * plane, plane, 128), idesc, ks > 0);
+        mma_commit(&bars->da_full[g]);
+        mma_commit(&bars->dz_free[g]);
+      };
+      // fixed service order D2(2q), D2(2q+1), BWD(2q), BWD(2q+1): consistent with each group's own sequence
+      for (int q = 0; q < n_local; q += 2) {
+        issue_d2(q);
+        if (q + 1 < n_local) issue_d2(q + 1);
+        issue_bwd(q);
+        if (q + 1 < n_local) issue_bwd(q + 1);
       }
       mma_commit(&bars->done);
     }
@@ -822,16 +854,16 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       bulk_copy_g2s(sW2T, P.w2t_img, convfwd::kW2Bytes, &bars->w_full);
       bulk_copy_g2s(sW2P, P.w2p_img, 128 * 128 * 2, &bars->w_full);
       for (int li = 0; li < n_local; ++li) {
-        const int b = li & 1;
-        mbar_wait(&bars->dz_free[b], (uint32_t)(((li >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&bars->dz_full[b], P.img_bytes);
-        bulk_copy_g2s(sDZb[b], P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[b]);
+        const int g = li & 1;
+        mbar_wait_relaxed(&bars->dz_free[g], (uint32_t)(((li >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&bars->dz_full[g], P.img_bytes);
+        bulk_copy_g2s(sDZb[g], P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[g]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == kL2MmaWarp) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace convbwd

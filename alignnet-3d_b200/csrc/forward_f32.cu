@@ -1,4 +1,6 @@
 // fp32 parity path: forward pass of get_model (models/tp8.py:135-158) with CUDA-core kernels.
+#include <algorithm>
+
 #include "kernels_f32.cuh"
 #include "bf16_path.cuh"
 #include "fc_gemm_bf16.cuh"
@@ -49,6 +51,26 @@ static int bn_forward(const BnView& v, const float* Z, int R, bool training, flo
   return AN3D_OK;
 }
 
+// bf16 mode: the producing GEMM's epilogue already accumulated sum z (acc0) and sum z^2 (acc1) per column
+static __global__ void bn_finalize_sums_kernel(const double* acc0, const double* acc1, double inv_rows, const float* gamma,
+                                               const float* beta, float* state_mean, float* state_var, float* mean,
+                                               float* inv, float* scale, float* shift, int C, float decay) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = acc0[c] * inv_rows;
+  const float mu = (float)m;
+  const float var = (float)fmax(acc1[c] * inv_rows - m * m, 0.0);
+  const float om = 1.f - decay;
+  state_mean[c] = state_mean[c] - om * (state_mean[c] - mu);
+  state_var[c] = state_var[c] - om * (state_var[c] - var);
+  const float rs = 1.0f / sqrtf(var + kBnEps);
+  const float sc = gamma[c] * rs;
+  mean[c] = mu;
+  inv[c] = rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - mu * sc;
+}
+
 static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, const float* params, float* state,
                               bool training, float decay, cudaStream_t st) {
   const int64_t M = p.M;
@@ -93,11 +115,35 @@ static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const fl
     f.A = g.A; f.lda = g.lda; f.a_mn = 0; f.B = g.B; f.ldb = g.ldb; f.b_mn = 1; f.C = g.C; f.ldc = g.ldc;
     f.M = g.M; f.N = g.N; f.K = g.K; f.bias = g.bias; f.pro_scale = g.pro_scale; f.pro_shift = g.pro_shift;
     f.pro_mask = g.pro_mask; f.pro_mask_scale = g.pro_mask_scale; f.ksplit = 1; f.accumulate = 0;
-    if (p.bf16 && fcgemm::usable(f)) AN3D_TRY(fcgemm::launch(f, st));
-    else AN3D_TRY(launch_gemm(g, false, false, st));
+    bool fused_stats = false;
+    if (p.bf16 && fcgemm::usable(f)) {
+      if (L.bn >= 0 && training) {   // column sums of z and z^2 come out of the GEMM epilogue
+        BnView v = bn_view(m, p, params, state, head, br, L.bn);
+        f.stat_sum = v.acc0;
+        f.stat_sq = v.acc1;
+        fused_stats = true;
+      }
+      if (!fused_stats) {   // few output tiles (inference batches): split K so that the launch fills the SMs
+        const int tiles = ((f.M + 127) / 128) * ((f.N + 127) / 128);
+        const int ks = std::min(f.K / 128, 148 / tiles);
+        if (ks > 1) {
+          f.ksplit = ks;
+          AN3D_CUDA_CHECK(cudaMemsetAsync(f.C, 0, sizeof(float) * (size_t)f.M * f.ldc, st));
+        }
+      }
+      AN3D_TRY(fcgemm::launch(f, st));
+    } else {
+      AN3D_TRY(launch_gemm(g, false, false, st));
+    }
     if (L.bn >= 0) {
       BnView v = bn_view(m, p, params, state, head, br, L.bn);
-      AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
+      if (fused_stats) {
+        bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
+                                                                    v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
+        AN3D_LAUNCH_CHECK();
+      } else {
+        AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
+      }
       psc = v.scale;
       psh = v.shift;
     }

@@ -2,6 +2,7 @@
 // bf16 tensor-core path with a caller-supplied upstream gradient, so the backward kernels can be
 // checked against autograd without the (discontinuous) rest of the model in between.
 #include "bf16_path.cuh"
+#include "fc_gemm_bf16.cuh"
 
 using namespace an3d;
 
@@ -37,4 +38,22 @@ extern "C" int an3d_selftest_conv_stack(const an3d_ctx* ctx, const float* params
   if (dangle) AN3D_CUDA_CHECK(cudaMemsetAsync(dangle, 0, sizeof(float) * batch, st));
   return conv_stack_backward_bf16(m, p, stage, branch, pcs, center, angle, dG, C3, params, grads, true, dcenter,
                                   angle ? dangle : nullptr, st);
+}
+
+extern "C" int an3d_selftest_fc_gemm(const float* a, int64_t lda, int32_t a_mn, const float* b, int64_t ldb, int32_t b_mn,
+                                     float* c, int64_t ldc, int32_t m, int32_t n, int32_t k, const float* bias,
+                                     const float* pro_scale, const float* pro_shift, const float* pro_mask,
+                                     float pro_mask_scale, int32_t ksplit, int32_t accumulate, double* stat_sum,
+                                     double* stat_sq, void* stream) {
+  if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || ksplit < 1 || (stat_sum && ksplit > 1) || (!stat_sum != !stat_sq) ||
+      (!pro_scale != !pro_shift)) {
+    set_error("an3d_selftest_fc_gemm: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  fcgemm::Params f;
+  f.A = a; f.lda = lda; f.a_mn = a_mn; f.B = b; f.ldb = ldb; f.b_mn = b_mn; f.C = c; f.ldc = ldc; f.M = m; f.N = n; f.K = k;
+  f.bias = bias; f.pro_scale = pro_scale; f.pro_shift = pro_shift; f.pro_mask = pro_mask; f.pro_mask_scale = pro_mask_scale;
+  f.ksplit = ksplit; f.accumulate = accumulate; f.stat_sum = stat_sum; f.stat_sq = stat_sq;
+  return fcgemm::launch(f, (cudaStream_t)stream);
 }

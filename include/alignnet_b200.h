@@ -191,6 +191,17 @@ int an3d_selftest_conv_stack(const an3d_ctx* ctx, const float* params, float* bn
                              int32_t num_points, const float* dG, float* g_out, float* grads, float* dcenter,
                              float* dangle, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Diagnostic (test-suite only): the tcgen05 GEMM that runs every FC layer of the bf16 mode (forward, wgrad and
+ * dgrad forms; replaces tf.matmul of utils/tf_util.py:337 and its gradients).
+ *   C[i,j] (+)= sum_k A(i,k) B(j,k) (+ bias[j]);  a_mn/b_mn = 0: operand[idx*ld + k], 1: operand[k*ld + idx];
+ * optional prologue on A: relu(a*scale[ch] + shift[ch]) * mask * mask_scale; ksplit > 1 or accumulate != 0
+ * reduces into C (pre-zeroed by the caller); stat_sum/stat_sq [N] (double, pre-zeroed) receive the column
+ * sums of C and C^2 (ksplit must be 1).  Operands are fp32, rounded to bf16 on load, fp32 accumulation. */
+int an3d_selftest_fc_gemm(const float* a, int64_t lda, int32_t a_mn, const float* b, int64_t ldb, int32_t b_mn, float* c,
+                          int64_t ldc, int32_t m, int32_t n, int32_t k, const float* bias, const float* pro_scale,
+                          const float* pro_shift, const float* pro_mask, float pro_mask_scale, int32_t ksplit,
+                          int32_t accumulate, double* stat_sum, double* stat_sq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,21 +68,23 @@ def _conv_stack(p, specs, branch, params, state, new_state, training, bn_decay):
 
 
 def _mlp(g, specs, branch, params, state, new_state, training, bn_decay, keep, mask):
-    """models/tp8.py:75-82.  With SIM_BF16 and a batch of at least 64 rows the hidden FC layers round
-    their inputs and weights to bf16 (the engine runs those GEMMs on the tensor cores; smaller
-    batches and the narrow output layer stay in fp32)."""
+    """models/tp8.py:75-82.  With SIM_BF16 every FC layer rounds its inputs and weights to bf16 (the
+    engine's bf16 mode runs all FC GEMMs on the tensor cores with fp32 accumulation)."""
     x = g
     for s in specs[:-1]:
         n = weight_names(s)
         w = params[n["weights"]]
-        if SIM_BF16 and x.shape[0] >= 64:
+        if SIM_BF16:
             x, w = _r16(x), _r16(w)
         z = x @ w + params[n["biases"]]
         x = torch.relu(_bn(z, s, branch, params, state, new_state, training, bn_decay, (0,)))
     if training and keep is not None and mask is not None:
         x = x / keep * mask
     n = weight_names(specs[-1])
-    return x @ params[n["weights"]] + params[n["biases"]]
+    w = params[n["weights"]]
+    if SIM_BF16:
+        x, w = _r16(x), _r16(w)
+    return x @ w + params[n["biases"]]
 
 
 def tf_get_angles(logits, nb: int):
