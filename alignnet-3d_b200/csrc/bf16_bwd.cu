@@ -127,15 +127,19 @@ __global__ void bn_bwd_coeff_kernel(const double* red, int C, double count, floa
   coef[2 * c + 1] = (float)(red[2 * c + 1] / count);
 }
 
-// layer-1 backward on CUDA cores: dz1 = s1 (dy1 - m0 - xhat1 m1); wgrad1; gradient of the stage input
-// reduced per cloud to d(center) and d(angle).  One block per item, 256 threads = 64 channels x 4.
-__global__ void __launch_bounds__(256) bwd_l1_kernel(const float* pcs, const float* center, const float* angle,
-                                                     const __nv_bfloat16* dy1, int N, int PC, int npc, const float* W1,
-                                                     const float* b1, const float* mean1, const float* inv1,
-                                                     const float* scale1, const float* coef1, float* gW1,
-                                                     float* dcenter, float* dangle, int want_input_grad) {
-  __shared__ float sp[256 * 3];
-  __shared__ float red[4][64][4];
+// layer-1 backward, finishing step.  bwd_l2_kernel left, per item and channel, S = sum_p dy1 * (1, x, y, z).  With
+// xhat1 = alpha . (x, y, z) + alpha0 (affine in the input) and the item's point moments P,
+//   A   = sum_p dz1     = s1 (S0 - n m0 - m1 sum_p xhat)
+//   B_d = sum_p dz1 q_d = s1 (S_d - m0 P_d - m1 sum_p xhat q_d),   d in {x, y, z}
+// give wgrad1 (sum of B over items) and the gradient of the stage input reduced per cloud to d(center) and
+// d(angle).  One block per item, 256 threads: point moments by block reduction, then 64 channel threads.
+__global__ void __launch_bounds__(256) bwd_l1_finish_kernel(const float* pcs, const float* center, const float* angle,
+                                                            const float* l1sums, int N, int PC, int npc, const float* W1,
+                                                            const float* b1, const float* mean1, const float* inv1,
+                                                            const float* scale1, const float* coef1, float* gW1,
+                                                            float* dcenter, float* dangle, int want_input_grad) {
+  __shared__ float wred[8][9];
+  __shared__ float mom[9];
   __shared__ float fin[64][4];
   const int it = blockIdx.x;
   const int cloud = it / npc, pchunk = it - cloud * npc;
@@ -145,34 +149,47 @@ __global__ void __launch_bounds__(256) bwd_l1_kernel(const float* pcs, const flo
   float sn = 0.f, cs = 1.f;
   if (angle) sincosf(angle[cloud], &sn, &cs);
   const float cx = center[cloud * 3], cy = center[cloud * 3 + 1], cz = center[cloud * 3 + 2];
+  float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // Px Py Pz Pxx Pxy Pxz Pyy Pyz Pzz
   for (int p = threadIdx.x; p < nvalid; p += 256) {
     const float* src = pcs + (row0 + p) * 3;
     const float x0 = src[0] - cx, y0 = src[1] - cy;
-    sp[p * 3] = x0 * cs - y0 * sn;
-    sp[p * 3 + 1] = x0 * sn + y0 * cs;
-    sp[p * 3 + 2] = src[2] - cz;
+    const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs, z = src[2] - cz;
+    m[0] += x; m[1] += y; m[2] += z;
+    m[3] = fmaf(x, x, m[3]); m[4] = fmaf(x, y, m[4]); m[5] = fmaf(x, z, m[5]);
+    m[6] = fmaf(y, y, m[6]); m[7] = fmaf(y, z, m[7]); m[8] = fmaf(z, z, m[8]);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q)
+    for (int o = 16; o > 0; o >>= 1) m[q] += __shfl_xor_sync(0xffffffffu, m[q], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int q = 0; q < 9; ++q) wred[threadIdx.x >> 5][q] = m[q];
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += wred[w][threadIdx.x];
+    mom[threadIdx.x] = t;
   }
   __syncthreads();
-  const int c = threadIdx.x & 63, gq = threadIdx.x >> 6;
-  const float wx = W1[c], wy = W1[64 + c], wz = W1[128 + c], bb = b1[c], mu = mean1[c], iv = inv1[c], s1 = scale1[c];
-  const float m0 = coef1[2 * c], m1 = coef1[2 * c + 1];
-  float a = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-  for (int p = gq; p < nvalid; p += 4) {
-    const float x = sp[p * 3], y = sp[p * 3 + 1], z = sp[p * 3 + 2];
-    const float xh = (fmaf(x, wx, fmaf(y, wy, fmaf(z, wz, bb))) - mu) * iv;
-    const float dz = s1 * (__bfloat162float(dy1[(row0 + p) * 64 + c]) - m0 - xh * m1);
-    a += dz; bx = fmaf(dz, x, bx); by = fmaf(dz, y, by); bz = fmaf(dz, z, bz);
-  }
-  red[gq][c][0] = a; red[gq][c][1] = bx; red[gq][c][2] = by; red[gq][c][3] = bz;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float v[4];
-    for (int j = 0; j < 4; ++j) v[j] = red[0][c][j] + red[1][c][j] + red[2][c][j] + red[3][c][j];
-    atomicAdd(gW1 + c, v[1]);
-    atomicAdd(gW1 + 64 + c, v[2]);
-    atomicAdd(gW1 + 128 + c, v[3]);
+  const int c = threadIdx.x;
+  if (c < 64) {
+    const float wx = W1[c], wy = W1[64 + c], wz = W1[128 + c];
+    const float iv = inv1[c], s1 = scale1[c], m0 = coef1[2 * c], m1 = coef1[2 * c + 1];
+    const float ax = iv * wx, ay = iv * wy, az = iv * wz, a0 = iv * (b1[c] - mean1[c]);
+    const float n = (float)nvalid;
+    const float4 S = reinterpret_cast<const float4*>(l1sums)[(size_t)it * 64 + c];
+    const float sxh = ax * mom[0] + ay * mom[1] + az * mom[2] + n * a0;
+    const float sxh_x = ax * mom[3] + ay * mom[4] + az * mom[5] + a0 * mom[0];
+    const float sxh_y = ax * mom[4] + ay * mom[6] + az * mom[7] + a0 * mom[1];
+    const float sxh_z = ax * mom[5] + ay * mom[7] + az * mom[8] + a0 * mom[2];
+    const float A = s1 * (S.x - n * m0 - m1 * sxh);
+    const float Bx = s1 * (S.y - m0 * mom[0] - m1 * sxh_x);
+    const float By = s1 * (S.z - m0 * mom[1] - m1 * sxh_y);
+    const float Bz = s1 * (S.w - m0 * mom[2] - m1 * sxh_z);
+    atomicAdd(gW1 + c, Bx);
+    atomicAdd(gW1 + 64 + c, By);
+    atomicAdd(gW1 + 128 + c, Bz);
     // d(sum_p dq_d) = sum_c W1[d,c] A_c ; d(angle) = sum_c (-W1[x,c] By_c + W1[y,c] Bx_c)
-    fin[c][0] = wx * v[0]; fin[c][1] = wy * v[0]; fin[c][2] = wz * v[0]; fin[c][3] = -wx * v[2] + wy * v[1];
+    fin[c][0] = wx * A; fin[c][1] = wy * A; fin[c][2] = wz * A; fin[c][3] = -wx * By + wy * Bx;
   }
   __syncthreads();
   if (want_input_grad && threadIdx.x < 4) {
@@ -299,7 +316,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     P2.w1f = q.w1f[s][br]; P2.c1f = q.c1f[s][br]; P2.W1 = params + L1.w; P2.b1 = params + L1.b; P2.mean1 = mean1;
     P2.inv1 = inv1; P2.gamma1 = gamma1; P2.beta1 = beta1; P2.w2t_img = q.w2t[s]; P2.w2p_img = q.w2p[s];
     P2.b2 = params + L2.b; P2.mean2 = mean2; P2.inv2 = inv2; P2.s2 = sc2; P2.coef2 = q.coef2; P2.gW2 = grads + L2.w;
-    P2.dy1 = q.dy1; P2.red1 = q.red1;
+    P2.l1sums = q.l1sums; P2.red1 = q.red1;
     const size_t smem = convbwd::l2_smem_bytes(q.PC);
     if (smem > (size_t)kMaxSmem) { set_error("bwd_l2 tile too large"); return AN3D_ERR_UNSUPPORTED; }
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::bwd_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -311,8 +328,9 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     AN3D_LAUNCH_CHECK();
   }
   // ---- layer 1 backward (CUDA cores) ----
-  bwd_l1_kernel<<<n_items, 256, 0, st>>>(pcs, center, angle, q.dy1, N, q.PC, q.npc, params + L1.w, params + L1.b, mean1,
-                                         inv1, sc1, q.coef1, grads + L1.w, dcenter, dangle, want_input_grad ? 1 : 0);
+  bwd_l1_finish_kernel<<<n_items, 256, 0, st>>>(pcs, center, angle, q.l1sums, N, q.PC, q.npc, params + L1.w, params + L1.b,
+                                                mean1, inv1, sc1, q.coef1, grads + L1.w, dcenter, dangle,
+                                                want_input_grad ? 1 : 0);
   AN3D_LAUNCH_CHECK();
   // biases of conv layers feed a batch-statistics BN: their gradient is identically zero (left at 0).
   return AN3D_OK;

@@ -293,7 +293,7 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
     q->dy2img = a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2));
     q->red2 = a.take<double>(256);
     q->coef2 = a.take<float>(256);
-    q->dy1 = a.take<__nv_bfloat16>(M * 64);
+    q->l1sums = a.take<float>((int64_t)B * q->npc * 256);
     q->red1 = a.take<double>(128);
     q->coef1 = a.take<float>(128);
   }

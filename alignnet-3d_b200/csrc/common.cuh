@@ -153,7 +153,7 @@ struct PlanBf16 {
   __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
   double* red2 = nullptr;                   // [128][2]
   float* coef2 = nullptr;                   // [128][2]  m0, m1
-  __nv_bfloat16* dy1 = nullptr;             // [M, 64] row-major
+  float* l1sums = nullptr;                  // [items][64][4]: sum_p dy1 * (1, x, y, z) per item and channel
   double* red1 = nullptr;                   // [64][2]
   float* coef1 = nullptr;                   // [64][2]
 };

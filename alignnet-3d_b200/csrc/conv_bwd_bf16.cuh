@@ -553,7 +553,9 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
 
 // =============================================================================================
 // layer-2 backward: dz2 = s2 (dy2 - m0 - xhat2 m1) ; wgrad2 += a1^T dz2 ; da1 = dz2 W2^T ;
-//                   dy1 = da1 * [a1 > 0] (+ BN1 backward sums), dy1 stored row-major bf16
+//                   dy1 = da1 * [a1 > 0] (+ BN1 backward sums); dy1 itself is never stored: layer 1 is linear in
+//                   the 3 input coordinates, so its whole backward needs only sum_p dy1 * (1, x, y, z) per item and
+//                   channel (l1sums; finished by bwd_l1_finish_kernel once the BN1 coefficients are known)
 // =============================================================================================
 struct L2Params {
   const float* pcs;
@@ -570,7 +572,7 @@ struct L2Params {
   const float* b2; const float* mean2; const float* inv2; const float* s2;
   const float* coef2;                       // [128][2] m0, m1
   float* gW2;                               // [64][128]
-  __nv_bfloat16* dy1;                       // [B*N][64]
+  float* l1sums;                            // [n_items][64][4]: per item and channel sum_p dy1 * (1, x, y, z)
   double* red1;                             // [64][2]
 };
 // Two worker groups of 8 warps walk alternate items (ping-pong): while one group is in a CUDA-core phase
@@ -585,7 +587,7 @@ constexpr uint32_t kL2AccWG = 448;                             // wgrad2 accumul
 
 inline size_t l2_smem_bytes(int PC) {
   return kL2Groups * (8 + 16) * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
-         kL2Groups * 256 * 3 * 4 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
+         kL2Groups * 256 * 3 * 4 + kL2Groups * 4 * 64 * 16 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
 }
 
 struct L2Bars {
@@ -604,7 +606,8 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
   uint8_t* sW2T = smem + 48 * plane;
   uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
   float* sPtsAll = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [groups][256][3] transformed points
-  float* sW1f = sPtsAll + kL2Groups * 768;   // 192
+  float4* sRedAll = reinterpret_cast<float4*>(sPtsAll + kL2Groups * 768);   // [groups][4 parts][64]
+  float* sW1f = reinterpret_cast<float*>(sRedAll + kL2Groups * 256);   // 192
   float* sC1f = sW1f + 192;      // 64
   float* sW1 = sC1f + 64;        // 192
   float* sL1 = sW1 + 192;        // b1, mean1, inv1, gamma1, beta1 : 5 x 64
@@ -649,6 +652,8 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
     uint8_t* sA1 = sA1b[grp];
     uint8_t* sDZ = sDZb[grp];
     float* sPts = sPtsAll + grp * 768;
+    float4* sRed = sRedAll + grp * 256;
+    int prev_it = -1;
     float* xf = bars->xf[grp];
     uint32_t ph = 0;                       // all per-item barriers of the group flip once per item
     double r0 = 0.0, r1 = 0.0;
@@ -677,16 +682,21 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       const int nvalid = min(P.PC, P.N - p0);
       const int NT = (nvalid + 15) & ~15;
       const int64_t row0 = (int64_t)cloud * P.N + p0;
-      // the previous item's readers of xf / sPts are past this point only after the barrier below; xf is
-      // written by thread 0 before it, which is safe because every reader of the previous values finished
-      // its dy1 phase before arriving here (same thread order) -- sPts is rewritten after the barrier
+      // barrier A: every thread of the group is past the previous item's dy1 phase (sRed complete, sPts / xf free)
       if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (t < 64 && prev_it >= 0) {
+        const float4 a = sRed[t], b = sRed[64 + t], c = sRed[128 + t], d = sRed[192 + t];
+        reinterpret_cast<float4*>(P.l1sums)[(size_t)prev_it * 64 + t] =
+            make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
+      }
+      prev_it = it;
       if (t == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(pf_ang, &sn, &cs);
         xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
+      // barrier B: xf visible; sRed has been flushed before this item's dy1 phase rewrites it
       if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
       const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
@@ -759,7 +769,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         const int nq = ((NT >> 2) + 15) & ~15;
         const int part = (k >> 6) + 2 * half;
         const int pbeg = min(NT, part * nq), pend = part == 3 ? NT : min(NT, (part + 1) * nq);
-        float s0 = 0.f, s1 = 0.f;
+        float s0 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
           tmem_ld16(tmem + lane_base + kD + g16, r);
@@ -768,23 +778,32 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           for (int j = 0; j < 16; ++j) {
             const int p = g16 + j;
             if (p < nvalid) {
-              const float z1 = fmaf(sPts[p * 3], wx, fmaf(sPts[p * 3 + 1], wy, fmaf(sPts[p * 3 + 2], wz, b1)));
-              const float xh = (z1 - mu1) * inv1;
-              const float dy = fmaf(g1, xh, be1) > 0.f ? __uint_as_float(r[j]) : 0.f;
-              const __nv_bfloat16 hb = __float2bfloat16_rn(dy);
-              const float dyr = __bfloat162float(hb);
-              s0 += dyr;
-              s1 = fmaf(dyr, xh, s1);
-              P.dy1[(row0 + p) * 64 + k1] = hb;
+              const float x = sPts[p * 3], y = sPts[p * 3 + 1], z = sPts[p * 3 + 2];
+              const float z1 = fmaf(x, wx, fmaf(y, wy, fmaf(z, wz, b1)));
+              const float dy = fmaf(g1, (z1 - mu1) * inv1, be1) > 0.f ? __uint_as_float(r[j]) : 0.f;
+              s0 += dy;
+              sx = fmaf(dy, x, sx);
+              sy = fmaf(dy, y, sy);
+              sz = fmaf(dy, z, sz);
             }
           }
         }
-        r0 += (double)s0; r1 += (double)s1;
+        sRed[part * 64 + k1] = make_float4(s0, sx, sy, sz);
+        // BN1 backward sums: xhat is affine in (x, y, z), so sum dy*xhat follows from the four sums
+        r0 += (double)s0;
+        r1 += (double)(inv1 * (wx * sx + wy * sy + wz * sz + (b1 - mu1) * s0));
       }
       tc_fence_before();
     }
     if (n_local > 0) {
       if (grp < n_local) {
+        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (t < 64) {
+          const float4 a = sRed[t], b = sRed[64 + t], c = sRed[128 + t], d = sRed[192 + t];
+          reinterpret_cast<float4*>(P.l1sums)[(size_t)prev_it * 64 + t] =
+              make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
+        }
         atomicAdd(P.red1 + 2 * (k & 63), r0);
         atomicAdd(P.red1 + 2 * (k & 63) + 1, r1);
       }

@@ -73,6 +73,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 struct Barriers {
   uint64_t w2_full;
   uint64_t w3_full[3];
@@ -95,10 +101,13 @@ __device__ __forceinline__ void reduce_group(const uint32_t (&r)[16], int col0, 
                                              float& m) {
   float gm = -INFINITY;
   if (col0 + 16 <= nvalid) {
+    // three-input max (FMNMX3): 8 instead of 16 max instructions per group
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
-      else gm = fmaxf(gm, __uint_as_float(r[q]));
+    for (int q = 0; q < 16; q += 2) {
+      if (MODE == MODE_FULL_TRAIN)
+        gm = fmax3(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q), __uint_as_float((r[q + 1] & ~15u) | (uint32_t)(q + 1)));
+      else
+        gm = fmax3(gm, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
     }
   } else {
 #pragma unroll

@@ -173,7 +173,7 @@ def test_bf16_matches_rounding_model(name, training):
             downstream = not ("transformer1" in k or "transformer2" in k)
             d = np.abs(st[k] - v.numpy())
             if downstream:
-                assert d.mean() < 2e-2, (k, float(d.mean()), float(d.max()))
+                assert d.mean() < 5e-2, (k, float(d.mean()), float(d.max()))
             else:
                 tol = 1e-2 if "/embedding/" in k else 6e-2
                 np.testing.assert_allclose(st[k], v.numpy(), atol=tol, rtol=tol, err_msg=k)
