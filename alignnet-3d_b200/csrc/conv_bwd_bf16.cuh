@@ -331,7 +331,11 @@ struct Dg3Params {
   int B, N, PC, npc, C3, n_items, items_per_cta;
   double* red2;                  // [128][2] sum dy2, sum dy2 * xhat2
 };
-constexpr int kDg3Threads = 288;   // 4 epilogue warps, 2 scatter warps, MMA, weight loader, tile loader
+// warps 0-7 epilogue (two per TMEM lane quarter, each takes half of the point columns), warps 8-11 two scatter
+// teams (team t fills S buffer t with the odd / even 64-channel half-chunks), 12 MMA, 13 weight loader, 14 tile loader
+constexpr int kDg3Threads = 480;
+constexpr int kDg3EpiThreads = 256;
+constexpr int kDg3MmaWarp = 12;
 
 inline size_t dg3_smem_bytes(int PC) {
   return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 3 * kWHalfBytes + 3 * 128 * 4 + 256;
@@ -357,14 +361,14 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
-  const int nhc = P.C3 / 64;
+  const int nhc = P.C3 / 64;           // even: C3 is a multiple of 128
   const int nring = 2 + nhc;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_free[i], 1);
-      mbar_init(&bars->sd_full[i], 64); mbar_init(&bars->sd_empty[i], 1);
-      mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 128);
+      mbar_init(&bars->sd_full[i], 2); mbar_init(&bars->sd_empty[i], 1);      // one arrival per warp of the team
+      mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], kDg3EpiThreads / 32);
     }
     for (int i = 0; i < 3; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     fence_barrier_init();
@@ -376,17 +380,18 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     const float gm = P.gamma2[tid];
     sIg[tid] = gm != 0.f ? 1.0f / gm : 0.f;
   }
-  if (warp == 6) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == kDg3MmaWarp) tmem_alloc(&bars->tmem_base, 512);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < 4) {
-    // ---- epilogue: lane = channel k of a2 ----
-    const int k = tid;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  if (warp < 8) {
+    // ---- epilogue: lane = channel k of a2; the warp pair of a lane quarter splits the point columns ----
+    const int k = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph_d[2] = {0, 0};
     double acc0 = 0.0, acc1 = 0.0;
     const float u = sU[k], beta = sBeta[k], ig = sIg[k];
@@ -395,12 +400,14 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
       const int nvalid = min(P.PC, P.N - pchunk * P.PC);
       const int NT = (nvalid + 15) & ~15;
+      const int nh = ((NT >> 1) + 15) & ~15;
+      const int pbeg = half ? min(nh, NT) : 0, pend = half ? NT : min(nh, NT);
       const int b = li & 1;
-      mbar_wait(&bars->d_full[b], ph_d[b]); ph_d[b] ^= 1;
+      mbar_wait_relaxed(&bars->d_full[b], ph_d[b]); ph_d[b] ^= 1;
       tc_fence_after();
       uint8_t* col = sA2[b] + (k >> 3) * plane + (k & 7) * 2;
       float s0 = 0.f, s1 = 0.f;
-      for (int g16 = 0; g16 < NT; g16 += 16) {
+      for (int g16 = pbeg; g16 < pend; g16 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + b * 256 + g16, r);
         tmem_ld_wait();
@@ -420,9 +427,10 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       }
       acc0 += (double)s0; acc1 += (double)s1;
       tc_fence_before();
-      mbar_arrive(&bars->d_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d_empty[b]);
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) {
         bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, sA2[b], P.img_bytes);
         bulk_wait_read_all();
@@ -433,26 +441,29 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       atomicAdd(P.red2 + 2 * k, acc0);
       atomicAdd(P.red2 + 2 * k + 1, acc1);
     }
-  } else if (warp < 6) {
-    // ---- scatter threads (next item's arg rows / weights prefetched into registers) ----
-    const int t = tid - 128;
-    int prev_off[2] = {-1, -1};
-    uint32_t ph_e[2] = {1, 1};
-    int g = 0;
-    constexpr int kMaxHc = 16;   // C3 <= 1024
-    int cur_idx[kMaxHc], nxt_idx[kMaxHc];
-    float cur_w[kMaxHc], nxt_w[kMaxHc];
-    auto fetch = [&](int li, int (&ix)[kMaxHc], float (&wv)[kMaxHc]) {
+  } else if (warp < 12) {
+    // ---- scatter teams (next item's arg rows / weights prefetched into registers).  Team `team` owns S buffer
+    // `team` and the half-chunks hc with hc % 2 == team, so the two buffers are filled concurrently. ----
+    const int team = (warp - 8) >> 1;
+    const int t = ((warp - 8) & 1) * 32 + lane;      // channel within the 64-channel half-chunk
+    int prev_off = -1;
+    uint32_t ph_e = 1;
+    constexpr int kMaxHcT = 8;   // half-chunks per team: C3 <= 1024
+    const int nhc_t = nhc >> 1;
+    int cur_idx[kMaxHcT], nxt_idx[kMaxHcT];
+    float cur_w[kMaxHcT], nxt_w[kMaxHcT];
+    auto fetch = [&](int li, int (&ix)[kMaxHcT], float (&wv)[kMaxHcT]) {
       const int cloud = (it_begin + li) / P.npc;
 #pragma unroll
-      for (int hc = 0; hc < kMaxHc; ++hc) {
-        if (hc < nhc) {
-          const int c = hc * 64 + t;
-          ix[hc] = P.gidx[(size_t)cloud * P.C3 + c];
-          wv[hc] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+      for (int h = 0; h < kMaxHcT; ++h) {
+        if (h < nhc_t) {
+          const int c = (2 * h + team) * 64 + t;
+          ix[h] = P.gidx[(size_t)cloud * P.C3 + c];
+          wv[h] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
         }
       }
     };
+    uint8_t* sS = sSd[team];
     if (n_local > 0) fetch(0, cur_idx, cur_w);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
@@ -461,31 +472,30 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       const int nvalid = min(P.PC, P.N - p0);
       if (li + 1 < n_local) fetch(li + 1, nxt_idx, nxt_w);
 #pragma unroll
-      for (int hc = 0; hc < kMaxHc; ++hc) {
-        if (hc >= nhc) break;
-        const int sb = g & 1;
-        mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
-        if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
-        const int row = cur_idx[hc] - p0;
-        const float w = cur_w[hc];
+      for (int h = 0; h < kMaxHcT; ++h) {
+        if (h >= nhc_t) break;
+        mbar_wait(&bars->sd_empty[team], ph_e); ph_e ^= 1;
+        if (prev_off >= 0) *reinterpret_cast<__nv_bfloat16*>(sS + prev_off) = __float2bfloat16_rn(0.f);
+        const int row = cur_idx[h] - p0;
+        const float w = cur_w[h];
         if (row >= 0 && row < nvalid && w != 0.f) {
           const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
-          prev_off[sb] = off;
+          *reinterpret_cast<__nv_bfloat16*>(sS + off) = __float2bfloat16_rn(w);
+          prev_off = off;
         } else {
-          prev_off[sb] = -1;
+          prev_off = -1;
         }
         fence_proxy_async_smem();
-        mbar_arrive(&bars->sd_full[sb]);
-        ++g;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->sd_full[team]);
       }
 #pragma unroll
-      for (int hc = 0; hc < kMaxHc; ++hc) { cur_idx[hc] = nxt_idx[hc]; cur_w[hc] = nxt_w[hc]; }
+      for (int h = 0; h < kMaxHcT; ++h) { cur_idx[h] = nxt_idx[h]; cur_w[h] = nxt_w[h]; }
     }
-  } else if (warp == 6) {
+  } else if (warp == kDg3MmaWarp) {
     if (n_local > 0) {
       uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0}, ph_w[3] = {0, 0, 0}, ph_de[2] = {1, 1};
-      int g = 0, wq = 0;
+      int wq = 0;
       for (int li = 0; li < n_local; ++li) {
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -506,7 +516,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           if (r < 2) {
             b_base = smem_u32(sA2[b]) + r * 8 * plane;
           } else {
-            sb = g & 1;
+            sb = (r - 2) & 1;
             mbar_wait(&bars->sd_full[sb], ph_sd[sb]); ph_sd[sb] ^= 1;
             b_base = smem_u32(sSd[sb]);
           }
@@ -515,20 +525,20 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           for (int ks = 0; ks < 4; ++ks)
             mma_bf16(d_tmem, make_desc(a_base + ks * 2 * kPlaneW, kPlaneW, 128), make_desc(b_base + ks * 2 * plane, plane, 128),
                      idesc, (r > 0 || ks > 0) ? 1u : 0u);
-          if (r >= 2) { mma_commit(&bars->sd_empty[sb]); ++g; }
+          if (r >= 2) mma_commit(&bars->sd_empty[sb]);
           mma_commit(&bars->w_empty[st]);
         }
         mma_commit(&bars->d_full[b]);
       }
     }
-  } else if (warp == 7) {
+  } else if (warp == kDg3MmaWarp + 1) {
     if (lane == 0 && n_local > 0) {
       uint32_t ph_e[3] = {1, 1, 1};
       int wq = 0;
       for (int li = 0; li < n_local; ++li) {
         for (int r = 0; r < nring; ++r, ++wq) {
           const int st = wq % 3;
-          mbar_wait(&bars->w_empty[st], ph_e[st]); ph_e[st] ^= 1;
+          mbar_wait_relaxed(&bars->w_empty[st], ph_e[st]); ph_e[st] ^= 1;
           mbar_arrive_expect_tx(&bars->w_full[st], kWHalfBytes);
           const __nv_bfloat16* src = r < 2 ? P.gq_img + (size_t)r * 8192 : P.w3n_img + (size_t)(r - 2) * 8192;
           bulk_copy_g2s(sW + (size_t)st * kWHalfBytes, src, kWHalfBytes, &bars->w_full[st]);
@@ -540,7 +550,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       uint32_t ph_f[2] = {1, 1};
       for (int li = 0; li < n_local; ++li) {
         const int b = li & 1;
-        mbar_wait(&bars->a2_free[b], ph_f[b]); ph_f[b] ^= 1;
+        mbar_wait_relaxed(&bars->a2_free[b], ph_f[b]); ph_f[b] ^= 1;
         mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
         bulk_copy_g2s(sA2[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
       }
@@ -548,7 +558,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem, 512);
+  if (warp == kDg3MmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
