@@ -187,35 +187,37 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
 }
 
 // dOh[:, :3] = dpred_t ; dOh[:, 3:] = drem ; dc2[0] = ds2c1 - dpred_t ; dc2[1] = ds2c2 + dpred_t  (tp8.py:155)
+// (one warp per sample)
 __global__ void assemble_head_grad_kernel(const float* dend, float* dOh, float* dc2a, float* dc2b, int B, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* ds2c1 = dend + (int64_t)2 * B * 3;
   const float* ds2c2 = dend + (int64_t)3 * B * 3;
   const float* dpt = dend + (int64_t)4 * B * 3;
   const float* drem = dend + (int64_t)5 * B * 3 + (int64_t)2 * B * 2 * nb;
   float* o = dOh + (int64_t)b * (3 + 2 * nb);
-  for (int d = 0; d < 3; ++d) {
-    const float g = dpt[b * 3 + d];
-    o[d] = g;
-    dc2a[b * 3 + d] = ds2c1[b * 3 + d] - g;
-    dc2b[b * 3 + d] = ds2c2[b * 3 + d] + g;
+  if (lane < 3) {
+    const float g = dpt[b * 3 + lane];
+    o[lane] = g;
+    dc2a[b * 3 + lane] = ds2c1[b * 3 + lane] - g;
+    dc2b[b * 3 + lane] = ds2c2[b * 3 + lane] + g;
   }
-  for (int j = 0; j < 2 * nb; ++j) o[3 + j] = drem[(int64_t)b * 2 * nb + j];
+  for (int j = lane; j < 2 * nb; j += 32) o[3 + j] = drem[(int64_t)b * 2 * nb + j];
 }
 
 // dO2[:, :3] = dc2 ; dO2[:, 3:] = dlg (+ dang*pi/nb at nb+k, tp8.py:298) ; dc1 = ds1c + dc2  (tp8.py:109,117)
 __global__ void assemble_s2_grad_kernel(const float* dlg, const float* dc2, const float* dang, const int32_t* angk,
                                         const float* ds1c, float* dO2, float* dc1, int B, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   float* o = dO2 + (int64_t)b * (3 + 2 * nb);
-  for (int d = 0; d < 3; ++d) {
-    o[d] = dc2[b * 3 + d];
-    dc1[b * 3 + d] = ds1c[b * 3 + d] + dc2[b * 3 + d];
+  if (lane < 3) {
+    o[lane] = dc2[b * 3 + lane];
+    dc1[b * 3 + lane] = ds1c[b * 3 + lane] + dc2[b * 3 + lane];
   }
-  for (int j = 0; j < 2 * nb; ++j) o[3 + j] = dlg[(int64_t)b * 2 * nb + j];
-  o[3 + nb + angk[b]] += dang[b] * (3.14159265358979323846f / (float)nb);
+  const int kk = nb + angk[b];
+  const float extra = dang[b] * (3.14159265358979323846f / (float)nb);
+  for (int j = lane; j < 2 * nb; j += 32) o[3 + j] = dlg[(int64_t)b * 2 * nb + j] + (j == kk ? extra : 0.f);
 }
 
 }  // namespace
@@ -239,7 +241,7 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
   AN3D_CUDA_CHECK(cudaMemsetAsync(grads, 0, sizeof(float) * m.n_trainable, st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));
-  const unsigned b_blocks = (unsigned)((B + 127) / 128);
+  const unsigned w_blocks = (unsigned)((B + 3) / 4);   // one warp per sample
   const float* masks[5];
   for (int i = 0; i < 5; ++i) {
     const int s = i < 2 ? S1 : (i < 4 ? S2 : HEAD);
@@ -247,7 +249,7 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
   }
   const int c_emb = m.conv[EMB].back().cout;
   // head
-  assemble_head_grad_kernel<<<b_blocks, 128, 0, st>>>(p.dend, p.dout, p.dc2[0], p.dc2[1], B, nb);
+  assemble_head_grad_kernel<<<w_blocks, 128, 0, st>>>(p.dend, p.dout, p.dc2[0], p.dc2[1], B, nb);
   AN3D_LAUNCH_CHECK();
   AN3D_TRY(mlp_backward(m, p, HEAD, 0, p.feat, 2 * c_emb, p.dout, params, grads, p.dfeat, 2 * c_emb, masks[4], st));
   const float* dlg[2] = {p.dend + (int64_t)5 * B * 3, p.dend + (int64_t)5 * B * 3 + (int64_t)B * 2 * nb};
@@ -264,7 +266,7 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
       AN3D_LAUNCH_CHECK();
     }
     // stage 2
-    assemble_s2_grad_kernel<<<b_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], p.dout,
+    assemble_s2_grad_kernel<<<w_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], p.dout,
                                                       p.dc1[br], B, nb);
     AN3D_LAUNCH_CHECK();
     const int c2w = m.conv[S2].back().cout;

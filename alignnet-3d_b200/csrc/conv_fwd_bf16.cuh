@@ -22,7 +22,8 @@ namespace convfwd {
 
 using namespace umma;
 
-constexpr int kThreads = 448;          // 4 back-end + 4 front-end warps, MMA warp, loader warp, 4 more back-end warps
+constexpr int kThreads = 576;          // warps 0-3 / 10-13 back-end, 4-7 / 14-17 front-end, 8 MMA, 9 weight loader
+constexpr int kFrontThreads = 256;
 constexpr int kMaxPC = 256;            // points per item
 constexpr uint32_t kW2Bytes = 128 * 64 * 2;
 constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
@@ -148,10 +149,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   if (tid == 0) {
     mbar_init(&bars->w2_full, 1);
     for (int i = 0; i < 3; ++i) { mbar_init(&bars->w3_full[i], 1); mbar_init(&bars->w3_empty[i], 1); }
-    mbar_init(&bars->a1_full, 128);
+    mbar_init(&bars->a1_full, kFrontThreads);
     mbar_init(&bars->d2_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a2_full[i], 128);
+      mbar_init(&bars->a2_full[i], kFrontThreads);
       mbar_init(&bars->a2_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1);
       mbar_init(&bars->acc_empty[i], 256);
@@ -168,16 +169,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp >= 4 && warp < 8) {
+  if ((warp >= 4 && warp < 8) || warp >= 14) {
     // ================================ front-end ================================
-    const int f = tid - 128;                       // 0..127: point slot (layer 1) / channel (layer-2 epilogue)
+    // 8 warps: layer 1 with one thread per point; layer-2 epilogue with two warps per TMEM lane quarter, each
+    // taking half of the point columns.  (The front end, not the tensor pipe, paces the narrow stages.)
+    const int fgroup = warp >= 14 ? 1 : 0;
+    const int k = (warp & 3) * 32 + lane;          // channel of the layer-2 epilogue (TMEM lane)
+    const int f = fgroup * 128 + k;                // 0..255: point slot of layer 1
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
     double st_s = 0.0, st_ss = 0.0, st_a2 = 0.0;
     const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
-    // register prefetch of the next item's transform (thread 0) and points (threads own points f, f+128):
+    // register prefetch of the next item's transform (thread 0) and point (thread f owns point f):
     // the global-load latency is paid behind the current item's work instead of in front of a barrier
-    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[2][3];
+    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
     auto prefetch = [&](int li) {
       const int it = it_begin + li;
       const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -188,13 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         pf_c[0] = P.center[cloud * 3]; pf_c[1] = P.center[cloud * 3 + 1]; pf_c[2] = P.center[cloud * 3 + 2];
         pf_ang = P.angle ? P.angle[cloud] : 0.f;
       }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int p = f + 128 * h;
-        if (p < nvalid) {
-          const float* src = P.pcs + (row0 + p) * 3;
-          pf_p[h][0] = src[0]; pf_p[h][1] = src[1]; pf_p[h][2] = src[2];
-        }
+      if (f < nvalid) {
+        const float* src = P.pcs + (row0 + f) * 3;
+        pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
       }
     };
     if (n_local > 0) prefetch(0);
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int p0 = pchunk * P.PC;
       const int nvalid = min(P.PC, P.N - p0);
       const int NT = (nvalid + 15) & ~15;
-      const int64_t row0 = (int64_t)cloud * P.N + p0;
       const int b = li & 1;
+      (void)cloud;
       if (MODE != MODE_STATS2 && li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
@@ -216,21 +217,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         float* xf = bars->xf + (li & 1) * 8;
         xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* xfr = bars->xf + (li & 1) * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
-      float cur_p[2][3];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) { cur_p[h][0] = pf_p[h][0]; cur_p[h][1] = pf_p[h][1]; cur_p[h][2] = pf_p[h][2]; }
+      const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
       if (li + 1 < n_local) prefetch(li + 1);
-      (void)row0;
       // ---- layer 1: y = relu(W1f^T p' + c1f), one thread per point, 8 channels per 16-byte chunk
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int p = f + 128 * hh;
-        if (p >= NT) continue;
+      if (f < NT) {
+        const int p = f;
         if (p < nvalid) {
-          const float x0 = cur_p[hh][0] - cx, y0 = cur_p[hh][1] - cy, z = cur_p[hh][2] - cz;
+          const float x0 = cur_p[0] - cx, y0 = cur_p[1] - cy, z = cur_p[2] - cz;
           const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
@@ -252,14 +248,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
-      // ---- layer-2 epilogue: channel k = f
+      // ---- layer-2 epilogue: channel k, point columns [pbeg, pend)
       mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
       tc_fence_after();
-      const int k = f;
       const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
       uint8_t* dst = sA2[b] + (k >> 3) * plane2 + (k & 7) * 2;
       float ts = 0.f, tss = 0.f, ta2 = 0.f;
-      for (int g16 = 0; g16 < NT; g16 += 16) {
+      const int nh = min(NT, ((NT >> 1) + 15) & ~15);
+      const int pbeg = fgroup ? nh : 0, pend = fgroup ? NT : nh;
+      for (int g16 = pbeg; g16 < pend; g16 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
         tmem_ld_wait();
@@ -285,18 +282,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         fence_proxy_async_smem();
         mbar_arrive(&bars->a2_full[b]);
         if (save_a2) {
-          asm volatile("bar.sync 2, 128;" ::: "memory");      // every front-end thread has written + fenced
+          asm volatile("bar.sync 2, 256;" ::: "memory");      // every front-end thread has written + fenced
           if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, sA2[b], a2_bytes);
         }
       }
     }
     if (save_a2 && f == 0) bulk_wait_read_all();
-    if (MODE == MODE_FULL_TRAIN && P.sa2 && n_local > 0) atomicAdd(P.sa2 + f, st_a2);
+    if (MODE == MODE_FULL_TRAIN && P.sa2 && n_local > 0) atomicAdd(P.sa2 + k, st_a2);
     if (MODE == MODE_STATS2 && n_local > 0) {
-      atomicAdd(P.stats2 + 2 * f, st_s);
-      atomicAdd(P.stats2 + 2 * f + 1, st_ss);
+      atomicAdd(P.stats2 + 2 * k, st_s);
+      atomicAdd(P.stats2 + 2 * k + 1, st_ss);
     }
-  } else if (warp < 4 || warp >= 10) {
+  } else if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ================================ back-end =================================
     // two warps per TMEM lane quarter (warps w and w+10 with equal w%4): the 16-column groups of every
     // accumulator half are dealt alternately to the two, which halves the latency of draining a half --

@@ -192,7 +192,7 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   float* c2[2] = {out->pred_s2_pc1centers, out->pred_s2_pc2centers};
   float* lg[2] = {out->pred_pc1angle_logits, out->pred_pc2angle_logits};
   const unsigned pt_blocks = (unsigned)((M + 255) / 256);
-  const unsigned b_blocks = (unsigned)((B + 127) / 128);
+  const unsigned w_blocks = (unsigned)((B + 3) / 4);   // one warp per sample
   for (int br = 0; br < 2; ++br) {
     centroid_kernel<<<(B + 3) / 4, 128, 0, st>>>(pcs[br], N, p.mu[br], B);
     AN3D_LAUNCH_CHECK();
@@ -218,7 +218,7 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
     }
     AN3D_TRY(mlp_forward(m, p, S2, br, p.g[S2][br], m.conv[S2].back().cout, params, state, training, bn_decay,
                          masks[2 + br], st));
-    post_s2_kernel<<<b_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
+    post_s2_kernel<<<w_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
                                              p.angk[br], B, nb);
     AN3D_LAUNCH_CHECK();
     // canonicalise + final embedding (tp8.py:122-130)
@@ -233,7 +233,7 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   // head (tp8.py:144-156)
   AN3D_TRY(mlp_forward(m, p, HEAD, 0, p.feat, 2 * m.conv[EMB].back().cout, params, state, training, bn_decay, masks[4],
                        st));
-  post_head_kernel<<<b_blocks, 128, 0, st>>>(p.fz[HEAD][m.fc[HEAD].size() - 1][0], c2[0], c2[1], out->pred_translations,
+  post_head_kernel<<<w_blocks, 128, 0, st>>>(p.fz[HEAD][m.fc[HEAD].size() - 1][0], c2[0], c2[1], out->pred_translations,
                                              out->pred_remaining_angle_logits, B, nb);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;

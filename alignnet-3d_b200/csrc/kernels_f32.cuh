@@ -303,28 +303,43 @@ __device__ __forceinline__ float decode_angle_scaled(const float* lg, int nb, in
   return floor_mod(a + pi, 2.0f * pi) - pi;
 }
 
-// o2 [B,3+2nb] -> c2 = o2[:, :3] + c1 (tp8.py:117), logits copy (:118), decoded yaw (:123)
+// o2 [B,3+2nb] -> c2 = o2[:, :3] + c1 (tp8.py:117), logits copy (:118), decoded yaw (:123).  One warp per sample:
+// coalesced copy, arg-max by shuffles with tf.argmax's first-maximum tie rule.
 static __global__ void post_s2_kernel(const float* o2, const float* c1, float* c2, float* logits, float* ang, int32_t* angk,
                                int B, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* o = o2 + (int64_t)b * (3 + 2 * nb);
-  for (int d = 0; d < 3; ++d) c2[b * 3 + d] = o[d] + c1[b * 3 + d];
   float* lg = logits + (int64_t)b * 2 * nb;
-  for (int j = 0; j < 2 * nb; ++j) lg[j] = o[3 + j];
-  int k;
-  ang[b] = decode_angle_scaled(o + 3, nb, &k);
-  angk[b] = k;
+  float best = -INFINITY;
+  int k = 0x7fffffff;
+  for (int j = lane; j < 2 * nb; j += 32) {
+    const float v = o[3 + j];
+    lg[j] = v;
+    if (j < nb && (v > best || k == 0x7fffffff)) { best = v; k = j; }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const float vo = __shfl_xor_sync(0xffffffffu, best, off);
+    const int ko = __shfl_xor_sync(0xffffffffu, k, off);
+    if (ko != 0x7fffffff && (k == 0x7fffffff || vo > best || (vo == best && ko < k))) { best = vo; k = ko; }
+  }
+  if (lane < 3) c2[b * 3 + lane] = o[lane] + c1[b * 3 + lane];
+  if (lane == 0) {
+    const float pi = 3.14159265358979323846f;
+    const float a = (float)k * (2.0f * pi / (float)nb) + o[3 + nb + k] * (pi / (float)nb);
+    ang[b] = floor_mod(a + pi, 2.0f * pi) - pi;
+    angk[b] = k;
+  }
 }
 
 // head out [B,3+2nb] -> pred_translations = o[:, :3] + (c2_2 - c2_1) (tp8.py:155), remaining logits (:156)
 static __global__ void post_head_kernel(const float* o, const float* c2a, const float* c2b, float* pred_t, float* rem, int B,
                                  int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* r = o + (int64_t)b * (3 + 2 * nb);
-  for (int d = 0; d < 3; ++d) pred_t[b * 3 + d] = r[d] + (c2b[b * 3 + d] - c2a[b * 3 + d]);
-  for (int j = 0; j < 2 * nb; ++j) rem[(int64_t)b * 2 * nb + j] = r[3 + j];
+  if (lane < 3) pred_t[b * 3 + lane] = r[lane] + (c2b[b * 3 + lane] - c2a[b * 3 + lane]);
+  for (int j = lane; j < 2 * nb; j += 32) rem[(int64_t)b * 2 * nb + j] = r[3 + j];
 }
 
 // Counter-based keep mask (splitmix64 hash of (seed, site, element)); value 1 with prob keep.

@@ -129,48 +129,44 @@ __global__ void loss_sample_kernel(LossScratch s, SampleArgs a) {
 
 // pairwise residual loss: S_j = sum_i huber(pred_j - label_ij), G_j = sum_i huber'(.)
 __global__ void loss_pair_kernel(LossScratch s, int B, int nb, int ichunk) {
+  __shared__ double sm[8];
   const int iv = blockIdx.z, inst = iv >> 1, v = iv & 1;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = blockIdx.y * ichunk, i1 = min(B, i0 + ichunk);
-  if (j >= B) return;
-  const float pred = s.pred[iv * B + j];
   float S = 0.f, G = 0.f;
-  if (inst < 2) {
-    const float* lab = s.lab + iv * B;
-    for (int i = i0; i < i1; ++i) {
-      const float d = pred - lab[i];
-      S += huber(d, 1.0f);
-      G += fminf(fmaxf(d, -1.0f), 1.0f);
+  if (j < B) {
+    const float pred = s.pred[iv * B + j];
+    if (inst < 2) {
+      const float* lab = s.lab + iv * B;
+      for (int i = i0; i < i1; ++i) {
+        const float d = pred - lab[i];
+        S += huber(d, 1.0f);
+        G += fminf(fmaxf(d, -1.0f), 1.0f);
+      }
+    } else {
+      const float pd = s.pd[j];
+      const float scale = kPi / (float)nb;
+      for (int i = i0; i < i1; ++i) {
+        float t = s.gt3[i] - pd;
+        if (v) t = t + kPi;
+        int cls;
+        float res;
+        angle2class(t, nb, &cls, &res);
+        const float d = pred - res / scale;
+        S += huber(d, 1.0f);
+        G += fminf(fmaxf(d, -1.0f), 1.0f);
+      }
     }
-  } else {
-    const float pd = s.pd[j];
-    const float scale = kPi / (float)nb;
-    for (int i = i0; i < i1; ++i) {
-      float t = s.gt3[i] - pd;
-      if (v) t = t + kPi;
-      int cls;
-      float res;
-      angle2class(t, nb, &cls, &res);
-      const float d = pred - res / scale;
-      S += huber(d, 1.0f);
-      G += fminf(fmaxf(d, -1.0f), 1.0f);
-    }
+    atomicAdd(s.G + iv * B + j, (double)G);
   }
-  atomicAdd(s.S + iv * B + j, (double)S);
-  atomicAdd(s.G + iv * B + j, (double)G);
+  // the loss value only needs sum_j S_j: one reduction per block instead of a [B] vector summed later
+  const double tot = block_sum((double)S, sm);
+  if (threadIdx.x == 0) atomicAdd(s.sums + 16 + iv, tot);
 }
 
 __global__ void loss_final_kernel(LossScratch s, float* loss_out, int B, float esf, float af, int accept_inverted) {
-  __shared__ double sm[8];
-  __shared__ double res_sum[6];
-  for (int iv = 0; iv < 6; ++iv) {
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < B; j += blockDim.x) acc += s.S[iv * B + j];
-    const double tot = block_sum(acc, sm);
-    if (threadIdx.x == 0) res_sum[iv] = tot;
-  }
-  __syncthreads();
   if (threadIdx.x != 0) return;
+  const double* res_sum = s.sums + 16;
   const double invB = 1.0 / B, inv3B = 1.0 / (3.0 * B);
   float total[3], clsl[3], resl[3];
   for (int inst = 0; inst < 3; ++inst) {
@@ -245,7 +241,7 @@ __global__ void loss_grad_kernel(LossScratch s, const float* lg1, const float* l
 LossScratch carve_loss_scratch(float* base, int B) {
   LossScratch s;
   char* p = reinterpret_cast<char*>(base);
-  s.sums = reinterpret_cast<double*>(p); p += 16 * sizeof(double);
+  s.sums = reinterpret_cast<double*>(p); p += 24 * sizeof(double);
   s.S = reinterpret_cast<double*>(p); p += 6 * (int64_t)B * sizeof(double);
   s.G = reinterpret_cast<double*>(p); p += 6 * (int64_t)B * sizeof(double);
   s.pd = reinterpret_cast<float*>(p); p += (int64_t)B * sizeof(float);
@@ -266,7 +262,7 @@ int run_loss(const Model& m, const an3d_labels* lb, const an3d_outputs* out, int
              float* dend, cudaStream_t st) {
   const int nb = m.nb;
   LossScratch s = carve_loss_scratch(scratch, B);
-  AN3D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (16 + 12 * (int64_t)B) * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (24 + 12 * (int64_t)B) * sizeof(double), st));
   const int tb = 128, nblk = (B + tb - 1) / tb;
   loss_angles_kernel<<<nblk, tb, 0, st>>>(s, out->pred_pc1angle_logits, out->pred_pc2angle_logits, lb->pc1_angles,
                                           lb->pc2_angles, B, nb);
@@ -289,7 +285,7 @@ int run_loss(const Model& m, const an3d_labels* lb, const an3d_outputs* out, int
   dim3 grid(nblk, (B + ichunk - 1) / ichunk, 6);
   loss_pair_kernel<<<grid, tb, 0, st>>>(s, B, nb, ichunk);
   AN3D_LAUNCH_CHECK();
-  loss_final_kernel<<<1, 256, 0, st>>>(s, loss_out, B, m.arch.early_stage_factor, m.arch.angle_factor,
+  loss_final_kernel<<<1, 32, 0, st>>>(s, loss_out, B, m.arch.early_stage_factor, m.arch.angle_factor,
                                        m.arch.accept_inverted_angle);
   AN3D_LAUNCH_CHECK();
   if (dend) {

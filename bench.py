@@ -32,6 +32,11 @@ WORKLOADS = {
     # BASELINE.json configs[2]: SynthCarsPersons synthetic B=4096, 200 pts, bf16, fwd+bwd training step
     "c3": dict(name="c3: SynthCarsPersons-shaped synthetic B=4096 N=200 bf16 fwd+bwd+Adam training step", B=4096,
                N=200, train=True, persons=0.2),
+    # BASELINE.json configs[3] / [4], per-GPU shard (global batch 8192 / 16384 over 4 / 8 GPUs = 2048 per GPU)
+    "c4": dict(name="c4: KITTITrackletsCars-shaped synthetic B=2048/GPU N=512 bf16 fwd+bwd+Adam (+ grad all-reduce)",
+               B=2048, N=512, train=True, persons=0.0),
+    "c5": dict(name="c5: KITTITrackletsCarsHard-shaped synthetic B=2048/GPU N=1024 bf16 fwd+bwd+Adam (+ grad all-reduce)",
+               B=2048, N=1024, train=True, persons=0.0),
 }
 DEFAULT_WORKLOAD = "c3"
 

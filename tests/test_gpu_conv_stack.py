@@ -24,7 +24,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("stage,branch,B,N,rotate", [(0, 0, 16, 200, False), (1, 1, 8, 64, False), (2, 0, 12, 200, True),
-                                                     (2, 1, 3, 450, True), (1, 0, 150, 24, False)])
+                                                     (2, 1, 3, 450, True), (1, 0, 150, 24, False),
+                                                     (2, 0, 4, 512, True), (0, 1, 3, 1024, False)])   # c4 / c5 cloud sizes
 def test_conv_stack_fwd_bwd(stage, branch, B, N, rotate):
     import __graft_entry__ as ge
     ge.build()
