@@ -98,7 +98,7 @@ struct Barriers {
 // index in the low mantissa bits: the column-in-group (an immediate) goes into the low 4 bits of every
 // element, the group's base index is spliced in only if the group wins.
 template <int MODE>
-__device__ __forceinline__ void reduce_group(const uint32_t (&r)[16], int col0, int nvalid, int p0, uint32_t idx_mask,
+__device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nvalid, int p0, uint32_t idx_mask,
                                              float& m) {
   float gm = -INFINITY;
   if (col0 + 16 <= nvalid) {
@@ -349,9 +349,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   } else if (warp == 8) {
     // ================================ MMA issuer (whole warp, one elected lane issues) ===============
     if (n_local > 0) {
-      uint32_t ph_a1 = 0, ph_a2f[2] = {0, 0}, ph_w3f[3] = {0, 0, 0}, ph_acce[2] = {1, 1};
-      uint32_t wcount = 0;
+      // phase bits live in scalar registers (dynamically indexed arrays would go to local memory); every group
+      // of MMAs and its commits is issued from one elected region with descriptors derived by constant increments
+      uint32_t ph_a1 = 0, ph_a2f = 0, ph_w3f = 0, ph_acce0 = 1, ph_acce1 = 1;
+      int stage = 0;
       mbar_wait(&bars->w2_full, 0);
+      const uint64_t w2_desc = make_desc(smem_u32(sW2), kPlaneW2, 128);
       auto issue_l2 = [&](int li) {
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
@@ -359,13 +362,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         const int NT = (nvalid + 15) & ~15;
         mbar_wait(&bars->a1_full, ph_a1); ph_a1 ^= 1;
         tc_fence_after();
-        const uint32_t idesc = make_idesc(128, NT, 0, 0);
-        const uint32_t a_base = smem_u32(sW2), b_base = smem_u32(sA2[li & 1]);
+        if (elect_one()) {
+          const uint32_t idesc = make_idesc(128, NT, 0, 0);
+          const uint64_t bd = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_bf16(tmem + kTmemD2, make_desc(a_base + ks * 2 * kPlaneW2, kPlaneW2, 128),
-                   make_desc(b_base + ks * 2 * plane1, plane1, 128), idesc, ks > 0);
-        mma_commit(&bars->d2_full);
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_raw(tmem + kTmemD2, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd, ks * 2 * plane1), idesc,
+                         ks > 0);
+          mma_commit_raw(&bars->d2_full);
+        }
+        __syncwarp();
       };
       issue_l2(0);
       for (int li = 0; li < n_local; ++li) {
@@ -379,30 +385,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         const int NT = (nvalid + 15) & ~15;
         int N0 = ((NT >> 1) + 15) & ~15;
         if (N0 > NT) N0 = NT;
-        const int Nh[2] = {N0, NT - N0};
+        const int N1 = NT - N0;
         const int b = li & 1;
-        mbar_wait(&bars->a2_full[b], ph_a2f[b]); ph_a2f[b] ^= 1;
+        mbar_wait(&bars->a2_full[b], (ph_a2f >> b) & 1u); ph_a2f ^= 1u << b;
         tc_fence_after();
-        const uint32_t b_base = smem_u32(sA2[b]);
+        const uint64_t b0_desc = make_desc(smem_u32(sA2[b]), plane2, 128);
+        const uint64_t b1_desc = desc_advance(b0_desc, N0 * 16);
+        const uint32_t idesc0 = make_idesc(128, N0, 0, 0), idesc1 = make_idesc(128, N1 > 0 ? N1 : 16, 0, 0);
+        bool l2_pending = li + 1 < n_local;
         for (int j = 0; j < P.nchunk; ++j) {
-          const int stage = wcount % P.nstages;
-          mbar_wait(&bars->w3_full[stage], ph_w3f[stage]); ph_w3f[stage] ^= 1;
-          const uint32_t a_base = smem_u32(sW3 + (size_t)stage * kW3ChunkBytes);
-          for (int h = 0; h < 2; ++h) {
-            if (Nh[h] == 0) continue;
-            mbar_wait(&bars->acc_empty[h], ph_acce[h]); ph_acce[h] ^= 1;
-            tc_fence_after();
-            const uint32_t idesc = make_idesc(128, Nh[h], 0, 0);
-            const uint32_t bh = b_base + (h ? N0 : 0) * 16;
+          mbar_wait(&bars->w3_full[stage], (ph_w3f >> stage) & 1u); ph_w3f ^= 1u << stage;
+          const uint64_t a_desc = make_desc(smem_u32(sW3 + (size_t)stage * kW3ChunkBytes), kPlaneW2, 128);
+          mbar_wait(&bars->acc_empty[0], ph_acce0); ph_acce0 ^= 1;
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_bf16(tmem + (h ? kTmemAcc1 : kTmemAcc0), make_desc(a_base + ks * 2 * kPlaneW2, kPlaneW2, 128),
-                       make_desc(bh + ks * 2 * plane2, plane2, 128), idesc, ks > 0);
-            mma_commit(&bars->acc_full[h]);
+              mma_bf16_raw(tmem + kTmemAcc0, desc_advance(a_desc, ks * 2 * kPlaneW2), desc_advance(b0_desc, ks * 2 * plane2),
+                           idesc0, ks > 0);
+            mma_commit_raw(&bars->acc_full[0]);
+          }
+          __syncwarp();
+          if (N1 > 0) {
+            mbar_wait(&bars->acc_empty[1], ph_acce1); ph_acce1 ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_bf16_raw(tmem + kTmemAcc1, desc_advance(a_desc, ks * 2 * kPlaneW2),
+                             desc_advance(b1_desc, ks * 2 * plane2), idesc1, ks > 0);
+              mma_commit_raw(&bars->acc_full[1]);
+            }
+            __syncwarp();
           }
           mma_commit(&bars->w3_empty[stage]);
-          ++wcount;
-          if (j == 0 && li + 1 < n_local) issue_l2(li + 1);
+          if (++stage == P.nstages) stage = 0;
+          // layer 2 of the NEXT item as soon as its A1 tile is ready -- probed without blocking after every chunk
+          // (the front end starts that tile only when this item's A2 tile is done, so a blocking wait after
+          // chunk 0 would stall this item's remaining chunks behind the front end); forced after the last chunk
+          if (l2_pending && (j == P.nchunk - 1 || __all_sync(0xffffffffu, mbar_try_wait(&bars->a1_full, ph_a1)))) {
+            issue_l2(li + 1);
+            l2_pending = false;
+          }
         }
         mma_commit(&bars->a2_empty[b]);
       }
