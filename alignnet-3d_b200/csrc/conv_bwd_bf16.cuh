@@ -494,41 +494,50 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     }
   } else if (warp == kDg3MmaWarp) {
     if (n_local > 0) {
-      uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0}, ph_w[3] = {0, 0, 0}, ph_de[2] = {1, 1};
-      int wq = 0;
+      // phase bits in scalar registers (dynamically indexed arrays would live in local memory), ring position by
+      // compare-and-reset, each ring step's four MMAs and commits issued from one elected region: the scalar
+      // instruction stream of this warp, not the tensor pipe, used to pace the kernel.
+      uint32_t ph_a2 = 0, ph_sd = 0, ph_w = 0, ph_de = 3;
+      int st = 0;
+      const uint32_t w_base = smem_u32(sW);
       for (int li = 0; li < n_local; ++li) {
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
         const int NT = (nvalid + 15) & ~15;
         const int b = li & 1;
-        mbar_wait(&bars->a2_full[b], ph_a2[b]); ph_a2[b] ^= 1;
-        mbar_wait(&bars->d_empty[b], ph_de[b]); ph_de[b] ^= 1;
+        (void)cloud;
+        mbar_wait(&bars->a2_full[b], (ph_a2 >> b) & 1u); ph_a2 ^= 1u << b;
+        mbar_wait(&bars->d_empty[b], (ph_de >> b) & 1u); ph_de ^= 1u << b;
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
         const uint32_t d_tmem = tmem + b * 256;
-        for (int r = 0; r < nring; ++r, ++wq) {
-          const int st = wq % 3;
-          mbar_wait(&bars->w_full[st], ph_w[st]); ph_w[st] ^= 1;
-          const uint32_t a_base = smem_u32(sW + (size_t)st * kWHalfBytes);
-          uint32_t b_base;
-          int sb = 0;
+        const uint64_t a2_desc = make_desc(smem_u32(sA2[b]), plane, 128);
+        const uint64_t sd_desc0 = make_desc(smem_u32(sSd[0]), plane, 128), sd_desc1 = make_desc(smem_u32(sSd[1]), plane, 128);
+        for (int r = 0; r < nring; ++r) {
+          mbar_wait(&bars->w_full[st], (ph_w >> st) & 1u); ph_w ^= 1u << st;
+          const uint64_t a_desc = make_desc(w_base + (uint32_t)st * kWHalfBytes, kPlaneW, 128);
+          uint64_t b_desc;
+          const int sb = r & 1;
           if (r < 2) {
-            b_base = smem_u32(sA2[b]) + r * 8 * plane;
+            b_desc = desc_advance(a2_desc, r * 8 * plane);
           } else {
-            sb = (r - 2) & 1;
-            mbar_wait(&bars->sd_full[sb], ph_sd[sb]); ph_sd[sb] ^= 1;
-            b_base = smem_u32(sSd[sb]);
+            mbar_wait(&bars->sd_full[sb], (ph_sd >> sb) & 1u); ph_sd ^= 1u << sb;
+            b_desc = sb ? sd_desc1 : sd_desc0;
           }
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16(d_tmem, make_desc(a_base + ks * 2 * kPlaneW, kPlaneW, 128), make_desc(b_base + ks * 2 * plane, plane, 128),
-                     idesc, (r > 0 || ks > 0) ? 1u : 0u);
-          if (r >= 2) mma_commit(&bars->sd_empty[sb]);
-          mma_commit(&bars->w_empty[st]);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_raw(d_tmem, desc_advance(a_desc, ks * 2 * kPlaneW), desc_advance(b_desc, ks * 2 * plane), idesc,
+                           (r > 0 || ks > 0) ? 1u : 0u);
+            if (r >= 2) mma_commit_raw(&bars->sd_empty[sb]);
+            mma_commit_raw(&bars->w_empty[st]);
+            if (r == nring - 1) mma_commit_raw(&bars->d_full[b]);
+          }
+          __syncwarp();
+          if (++st == 3) st = 0;
         }
-        mma_commit(&bars->d_full[b]);
       }
     }
   } else if (warp == kDg3MmaWarp + 1) {
@@ -840,16 +849,25 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
         return (nvalid + 15) & ~15;
       };
+      const uint64_t w2t_desc = make_desc(smem_u32(sW2T), kPlaneW, 128), w2p_desc = make_desc(smem_u32(sW2P), kPlaneW, 128);
+      const uint64_t a1k_desc[2] = {make_desc(smem_u32(sA1b[0]), plane, 128), make_desc(smem_u32(sA1b[1]), plane, 128)};
+      const uint64_t a1m_desc[2] = {make_desc(smem_u32(sA1b[0]), 128, plane), make_desc(smem_u32(sA1b[1]), 128, plane)};
+      const uint64_t dzk_desc[2] = {make_desc(smem_u32(sDZb[0]), plane, 128), make_desc(smem_u32(sDZb[1]), plane, 128)};
+      const uint64_t dzm_desc[2] = {make_desc(smem_u32(sDZb[0]), 128, plane), make_desc(smem_u32(sDZb[1]), 128, plane)};
+      // every group of MMAs and its commits is issued from one elected region (see umma.cuh)
       auto issue_d2 = [&](int li) {
         const int g = li & 1;
         mbar_wait(&bars->a1_full[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, nt_of(li), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_bf16(tmem + g * kL2AccStride, make_desc(smem_u32(sW2T) + ks * 2 * kPlaneW, kPlaneW, 128),
-                   make_desc(smem_u32(sA1b[g]) + ks * 2 * plane, plane, 128), idesc, ks > 0);
-        mma_commit(&bars->d2_full[g]);
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_raw(tmem + g * kL2AccStride, desc_advance(w2t_desc, ks * 2 * kPlaneW),
+                         desc_advance(g ? a1k_desc[1] : a1k_desc[0], ks * 2 * plane), idesc, ks > 0);
+          mma_commit_raw(&bars->d2_full[g]);
+        }
+        __syncwarp();
       };
       auto issue_bwd = [&](int li) {
         const int g = li & 1;
@@ -857,16 +875,21 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         mbar_wait(&bars->dz_ready[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
         const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
-        for (int ks = 0; ks < NT / 16; ++ks)
-          mma_bf16(tmem + kL2AccWG, make_desc(smem_u32(sDZb[g]) + ks * 256, 128, plane),
-                   make_desc(smem_u32(sA1b[g]) + ks * 256, 128, plane), idesc_w, (li > 0 || ks > 0) ? 1u : 0u);
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        if (elect_one()) {
+          const uint64_t dzm = g ? dzm_desc[1] : dzm_desc[0], a1m = g ? a1m_desc[1] : a1m_desc[0];
+          const uint64_t dzk = g ? dzk_desc[1] : dzk_desc[0];
+          for (int ks = 0; ks < NT / 16; ++ks)
+            mma_bf16_raw(tmem + kL2AccWG, desc_advance(dzm, ks * 256), desc_advance(a1m, ks * 256), idesc_w,
+                         (li > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          mma_bf16(tmem + g * kL2AccStride, make_desc(smem_u32(sW2P) + ks * 2 * kPlaneW, kPlaneW, 128),
-                   make_desc(smem_u32(sDZb[g]) + ks * 2 * plane, plane, 128), idesc, ks > 0);
-        mma_commit(&bars->da_full[g]);
-        mma_commit(&bars->dz_free[g]);
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_raw(tmem + g * kL2AccStride, desc_advance(w2p_desc, ks * 2 * kPlaneW), desc_advance(dzk, ks * 2 * plane),
+                         idesc, ks > 0);
+          mma_commit_raw(&bars->da_full[g]);
+          mma_commit_raw(&bars->dz_free[g]);
+        }
+        __syncwarp();
       };
       // fixed service order D2(2q), D2(2q+1), BWD(2q), BWD(2q+1): consistent with each group's own sequence
       for (int q = 0; q < n_local; q += 2) {
