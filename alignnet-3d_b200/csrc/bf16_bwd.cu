@@ -71,32 +71,35 @@ __global__ void bwd3_coeff_kernel(const double* red3, int C3, double count, cons
   coef3[C3 + c] = (float)pp;
 }
 
-// Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights) and u[k] = sum_c p'[c] W3b[k,c]:
-// partial sums over 128-channel slices (grid = 128 k' x C3/128), accumulated in fp32 ...
-__global__ void __launch_bounds__(128) gq_partial_kernel(const float* W3, const float* coef3, int C3, float* gq_f32,
+// Gq[k', k] = sum_c W3b[k',c] q[c] W3b[k,c] (bf16-rounded weights) and u[k] = sum_c p'[c] W3b[k,c].
+// Block = 32 x 32 tile of Gq over a 64-channel slice (grid 4 x 4 x C3/64), both weight tiles staged in shared
+// memory once; partial sums accumulated in fp32 with atomics ...
+__global__ void __launch_bounds__(256) gq_partial_kernel(const float* W3, const float* coef3, int C3, float* gq_f32,
                                                          float* uvec) {
-  __shared__ float sw[128][33];
-  __shared__ float sq[32], sp[32];
-  const int kp = blockIdx.x, k = threadIdx.x;
-  const int cbeg = blockIdx.y * 128;
-  float acc = 0.f, uacc = 0.f;
-  for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 128 * 32; i += 128) {
-      const int r = i >> 5, cc = i & 31;
-      sw[r][cc] = bf16r(W3[(size_t)r * C3 + c0 + cc]);
-    }
-    if (threadIdx.x < 32) { sq[threadIdx.x] = coef3[c0 + threadIdx.x]; sp[threadIdx.x] = coef3[C3 + c0 + threadIdx.x]; }
-    __syncthreads();
-#pragma unroll 8
-    for (int cc = 0; cc < 32; ++cc) {
-      const float wk = sw[k][cc];
-      acc = fmaf(sw[kp][cc] * sq[cc], wk, acc);
-      uacc = fmaf(sp[cc], wk, uacc);
-    }
+  __shared__ float sa[32][65];   // rows k' (scaled by q)
+  __shared__ float sb[32][65];   // rows k
+  const int kp0 = blockIdx.x * 32, k0 = blockIdx.y * 32, c0 = blockIdx.z * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+    const int r = i >> 6, cc = i & 63;
+    sa[r][cc] = bf16r(W3[(size_t)(kp0 + r) * C3 + c0 + cc]) * coef3[c0 + cc];
+    sb[r][cc] = bf16r(W3[(size_t)(k0 + r) * C3 + c0 + cc]);
   }
-  atomicAdd(gq_f32 + kp * 128 + k, acc);
-  if (kp == 0) atomicAdd(uvec + k, uacc);
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int cc = 0; cc < 64; ++cc) {
+    const float wk = sb[tx][cc];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[ty + 8 * r][cc], wk, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) atomicAdd(gq_f32 + (size_t)(kp0 + ty + 8 * r) * 128 + k0 + tx, acc[r]);
+  if (blockIdx.x == 0 && ty == 0) {
+    float u = 0.f;
+    for (int cc = 0; cc < 64; ++cc) u = fmaf(coef3[C3 + c0 + cc], sb[tx][cc], u);
+    atomicAdd(uvec + k0 + tx, u);
+  }
 }
 
 // ... then packed as the two K-half bf16 images of the A operand (rows k, contraction k')
@@ -134,76 +137,94 @@ __global__ void bn_bwd_coeff_kernel(const double* red, int C, double count, floa
 // give wgrad1 (sum of B over items) and the gradient of the stage input reduced per cloud to d(center) and
 // d(angle).  One block per item, 256 threads: point moments by block reduction, then 64 channel threads.
 __global__ void __launch_bounds__(256) bwd_l1_finish_kernel(const float* pcs, const float* center, const float* angle,
-                                                            const float* l1sums, int N, int PC, int npc, const float* W1,
-                                                            const float* b1, const float* mean1, const float* inv1,
-                                                            const float* scale1, const float* coef1, float* gW1,
-                                                            float* dcenter, float* dangle, int want_input_grad) {
+                                                            const float* l1sums, int N, int PC, int npc, int n_items,
+                                                            int items_per_block, const float* W1, const float* b1,
+                                                            const float* mean1, const float* inv1, const float* scale1,
+                                                            const float* coef1, float* gW1, float* dcenter, float* dangle,
+                                                            int want_input_grad) {
   __shared__ float wred[8][9];
   __shared__ float mom[9];
   __shared__ float fin[64][4];
-  const int it = blockIdx.x;
-  const int cloud = it / npc, pchunk = it - cloud * npc;
-  const int p0 = pchunk * PC;
-  const int nvalid = min(PC, N - p0);
-  const int64_t row0 = (int64_t)cloud * N + p0;
-  float sn = 0.f, cs = 1.f;
-  if (angle) sincosf(angle[cloud], &sn, &cs);
-  const float cx = center[cloud * 3], cy = center[cloud * 3 + 1], cz = center[cloud * 3 + 2];
-  float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // Px Py Pz Pxx Pxy Pxz Pyy Pyz Pzz
-  for (int p = threadIdx.x; p < nvalid; p += 256) {
-    const float* src = pcs + (row0 + p) * 3;
-    const float x0 = src[0] - cx, y0 = src[1] - cy;
-    const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs, z = src[2] - cz;
-    m[0] += x; m[1] += y; m[2] += z;
-    m[3] = fmaf(x, x, m[3]); m[4] = fmaf(x, y, m[4]); m[5] = fmaf(x, z, m[5]);
-    m[6] = fmaf(y, y, m[6]); m[7] = fmaf(y, z, m[7]); m[8] = fmaf(z, z, m[8]);
-  }
-#pragma unroll
-  for (int q = 0; q < 9; ++q)
-    for (int o = 16; o > 0; o >>= 1) m[q] += __shfl_xor_sync(0xffffffffu, m[q], o);
-  if ((threadIdx.x & 31) == 0)
-    for (int q = 0; q < 9; ++q) wred[threadIdx.x >> 5][q] = m[q];
-  __syncthreads();
-  if (threadIdx.x < 9) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += wred[w][threadIdx.x];
-    mom[threadIdx.x] = t;
-  }
-  __syncthreads();
   const int c = threadIdx.x;
+  float wx = 0.f, wy = 0.f, wz = 0.f, s1 = 0.f, m0 = 0.f, m1 = 0.f, ax = 0.f, ay = 0.f, az = 0.f, a0 = 0.f;
   if (c < 64) {
-    const float wx = W1[c], wy = W1[64 + c], wz = W1[128 + c];
-    const float iv = inv1[c], s1 = scale1[c], m0 = coef1[2 * c], m1 = coef1[2 * c + 1];
-    const float ax = iv * wx, ay = iv * wy, az = iv * wz, a0 = iv * (b1[c] - mean1[c]);
-    const float n = (float)nvalid;
-    const float4 S = reinterpret_cast<const float4*>(l1sums)[(size_t)it * 64 + c];
-    const float sxh = ax * mom[0] + ay * mom[1] + az * mom[2] + n * a0;
-    const float sxh_x = ax * mom[3] + ay * mom[4] + az * mom[5] + a0 * mom[0];
-    const float sxh_y = ax * mom[4] + ay * mom[6] + az * mom[7] + a0 * mom[1];
-    const float sxh_z = ax * mom[5] + ay * mom[7] + az * mom[8] + a0 * mom[2];
-    const float A = s1 * (S.x - n * m0 - m1 * sxh);
-    const float Bx = s1 * (S.y - m0 * mom[0] - m1 * sxh_x);
-    const float By = s1 * (S.z - m0 * mom[1] - m1 * sxh_y);
-    const float Bz = s1 * (S.w - m0 * mom[2] - m1 * sxh_z);
-    atomicAdd(gW1 + c, Bx);
-    atomicAdd(gW1 + 64 + c, By);
-    atomicAdd(gW1 + 128 + c, Bz);
-    // d(sum_p dq_d) = sum_c W1[d,c] A_c ; d(angle) = sum_c (-W1[x,c] By_c + W1[y,c] Bx_c)
-    fin[c][0] = wx * A; fin[c][1] = wy * A; fin[c][2] = wz * A; fin[c][3] = -wx * By + wy * Bx;
+    wx = W1[c]; wy = W1[64 + c]; wz = W1[128 + c];
+    const float iv = inv1[c];
+    s1 = scale1[c]; m0 = coef1[2 * c]; m1 = coef1[2 * c + 1];
+    ax = iv * wx; ay = iv * wy; az = iv * wz; a0 = iv * (b1[c] - mean1[c]);
   }
-  __syncthreads();
-  if (want_input_grad && threadIdx.x < 4) {
-    float s = 0.f;
-    for (int i = 0; i < 64; ++i) s += fin[i][threadIdx.x];
-    fin[0][threadIdx.x] = s;
+  float gwx = 0.f, gwy = 0.f, gwz = 0.f;     // wgrad1 partial sums over this block's items (one atomic each at the end)
+  const int it_end = min(n_items, (int)(blockIdx.x + 1) * items_per_block);
+  for (int it = blockIdx.x * items_per_block; it < it_end; ++it) {
+    const int cloud = it / npc, pchunk = it - cloud * npc;
+    const int p0 = pchunk * PC;
+    const int nvalid = min(PC, N - p0);
+    const int64_t row0 = (int64_t)cloud * N + p0;
+    float sn = 0.f, cs = 1.f;
+    if (angle) sincosf(angle[cloud], &sn, &cs);
+    const float cx = center[cloud * 3], cy = center[cloud * 3 + 1], cz = center[cloud * 3 + 2];
+    float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // Px Py Pz Pxx Pxy Pxz Pyy Pyz Pzz
+    for (int p = threadIdx.x; p < nvalid; p += 256) {
+      const float* src = pcs + (row0 + p) * 3;
+      const float x0 = src[0] - cx, y0 = src[1] - cy;
+      const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs, z = src[2] - cz;
+      m[0] += x; m[1] += y; m[2] += z;
+      m[3] = fmaf(x, x, m[3]); m[4] = fmaf(x, y, m[4]); m[5] = fmaf(x, z, m[5]);
+      m[6] = fmaf(y, y, m[6]); m[7] = fmaf(y, z, m[7]); m[8] = fmaf(z, z, m[8]);
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+      for (int o = 16; o > 0; o >>= 1) m[q] += __shfl_xor_sync(0xffffffffu, m[q], o);
+    __syncthreads();     // previous item's readers of wred / mom / fin are done
+    if ((threadIdx.x & 31) == 0)
+      for (int q = 0; q < 9; ++q) wred[threadIdx.x >> 5][q] = m[q];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += wred[w][threadIdx.x];
+      mom[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (c < 64) {
+      const float n = (float)nvalid;
+      const float4 S = reinterpret_cast<const float4*>(l1sums)[(size_t)it * 64 + c];
+      const float sxh = ax * mom[0] + ay * mom[1] + az * mom[2] + n * a0;
+      const float sxh_x = ax * mom[3] + ay * mom[4] + az * mom[5] + a0 * mom[0];
+      const float sxh_y = ax * mom[4] + ay * mom[6] + az * mom[7] + a0 * mom[1];
+      const float sxh_z = ax * mom[5] + ay * mom[7] + az * mom[8] + a0 * mom[2];
+      const float A = s1 * (S.x - n * m0 - m1 * sxh);
+      const float Bx = s1 * (S.y - m0 * mom[0] - m1 * sxh_x);
+      const float By = s1 * (S.z - m0 * mom[1] - m1 * sxh_y);
+      const float Bz = s1 * (S.w - m0 * mom[2] - m1 * sxh_z);
+      gwx += Bx; gwy += By; gwz += Bz;
+      // d(sum_p dq_d) = sum_c W1[d,c] A_c ; d(angle) = sum_c (-W1[x,c] By_c + W1[y,c] Bx_c)
+      fin[c][0] = wx * A; fin[c][1] = wy * A; fin[c][2] = wz * A; fin[c][3] = -wx * By + wy * Bx;
+    }
+    if (want_input_grad) {
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        float s = 0.f;
+        for (int i = 0; i < 64; ++i) s += fin[i][threadIdx.x];
+        // one writer per (cloud, component) when a cloud is one item; atomics keep multi-item clouds correct
+        if (threadIdx.x == 3) {
+          if (dangle) atomicAdd(dangle + cloud, s);
+        } else {
+          wred[0][threadIdx.x] = s;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const float gx = wred[0][0], gy = wred[0][1], gz = wred[0][2];
+        atomicAdd(dcenter + cloud * 3, -(gx * cs + gy * sn));
+        atomicAdd(dcenter + cloud * 3 + 1, -(-gx * sn + gy * cs));
+        atomicAdd(dcenter + cloud * 3 + 2, -gz);
+      }
+    }
   }
-  __syncthreads();
-  if (want_input_grad && threadIdx.x == 0) {
-    const float gx = fin[0][0], gy = fin[0][1], gz = fin[0][2];
-    atomicAdd(dcenter + cloud * 3, -(gx * cs + gy * sn));
-    atomicAdd(dcenter + cloud * 3 + 1, -(-gx * sn + gy * cs));
-    atomicAdd(dcenter + cloud * 3 + 2, -gz);
-    if (dangle) atomicAdd(dangle + cloud, fin[0][3]);
+  if (c < 64) {
+    atomicAdd(gW1 + c, gwx);
+    atomicAdd(gW1 + 64 + c, gwy);
+    atomicAdd(gW1 + 128 + c, gwz);
   }
 }
 
@@ -250,7 +271,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
   {
-    const int bchunk = 16;
+    const int bchunk = 64;     // fewer, fatter blocks: the per-channel double atomics were contended
     dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
     pool_bwd_prep_kernel<<<grid, 128, 0, st>>>(dG, lddg, p.g[s][br], ldg, q.zext[s][br], B, C3, gamma3, params + L3.b, mean3,
                                                inv3, q.idx_mask, q.dyext, q.red3, bchunk);
@@ -260,7 +281,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     AN3D_LAUNCH_CHECK();
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.gq_f32, 0, 128 * 128 * sizeof(float), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.uvec, 0, 128 * sizeof(float), st));
-    gq_partial_kernel<<<dim3(128, C3 / 128), 128, 0, st>>>(params + L3.w, q.coef3, C3, q.gq_f32, q.uvec);
+    gq_partial_kernel<<<dim3(4, 4, C3 / 64), 256, 0, st>>>(params + L3.w, q.coef3, C3, q.gq_f32, q.uvec);
     AN3D_LAUNCH_CHECK();
     gq_pack_kernel<<<64, 256, 0, st>>>(q.gq_f32, q.gq);
     AN3D_LAUNCH_CHECK();
@@ -328,10 +349,13 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     AN3D_LAUNCH_CHECK();
   }
   // ---- layer 1 backward (CUDA cores) ----
-  bwd_l1_finish_kernel<<<n_items, 256, 0, st>>>(pcs, center, angle, q.l1sums, N, q.PC, q.npc, params + L1.w, params + L1.b,
-                                                mean1, inv1, sc1, q.coef1, grads + L1.w, dcenter, dangle,
-                                                want_input_grad ? 1 : 0);
-  AN3D_LAUNCH_CHECK();
+  {
+    const int ipb = std::max(1, (n_items + 4 * sms - 1) / (4 * sms));     // ~4 blocks per SM, wgrad1 atomics once per block
+    bwd_l1_finish_kernel<<<(n_items + ipb - 1) / ipb, 256, 0, st>>>(pcs, center, angle, q.l1sums, N, q.PC, q.npc, n_items, ipb,
+                                                                  params + L1.w, params + L1.b, mean1, inv1, sc1, q.coef1,
+                                                                  grads + L1.w, dcenter, dangle, want_input_grad ? 1 : 0);
+    AN3D_LAUNCH_CHECK();
+  }
   // biases of conv layers feed a batch-statistics BN: their gradient is identically zero (left at 0).
   return AN3D_OK;
 }

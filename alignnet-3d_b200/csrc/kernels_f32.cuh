@@ -147,19 +147,34 @@ static __global__ void __launch_bounds__(256) col_reduce_kernel(ColArgs a, int r
     float mean = 0.f, inv = 0.f, sc = 0.f, sh = 0.f;
     if (MODE != COL_SUM) mean = a.mean[c];
     if (MODE == COL_DY) { inv = a.inv[c]; sc = a.scale[c]; sh = a.shift[c]; }
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float z = a.Z[(int64_t)r * a.ldz + c];
-      if (MODE == COL_SUM) {
-        s0 += (double)z;
-      } else if (MODE == COL_SQDIFF) {
-        const float d = z - mean;
-        s1 += (double)d * (double)d;
-      } else {
-        float dy = a.dA[(int64_t)r * a.ldd + c];
-        if (a.mask) dy *= a.mask[(int64_t)r * a.ldd + c] * a.mask_scale;
-        if (!(fmaf(z, sc, sh) > 0.f)) dy = 0.f;
-        s0 += (double)dy;
-        s1 += (double)dy * (double)((z - mean) * inv);
+    // four rows per iteration: the loads of a batch are independent and in flight together
+    for (int rb = r0 + threadIdx.y; rb < r1; rb += 32) {
+      float z[4], dy[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + 8 * u;
+        z[u] = 0.f; dy[u] = 0.f;
+        if (r < r1) {
+          z[u] = a.Z[(int64_t)r * a.ldz + c];
+          if (MODE == COL_DY) {
+            dy[u] = a.dA[(int64_t)r * a.ldd + c];
+            if (a.mask) dy[u] *= a.mask[(int64_t)r * a.ldd + c] * a.mask_scale;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rb + 8 * u >= r1) continue;
+        if (MODE == COL_SUM) {
+          s0 += (double)z[u];
+        } else if (MODE == COL_SQDIFF) {
+          const float d = z[u] - mean;
+          s1 += (double)d * (double)d;
+        } else {
+          const float g = fmaf(z[u], sc, sh) > 0.f ? dy[u] : 0.f;
+          s0 += (double)g;
+          s1 += (double)g * (double)((z[u] - mean) * inv);
+        }
       }
     }
   }
@@ -177,7 +192,7 @@ static __global__ void __launch_bounds__(256) col_reduce_kernel(ColArgs a, int r
 
 inline int launch_col_reduce(const ColArgs& a, int mode, cudaStream_t st) {
   if (a.R <= 0 || a.C <= 0) return AN3D_OK;
-  int rows_per_block = 256;
+  const int rows_per_block = 128;
   dim3 grid((a.C + 31) / 32, (a.R + rows_per_block - 1) / rows_per_block);
   dim3 block(32, 8);
   if (mode == COL_SUM) col_reduce_kernel<COL_SUM><<<grid, block, 0, st>>>(a, rows_per_block);
