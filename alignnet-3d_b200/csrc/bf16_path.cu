@@ -135,6 +135,39 @@ __global__ void fold_acc_kernel(const double* stats, double count, const float* 
   if (shift_folded) shift_folded[c] = sc * bias[c] + sh;
 }
 
+// Layer-2 batch statistics from the Gram matrix of the layer-1 activations (MODE_STATS2 of the conv kernel):
+//   stats2[c] = ( sum_k sa1[k] w[k,c] ,  sum_{k,k'} w[k,c] G1[k,k'] w[k',c] ),  w = bf16-rounded W2 [64][128].
+// Grid 8 x 128 threads = 16 channels x 8 row groups per block.
+__global__ void __launch_bounds__(128) stats2_from_gram1_kernel(const float* W2, const float* gram1, double* stats2) {
+  __shared__ float sg[64][81];
+  __shared__ float sw[64][17];
+  __shared__ double red[2][8][16];
+  const int c0 = blockIdx.x * 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int i = threadIdx.x; i < 64 * 80; i += 128) sg[i / 80][i % 80] = gram1[i];
+  for (int i = threadIdx.x; i < 64 * 16; i += 128) {
+    const int k = i >> 4, cc = i & 15;
+    sw[k][cc] = __bfloat162float(__float2bfloat16_rn(W2[k * 128 + c0 + cc]));
+  }
+  __syncthreads();
+  double m = 0.0, qd = 0.0;
+  for (int k = ty * 8; k < ty * 8 + 8; ++k) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int kp = 0; kp < 64; ++kp) t = fmaf(sg[k][kp], sw[kp][tx], t);
+    qd += (double)sw[k][tx] * (double)t;
+    m += (double)sg[k][64] * (double)sw[k][tx];
+  }
+  red[0][ty][tx] = m;
+  red[1][ty][tx] = qd;
+  __syncthreads();
+  if (ty == 0) {
+    for (int i = 1; i < 8; ++i) { m += red[0][i][tx]; qd += red[1][i][tx]; }
+    stats2[2 * (c0 + tx)] = m;
+    stats2[2 * (c0 + tx) + 1] = qd;
+  }
+}
+
 // Layer-3 batch statistics without touching the [M, C3] accumulator: with r3 = a2 W3b,
 //   sum_m r3[m,c]   = sa2 . w_c              sum_m r3[m,c]^2 = w_c^T (A2^T A2) w_c
 // (bf16-rounded weights, Gram matrix from the tensor-core pass).  The product GW = (A2^T A2) W3b is kept
@@ -267,6 +300,7 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
       q->t2f[s][br] = a.take<float>(128);
       q->moments[s][br] = a.take<double>(16);
       q->stats2[s][br] = a.take<double>(256);
+      q->gram1[s][br] = a.take<float>(64 * 80);
       q->stats3[s][br] = a.take<double>(2 * (int64_t)C3);
       q->zext[s][br] = a.take<uint32_t>((int64_t)B * C3);
       q->a2img[s][br] = training ? a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2)) : nullptr;
@@ -336,7 +370,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   P.w1f = q.w1f[s][br]; P.c1f = q.c1f[s][br]; P.w2t_img = q.w2t[s]; P.s2 = io2.scale; P.t2f = q.t2f[s][br];
   P.w3t_img = q.w3t[s][br]; P.nchunk = C3 / 128;
   P.nstages = convfwd::smem_bytes(q.PC, 3) <= (size_t)kMaxSmem ? 3 : 2;
-  P.zext = q.zext[s][br]; P.stats2 = q.stats2[s][br]; P.stats3 = q.stats3[s][br];
+  P.zext = q.zext[s][br]; P.gram1 = q.gram1[s][br]; P.stats3 = q.stats3[s][br];
   P.a2_img = training ? q.a2img[s][br] : nullptr; P.sa2 = training ? q.sa2[s][br] : nullptr;
   P.idx_mask = q.idx_mask;
   const size_t smem = convfwd::smem_bytes(q.PC, P.nstages);
@@ -347,7 +381,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
 
   if (training) {
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.moments[s][br], 0, 16 * sizeof(double), st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.stats2[s][br], 0, 256 * sizeof(double), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram1[s][br], 0, 64 * 80 * sizeof(float), st));
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.sa2[s][br], 0, 128 * sizeof(double), st));
     const int mb = (int)std::min<int64_t>((M + 255) / 256, 4 * sms);
     moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
@@ -356,7 +390,11 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   fold_l1_kernel<<<1, 64, 0, st>>>(q.moments[s][br], (double)M, params + L1.w, params + L1.b, io1, training ? 1 : 0, decay,
                                    q.w1f[s][br], q.c1f[s][br]);
   AN3D_LAUNCH_CHECK();
-  if (training) AN3D_TRY(launch_fused<convfwd::MODE_STATS2>(P, grid, smem, st));
+  if (training) {
+    AN3D_TRY(launch_fused<convfwd::MODE_STATS2>(P, grid, smem, st));
+    stats2_from_gram1_kernel<<<8, 128, 0, st>>>(params + L2.w, q.gram1[s][br], q.stats2[s][br]);
+    AN3D_LAUNCH_CHECK();
+  }
   fold_acc_kernel<<<1, 128, 0, st>>>(q.stats2[s][br], (double)M, params + L2.b, io2, 128, training ? 1 : 0, decay, 0,
                                      q.t2f[s][br]);
   AN3D_LAUNCH_CHECK();

@@ -134,6 +134,7 @@ struct PlanBf16 {
   double* moments[3][2];                    // first/second moments of the stage input points
   double* stats2[3][2];                     // sum / sum-of-squares of the raw layer-2 accumulator [128][2]
   double* stats3[3][2];                     // same for layer 3 [C3][2]
+  float* gram1[3][2];                       // [64][80] Gram matrix + column sums of the layer-1 activations (layer-2 BN statistics)
   uint32_t* zext[3][2];                     // packed pooled extreme [B][C3]
   __nv_bfloat16* a2img[3][2];               // saved layer-2 activations (training): per item the A2 smem tile image
   int64_t img_bytes = 0;                    // bytes of one item image (16 planes)

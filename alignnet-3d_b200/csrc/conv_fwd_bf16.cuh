@@ -31,6 +31,11 @@ constexpr uint32_t kPlaneW2 = 128 * 16;   // plane stride of the weight images (
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;
 
+// MODE_STATS2: layer-2 BATCH statistics without running layer 2.  With z2 = a1 W2 (bias apart),
+//   sum_p z2[p,c] = (sum_p a1[p,:]) . w_c        sum_p z2[p,c]^2 = w_c^T (A1^T A1) w_c
+// so the pass only computes layer 1 and accumulates the 64 x 64 Gram matrix of its (bf16) activations plus their
+// column sums on the tensor cores (contraction over points, MN-major operands straight from the A1 tile, one extra
+// 'ones' plane) -- no per-item accumulator read-back at all.
 enum Mode { MODE_STATS2 = 0, MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
 
 struct Params {
@@ -50,7 +55,8 @@ struct Params {
   int nchunk;             // C3 / 128
   int nstages;            // W3 ring depth (2 or 3)
   uint32_t* zext;         // [B][C3] ordered-uint packed max of the raw layer-3 accumulator
-  double* stats2;         // [128][2]  sum, sum of squares of the raw layer-2 accumulator
+  float* gram1;           // MODE_STATS2: [64][80] += A1^T [A1 | 1 | 0]  (Gram matrix and column sums of the bf16 layer-1
+                          // activations over all points; gives the layer-2 batch statistics in closed form)
   double* stats3;         // [C3][2]   same for layer 3 (sign-folded)
   __nv_bfloat16* a2_img;  // optional: per item, the A2 tile exactly as staged in shared memory (16 planes),
                           // saved for the backward kernels (bulk store, TMA unit)
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int NT = (nvalid + 15) & ~15;
       const int b = li & 1;
       (void)cloud;
-      if (MODE != MODE_STATS2 && li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
+      if (li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
       uint8_t* sA1 = sA2[b];
@@ -245,9 +251,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
         }
+        if (MODE == MODE_STATS2) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
+          *reinterpret_cast<uint4*>(sA1 + 8 * plane1 + p * 16) = make_uint4(p < nvalid ? 0x00003f80u : 0u, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sA1 + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
+      if (MODE == MODE_STATS2) continue;   // the Gram MMAs need no per-item epilogue
       // ---- layer-2 epilogue: channel k, point columns [pbeg, pend)
       mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
       tc_fence_after();
@@ -289,10 +300,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     }
     if (save_a2 && f == 0) bulk_wait_read_all();
     if (MODE == MODE_FULL_TRAIN && P.sa2 && n_local > 0) atomicAdd(P.sa2 + k, st_a2);
-    if (MODE == MODE_STATS2 && n_local > 0) {
-      atomicAdd(P.stats2 + 2 * k, st_s);
-      atomicAdd(P.stats2 + 2 * k + 1, st_ss);
+    if (MODE == MODE_STATS2 && n_local > 0 && k < 64) {
+      // Gram accumulator of the whole item range: lanes = layer-1 channel k, 80 columns (64 channels, sums, pad)
+      mbar_wait_relaxed(&bars->d2_full, 0);
+      tc_fence_after();
+      const int cbeg = fgroup ? 48 : 0, cend = fgroup ? 80 : 48;
+      for (int g16 = cbeg; g16 < cend; g16 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(P.gram1 + k * 80 + g16 + j, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
     }
+    (void)st_s; (void)st_ss;
   } else if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ================================ back-end =================================
     // two warps per TMEM lane quarter (warps w and w+10 with equal w%4): the 16-column groups of every
@@ -373,12 +395,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         }
         __syncwarp();
       };
+      if (MODE == MODE_STATS2) {
+        const uint32_t idesc = make_idesc(128, 80, 1, 1);
+        uint32_t ph = 0;
+        for (int li = 0; li < n_local; ++li) {
+          const int it = it_begin + li;
+          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+          const int NT = (nvalid + 15) & ~15;
+          (void)cloud;
+          mbar_wait(&bars->a1_full, ph); ph ^= 1;
+          tc_fence_after();
+          if (elect_one()) {
+            // contraction over the item's points: both operands are the A1 tile read MN-major (rows = points)
+            const uint64_t d = make_desc(smem_u32(sA2[li & 1]), 128, plane1);
+            for (int ks = 0; ks < NT / 16; ++ks)
+              mma_bf16_raw(tmem + kTmemD2, desc_advance(d, ks * 256), desc_advance(d, ks * 256), idesc,
+                           (li > 0 || ks > 0) ? 1u : 0u);
+            mma_commit_raw(&bars->a2_empty[li & 1]);
+            if (li == n_local - 1) mma_commit_raw(&bars->d2_full);
+          }
+          __syncwarp();
+        }
+      } else {
       issue_l2(0);
       for (int li = 0; li < n_local; ++li) {
-        if (MODE == MODE_STATS2) {
-          if (li + 1 < n_local) issue_l2(li + 1);
-          continue;
-        }
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
@@ -429,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           }
         }
         mma_commit(&bars->a2_empty[b]);
+      }
       }
     }
   } else {
