@@ -68,7 +68,8 @@ __host__ __device__ inline uint32_t plane_stride(int rows) { return (uint32_t)ro
 
 inline size_t smem_bytes(int PC, int nstages) {
   const size_t a2 = 16 * (size_t)plane_stride(PC);
-  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,s2,t2f*/ + 256 /*barriers*/ + 128;
+  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,s2,t2f*/ + 2 * kMaxPC * 16 /*raw points*/ +
+         256 /*barriers*/ + 128;
 }
 
 __device__ __forceinline__ uint32_t to_ordered(uint32_t bits) {
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   float* sC1f = sW1f + 192;
   float* sS2 = sC1f + 64;
   float* sT2f = sS2 + 128;
-  Barriers* bars = reinterpret_cast<Barriers*>(sT2f + 128);
+  float4* sRaw = reinterpret_cast<float4*>(sT2f + 128);      // [2][kMaxPC] raw points (w = 1 for real points)
+  Barriers* bars = reinterpret_cast<Barriers*>(sRaw + 2 * kMaxPC);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
@@ -204,6 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
       }
     };
+    const int fg8 = fgroup * 4 + (warp & 3);       // channel group (A1 plane) of this warp in layer 1
+    float w1x[8], w1y[8], w1z[8], c1r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w1x[j] = sW1f[fg8 * 8 + j]; w1y[j] = sW1f[64 + fg8 * 8 + j]; w1z[j] = sW1f[128 + fg8 * 8 + j]; c1r[j] = sC1f[fg8 * 8 + j];
+    }
     if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
@@ -223,36 +231,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         float* xf = bars->xf + (li & 1) * 8;
         xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
       }
+      // the prefetched raw point of thread f goes to shared memory: layer 1 below is organised by channel group
+      if (f < NT) sRaw[b * kMaxPC + f] = f < nvalid ? make_float4(pf_p[0], pf_p[1], pf_p[2], 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* xfr = bars->xf + (li & 1) * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
-      const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
       if (li + 1 < n_local) prefetch(li + 1);
-      // ---- layer 1: y = relu(W1f^T p' + c1f), one thread per point, 8 channels per 16-byte chunk
-      if (f < NT) {
-        const int p = f;
-        if (p < nvalid) {
-          const float x0 = cur_p[0] - cx, y0 = cur_p[1] - cy, z = cur_p[2] - cz;
+      // ---- layer 1: y = relu(W1f^T p' + c1f).  Warp g of the 8 front-end warps owns channels 8g..8g+7 (= plane g
+      // of the A1 tile) for ALL points: its 32 folded weights live in registers (the thread-per-point form spent
+      // 4 shared-memory loads per channel on them), lanes walk consecutive points, so the raw-point loads and the
+      // 16-byte tile stores are conflict-free.
+      for (int p = lane; p < NT; p += 32) {
+        const float4 raw = sRaw[b * kMaxPC + p];
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (raw.w != 0.f) {
+          const float x0 = raw.x - cx, y0 = raw.y - cy, z = raw.z - cz;
           const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
+          float v[8];
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c8 * 8 + j;
-              v[j] = fmaxf(fmaf(x, sW1f[c], fmaf(y, sW1f[64 + c], fmaf(z, sW1f[128 + c], sC1f[c]))), 0.f);
-            }
-            uint4 q;
-            q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-            q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = q;
-          }
-        } else {
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j]))), 0.f);
+          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+          q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         }
-        if (MODE == MODE_STATS2) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
-          *reinterpret_cast<uint4*>(sA1 + 8 * plane1 + p * 16) = make_uint4(p < nvalid ? 0x00003f80u : 0u, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) = q;
+        if (MODE == MODE_STATS2 && fg8 == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
+          *reinterpret_cast<uint4*>(sA1 + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
           *reinterpret_cast<uint4*>(sA1 + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
         }
       }

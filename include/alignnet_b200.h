@@ -182,6 +182,12 @@ int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag);
 int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn,
                        int32_t b_mn, void* stream);
 
+/* Diagnostic micro-benchmark: `ctas` CTAs each issue `iters` tcgen05 MMAs of shape 128 x n x 16 (bf16, operands in
+ * the given majors, un-swizzled plane layout over a k-deep resident tile); cycles_per_mma_dev[cta] receives the
+ * measured SM cycles per MMA.  Used to choose operand layouts, not on the hot path. */
+int an3d_bench_umma(int32_t n, int32_t k, int32_t a_mn, int32_t b_mn, int32_t iters, int32_t ctas,
+                    float* cycles_per_mma_dev, void* stream);
+
 /* Diagnostic (test-suite only): training-mode forward + backward of ONE conv stack (stage 0..2) of
  * ONE branch on the bf16 tensor-core path with a caller-supplied upstream gradient dG [B, C3].
  * g_out [B, C3] receives the pooled feature, grads (flat, zeroed first) the parameter gradients of
