@@ -44,7 +44,7 @@ class Labels(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("masks", C.c_void_p * 5)]
+    _fields_ = [("seed", C.c_uint64), ("masks", C.c_void_p * 5), ("seed_dev", C.c_void_p)]
 
 
 # symbol -> (restype, argtypes); mirrors include/alignnet_b200.h one to one
@@ -68,6 +68,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "an3d_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int64,
                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "an3d_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "an3d_adam_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "an3d_decode_angles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "an3d_rigid_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p]),

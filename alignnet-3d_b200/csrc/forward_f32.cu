@@ -181,7 +181,7 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
       } else {
         const uint64_t seed = dropout ? dropout->seed : 0;
         dropout_mask_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(p.mask[i], cnt, seed, (uint32_t)i,
-                                                                          m.arch.keep_prob[s]);
+                                                                          m.arch.keep_prob[s], dropout ? dropout->seed_dev : nullptr);
         AN3D_LAUNCH_CHECK();
       }
       masks[i] = p.mask[i];

@@ -358,9 +358,11 @@ static __global__ void post_head_kernel(const float* o, const float* c2a, const 
 }
 
 // Counter-based keep mask (splitmix64 hash of (seed, site, element)); value 1 with prob keep.
-static __global__ void dropout_mask_kernel(float* mask, int64_t count, uint64_t seed, uint32_t site, float keep) {
+static __global__ void dropout_mask_kernel(float* mask, int64_t count, uint64_t seed, uint32_t site, float keep,
+                                           const uint64_t* seed_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  if (seed_dev) seed = *seed_dev;
   uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1) + ((uint64_t)site << 56);
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;

@@ -12,7 +12,11 @@ constexpr float kPi = 3.14159265358979323846f;
 // p <- p - lr_t m / (sqrt(v) + eps),  lr_t = lr sqrt(1-b2^t)/(1-b1^t)  (train.py:212-217)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float grad_scale, float b1, float b2,
-                            float eps) {
+                            float eps, const int64_t* __restrict__ step_dev, float lr) {
+  if (step_dev) {   // graph-replay form: bias correction from the device-resident step count
+    const double t = (double)*step_dev;
+    lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 + 3 < n) {
     const float4 gg = *reinterpret_cast<const float4*>(g + i4);
@@ -121,7 +125,44 @@ int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_
   if (nthreads == 0) return AN3D_OK;
   adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, count,
                                                                                    (float)lr_t, grad_scale, beta1,
-                                                                                   beta2, eps);
+                                                                                   beta2, eps, nullptr, lr);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+static __global__ void step_advance_kernel(int64_t* step, uint64_t* seed, uint64_t seed_base) {
+  const int64_t t = *step + 1;
+  *step = t;
+  if (seed) *seed = seed_base + (uint64_t)t;
+}
+
+int an3d_step_advance(int64_t* step_dev, uint64_t* seed_dev, uint64_t seed_base, void* stream) {
+  if (!step_dev) {
+    set_error("an3d_step_advance: step_dev is null");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, seed_dev, seed_base);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_adam_step_dev(float* params, const float* grads, float* m, float* v, int64_t count, float lr,
+                       const int64_t* step_dev, float grad_scale, float beta1, float beta2, float eps, void* stream) {
+  if (!params || !grads || !m || !v || count < 0 || !step_dev) {
+    set_error("an3d_adam_step_dev: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) {
+    set_error("an3d_adam_step_dev: buffers must be 16-byte aligned");
+    return AN3D_ERR_ALIGN;
+  }
+  AN3D_TRY(check_device());
+  const int64_t nthreads = (count + 3) / 4;
+  if (nthreads == 0) return AN3D_OK;
+  adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, count, 0.f,
+                                                                                   grad_scale, beta1, beta2, eps, step_dev,
+                                                                                   lr);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }

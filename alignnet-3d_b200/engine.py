@@ -101,6 +101,10 @@ class Engine:
             self.adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.bn_state = torch.zeros(self.state_layout.total, dtype=torch.float32, device=self.device)
             self.loss_buf = torch.zeros(20, dtype=torch.float32, device=self.device)
+            # device-resident copies of the global step and the dropout seed: what a captured CUDA graph reads
+            self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._graphs: Dict[tuple, tuple] = {}
             self.set_params(self.init_params(seed))
 
     def __del__(self):
@@ -227,7 +231,8 @@ class Engine:
 
     # ---- compute --------------------------------------------------------------------------
     def forward(self, pcs1: torch.Tensor, pcs2: torch.Tensor, is_training: bool, bn_decay: Optional[float] = None,
-                masks: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0) -> Dict[str, torch.Tensor]:
+                masks: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0,
+                seed_on_device: bool = False) -> Dict[str, torch.Tensor]:
         """get_model (models/tp8.py:135-158).  Returns the 8 end_points as CUDA tensors (buffers are
         reused between calls with the same batch size)."""
         B, N = int(pcs1.shape[0]), int(pcs1.shape[1])
@@ -239,6 +244,8 @@ class Engine:
         ostruct = self._out_struct(out)
         d = _lib.Dropout()
         d.seed = int(seed)
+        if seed_on_device:
+            d.seed_dev = self.seed_dev.data_ptr()
         if masks is not None:
             for i, k in enumerate(MASK_KEYS):
                 if k in masks and masks[k] is not None:
@@ -294,6 +301,80 @@ class Engine:
         if allreduce is not None:
             scale = allreduce(self.grads)
         self.adam_step(lr, grad_scale=scale)
+        return loss
+
+    # ---- CUDA-graph replay ----------------------------------------------------------------------
+    # The step is ~250 dependent launches; replaying it as a CUDA graph removes the per-launch gaps on the GPU
+    # timeline (c3: 8.3 -> 7.9 ms, c2: 0.83 -> 0.65 ms).  Everything that changes from step to step lives in
+    # device memory: the batch (static buffers the caller refills), the global step and the dropout seed
+    # (advanced by a one-thread kernel inside the graph).  lr and bn_decay are staircase schedules
+    # (train.py:133-174): a new value simply captures a new graph.
+    def _capture(self, key, fn):
+        """Returns (graph, outputs, fresh).  The first call runs `fn` once for real (workspace allocation,
+        kernel attributes) and then captures it; `fresh` tells the caller that this call's work is already done."""
+        if key in self._graphs:
+            g, out = self._graphs[key]
+            return g, out, False
+        out = fn()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        self._graphs[key] = (g, out)
+        return g, out, True
+
+    def forward_graph(self, pcs1: torch.Tensor, pcs2: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Eval-mode get_model replayed as a CUDA graph over the caller's STATIC input buffers (refill them in
+        place between calls).  Returns the same 8 end_points buffers on every call."""
+        key = ("fwd", pcs1.data_ptr(), pcs2.data_ptr(), tuple(pcs1.shape), self.pflag)
+        g, out, fresh = self._capture(key, lambda: self.forward(pcs1, pcs2, False))
+        if not fresh:
+            g.replay()
+        return out
+
+    def _advance_step(self) -> None:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.an3d_step_advance(self.step_dev.data_ptr(), self.seed_dev.data_ptr(), 0, stream),
+                   "an3d_step_advance")
+
+    def _adam_step_dev(self, lr: float, grad_scale: float, beta1=0.9, beta2=0.999, eps=1e-8) -> None:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.an3d_adam_step_dev(self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                               self.adam_v.data_ptr(), self.params.numel(), lr, self.step_dev.data_ptr(),
+                                               grad_scale, beta1, beta2, eps, stream), "an3d_adam_step_dev")
+
+    def train_step_graph(self, batch: Dict[str, torch.Tensor], lr: float, bn_decay: float, allreduce=None) -> torch.Tensor:
+        """`Engine.train_step` replayed as CUDA graphs over the caller's STATIC batch buffers.  Without an
+        all-reduce the whole step is one graph; with one (data parallel) the graph is split around the collective:
+        [advance step, forward, loss + backward] -> all-reduce (eager, NCCL) -> [Adam]."""
+        if getattr(self, "_step_dev_shadow", None) != self.step:      # eager steps ran in between: resynchronise
+            self.step_dev.fill_(self.step)
+        ptrs = tuple(batch[k].data_ptr() for k in sorted(batch))
+        shape = tuple(batch["pcs1"].shape)
+
+        def fwd_bwd():
+            self._advance_step()
+            ep = self.forward(batch["pcs1"], batch["pcs2"], True, bn_decay, None, seed_on_device=True)
+            return self.backward(batch["pcs1"], batch["pcs2"], batch, ep)
+
+        if allreduce is None:
+            def whole():
+                loss = fwd_bwd()
+                self._adam_step_dev(lr, 1.0)
+                return loss
+            g, loss, fresh = self._capture(("train", ptrs, shape, float(lr), float(bn_decay), self.pflag), whole)
+            if not fresh:
+                g.replay()
+        else:
+            g1, loss, fresh = self._capture(("train-a", ptrs, shape, float(bn_decay), self.pflag), fwd_bwd)
+            if not fresh:
+                g1.replay()
+            scale = float(allreduce(self.grads))
+            g2, _, fresh2 = self._capture(("train-b", float(lr), scale), lambda: self._adam_step_dev(lr, scale))
+            if not fresh2:
+                g2.replay()
+        self.step += 1
+        self._step_dev_shadow = self.step
         return loss
 
     # ---- small utilities on the same ABI ----------------------------------------------------

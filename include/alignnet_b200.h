@@ -96,6 +96,8 @@ typedef struct an3d_labels {
 typedef struct an3d_dropout {
   uint64_t seed;
   const float* masks[5];
+  const uint64_t* seed_dev; /* optional device pointer: when non-NULL the seed is read from device memory at
+                               execution time (lets a captured CUDA graph draw fresh masks on every replay) */
 } an3d_dropout;
 
 /* ---- host-only ------------------------------------------------------------------------ */
@@ -152,6 +154,14 @@ int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_
 
 /* tf_get_angles (models/tp8.py:294-301; scaled=1: residual * pi/nb, floor-mod wrap) or
  * classLogits2angle (tp8.py:229-244; scaled=0: unscaled residual, `if a > pi: a -= 2pi`). */
+/* Device-resident step state for CUDA-graph replay of the training step (train.py:212-217 keeps the global
+ * step in a tf.Variable for the same reason: it must advance inside the executed graph).
+ *   an3d_step_advance: *step_dev += 1 ; *seed_dev = seed_base + *step_dev   (one thread)
+ *   an3d_adam_step_dev: as an3d_adam_step with t = *step_dev read on the device (t >= 1). */
+int an3d_step_advance(int64_t* step_dev, uint64_t* seed_dev, uint64_t seed_base, void* stream);
+int an3d_adam_step_dev(float* params, const float* grads, float* m, float* v, int64_t count, float lr,
+                       const int64_t* step_dev, float grad_scale, float beta1, float beta2, float eps, void* stream);
+
 int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_t num_bins, int32_t scaled,
                        void* stream);
 

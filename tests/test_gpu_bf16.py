@@ -262,3 +262,47 @@ def test_bf16_train_step_runs_and_learns():
         losses.append(float(e.train_step(batch, lr=0.002, bn_decay=0.5, seed=i)[0].cpu()))
     assert np.isfinite(losses).all()
     assert min(losses[-3:]) < losses[0], losses
+
+
+def test_graph_replay_matches_eager_steps():
+    """Engine.train_step_graph / forward_graph (CUDA-graph replay with the global step and the dropout seed in
+    device memory) against the eager calls."""
+    from alignnet_b200 import synth
+    arch = A.Arch()
+    params = A.init_params(arch, 3)
+    batch = to_dev(synth.make_batch_fast(64, 200, seed=5))
+    ea, eb, ec = (make_engine(arch, params, A.init_state(arch)) for _ in range(3))
+    # first step: same parameters, same dropout seed (the graph path seeds with the new step count t = 1).  Two
+    # eager runs of the bf16 step differ by the reordering of fp32 atomics; the graph run must sit inside that noise.
+    l_a = float(ea.train_step(batch, lr=0.002, bn_decay=0.5, seed=1)[0].cpu())
+    l_c = float(ec.train_step(batch, lr=0.002, bn_decay=0.5, seed=1)[0].cpu())
+    l_b = float(eb.train_step_graph(batch, lr=0.002, bn_decay=0.5)[0].cpu())
+    noise = abs(l_a - l_c)
+    assert abs(l_b - l_a) <= 3 * noise + 5e-3 * abs(l_a), (l_a, l_c, l_b)
+    # a different seed gives a visibly different loss (the mask really comes from the device-side seed)
+    ed = make_engine(arch, params, A.init_state(arch))
+    l_d = float(ed.train_step(batch, lr=0.002, bn_decay=0.5, seed=12345)[0].cpu())
+    assert abs(l_d - l_a) > 10 * (abs(l_b - l_a) + 1e-6) or abs(l_d - l_a) > 1e-3
+    losses = [l_b]
+    for _ in range(4):
+        losses.append(float(eb.train_step_graph(batch, lr=0.002, bn_decay=0.5)[0].cpu()))
+    assert eb.step == 5 and int(eb.step_dev.cpu()) == 5 and int(eb.seed_dev.cpu()) == 5
+    assert np.isfinite(losses).all() and len(set(losses)) == 5          # every replay is a new step
+    # Adam with the step count read on the device == Adam with the host step count
+    g = torch.randn_like(ea.grads)
+    for e in (ea, ec):
+        e.set_params(params); e.adam_m.zero_(); e.adam_v.zero_(); e.grads.copy_(g)
+    ea.step = 6
+    ea.adam_step(0.01)                           # host t = 7
+    ec.step_dev.fill_(7)
+    ec._adam_step_dev(0.01, 1.0)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ec.params.cpu().numpy(), ea.params.cpu().numpy(), rtol=0, atol=2e-7)
+    # eval forward: replay == eager call
+    x = ea.forward(batch["pcs1"], batch["pcs2"], False)
+    xa = {k: v.clone() for k, v in x.items()}
+    for _ in range(2):
+        xg = ea.forward_graph(batch["pcs1"], batch["pcs2"])
+    for k in xa:
+        # (split-K reductions of the small-batch FC GEMMs reorder fp32 sums between runs)
+        np.testing.assert_allclose(xg[k].cpu().numpy(), xa[k].cpu().numpy(), atol=1e-3, rtol=1e-4)
