@@ -42,15 +42,31 @@ __global__ void pool_bwd_prep_kernel(const float* dG, int64_t lddg, const float*
   const float sg = gamma[c] < 0.f ? -1.f : 1.f;
   const float bi = bias[c], mu = mean[c], iv = inv[c];
   double s0 = 0.0, s1 = 0.0;
-  for (int b = b0; b < b1; ++b) {
-    const float g = G[(int64_t)b * ldg + c];
-    const float d = g > 0.f ? dG[(int64_t)b * lddg + c] : 0.f;
-    dyext[(int64_t)b * C3 + c] = d;
-    const uint32_t key = zext[(int64_t)b * C3 + c];
-    const uint32_t bits = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
-    const float z = sg * __uint_as_float(bits & ~idx_mask) + bi;
-    s0 += (double)d;
-    s1 += (double)d * (double)((z - mu) * iv);
+  // four samples per iteration: their twelve loads are independent and in flight together
+  for (int bb = b0; bb < b1; bb += 4) {
+    float g[4], dg[4];
+    uint32_t key[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = bb + u;
+      g[u] = 0.f; dg[u] = 0.f; key[u] = 0u;
+      if (b < b1) {
+        g[u] = G[(int64_t)b * ldg + c];
+        dg[u] = dG[(int64_t)b * lddg + c];
+        key[u] = zext[(int64_t)b * C3 + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = bb + u;
+      if (b >= b1) continue;
+      const float d = g[u] > 0.f ? dg[u] : 0.f;
+      dyext[(int64_t)b * C3 + c] = d;
+      const uint32_t bits = (key[u] & 0x80000000u) ? (key[u] & 0x7fffffffu) : ~key[u];
+      const float z = sg * __uint_as_float(bits & ~idx_mask) + bi;
+      s0 += (double)d;
+      s1 += (double)d * (double)((z - mu) * iv);
+    }
   }
   atomicAdd(red3 + c, s0);
   atomicAdd(red3 + C3 + c, s1);
@@ -271,7 +287,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
   {
-    const int bchunk = 64;     // fewer, fatter blocks: the per-channel double atomics were contended
+    const int bchunk = 16;
     dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
     pool_bwd_prep_kernel<<<grid, 128, 0, st>>>(dG, lddg, p.g[s][br], ldg, q.zext[s][br], B, C3, gamma3, params + L3.b, mean3,
                                                inv3, q.idx_mask, q.dyext, q.red3, bchunk);

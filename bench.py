@@ -53,6 +53,15 @@ def emb_full_flops_per_pair(N: int) -> float:
     return 2.0 * 2.0 * N * 254528.0
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's EMB-stage launch from the committed
+    `ncu --set full` capture (profiles/r1b_roofline_traffic.json, written by tools/ncu_summary.py --traffic)."""
+    path = os.path.join(ROOT, "profiles", "r1b_roofline_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("conv_stack_fwd_kernel<1>")
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -342,7 +351,7 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                         "frac": achieved / pk["bf16_sustained"], "traffic": measured_traffic() if train else None,
                          "kernel": "conv_stack_fwd_kernel (full pass), 6 launches/step", "kernel_ms_per_step": k_ms,
                          "peak_source": pk["source"] + ", sustained bf16"},
             "clocks": clocks,
