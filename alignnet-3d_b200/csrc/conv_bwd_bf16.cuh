@@ -264,11 +264,13 @@ static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Param
 
   const int c = tid;                       // blockDim.x == C3 (<= 1024)
   const float s3c = P.s3[c];
+  const bool one_item_per_cloud = P.npc == 1;      // the common case: no integer division per item
   auto fetch = [&](int li, float& w, int& row) {
     w = 0.f; row = -1;
     if (li < n_local) {
       const int it = it_begin + li;
-      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+      const int cloud = one_item_per_cloud ? it : it / P.npc;
+      const int pchunk = one_item_per_cloud ? 0 : it - cloud * P.npc;
       const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
       const float wv = s3c * P.dyext[(size_t)cloud * P.C3 + c];
       const int r = P.gidx[(size_t)cloud * P.C3 + c] - p0;
@@ -278,35 +280,45 @@ static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Param
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  float w0, w1, w2; int r0, r1, r2;
-  fetch(0, w0, r0);
-  fetch(1, w1, r1);
-  for (int li = 0; li < n_local; ++li) {
-    const int st = li % kT1Stages;
-    fetch(li + 2, w2, r2);
-    // refill the stage drained one iteration ago (every warp has arrived on its `empty` barrier by now, or will shortly)
-    if (tid == 0 && li >= 1 && li - 1 + kT1Stages < n_local) {
-      const int sp = (li - 1) % kT1Stages;
-      mbar_wait(&empty[sp], (uint32_t)(((li - 1) / kT1Stages) & 1));
-      load_img(li - 1 + kT1Stages);
-    }
-    mbar_wait(&full[st], (uint32_t)((li / kT1Stages) & 1));
-    if (r0 >= 0) {
-      const uint8_t* src = sA + (size_t)st * qbytes + (uint32_t)r0 * 16u;
+  // (arg row, weight) pairs are fetched kT1Look items ahead into a register ring with compile-time slots (the item
+  // loop is unrolled by the ring size): one or two items of look-ahead left the kernel waiting on these loads
+  constexpr int kT1Look = 4;
+  float wq[kT1Look];
+  int rq[kT1Look];
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + kc * plane);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  for (int u = 0; u < kT1Look; ++u) fetch(u, wq[u], rq[u]);
+  for (int li0 = 0; li0 < n_local; li0 += kT1Look) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          acc[kc * 8 + 2 * h] = fmaf(w0, __uint_as_float(u[h] << 16), acc[kc * 8 + 2 * h]);
-          acc[kc * 8 + 2 * h + 1] = fmaf(w0, __uint_as_float(u[h] & 0xffff0000u), acc[kc * 8 + 2 * h + 1]);
+    for (int u = 0; u < kT1Look; ++u) {
+      const int li = li0 + u;
+      if (li >= n_local) break;
+      const int st = li % kT1Stages;
+      const float w0 = wq[u];
+      const int r0 = rq[u];
+      fetch(li + kT1Look, wq[u], rq[u]);
+      // refill the stage drained one iteration ago (every warp has arrived on its `empty` barrier by now, or will shortly)
+      if (tid == 0 && li >= 1 && li - 1 + kT1Stages < n_local) {
+        const int sp = (li - 1) % kT1Stages;
+        mbar_wait(&empty[sp], (uint32_t)(((li - 1) / kT1Stages) & 1));
+        load_img(li - 1 + kT1Stages);
+      }
+      mbar_wait(&full[st], (uint32_t)((li / kT1Stages) & 1));
+      if (r0 >= 0) {
+        const uint8_t* src = sA + (size_t)st * qbytes + (uint32_t)r0 * 16u;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + kc * plane);
+          const uint32_t uu[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            acc[kc * 8 + 2 * h] = fmaf(w0, __uint_as_float(uu[h] << 16), acc[kc * 8 + 2 * h]);
+            acc[kc * 8 + 2 * h + 1] = fmaf(w0, __uint_as_float(uu[h] & 0xffff0000u), acc[kc * 8 + 2 * h + 1]);
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-    w0 = w1; r0 = r1; w1 = w2; r1 = r2;
   }
   float* dst = P.t1 + (size_t)(kq * 32) * P.C3 + c;
 #pragma unroll
