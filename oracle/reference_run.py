@@ -74,7 +74,7 @@ def configure(config_name: str = "SynthCars", overrides: Optional[dict] = None):
     return config.configGlobal
 
 
-def arch_overrides(arch) -> dict:
+def arch_overrides(arch, loss: str = "separate") -> dict:
     """oracle.arch.Arch -> the config keys models/tp8.py reads."""
     return {"model": {"backbone": "pointnet",
                       "options": {"angle_factor": arch.angle_factor, "early_stage_factor": arch.early_stage_factor,
@@ -83,16 +83,16 @@ def arch_overrides(arch) -> dict:
                                   "embedding": list(arch.emb_conv),
                                   "remaining_transform_prediction": [list(arch.head_fc), arch.head_keep]},
                       "angles": {"num_bins": arch.num_bins, "accept_inverted_angle": arch.accept_inverted_angle}},
-            "training": {"loss": {"loss": "separate", "options": {"soft_angle_classes": False}}}}
+            "training": {"loss": {"loss": loss, "options": {"soft_angle_classes": False}}}}
 
 
 def run(batch: Dict[str, np.ndarray], arch, params: Dict[str, np.ndarray], state: Dict[str, np.ndarray],
         is_training: bool, bn_decay: Optional[float] = None, masks: Optional[Dict[str, np.ndarray]] = None,
-        double: bool = False, with_loss: bool = True, with_grads: bool = False):
+        double: bool = False, with_loss: bool = True, with_grads: bool = False, loss: str = "separate"):
     """One evaluation of the reference graph.  Returns dict(end_points, loss, grads, new_state, var_names, ...)."""
     import torch
     tf, tp8, _ = load()
-    configure("SynthCars", arch_overrides(arch))
+    configure("SynthCars", arch_overrides(arch, loss))
     tf.reset()
     dt = torch.float64 if double else torch.float32
     tf.set_float_dtype(dt)

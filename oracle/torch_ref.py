@@ -221,6 +221,19 @@ def get_loss(translations, rel_angles, pc1_centers, pc2_centers, pc1_angles, pc2
     return per_transform
 
 
+def get_loss_p2p(pcs1, pc1_centers, end_points):
+    """models/tp8.py:374-398 _get_loss_p2p as the reference actually computes it (quirk Q6, a21).
+    `tf_translate_pcs` (tp8.py:357-358) RETURNS the tiled translation instead of adding it, so every step of
+    `tf_transform_pcs` (:361-371) overwrites the cloud and the result is tile(rotation_centers); the predicted
+    translation and angle drop out.  `tf.norm(..., axis=1)` (:386) reduces over the POINT axis, hence
+        loss = mean_{b,d} N * (pred_s2_pc1centers - pc1_centers)^2 ;   per_transform_loss = loss / B,
+    and the `accept_inverted_angle` variant (:388-393) is identical to it.  No shipped config selects this loss
+    (`default.json` training.loss.loss = 'separate'); the engine rejects it, the oracle restates it for the record."""
+    B, N = pcs1.shape[0], pcs1.shape[1]
+    d = end_points["pred_s2_pc1centers"] - pc1_centers
+    return (N * d * d).mean() / B
+
+
 # --------------------------------------------------------------------------------------
 # optimiser + schedules (train.py:133-174, 211-217) [TF-sem for Adam]
 # --------------------------------------------------------------------------------------

@@ -158,6 +158,20 @@ def test_live_placeholder_contract():
 
 
 @live
+def test_p2p_loss_quirk_q6_matches_reference_code():
+    """a21: the reference's own _get_loss_p2p (executed) against the closed form the oracle states for it."""
+    g, arch, params, state, batch, masks = golden_case("tiny_B4_N16")
+    for inv in (True, False):
+        arch.accept_inverted_angle = inv
+        out = RR.run(batch, arch, params, state, False, double=True, loss="p2p")
+        ep = {k: torch.tensor(v) for k, v in out["end_points"].items()}
+        ours = TR.get_loss_p2p(torch.tensor(batch["pcs1"], dtype=torch.float64),
+                               torch.tensor(batch["pc1_centers"], dtype=torch.float64), ep)
+        assert abs(float(ours) - out["loss"]) < 1e-10 * max(1.0, abs(out["loss"])), (float(ours), out["loss"])
+    assert out["loss"] > 0
+
+
+@live
 def test_shim_scoping_follows_tf1():
     tf, _, _ = RR.load()
     tf.reset()
