@@ -1,6 +1,8 @@
 // Flat-buffer TF-Adam, host-decode of angle logits, batched z-axis rigid transforms.
 #include <cmath>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace an3d {
@@ -126,6 +128,73 @@ int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_
   adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, count,
                                                                                    (float)lr_t, grad_scale, beta1,
                                                                                    beta2, eps, nullptr, lr);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+// ---- evaluation metrics (evaluation.py:16-46,128-211) -----------------------------------------------------------
+static __device__ __forceinline__ double floor_mod_d(double x, double y) {
+  double r = fmod(x, y);
+  if (r != 0.0 && ((y < 0.0) != (r < 0.0))) r += y;
+  return r;
+}
+static __device__ __forceinline__ double angle_diff_d(double a, double b) {       // evaluation.py:26-28
+  const double pi = 3.14159265358979323846;
+  return floor_mod_d(b - a + pi, 2.0 * pi) - pi;
+}
+
+static __global__ void __launch_bounds__(256) evaluate_kernel(const double* pt, const double* pa, const double* pc,
+                                                              const double* gt, const double* ga, const double* gc,
+                                                              const uint8_t* is_test, int n, int inverted, double* acc) {
+  __shared__ double sacc[3 * 5 * 14];
+  for (int i = threadIdx.x; i < 210; i += blockDim.x) sacc[i] = 0.0;
+  __syncthreads();
+  const double pi = 3.14159265358979323846;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // translate_transform_to_new_center_of_rotation (pointcloud.py:309-318): t' = -d + Rz(a) d + t, d = c_gt - c_pred
+    const double a = pa[i];
+    const double dx = gc[3 * i] - pc[3 * i], dy = gc[3 * i + 1] - pc[3 * i + 1];
+    const double cs = cos(a), sn = sin(a);
+    const double tx = -dx + (cs * dx - sn * dy) + pt[3 * i], ty = -dy + (sn * dx + cs * dy) + pt[3 * i + 1];
+    const double ex = tx - gt[3 * i], ey = ty - gt[3 * i + 1];
+    const double dist_t = sqrt(ex * ex + ey * ey);
+    double dist_a = fabs(angle_diff_d(a, ga[i])) / pi * 180.0;
+    if (inverted) dist_a = fmin(dist_a, fabs(angle_diff_d(a + pi, ga[i])) / pi * 180.0);
+    if (dist_t > 10000.0) continue;                                               // evaluation.py:168
+    const double lt[3] = {dist_t < 0.02 ? 1.0 : 0.0, dist_t < 0.1 ? 1.0 : 0.0, dist_t < 0.2 ? 1.0 : 0.0};
+    const double la[3] = {dist_a < 1.0 ? 1.0 : 0.0, dist_a < 5.0 ? 1.0 : 0.0, dist_a < 10.0 ? 1.0 : 0.0};
+    const double row[14] = {1.0, lt[0], lt[1], lt[2], dist_t, dist_t * dist_t, la[0], la[1], la[2], dist_a, dist_a * dist_a,
+                            fmin(lt[0], la[0]), fmin(lt[1], la[1]), fmin(lt[2], la[2])};
+    const double cd = sqrt(gc[3 * i] * gc[3 * i] + gc[3 * i + 1] * gc[3 * i + 1] + gc[3 * i + 2] * gc[3 * i + 2]);
+    const bool test = is_test ? is_test[i] != 0 : false;
+    const double lim[5] = {1e300, 5.0, 10.0, 15.0, 20.0};
+    for (int s = 0; s < 3; ++s) {
+      if ((s == 1 && test) || (s == 2 && !test)) continue;
+      for (int r = 0; r < 5; ++r) {
+        if (cd > lim[r]) continue;
+        for (int q = 0; q < 14; ++q)
+          if (row[q] != 0.0) atomicAdd(&sacc[(s * 5 + r) * 14 + q], row[q]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 210; i += blockDim.x)
+    if (sacc[i] != 0.0) atomicAdd(acc + i, sacc[i]);
+}
+
+int an3d_evaluate(const double* pred_translations, const double* pred_angles, const double* pred_centers,
+                  const double* gt_translations, const double* gt_angles, const double* gt_pc1centers,
+                  const uint8_t* is_test, int32_t n, int32_t accept_inverted_angle, double* acc, void* stream) {
+  if (!pred_translations || !pred_angles || !pred_centers || !gt_translations || !gt_angles || !gt_pc1centers || !acc || n < 0) {
+    set_error("an3d_evaluate: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  AN3D_CUDA_CHECK(cudaMemsetAsync(acc, 0, 210 * sizeof(double), (cudaStream_t)stream));
+  if (n == 0) return AN3D_OK;
+  const int blocks = std::min(296, (n + 255) / 256);
+  evaluate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred_translations, pred_angles, pred_centers, gt_translations,
+                                                          gt_angles, gt_pc1centers, is_test, n, accept_inverted_angle, acc);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }

@@ -192,6 +192,17 @@ int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag);
 int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn,
                        int32_t b_mn, void* stream);
 
+/* Evaluation metrics on the device (evaluation.py:16-46,128-211).  For every predicted
+ * transform: centre-of-rotation correction of the translation (pointcloud.py:309-318), xy translation error with the
+ * 0.02 / 0.1 / 0.2 m levels, yaw error in degrees (optionally min with the 180-degree flip) with the 1 / 5 / 10
+ * levels, joint levels; accumulated over the sets {all, val, test} (is_test: n bytes, NULL = all val) and the ranges
+ * {all, 5 m, 10 m, 15 m, 20 m} of |gt_pc1center|.  Inputs are device double arrays ([n,3] / [n]); acc receives the
+ * raw sums [3][5][14] (num, 3 translation levels, sum d_t, sum d_t^2, 3 angle levels, sum d_a, sum d_a^2, 3 joint
+ * levels) and is zeroed by the call; the means / RMS of eval.json are a division on the host. */
+int an3d_evaluate(const double* pred_translations, const double* pred_angles, const double* pred_centers,
+                  const double* gt_translations, const double* gt_angles, const double* gt_pc1centers,
+                  const uint8_t* is_test, int32_t n, int32_t accept_inverted_angle, double* acc, void* stream);
+
 /* Diagnostic micro-benchmark: `ctas` CTAs each issue `iters` tcgen05 MMAs of shape 128 x n x 16 (bf16, operands in
  * the given majors, un-swizzled plane layout over a k-deep resident tile); cycles_per_mma_dev[cta] receives the
  * measured SM cycles per MMA.  Used to choose operand layouts, not on the hot path. */
