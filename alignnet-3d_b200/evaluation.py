@@ -40,6 +40,8 @@ def accumulate(all_pred_translations, all_pred_angles, all_gt_translations, all_
         flags = torch.as_tensor(np.asarray(is_test, dtype=np.uint8)).contiguous().to(device)
         if flags.numel() != n:
             raise ValueError("evaluate: is_test must have one entry per transform")
+    if n == 0:                       # nothing to reduce (empty tensors have no device address to pass)
+        return np.zeros((3, 5, 14))
     acc = torch.empty(210, dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream(torch.device(device)).cuda_stream
     _lib.check(lib.an3d_evaluate(pt.data_ptr(), pa.data_ptr(), pc.data_ptr(), gt.data_ptr(), ga.data_ptr(), gc.data_ptr(),
