@@ -61,7 +61,7 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     f.M = L.cin; f.N = L.cout; f.K = R; f.bias = nullptr; f.pro_scale = psc; f.pro_shift = psh; f.pro_mask = pmask;
     f.pro_mask_scale = pmask_scale; f.accumulate = 1;
     const int tiles = ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
-    f.ksplit = std::max(1, std::min((R + 511) / 512, (296 + tiles - 1) / tiles));
+    f.ksplit = std::max(1, std::min((R + 255) / 256, (296 + tiles - 1) / tiles));   // fill the SMs: wgrad has few output tiles
     if (fcgemm::usable(f)) { AN3D_TRY(fcgemm::launch(f, st)); wgrad_done = true; }
     if (dX) {
       fcgemm::Params d;
