@@ -35,6 +35,7 @@ struct Params {
   double* stat_sum = nullptr;               // optional [N]: += column sums of C (bias included); needs ksplit == 1
   double* stat_sq = nullptr;                // optional [N]: += column sums of C^2
   int a_vec = 1, b_vec = 1, c_vec = 1;      // set by launch(): 16-byte vector access legal for A / B / C
+  int nbatch = 1;                           // set by launch(): 2 = two problems of identical shape in one launch (grid.z)
 };
 
 constexpr int kLoaderThreads = 256;
@@ -141,7 +142,11 @@ __device__ __forceinline__ void tile_finish(const TileRegs& R, uint8_t* dst, int
   }
 }
 
-static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Params P) {
+// Two problems of identical shape (the two siamese branches of one FC layer: same weights, their own activations,
+// BN prologue, statistics and output) can share a launch: blockIdx.z = batch * ksplit + k-slice.
+static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Params P0, const Params P1) {
+  const int bz = (int)blockIdx.z / P0.ksplit, kz = (int)blockIdx.z - bz * P0.ksplit;
+  const Params P = bz ? P1 : P0;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kTileStride;
@@ -150,7 +155,7 @@ static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Param
   const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128;
   int kchunk = (P.K + P.ksplit - 1) / P.ksplit;
   kchunk = (kchunk + 63) & ~63;
-  const int kbeg = blockIdx.z * kchunk, kend = min(P.K, kbeg + kchunk);
+  const int kbeg = kz * kchunk, kend = min(P.K, kbeg + kchunk);
   const int nkb = kend > kbeg ? (kend - kbeg + 63) / 64 : 0;
 
   if (tid == 0) {
@@ -224,7 +229,7 @@ static __global__ void __launch_bounds__(kThreads, 1) fc_gemm_kernel(const Param
         const int j = j0 + g16 + j4;
         float v[4] = {__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
                       __uint_as_float(r[j4 + 3])};
-        if (P.bias && blockIdx.z == 0) {
+        if (P.bias && kz == 0) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             if (j + e < P.N) v[e] += P.bias[j + e];
@@ -279,21 +284,36 @@ inline bool usable(const Params& p) {
   return p.M > 0 && p.N > 0 && p.K > 0 && 2.0 * p.M * p.N * p.K >= min_flop() && !(p.stat_sum && p.ksplit > 1);
 }
 
-static int launch(Params p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AN3D_CUDA_CHECK(cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
+inline void finish_params(Params& p) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int a_contig = p.a_mn ? p.M : p.K, b_contig = p.b_mn ? p.N : p.K;
   p.a_vec = al(p.A) && p.lda % 4 == 0 && a_contig % 8 == 0 && (!p.pro_scale || (al(p.pro_scale) && al(p.pro_shift))) &&
             (!p.pro_mask || al(p.pro_mask));
   p.b_vec = al(p.B) && p.ldb % 4 == 0 && b_contig % 8 == 0;
   p.c_vec = al(p.C) && p.ldc % 4 == 0 && p.N % 4 == 0;
-  dim3 grid((p.M + 127) / 128, (p.N + 127) / 128, p.ksplit);
+}
+
+// p1 == nullptr: one problem; otherwise two problems of identical shape / majors / ksplit in one launch
+static int launch(Params p, cudaStream_t st, const Params* p1 = nullptr) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  finish_params(p);
+  Params q = p;
+  if (p1) {
+    q = *p1;
+    if (q.M != p.M || q.N != p.N || q.K != p.K || q.a_mn != p.a_mn || q.b_mn != p.b_mn || q.ksplit != p.ksplit) {
+      set_error("fcgemm::launch: batched problems must have identical shapes");
+      return AN3D_ERR_INVALID;
+    }
+    finish_params(q);
+  }
+  p.nbatch = q.nbatch = p1 ? 2 : 1;
+  dim3 grid((p.M + 127) / 128, (p.N + 127) / 128, p.ksplit * p.nbatch);
   prof_mark(PROF_FC, true, st);
-  fc_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+  fc_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(p, q);
   prof_mark(PROF_FC, false, st);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;

@@ -153,6 +153,65 @@ static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const fl
   return AN3D_OK;
 }
 
+// get_mlp for BOTH siamese branches of stage s in the bf16 mode: every layer is one launch of the tcgen05 GEMM with
+// the two branches as a batch of two problems (same weights; their own input, BN prologue, statistics, mask, output).
+static int mlp_forward_pair(const Model& m, const PlanF32& p, int s, const float* const x_in[2], int64_t ldx_in,
+                            const float* params, float* state, bool training, float decay, const float* const mask[2],
+                            cudaStream_t st) {
+  const float* x[2] = {x_in[0], x_in[1]};
+  int64_t ldx = ldx_in;
+  const float *psc[2] = {nullptr, nullptr}, *psh[2] = {nullptr, nullptr};
+  const size_t nl = m.fc[s].size();
+  for (size_t l = 0; l < nl; ++l) {
+    const Lin& L = m.fc[s][l];
+    fcgemm::Params f[2];
+    bool fused_stats = L.bn >= 0 && training;
+    for (int br = 0; br < 2; ++br) {
+      fcgemm::Params& q = f[br];
+      q.A = x[br]; q.lda = ldx; q.a_mn = 0; q.B = params + L.w; q.ldb = L.cout; q.b_mn = 1; q.C = p.fz[s][l][br]; q.ldc = L.cout;
+      q.M = p.B; q.N = L.cout; q.K = L.cin; q.bias = params + L.b; q.pro_scale = psc[br]; q.pro_shift = psh[br];
+      if (l == nl - 1 && training && mask[br]) {
+        q.pro_mask = mask[br];
+        q.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
+      }
+      q.ksplit = 1; q.accumulate = 0;
+      if (fused_stats) {
+        BnView v = bn_view(m, p, params, state, false, br, L.bn);
+        q.stat_sum = v.acc0;
+        q.stat_sq = v.acc1;
+      }
+    }
+    if (!fused_stats) {   // few output tiles (inference batches, narrow output layers): split K so that the launch fills the SMs
+      const int tiles = 2 * ((f[0].M + 127) / 128) * ((f[0].N + 127) / 128);
+      const int ks = std::min(f[0].K / 128, 148 / tiles);
+      if (ks > 1) {
+        for (int br = 0; br < 2; ++br) {
+          f[br].ksplit = ks;
+          AN3D_CUDA_CHECK(cudaMemsetAsync(f[br].C, 0, sizeof(float) * (size_t)f[br].M * f[br].ldc, st));
+        }
+      }
+    }
+    AN3D_TRY(fcgemm::launch(f[0], st, &f[1]));
+    for (int br = 0; br < 2; ++br) {
+      if (L.bn >= 0) {
+        BnView v = bn_view(m, p, params, state, false, br, L.bn);
+        if (fused_stats) {
+          bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
+                                                                      v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
+          AN3D_LAUNCH_CHECK();
+        } else {
+          AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
+        }
+        psc[br] = v.scale;
+        psh[br] = v.shift;
+      }
+      x[br] = p.fz[s][l][br];
+    }
+    ldx = L.cout;
+  }
+  return AN3D_OK;
+}
+
 int forward_impl(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
                 int flags, float bn_decay, const an3d_dropout* dropout, const an3d_outputs* out, void* workspace,
                 int64_t workspace_bytes, cudaStream_t st) {
@@ -193,42 +252,63 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   float* lg[2] = {out->pred_pc1angle_logits, out->pred_pc2angle_logits};
   const unsigned pt_blocks = (unsigned)((M + 255) / 256);
   const unsigned w_blocks = (unsigned)((B + 3) / 4);   // one warp per sample
+  if (bf16) {
+    // stage-major order: the two branches of a stage are independent, so their FC layers share launches
+    // (mlp_forward_pair) and every under-filled GEMM gets twice the CTAs
+    for (int br = 0; br < 2; ++br) {
+      centroid_kernel<<<(B + 3) / 4, 128, 0, st>>>(pcs[br], N, p.mu[br], B);
+      AN3D_LAUNCH_CHECK();
+    }
+    const float* mk1[2] = {masks[0], masks[1]};
+    const float* mk2[2] = {masks[2], masks[3]};
+    // stage 1 (tp8.py:106-109)
+    for (int br = 0; br < 2; ++br)
+      AN3D_TRY(conv_stack_forward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, params, state, training, bn_decay, st));
+    const float* g1[2] = {p.g[S1][0], p.g[S1][1]};
+    AN3D_TRY(mlp_forward_pair(m, p, S1, g1, m.conv[S1].back().cout, params, state, training, bn_decay, mk1, st));
+    for (int br = 0; br < 2; ++br) {
+      post_s1_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(p.fz[S1][m.fc[S1].size() - 1][br], p.mu[br], c1[br], B);
+      AN3D_LAUNCH_CHECK();
+    }
+    // stage 2 (tp8.py:113-118)
+    for (int br = 0; br < 2; ++br)
+      AN3D_TRY(conv_stack_forward_bf16(m, p, S2, br, pcs[br], c1[br], nullptr, params, state, training, bn_decay, st));
+    const float* g2[2] = {p.g[S2][0], p.g[S2][1]};
+    AN3D_TRY(mlp_forward_pair(m, p, S2, g2, m.conv[S2].back().cout, params, state, training, bn_decay, mk2, st));
+    for (int br = 0; br < 2; ++br) {
+      post_s2_kernel<<<w_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
+                                               p.angk[br], B, nb);
+      AN3D_LAUNCH_CHECK();
+    }
+    // canonicalise + final embedding (tp8.py:122-130)
+    for (int br = 0; br < 2; ++br)
+      AN3D_TRY(conv_stack_forward_bf16(m, p, EMB, br, pcs[br], c2[br], p.ang[br], params, state, training, bn_decay, st));
+  } else {
   for (int br = 0; br < 2; ++br) {
     centroid_kernel<<<(B + 3) / 4, 128, 0, st>>>(pcs[br], N, p.mu[br], B);
     AN3D_LAUNCH_CHECK();
     // stage 1 (tp8.py:106-109)
-    if (bf16) {
-      AN3D_TRY(conv_stack_forward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, params, state, training, bn_decay, st));
-    } else {
-      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], p.mu[br], nullptr, p.pin[S1][br], N, M);
-      AN3D_LAUNCH_CHECK();
-      AN3D_TRY(conv_stack_forward(m, p, S1, br, params, state, training, bn_decay, st));
-    }
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], p.mu[br], nullptr, p.pin[S1][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, S1, br, params, state, training, bn_decay, st));
     AN3D_TRY(mlp_forward(m, p, S1, br, p.g[S1][br], m.conv[S1].back().cout, params, state, training, bn_decay,
                          masks[br], st));
     post_s1_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(p.fz[S1][m.fc[S1].size() - 1][br], p.mu[br], c1[br], B);
     AN3D_LAUNCH_CHECK();
     // stage 2 (tp8.py:113-118)
-    if (bf16) {
-      AN3D_TRY(conv_stack_forward_bf16(m, p, S2, br, pcs[br], c1[br], nullptr, params, state, training, bn_decay, st));
-    } else {
-      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c1[br], nullptr, p.pin[S2][br], N, M);
-      AN3D_LAUNCH_CHECK();
-      AN3D_TRY(conv_stack_forward(m, p, S2, br, params, state, training, bn_decay, st));
-    }
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c1[br], nullptr, p.pin[S2][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, S2, br, params, state, training, bn_decay, st));
     AN3D_TRY(mlp_forward(m, p, S2, br, p.g[S2][br], m.conv[S2].back().cout, params, state, training, bn_decay,
                          masks[2 + br], st));
     post_s2_kernel<<<w_blocks, 128, 0, st>>>(p.fz[S2][m.fc[S2].size() - 1][br], c1[br], c2[br], lg[br], p.ang[br],
                                              p.angk[br], B, nb);
     AN3D_LAUNCH_CHECK();
     // canonicalise + final embedding (tp8.py:122-130)
-    if (bf16) {
-      AN3D_TRY(conv_stack_forward_bf16(m, p, EMB, br, pcs[br], c2[br], p.ang[br], params, state, training, bn_decay, st));
-    } else {
-      stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c2[br], p.ang[br], p.pin[EMB][br], N, M);
-      AN3D_LAUNCH_CHECK();
-      AN3D_TRY(conv_stack_forward(m, p, EMB, br, params, state, training, bn_decay, st));
-    }
+    stage_input_kernel<<<pt_blocks, 256, 0, st>>>(pcs[br], c2[br], p.ang[br], p.pin[EMB][br], N, M);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(conv_stack_forward(m, p, EMB, br, params, state, training, bn_decay, st));
+  }
   }
   // head (tp8.py:144-156)
   AN3D_TRY(mlp_forward(m, p, HEAD, 0, p.feat, 2 * m.conv[EMB].back().cout, params, state, training, bn_decay, masks[4],
