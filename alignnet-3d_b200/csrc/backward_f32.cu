@@ -186,6 +186,77 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
   return AN3D_OK;
 }
 
+// bf16 mode, both siamese branches of one FC stack at once: the BN/ReLU backward runs per branch, the wgrad and dgrad
+// GEMMs of a layer are ONE launch each with the two branches as a batch (wgrad accumulates both into grads.W).
+int mlp_backward_pair(const Model& m, const PlanF32& p, int s, const float* const x[2], int64_t ldx, const float* const dOut[2],
+                      const float* params, float* grads, float* const dIn[2], int64_t lddin, const float* const mask[2],
+                      cudaStream_t st) {
+  const int nl = (int)m.fc[s].size();
+  const float* dZ[2] = {dOut[0], dOut[1]};
+  float* const scratch[2][2] = {{p.dfc[0], p.dfc[1]}, {p.dfc_b[0], p.dfc_b[1]}};
+  int cur = 0;
+  for (int l = nl - 1; l >= 0; --l) {
+    const Lin& L = m.fc[s][l];
+    const int R = p.B;
+    for (int br = 0; br < 2; ++br) {
+      if (L.bn < 0) continue;
+      BnRef v = bn_ref(m, p, grads, false, br, L.bn);
+      const bool dropped = (l == nl - 2) && mask[br];
+      const float ms = mask[br] ? 1.0f / m.arch.keep_prob[s] : 1.f;
+      AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], R, dZ[br], L.cout, dropped ? mask[br] : nullptr, ms,
+                                const_cast<float*>(dZ[br]), L.cout, st));
+    }
+    fcgemm::Params w[2], d[2];
+    float* dX[2];
+    int64_t lddx;
+    for (int br = 0; br < 2; ++br) {
+      const float *X, *psc = nullptr, *psh = nullptr, *pm = nullptr;
+      int64_t lx;
+      if (l > 0) {
+        const Lin& P = m.fc[s][l - 1];
+        X = p.fz[s][l - 1][br];
+        lx = P.cout;
+        const int64_t sl = m.bn_slot_off(false, br, P.bn);
+        psc = p.bn.scale + sl;
+        psh = p.bn.shift + sl;
+        if (l == nl - 1) pm = mask[br];
+        dX[br] = scratch[br][cur];
+        lddx = L.cin;
+      } else {
+        X = x[br];
+        lx = ldx;
+        dX[br] = dIn[br];
+        lddx = lddin;
+      }
+      fcgemm::Params& f = w[br];
+      f.A = X; f.lda = lx; f.a_mn = 1; f.B = dZ[br]; f.ldb = L.cout; f.b_mn = 1; f.C = grads + L.w; f.ldc = L.cout;
+      f.M = L.cin; f.N = L.cout; f.K = R; f.pro_scale = psc; f.pro_shift = psh; f.pro_mask = pm;
+      f.pro_mask_scale = mask[br] ? 1.0f / m.arch.keep_prob[s] : 1.f; f.accumulate = 1;
+      const int tiles = 2 * ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
+      f.ksplit = std::max(1, std::min((R + 255) / 256, (296 + tiles - 1) / tiles));
+      fcgemm::Params& g = d[br];
+      g.A = dZ[br]; g.lda = L.cout; g.a_mn = 0; g.B = params + L.w; g.ldb = L.cout; g.b_mn = 0; g.C = dX[br]; g.ldc = lddx;
+      g.M = R; g.N = L.cin; g.K = L.cout; g.ksplit = 1; g.accumulate = 0;
+    }
+    AN3D_TRY(fcgemm::launch(w[0], st, &w[1]));
+    if (L.bn < 0) {   // only a bias that does not feed a batch-statistics BN has a non-zero gradient
+      for (int br = 0; br < 2; ++br) {
+        AN3D_CUDA_CHECK(cudaMemsetAsync(p.dbias_acc, 0, sizeof(double) * L.cout, st));
+        ColArgs a;
+        a.Z = dZ[br]; a.ldz = L.cout; a.R = R; a.C = L.cout; a.acc0 = p.dbias_acc;
+        AN3D_TRY(launch_col_reduce(a, COL_SUM, st));
+        add_double_to_float_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(p.dbias_acc, grads + L.b, L.cout);
+        AN3D_LAUNCH_CHECK();
+      }
+    }
+    AN3D_TRY(fcgemm::launch(d[0], st, &d[1]));
+    dZ[0] = dX[0];
+    dZ[1] = dX[1];
+    cur ^= 1;
+  }
+  return AN3D_OK;
+}
+
 // dOh[:, :3] = dpred_t ; dOh[:, 3:] = drem ; dc2[0] = ds2c1 - dpred_t ; dc2[1] = ds2c2 + dpred_t  (tp8.py:155)
 // (one warp per sample)
 __global__ void assemble_head_grad_kernel(const float* dend, float* dOh, float* dc2a, float* dc2b, int B, int nb) {
@@ -254,6 +325,40 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
   AN3D_TRY(mlp_backward(m, p, HEAD, 0, p.feat, 2 * c_emb, p.dout, params, grads, p.dfeat, 2 * c_emb, masks[4], st));
   const float* dlg[2] = {p.dend + (int64_t)5 * B * 3, p.dend + (int64_t)5 * B * 3 + (int64_t)B * 2 * nb};
   const float* ds1c[2] = {p.dend, p.dend + (int64_t)B * 3};
+  if (bf16) {
+    // stage-major order (mirrors the forward): both branches' FC layers share launches
+    const int c2w = m.conv[S2].back().cout, c1w = m.conv[S1].back().cout;
+    float* const dO[2] = {p.dout, p.dout_b};
+    float* const dGs[2] = {p.dg, p.dg_b};
+    for (int br = 0; br < 2; ++br) {
+      AN3D_CUDA_CHECK(cudaMemsetAsync(p.dang[br], 0, sizeof(float) * B, st));
+      AN3D_TRY(conv_stack_backward_bf16(m, p, EMB, br, pcs[br], c2o[br], p.ang[br], p.dfeat + (int64_t)br * c_emb,
+                                        2 * c_emb, params, grads, true, p.dc2[br], p.dang[br], st));
+      assemble_s2_grad_kernel<<<w_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], dO[br],
+                                                        p.dc1[br], B, nb);
+      AN3D_LAUNCH_CHECK();
+    }
+    {
+      const float* x[2] = {p.g[S2][0], p.g[S2][1]};
+      const float* dOut[2] = {dO[0], dO[1]};
+      const float* mk[2] = {masks[2], masks[3]};
+      AN3D_TRY(mlp_backward_pair(m, p, S2, x, c2w, dOut, params, grads, dGs, c2w, mk, st));
+    }
+    for (int br = 0; br < 2; ++br)
+      AN3D_TRY(conv_stack_backward_bf16(m, p, S2, br, pcs[br], c1o[br], nullptr, dGs[br], c2w, params, grads, true,
+                                        p.dc1[br], nullptr, st));
+    {
+      // stage 1: d(delta1) = dc1 (tp8.py:109); its input p - mean(p) carries no parameter gradient
+      const float* x[2] = {p.g[S1][0], p.g[S1][1]};
+      const float* dOut[2] = {p.dc1[0], p.dc1[1]};
+      const float* mk[2] = {masks[0], masks[1]};
+      AN3D_TRY(mlp_backward_pair(m, p, S1, x, c1w, dOut, params, grads, dGs, c1w, mk, st));
+    }
+    for (int br = 0; br < 2; ++br)
+      AN3D_TRY(conv_stack_backward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, dGs[br], c1w, params, grads, false,
+                                        nullptr, nullptr, st));
+    return AN3D_OK;
+  }
   for (int br = 0; br < 2; ++br) {
     // final embedding stack: input q = Rz(a)(p - c2)
     if (bf16) {

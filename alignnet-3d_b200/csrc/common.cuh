@@ -183,6 +183,10 @@ struct PlanF32 {
   float* dg = nullptr;                      // [B, max C3] pooled-feature gradient
   float* dout = nullptr;                    // [B, 3+2nb] MLP output gradient
   double* dbias_acc = nullptr;              // [max ch] bias-gradient reduction scratch
+  // second set for branch 2 when the bf16 path walks the backward stage by stage with both branches' FC layers batched
+  float* dfc_b[2] = {nullptr, nullptr};
+  float* dg_b = nullptr;
+  float* dout_b = nullptr;
   float* dend = nullptr;                    // gradients of the 8 end_points, packed (see loss.cu)
   float* dc1[2];                            // [B,3] accumulated centre gradients
   float* dc2[2];

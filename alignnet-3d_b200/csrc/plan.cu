@@ -83,6 +83,12 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     p->dg = a.take<float>((int64_t)B * max_c3);
     p->dout = a.take<float>((int64_t)B * (3 + 2 * m.nb));
     p->dbias_acc = a.take<double>(std::max<int64_t>(std::max(max_conv_ch, max_fc_ch), 3 + 2 * m.nb));
+    if (bf16) {
+      p->dfc_b[0] = a.take<float>((int64_t)B * max_fc_ch);
+      p->dfc_b[1] = a.take<float>((int64_t)B * max_fc_ch);
+      p->dg_b = a.take<float>((int64_t)B * max_c3);
+      p->dout_b = a.take<float>((int64_t)B * (3 + 2 * m.nb));
+    }
     for (int br = 0; br < 2; ++br) {
       p->dc1[br] = a.take<float>((int64_t)B * 3);
       p->dc2[br] = a.take<float>((int64_t)B * 3);
