@@ -132,6 +132,38 @@ int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_
   return AN3D_OK;
 }
 
+// ---- batch assembly (provider.py:60-71,97-98,125-126) -----------------------------------------------------------
+static __global__ void resample_gather_kernel(const float* __restrict__ pts, const int64_t* __restrict__ off,
+                                              const int32_t* __restrict__ idx, int64_t total, int N, int stride,
+                                              const float* __restrict__ jitter, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / N);
+  const int r = idx[i];
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (r >= 0) {
+    const float* src = pts + (off[b] + r) * stride;
+    x = src[0]; y = src[1]; z = src[2];
+  }
+  if (jitter) { x += jitter[3 * i]; y += jitter[3 * i + 1]; z += jitter[3 * i + 2]; }
+  out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+}
+
+int an3d_resample_gather(const float* points, const int64_t* cloud_offset, const int32_t* sample_idx, int32_t batch,
+                         int32_t num_points, int32_t stride, const float* jitter, float* out, void* stream) {
+  if (!cloud_offset || !sample_idx || !out || batch < 0 || num_points < 0 || stride < 3) {
+    set_error("an3d_resample_gather: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  const int64_t total = (int64_t)batch * num_points;
+  if (total == 0) return AN3D_OK;
+  resample_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, cloud_offset, sample_idx,
+                                                                                           total, num_points, stride, jitter, out);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
 // ---- evaluation metrics (evaluation.py:16-46,128-211) -----------------------------------------------------------
 static __device__ __forceinline__ double floor_mod_d(double x, double y) {
   double r = fmod(x, y);

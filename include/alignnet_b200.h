@@ -192,6 +192,15 @@ int an3d_profile_end(float* ms_by_tag, int32_t* launches_by_tag);
 int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn,
                        int32_t b_mn, void* stream);
 
+/* Batch assembly on the device (provider.py:60-71,85-136).  `points` holds the ragged
+ * clouds of a batch back to back ([total, stride] floats, the first three columns are xyz, provider.py:125-126),
+ * cloud b starting at row cloud_offset[b]; out[b, n, :] = points[cloud_offset[b] + sample_idx[b, n], :3]
+ * (+ jitter[b, n, :] when given) -- the resample-with-replacement of provider.py:97-98 with the drawn indices, and
+ * jitter_point_cloud (:60-71) with the drawn, already clipped noise.  sample_idx < 0 yields a zero point (the
+ * reference substitutes zeros for an empty cloud, :97). */
+int an3d_resample_gather(const float* points, const int64_t* cloud_offset, const int32_t* sample_idx, int32_t batch,
+                         int32_t num_points, int32_t stride, const float* jitter, float* out, void* stream);
+
 /* Evaluation metrics on the device (evaluation.py:16-46,128-211).  For every predicted
  * transform: centre-of-rotation correction of the translation (pointcloud.py:309-318), xy translation error with the
  * 0.02 / 0.1 / 0.2 m levels, yaw error in degrees (optionally min with the 180-degree flip) with the 1 / 5 / 10
