@@ -313,3 +313,22 @@ def test_graph_replay_matches_eager_steps():
         a, b = xg[k].cpu().numpy(), xa[k].cpu().numpy()
         close = np.abs(a - b) <= 1e-3 + 1e-3 * np.abs(b)
         assert close.mean() > 0.9 and np.abs(a - b).max() <= 5e-2 * max(1.0, np.abs(b).max()), (k, close.mean())
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 200), (2, 15), (300, 8)])
+def test_bf16_edge_shapes_run_and_stay_finite(B, N):
+    """Degenerate shapes on the tensor-core path: a single pair, a single point, fewer items than SMs, more items
+    than SMs with tiny clouds.  Eval against the oracle on the bf16 bound; a training step must stay finite."""
+    from alignnet_b200 import synth
+    arch = A.Arch()
+    params, state = A.randomize_for_test(arch, A.init_params(arch, 40), A.init_state(arch), 41)
+    batch = synth.make_batch_fast(B, N, seed=B * 1000 + N)
+    ref, _ = NF.get_model(batch["pcs1"], batch["pcs2"], arch, params, state, False)
+    e = make_engine(arch, params, state)
+    dev = to_dev(batch)
+    ep = e.forward(dev["pcs1"], dev["pcs2"], False)
+    torch.cuda.synchronize()
+    compare(ep, ref, arch)
+    loss = e.train_step(dev, lr=0.001, bn_decay=0.5, seed=1)
+    torch.cuda.synchronize()
+    assert np.isfinite(loss.cpu().numpy()).all() and torch.isfinite(e.params).all() and torch.isfinite(e.grads).all()
