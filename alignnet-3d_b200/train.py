@@ -6,9 +6,9 @@
 Same CLI (train.py:31-39), config schema (the reference's configs/*.json load unchanged), schedules
 (train.py:133-174), epoch structure (train.py:296-326: train one epoch, evaluate, checkpoint on even / every fifth /
 last epoch) and output files: `<logdir>/config.json`, `<logdir>/out.log`, `<logdir>/val/eval%06d/{eval.json,
-eval_180.json, pred_*.npy}` (train.py:399-407,487-543, evaluation.py:274-287).  Differences, all deliberate:
-checkpoints are `model.ckpt.npz` / `model-<epoch>.npz` (flat dictionaries keyed by the TF variable names; reading
-TensorFlow's bundle format is row N1), there is no TensorBoard writer, `--refineICP` is rejected (row N4), and the
+eval_180.json, pred_*.npy}` (train.py:399-407,487-543, evaluation.py:274-287), `<logdir>/model.ckpt.*` and
+`<logdir>/model-<epoch>.*` in TensorFlow's checkpoint format (`alignnet_b200.tf_checkpoint`, train.py:316-322).
+Differences, all deliberate: there is no TensorBoard writer, `--refineICP` is rejected (row N4), and the
 val/test split of the synthetic sets (evaluation.py:161-162: idx >= 1000) is computed here and passed to the device
 evaluation.  One process per GPU; under torchrun the gradient all-reduce is the only collective."""
 from __future__ import annotations
@@ -27,7 +27,7 @@ import torch
 from . import config as C
 from . import dist as D
 from . import engine as E
-from . import evaluation, provider, schedules
+from . import evaluation, provider, schedules, tf_checkpoint
 
 logger = logging.getLogger("tp")
 
@@ -56,21 +56,15 @@ def _is_test(cfg, idxs: List[int]) -> np.ndarray:
     return np.arange(len(idxs)) >= 1000
 
 
-def save_checkpoint(eng: E.Engine, path: str) -> None:
-    blob = {"param/" + k: v for k, v in eng.get_params().items()}
-    blob.update({"state/" + k: v for k, v in eng.get_state().items()})
-    blob["adam_m"], blob["adam_v"] = eng.adam_m.cpu().numpy(), eng.adam_v.cpu().numpy()
-    blob["global_step"] = np.int64(eng.step)
-    np.savez(path, **blob)
+def save_checkpoint(eng: E.Engine, prefix: str) -> None:
+    """saver.save (train.py:316-322): a TensorFlow tensor-bundle checkpoint `<prefix>.index` + `<prefix>.data-*` with the
+    reference graph's variable names (parameters, BN shadows, Adam slots, global step)."""
+    tf_checkpoint.save_from_engine(eng, prefix)
 
 
-def load_checkpoint(eng: E.Engine, path: str) -> None:
-    blob = np.load(path)
-    eng.set_params({k[6:]: blob[k] for k in blob.files if k.startswith("param/")})
-    eng.set_state({k[6:]: blob[k] for k in blob.files if k.startswith("state/")})
-    eng.adam_m.copy_(torch.from_numpy(blob["adam_m"]))
-    eng.adam_v.copy_(torch.from_numpy(blob["adam_v"]))
-    eng.step = int(blob["global_step"])
+def load_checkpoint(eng: E.Engine, prefix: str) -> None:
+    """saver.restore (train.py:250-293); also reads checkpoints written by the reference itself."""
+    tf_checkpoint.load_into_engine(eng, prefix)
 
 
 def train_one_epoch(cfg, eng: E.Engine, train_idxs: List[int], epoch: int, rank: int, world: int) -> float:
@@ -171,13 +165,13 @@ def main(argv=None) -> Dict:
     torch.cuda.set_device(local)
     eng = E.Engine(C.arch_from_config(cfg), device, flags.precision, seed=0)
     start_epoch = 0
-    ckpt = f"{cfg.logging.logdir}/model.ckpt.npz"
+    ckpt = f"{cfg.logging.logdir}/model.ckpt"
     eval_only = flags.operation == "eval_only"
     if eval_only:
-        path = f"{cfg.logging.logdir}/model-{int(flags.eval_epoch)}.npz"
-        load_checkpoint(eng, path if os.path.isfile(path) else ckpt)
+        path = f"{cfg.logging.logdir}/model-{int(flags.eval_epoch)}"
+        load_checkpoint(eng, path if os.path.isfile(path + ".index") else ckpt)
         start_epoch = int(flags.eval_epoch)
-    elif os.path.isfile(ckpt):                                   # resume (train.py:267-270)
+    elif os.path.isfile(ckpt + ".index"):                        # resume (train.py:267-270)
         load_checkpoint(eng, ckpt)
         start_epoch = eng.step // max(1, len(train_idxs) // cfg.training.batch_size)
     last = {}
@@ -195,7 +189,7 @@ def main(argv=None) -> Dict:
         if rank == 0 and (epoch % 2 == 0 or was_last):
             save_checkpoint(eng, ckpt)
         if rank == 0 and (epoch % 5 == 0 or was_last or cfg.evaluation.save_every_epoch):
-            save_checkpoint(eng, f"{cfg.logging.logdir}/model-{epoch}.npz")
+            save_checkpoint(eng, f"{cfg.logging.logdir}/model-{epoch}")
     logger.info("Finished Training")
     return last
 

@@ -1,0 +1,110 @@
+"""Row N1: TensorFlow checkpoint (tensor bundle) reader / writer without TensorFlow.
+PARITY UNPINNED: no TensorFlow-written checkpoint exists offline, so the two directions are validated against each
+other, against hand-built table blocks / snappy streams, and against the published crc32c check value."""
+import struct
+
+import numpy as np
+import pytest
+
+from alignnet_b200 import tf_checkpoint as T
+
+
+def _tensors():
+    rng = np.random.default_rng(0)
+    t = {f"siamese/transformer1/embedding/conv{i}/weights": rng.normal(size=(1, 3 if i == 1 else 1, 4, 8)).astype(np.float32)
+         for i in (1, 2, 3)}
+    t.update({f"siamese/transformer1/mlp/fc{i}/biases": rng.normal(size=(5 + i,)).astype(np.float32) for i in range(40)})
+    t["Variable"] = np.array(1234, np.int32)
+    t["beta1_power"] = np.array(0.5, np.float32)
+    t["counts"] = np.arange(7, dtype=np.int64).reshape(7, 1)
+    t["flags"] = np.array([True, False, True])
+    t["empty"] = np.zeros((0, 3), np.float32)
+    return t
+
+
+@pytest.mark.parametrize("block_size,restart", [(4096, 16), (64, 1), (200, 4), (1 << 20, 1000)])
+def test_round_trip(tmp_path, block_size, restart):
+    t = _tensors()
+    prefix = str(tmp_path / "model.ckpt")
+    T.write_checkpoint(prefix, t, block_size=block_size, restart_interval=restart)
+    back = T.read_checkpoint(prefix)
+    assert set(back) == set(t)
+    for k in t:
+        assert back[k].dtype == t[k].dtype and back[k].shape == t[k].shape, k
+        np.testing.assert_array_equal(back[k], t[k])
+    raw = open(prefix + ".index", "rb").read()
+    assert struct.unpack("<Q", raw[-8:])[0] == 0xDB4775248B80FB57 and raw[-8:] == bytes.fromhex("57fb808b247547db")
+    keys = [k for k, _ in T.read_table(prefix + ".index")]
+    assert keys == sorted(keys) and keys[0] == b""                      # header entry first, names in byte order
+
+
+def test_crc32c_and_mask_known_answers():
+    assert T.crc32c(b"123456789") == 0xE3069283                         # the standard CRC-32C check value
+    assert T.crc32c(b"") == 0
+    assert T.mask_crc(0) == 0xA282EAD8
+    # the chunk-parallel path (large tensors) agrees with the byte-serial definition, ragged tail included
+    rng = np.random.default_rng(1)
+    for n in (64 * 1024, 64 * 1024 + 1, 200_003):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert T.crc32c(data) == T._crc32c_scalar(data), n
+
+
+def test_snappy_blocks_and_prefix_compressed_keys():
+    # literal 'abc' + copy(offset 3, length 6): "abcabcabc"
+    assert T.snappy_decompress(bytes([9, (3 - 1) << 2]) + b"abc" + bytes([((6 - 4) << 2) | 1, 3])) == b"abcabcabc"
+    # long literal (one extra length byte: tag 60)
+    payload = bytes(range(200))
+    assert T.snappy_decompress(T._put_varint(len(payload)) + bytes([60 << 2, len(payload) - 1]) + payload) == payload
+    # overlapping copy (run-length): 'a' + copy(offset 1, length 7)
+    assert T.snappy_decompress(bytes([8, 0]) + b"a" + bytes([((7 - 4) << 2) | 1, 1])) == b"a" * 8
+    block = T._build_block([(b"siamese/a", b"1"), (b"siamese/ab", b"22"), (b"siamese_1/a", b"333")], restart_interval=16)
+    assert T._block_entries(block) == [(b"siamese/a", b"1"), (b"siamese/ab", b"22"), (b"siamese_1/a", b"333")]
+    assert len(block) < sum(len(k) + len(v) for k, v in T._block_entries(block)) + 3 * 3 + 8   # prefixes were shared
+    # a snappy-compressed block (literal-only stream) is read like an uncompressed one
+    comp = T._put_varint(len(block)) + bytes([(len(block) - 1) << 2]) + block if len(block) <= 60 else None
+    if comp is not None:
+        assert T._read_block(comp + b"\x01" + b"\0\0\0\0", 0, len(comp)) == block
+
+
+def test_doubled_scope_ema_names_are_found():
+    name = "siamese/transformer1/embedding/conv1/bn/moments/Squeeze/ExponentialMovingAverage"
+    doubled = "siamese/transformer1/embedding/conv1/bn/" + name
+    v = np.ones(4, np.float32)
+    assert T._lookup({name: v}, name) is v
+    assert T._lookup({doubled: v}, name) is v
+    assert T._lookup({"other": v}, name) is None
+
+
+def test_bad_files_are_rejected(tmp_path):
+    p = tmp_path / "x.index"
+    p.write_bytes(b"\0" * 100)
+    with pytest.raises(ValueError):
+        T.read_table(str(p))
+
+
+@pytest.mark.gpu
+def test_engine_export_import_round_trip(tmp_path):
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    from alignnet_b200 import engine, synth
+    a = engine.Engine(engine.shipped_arch(), "cuda:0", "fp32", seed=1)
+    batch = {k: torch.from_numpy(v).cuda() for k, v in synth.make_batch_fast(8, 32, seed=2).items()}
+    for i in range(2):
+        a.train_step(batch, lr=0.01, bn_decay=0.5, seed=i)
+    prefix = str(tmp_path / "model.ckpt")
+    T.save_from_engine(a, prefix)
+    ck = T.read_checkpoint(prefix)
+    assert ck["siamese/transformer1/embedding/conv1/weights"].shape == (1, 3, 1, 64)      # TF kernel shape
+    assert ck["fc3/weights"].shape == (256, 103) and int(ck["Variable"]) == 2
+    b = engine.Engine(engine.shipped_arch(), "cuda:0", "fp32", seed=99)
+    info = T.load_into_engine(b, prefix)
+    assert info["missing"] == [] and info["unused"] == []
+    assert b.step == 2
+    torch.testing.assert_close(b.params, a.params, rtol=0, atol=0)
+    torch.testing.assert_close(b.bn_state, a.bn_state, rtol=0, atol=0)
+    torch.testing.assert_close(b.adam_m, a.adam_m, rtol=0, atol=0)
+    torch.testing.assert_close(b.adam_v, a.adam_v, rtol=0, atol=0)
+    ea, eb = a.forward(batch["pcs1"], batch["pcs2"], False), b.forward(batch["pcs1"], batch["pcs2"], False)
+    for k in ea:
+        torch.testing.assert_close(eb[k], ea[k], rtol=0, atol=1e-6)

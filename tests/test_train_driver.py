@@ -42,15 +42,18 @@ def test_train_then_eval_only_round_trip(tmp_path):
     C.reset_config()
     np.random.seed(3)
     last = train.main(["train", "--config", cfg_path, "--precision", "fp32"])
-    for rel in ("config.json", "out.log", "model.ckpt.npz", "model-0.npz", "model-1.npz", "val/eval000001/eval.json",
+    for rel in ("config.json", "out.log", "model.ckpt.index", "model.ckpt.data-00000-of-00001", "model-0.index", "model-1.index", "val/eval000001/eval.json",
                 "val/eval000001/eval_180.json", "val/eval000001/pred_translations.npy", "val/eval000001/pred_angles.npy",
                 "val/eval000001/pred_s2_pc1centers.npy"):
         assert (logdir / rel).exists(), rel
     d = json.load(open(logdir / "val/eval000001/eval.json"))
     assert d["num"] == 6 and set(d) >= {"corr_levels", "eval_5m", "val", "test", "reg_eval", "mean_time"}
     assert last["eval"]["num"] == 6
-    ck = np.load(logdir / "model-1.npz")
-    assert int(ck["global_step"]) == 6 and "param/siamese/embedding/conv3/weights" in ck.files
+    from alignnet_b200 import tf_checkpoint
+    ck = tf_checkpoint.read_checkpoint(str(logdir / "model-1"))
+    w3 = ck["siamese/embedding/conv3/weights"]
+    assert int(ck["Variable"]) == 6 and w3.ndim == 4 and w3.shape[:2] == (1, 1)          # TF kernel shape [1, 1, Cin, Cout]
+    assert ck["siamese/embedding/conv1/weights"].shape[:3] == (1, 3, 1)
     # eval_only restores the checkpoint and reproduces the predictions (same resampling draws with the same seed)
     pred_a = np.load(logdir / "val/eval000001/pred_translations.npy")
     C.reset_config()
