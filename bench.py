@@ -245,6 +245,7 @@ def run_ours(args, wl):
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     resident = {k: t.to(dev) for k, t in pinned.items()}
     staging = {k: torch.empty_like(t, device=dev) for k, t in pinned.items()}
+    staging2 = {k: torch.empty_like(t, device=dev) for k, t in pinned.items()}     # second buffer set: double-buffered H2D
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     in_keys = list(host.keys()) if train else ["pcs1", "pcs2"]
     h2d_bytes = sum(pinned[k].numel() * 4 for k in in_keys)
@@ -291,6 +292,53 @@ def run_ours(args, wl):
             out_host.copy_(out["pred_translations"], non_blocking=True)
             ang_host.copy_(eng.pred_angles(out), non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+    copy_stream = torch.cuda.Stream(device=dev)
+    sets = [staging, staging2]
+
+    def e2e_pipelined(steps):
+        """The serving / training loop a user of the API writes: step i computes on buffer set i % 2 while the pinned
+        host batch of step i + 1 is copied into the other set on a copy stream.  EVERY step's H2D copy and D2H read of
+        the result is issued inside the timed region; the region is one CUDA-event bracket over all `steps` steps
+        (per-step working set >> L2, so no flush is needed between them)."""
+        main = torch.cuda.current_stream()
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue_copy(i):
+            s_ = i % 2
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(done[s_])           # the step that last read this set has finished
+                for k in in_keys:
+                    sets[s_][k].copy_(pinned[k], non_blocking=True)
+                ready[s_].record(copy_stream)
+
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        copy_stream.wait_event(e0)
+        issue_copy(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                issue_copy(i + 1)
+            main.wait_event(ready[i % 2])
+            out = step(sets[i % 2])
+            done[i % 2].record(main)
+            if train:
+                loss_host.copy_(out, non_blocking=True)
+            else:
+                out_host.copy_(out["pred_translations"], non_blocking=True)
+                ang_host.copy_(eng.pred_angles(out), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     d2h_bytes = 80 if train else B * 16
 
     def timed(fn, steps):
@@ -328,7 +376,12 @@ def run_ours(args, wl):
     ms_tags, n_tags = (C.c_float * 8)(), (C.c_int32 * 8)()
     lib.an3d_profile_end(C.byref(ms_tags), C.byref(n_tags))
     launches = (lib.an3d_launch_count() - launches0) // args.steps
-    ms_e2e = timed(step_e2e, args.steps)
+    for k_ in in_keys:                      # capture the graph of the second buffer set outside the timed region
+        staging2[k_].copy_(pinned[k_], non_blocking=True)
+    step(staging2)
+    torch.cuda.synchronize()
+    e2e_pipelined(2)
+    ms_e2e = e2e_pipelined(args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -347,6 +400,7 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"], "batch_per_gpu": B, "num_points": N, "mode": "train" if train else "eval",
                        "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
                        "launch": "eager stream launches" if args.no_graph else "CUDA-graph replay of the step (Engine.train_step_graph / forward_graph)",
+                       "e2e": "pinned host batch -> H2D every step (double-buffered on a copy stream, overlapped with the previous step) -> step -> D2H of the result; one event bracket over all steps",
                        "whole_step_tensor_frac": value / world * flops_per_pair(N, train) / (pk["bf16_sustained"] * 1e12)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),
