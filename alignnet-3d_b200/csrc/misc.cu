@@ -132,6 +132,121 @@ int an3d_adam_step(float* params, const float* grads, float* m, float* v, int64_
   return AN3D_OK;
 }
 
+// ---- yaw-constrained point-to-point ICP (icp.py:69-78) -------------------------------------------------------------
+constexpr int kIcpThreads = 256;
+constexpr int kIcpTile = 1024;        // target points staged per shared-memory tile
+
+static __device__ __forceinline__ double block_sum_d(double v, double* sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < kIcpThreads / 32; ++i) r += sm[i];
+  return r;                            // every thread gets the total
+}
+
+static __global__ void __launch_bounds__(kIcpThreads) icp_yaw_kernel(const float* src, const int64_t* src_off,
+                                                                     const int32_t* src_n, const float* tgt,
+                                                                     const int64_t* tgt_off, const int32_t* tgt_n,
+                                                                     const float* init, float radius, int its, float* out,
+                                                                     float* stats) {
+  __shared__ float st[kIcpTile * 3];
+  __shared__ double red[kIcpThreads / 32];
+  const int pair = blockIdx.x;
+  const float* S = src + src_off[pair] * 3;
+  const float* Q = tgt + tgt_off[pair] * 3;
+  const int ns = src_n[pair], nt = tgt_n[pair];
+  double T[12];                        // rows of [R | t], replicated in every thread
+  for (int i = 0; i < 12; ++i) T[i] = (double)init[pair * 16 + i];
+  double fitness = 0.0, rmse = 0.0;
+  int it_done = 0;
+  const float r2 = radius * radius;
+  // correspondences of the current transform: per source point the nearest target (index kept as coordinates)
+  // sums over inliers: count, sum d2, sum p, sum q, sum px*qx + py*qy, sum px*qy - py*qx, (centred later)
+  auto pass = [&](double (&acc)[11]) {
+    for (int i = 0; i < 11; ++i) acc[i] = 0.0;
+    for (int base = 0; base < ns; base += kIcpThreads) {
+      const int i = base + threadIdx.x;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (i < ns) {
+        const float x = S[3 * i], y = S[3 * i + 1], z = S[3 * i + 2];
+        px = (float)(T[0] * x + T[1] * y + T[2] * z + T[3]);
+        py = (float)(T[4] * x + T[5] * y + T[6] * z + T[7]);
+        pz = (float)(T[8] * x + T[9] * y + T[10] * z + T[11]);
+      }
+      float best = 3.0e38f, bx = 0.f, by = 0.f, bz = 0.f;
+      for (int t0 = 0; t0 < nt; t0 += kIcpTile) {
+        const int cnt = min(kIcpTile, nt - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt * 3; k += kIcpThreads) st[k] = Q[(size_t)t0 * 3 + k];
+        __syncthreads();
+        if (i < ns) {
+          for (int k = 0; k < cnt; ++k) {
+            const float dx = st[3 * k] - px, dy = st[3 * k + 1] - py, dz = st[3 * k + 2] - pz;
+            const float d = dx * dx + dy * dy + dz * dz;
+            if (d < best) { best = d; bx = st[3 * k]; by = st[3 * k + 1]; bz = st[3 * k + 2]; }
+          }
+        }
+      }
+      if (i < ns && best <= r2) {
+        acc[0] += 1.0; acc[1] += (double)best;
+        acc[2] += px; acc[3] += py; acc[4] += pz; acc[5] += bx; acc[6] += by; acc[7] += bz;
+        acc[8] += (double)px * bx + (double)py * by;
+        acc[9] += (double)px * by - (double)py * bx;
+      }
+    }
+    for (int i = 0; i < 10; ++i) acc[i] = block_sum_d(acc[i], red);
+  };
+  double acc[11];
+  if (ns > 0 && nt > 0) {
+    pass(acc);
+    fitness = acc[0] / ns;
+    rmse = acc[0] > 0.0 ? sqrt(acc[1] / acc[0]) : 0.0;
+    for (int it = 0; it < its; ++it) {
+      const double n = acc[0];
+      if (n <= 0.0) break;
+      const double pbx = acc[2] / n, pby = acc[3] / n, pbz = acc[4] / n, qbx = acc[5] / n, qby = acc[6] / n, qbz = acc[7] / n;
+      // centred sums: sum (p - pb).(q - qb) = sum p.q - n pb.qb  (xy only), likewise the cross term
+      const double dot = acc[8] - n * (pbx * qbx + pby * qby), crs = acc[9] - n * (pbx * qby - pby * qbx);
+      const double th = atan2(crs, dot), c = cos(th), s = sin(th);
+      const double ux = qbx - (c * pbx - s * pby), uy = qby - (s * pbx + c * pby), uz = qbz - pbz;
+      double N[12];                    // U * T with U = [Rz(th) | u]
+      for (int j = 0; j < 4; ++j) {
+        N[j] = c * T[j] - s * T[4 + j];
+        N[4 + j] = s * T[j] + c * T[4 + j];
+        N[8 + j] = T[8 + j];
+      }
+      N[3] += ux; N[7] += uy; N[11] += uz;
+      for (int j = 0; j < 12; ++j) T[j] = N[j];
+      it_done = it + 1;
+      const double pf = fitness, pr = rmse;
+      pass(acc);
+      fitness = acc[0] / ns;
+      rmse = acc[0] > 0.0 ? sqrt(acc[1] / acc[0]) : 0.0;
+      if (fabs(pf - fitness) < 1e-6 && fabs(pr - rmse) < 1e-6) break;
+    }
+  }
+  if (threadIdx.x < 12) out[pair * 16 + threadIdx.x] = (float)T[threadIdx.x];
+  if (threadIdx.x >= 12 && threadIdx.x < 16) out[pair * 16 + threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
+  if (threadIdx.x == 0) { stats[pair * 3] = (float)fitness; stats[pair * 3 + 1] = (float)rmse; stats[pair * 3 + 2] = (float)it_done; }
+}
+
+int an3d_icp_yaw(const float* src, const int64_t* src_off, const int32_t* src_n, const float* tgt, const int64_t* tgt_off,
+                 const int32_t* tgt_n, const float* init, int32_t pairs, float radius, int32_t its, float* out,
+                 float* stats, void* stream) {
+  if (!src_off || !src_n || !tgt_off || !tgt_n || !init || !out || !stats || pairs < 0 || its < 0 || !(radius > 0.f)) {
+    set_error("an3d_icp_yaw: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  if (pairs == 0) return AN3D_OK;
+  icp_yaw_kernel<<<pairs, kIcpThreads, 0, (cudaStream_t)stream>>>(src, src_off, src_n, tgt, tgt_off, tgt_n, init, radius, its,
+                                                                out, stats);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
 // ---- batch assembly (provider.py:60-71,97-98,125-126) -----------------------------------------------------------
 static __global__ void resample_gather_kernel(const float* __restrict__ pts, const int64_t* __restrict__ off,
                                               const int32_t* __restrict__ idx, int64_t total, int N, int stride,

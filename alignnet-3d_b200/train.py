@@ -8,7 +8,8 @@ Same CLI (train.py:31-39), config schema (the reference's configs/*.json load un
 last epoch) and output files: `<logdir>/config.json`, `<logdir>/out.log`, `<logdir>/val/eval%06d/{eval.json,
 eval_180.json, pred_*.npy}` (train.py:399-407,487-543, evaluation.py:274-287), `<logdir>/model.ckpt.*` and
 `<logdir>/model-<epoch>.*` in TensorFlow's checkpoint format (`alignnet_b200.tf_checkpoint`, train.py:316-322).
-Differences, all deliberate: there is no TensorBoard writer, `--refineICP` is rejected (row N4), and the
+Differences, all deliberate: there is no TensorBoard writer, `--refineICP` runs the batched device ICP of `alignnet_b200.icp` instead of the
+authors' Open3D fork (row N4, parity unpinned; `--use_old_results` is accepted and ignored), and the
 val/test split of the synthetic sets (evaluation.py:161-162: idx >= 1000) is computed here and passed to the device
 evaluation.  One process per GPU; under torchrun the gradient all-reduce is the only collective."""
 from __future__ import annotations
@@ -27,7 +28,7 @@ import torch
 from . import config as C
 from . import dist as D
 from . import engine as E
-from . import evaluation, provider, schedules, tf_checkpoint
+from . import evaluation, icp, provider, schedules, tf_checkpoint
 
 logger = logging.getLogger("tp")
 
@@ -36,7 +37,7 @@ def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("operation", choices=["train", "eval_only"], help="Operation to run")
     p.add_argument("--config", required=True, default="", help="Config file")
-    p.add_argument("--refineICP", action="store_true", help="(row N4, not implemented: rejected)")
+    p.add_argument("--refineICP", action="store_true", help="refine the predictions with yaw-constrained ICP (eval_only; row N4)")
     p.add_argument("--its", required=False, default=30)
     p.add_argument("--use_old_results", action="store_true")
     p.add_argument("--refineICPmethod", required=False, default="p2p", choices=["p2p"])
@@ -90,10 +91,13 @@ def train_one_epoch(cfg, eng: E.Engine, train_idxs: List[int], epoch: int, rank:
     return mean
 
 
-def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int) -> Dict:
+def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int, refine_icp: bool = False, its: int = 30,
+                   icp_method: str = "p2p") -> Dict:
     """train.py:396-545: eval-mode forward over the validation split, host decode of the angles (quirk Q1), the
     eval.json metrics with and without accepting the 180-degree flip."""
     eval_dir = f"{cfg.logging.logdir}/val/eval{str(epoch).zfill(6)}"
+    if refine_icp:                                               # train.py:401-402
+        eval_dir = f'{eval_dir}/refined_{icp_method}{"_" + str(its) if int(its) != 30 else ""}'
     if os.path.isdir(eval_dir):                                  # keep earlier results (train.py:404-405)
         backup, n = f"{eval_dir}_backup_{int(time.time())}", 0
         while os.path.exists(backup if n == 0 else f"{backup}_{n}"):
@@ -119,10 +123,23 @@ def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int) -> Dict:
         torch.cuda.synchronize()
         t_exec.append((time.time() - t0) / bs)
         loss_sum += float(loss[0].cpu())
-        keep["pred_translations"].append(ep["pred_translations"][:valid].cpu().numpy())
-        keep["pred_angles"].append(pa[:valid].cpu().numpy()[:, None])
-        for k in ("pred_s1_pc1centers", "pred_s1_pc2centers", "pred_s2_pc1centers", "pred_s2_pc2centers"):
-            keep[k].append(ep[k][:valid].cpu().numpy())
+        pt, pang = ep["pred_translations"][:valid].cpu().numpy(), pa[:valid].cpu().numpy()
+        centers = {k: ep[k][:valid].cpu().numpy() for k in ("pred_s1_pc1centers", "pred_s1_pc2centers", "pred_s2_pc1centers",
+                                                            "pred_s2_pc2centers")}
+        if refine_icp:                                           # train.py:463-484, the whole batch in one launch
+            full1 = [np.load(f"{cfg.data.basepath}/pointcloud1/{str(i).zfill(8)}.npy")[:, :3] for i in chunk[:valid]]
+            full2 = [np.load(f"{cfg.data.basepath}/pointcloud2/{str(i).zfill(8)}.npy")[:, :3] for i in chunk[:valid]]
+            inits = np.stack([icp.get_mat_angle(pt[i], float(pang[i]), centers["pred_s2_pc1centers"][i]) for i in range(valid)])
+            t1 = time.time()
+            refined, _ = icp.refine(full1, full2, inits, radius=0.1, its=int(its), device=str(eng.device))
+            t_exec[-1] += (time.time() - t1) / max(valid, 1)
+            rt, ra = icp.to_translation_angle(refined)
+            pt, pang = rt.astype(pt.dtype), ra.astype(pang.dtype)
+            centers["pred_s2_pc1centers"] = np.zeros_like(centers["pred_s2_pc1centers"])       # rotation about the origin now
+        keep["pred_translations"].append(pt)
+        keep["pred_angles"].append(pang[:, None])
+        for k, v in centers.items():
+            keep[k].append(v)
         keep["gt_translations"].append(batch["translations"][:valid].cpu().numpy())
         keep["gt_angles"].append(batch["rel_angles"][:valid].cpu().numpy())
         keep["gt_pc1centers"].append(batch["pc1_centers"][:valid].cpu().numpy())
@@ -146,8 +163,8 @@ def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int) -> Dict:
 
 def main(argv=None) -> Dict:
     flags = parse_args(argv)
-    if flags.refineICP:
-        raise NotImplementedError("--refineICP drives the reference's Open3D fork (row N4): not implemented")
+    if flags.refineICP and flags.operation != "eval_only":
+        raise ValueError("--refineICP only applies to eval_only (train.py:463)")
     cfg = C.load_config(flags.config)
     C.validate(cfg)
     rank, world, local = D.init() if "RANK" in os.environ else (0, 1, 0)
@@ -182,7 +199,8 @@ def main(argv=None) -> Dict:
         if not eval_only:
             train_one_epoch(cfg, eng, train_idxs, epoch, rank, world)
         if rank == 0:
-            last = eval_one_epoch(cfg, eng, val_idxs, epoch)
+            last = eval_one_epoch(cfg, eng, val_idxs, epoch, refine_icp=bool(flags.refineICP), its=int(flags.its),
+                                  icp_method=flags.refineICPmethod)
         if eval_only:
             break
         was_last = epoch == cfg.training.num_epochs - 1

@@ -201,6 +201,17 @@ int an3d_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t
 int an3d_resample_gather(const float* points, const int64_t* cloud_offset, const int32_t* sample_idx, int32_t batch,
                          int32_t num_points, int32_t stride, const float* jitter, float* out, void* stream);
 
+/* Yaw-constrained point-to-point ICP refinement (replaces o3.registration_icp with
+ * TransformationEstimationPointToPoint(with_constraint=True) of icp.py:69-78, driven from train.py:463-484).  One CTA
+ * per pair: nearest target point of every transformed source point within `radius` (brute force over the target
+ * cloud staged through shared memory), closed-form yaw + translation update, `its` iterations or until fitness and
+ * inlier RMSE both change by less than 1e-6.  src/tgt: ragged clouds back to back ([total,3] floats) with per-pair
+ * row offsets and counts; init / out: [pairs,16] row-major 4x4 transforms; stats: [pairs,3] = fitness, inlier RMSE,
+ * iterations run. */
+int an3d_icp_yaw(const float* src, const int64_t* src_off, const int32_t* src_n, const float* tgt, const int64_t* tgt_off,
+                 const int32_t* tgt_n, const float* init, int32_t pairs, float radius, int32_t its, float* out,
+                 float* stats, void* stream);
+
 /* Evaluation metrics on the device (evaluation.py:16-46,128-211).  For every predicted
  * transform: centre-of-rotation correction of the translation (pointcloud.py:309-318), xy translation error with the
  * 0.02 / 0.1 / 0.2 m levels, yaw error in degrees (optionally min with the 180-degree flip) with the 1 / 5 / 10

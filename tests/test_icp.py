@@ -1,0 +1,71 @@
+"""Row N4: yaw-constrained point-to-point ICP.  PARITY UNPINNED (the reference drives the authors'
+Open3D fork, icp.py:69-78, which is not vendored): the restated algorithm (oracle/icp_ref.py) is validated on synthetic
+ground truth, and the device kernel against that restatement."""
+import numpy as np
+import pytest
+
+from oracle import icp_ref as I
+
+
+def _pair(rng, n=500, noise=0.003):
+    src = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1, 1, n), rng.uniform(0, 1.5, n)], 1)
+    src[:n // 2, 1] = -1.0
+    src[n // 2:, 0] = 2.0                                      # two visible faces of a box
+    src += rng.normal(size=3) * 5
+    th, t = rng.uniform(-0.3, 0.3), rng.normal(size=3) * np.array([0.4, 0.4, 0.05])
+    tgt = src @ I.rot_z(th).T + t + rng.normal(0, noise, (n, 3))
+    tgt = tgt[rng.permutation(n)[: n - n // 7]]                # different sampling / size
+    init = np.eye(4)
+    init[:3, :3] = I.rot_z(th + rng.uniform(-0.03, 0.03))
+    init[:3, 3] = t + rng.normal(size=3) * 0.03
+    return src, tgt, init, th, t
+
+
+def test_restated_icp_recovers_ground_truth():
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        src, tgt, init, th, t = _pair(rng)
+        T, fit, rmse, its = I.icp_yaw(src, tgt, init, radius=0.1, its=30)
+        yaw = np.arctan2(T[1, 0], T[0, 0])
+        assert abs(yaw - th) < 2e-3
+        moved = src @ T[:3, :3].T + T[:3, 3]
+        truth = src @ I.rot_z(th).T + t
+        assert np.abs(moved - truth).max() < 0.01
+        assert fit > 0.8 and rmse < 0.04 and 1 <= its <= 30      # a seventh of the sources lost their twin
+        assert abs(T[2, 2] - 1) < 1e-12 and abs(T[2, 0]) < 1e-12 and abs(T[0, 2]) < 1e-12      # rotation is pure yaw
+    # no correspondences within the radius: the initial transform is returned untouched
+    far = np.eye(4)
+    far[:3, 3] = 100.0
+    T, fit, rmse, its = I.icp_yaw(src, tgt, far, radius=0.1, its=30)
+    assert np.array_equal(T, far) and fit == 0.0 and its == 0
+    T, fit, _, its = I.icp_yaw(np.zeros((0, 3)), tgt, far)
+    assert np.array_equal(T, far) and its == 0
+
+
+@pytest.mark.gpu
+def test_device_icp_matches_restatement_and_ground_truth():
+    import __graft_entry__ as ge
+    ge.build()
+    from alignnet_b200 import icp
+    rng = np.random.default_rng(1)
+    cases = [_pair(rng, n=n) for n in (64, 500, 1500, 2300)]
+    far = np.eye(4)
+    far[:3, 3] = 100.0
+    srcs = [c[0] for c in cases] + [cases[0][0], np.zeros((0, 3))]
+    tgts = [c[1] for c in cases] + [cases[0][1], cases[0][1]]
+    inits = np.stack([c[2] for c in cases] + [far, far])
+    T, stats = icp.refine(srcs, tgts, inits, radius=0.1, its=30)
+    for i, (src, tgt, init, th, t) in enumerate(cases):
+        Tr, fit, rmse, its = I.icp_yaw(src, tgt, init, radius=0.1, its=30)
+        moved, ref = src @ T[i, :3, :3].T + T[i, :3, 3], src @ Tr[:3, :3].T + Tr[:3, 3]
+        assert np.abs(moved - ref).max() < 2e-3, i                       # fp32 distances may pick another neighbour here and there
+        if len(src) >= 500:                                              # 64 points: 9% inliers, the algorithm itself stalls
+            assert np.abs(moved - (src @ I.rot_z(th).T + t)).max() < 0.012, i
+        assert abs(stats[i, 0] - fit) < 0.02 and abs(stats[i, 1] - rmse) < 1e-3
+    np.testing.assert_allclose(T[4], far, atol=1e-6)
+    np.testing.assert_allclose(T[5], far, atol=1e-6)
+    assert stats[4, 0] == 0 and stats[4, 2] == 0 and stats[5, 2] == 0
+    tr, ang = icp.to_translation_angle(T[:4])
+    assert tr.shape == (4, 3) and np.abs(ang - np.array([c[3] for c in cases]))[1:].max() < 3e-3
+    np.testing.assert_allclose(icp.get_mat_angle([1, 2, 3], 0.3, [4, 5, 6])[:3, 3],
+                               np.array([4, 5, 6]) + np.array([1, 2, 3]) - I.rot_z(0.3) @ np.array([4, 5, 6]), atol=1e-12)

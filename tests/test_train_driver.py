@@ -66,5 +66,13 @@ def test_train_then_eval_only_round_trip(tmp_path):
     second = np.load(logdir / "val/eval000001/pred_translations.npy")
     np.testing.assert_allclose(first, second, atol=1e-5)
     assert np.isfinite(pred_a).all() and pred_a.shape == (6, 3)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         train.main(["train", "--config", cfg_path, "--refineICP"])
+    # eval_only --refineICP (row N4): results go to the refined_p2p directory, rotation centres are the origin
+    C.reset_config()
+    np.random.seed(11)
+    ref = train.main(["eval_only", "--config", cfg_path, "--eval_epoch", "1", "--precision", "fp32", "--refineICP"])
+    rdir = logdir / "val/eval000001/refined_p2p"
+    assert (rdir / "eval.json").exists() and ref["eval"]["num"] == 6
+    assert not np.load(rdir / "pred_s2_pc1centers.npy").any()
+    assert np.isfinite(np.load(rdir / "pred_translations.npy")).all() and np.isfinite(np.load(rdir / "pred_angles.npy")).all()
