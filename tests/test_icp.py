@@ -42,6 +42,23 @@ def test_restated_icp_recovers_ground_truth():
     assert np.array_equal(T, far) and its == 0
 
 
+def test_init_and_result_conversions_match_reference_fixture():
+    """`icp.get_mat_angle` builds the ICP seed of train.py:465-467 -- checked against the matrices the reference's own
+    `pointcloud.get_mat_angle` produced (tests/golden/reference_rigid.npz); `to_translation_angle` inverts it for a
+    rotation about the origin (train.py:474-484)."""
+    import os
+    from alignnet_b200 import icp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rigid.npz"))
+    mats = np.stack([icp.get_mat_angle(g["t"][i], float(g["theta"][i]), g["c"][i]) for i in range(len(g["t"]))])
+    np.testing.assert_allclose(mats, g["mats"], atol=1e-12)
+    tr, ang = icp.to_translation_angle(mats)
+    np.testing.assert_allclose(ang, g["theta"], atol=1e-12)
+    np.testing.assert_allclose(tr, mats[:, :3, 3])
+    # a world-space transform (centre 0) moves points like the (t, angle, centre) triple it was seeded from
+    moved = np.einsum("bij,bnj->bni", mats[:, :3, :3], g["pts"]) + mats[:, None, :3, 3]
+    np.testing.assert_allclose(moved, g["moved"][..., :3], atol=1e-9)
+
+
 @pytest.mark.gpu
 def test_device_icp_matches_restatement_and_ground_truth():
     import __graft_entry__ as ge
