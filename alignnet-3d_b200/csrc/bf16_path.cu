@@ -252,13 +252,25 @@ BnIo bn_io(const Model& m, const PlanF32& p, const float* params, float* state, 
   return io;
 }
 
+// AN3D_FWD_RING=1 selects the experimental three-slot accumulator ring of the full passes (conv_fwd_bf16.cuh); read once.
+bool fwd_ring_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AN3D_FWD_RING");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 template <int MODE>
 int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
-  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+  constexpr bool kHasRing = MODE != convfwd::MODE_STATS2;
+  const bool ring = kHasRing && fwd_ring_enabled();
+  auto* kern = convfwd::conv_stack_fwd_kernel<MODE, 0>;
+  if (ring) kern = convfwd::conv_stack_fwd_kernel<MODE, kHasRing ? 1 : 0>;
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tag = MODE == convfwd::MODE_STATS2 ? PROF_CONV_STATS2 : PROF_CONV_FULL;
   prof_mark(tag, true, st);
-  convfwd::conv_stack_fwd_kernel<MODE><<<grid, convfwd::kThreads, smem, st>>>(P);
+  kern<<<grid, convfwd::kThreads, smem, st>>>(P);
   prof_mark(tag, false, st);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;

@@ -30,6 +30,12 @@ constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
 constexpr uint32_t kPlaneW2 = 128 * 16;   // plane stride of the weight images (rows = 128 channels)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;
+// RING variant (template parameter, experimental, off by default -- selected with AN3D_FWD_RING=1): THREE layer-3
+// accumulator slots of 128 columns (the MMA warp may run two half-tiles ahead of the max-reduction warps; with two
+// slots the drain + handshake latency of one half, ~800 cycles, exceeds the ~420 cycles the other half's MMAs take
+// and the tensor pipe idles), and the layer-2 accumulator delivered in two point-halves through ONE 128-column
+// region (512 TMEM columns do not hold 3 slots + a 256-column layer-2 tile).
+constexpr uint32_t kRingSlots = 3, kRingSlotCols = 128, kTmemD2Ring = 384;
 
 // MODE_STATS2: layer-2 BATCH statistics without running layer 2.  With z2 = a1 W2 (bias apart),
 //   sum_p z2[p,c] = (sum_p a1[p,:]) . w_c        sum_p z2[p,c]^2 = w_c^T (A1^T A1) w_c
@@ -95,8 +101,10 @@ struct Barriers {
   uint64_t d2_full;
   uint64_t a2_full[2];
   uint64_t a2_empty[2];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
+  uint64_t acc_full[3];   // [2] only in the RING variant
+  uint64_t acc_empty[3];
+  uint64_t d2_full1;      // RING: second point-half of the layer-2 accumulator
+  uint64_t d2_empty;      // RING: the first half has been drained (128 arrivals: front-end group 0)
   uint32_t tmem_base;
   float xf[16];  // per-item transform (double-buffered): cx, cy, cz, cos, sin
 };
@@ -133,8 +141,9 @@ __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nv
   }
 }
 
-template <int MODE>
+template <int MODE, int RING = 0>
 __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
+  static_assert(!RING || MODE != MODE_STATS2, "the ring variant only exists for the full passes");
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
   const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
@@ -164,6 +173,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_init(&bars->a2_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1);
       mbar_init(&bars->acc_empty[i], 256);
+    }
+    if (RING) {
+      mbar_init(&bars->acc_full[2], 1);
+      mbar_init(&bars->acc_empty[2], 256);
+      mbar_init(&bars->d2_full1, 1);
+      mbar_init(&bars->d2_empty, kFrontThreads / 2);
     }
     fence_barrier_init();
   }
@@ -263,16 +278,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_arrive(&bars->a1_full);
       if (MODE == MODE_STATS2) continue;   // the Gram MMAs need no per-item epilogue
       // ---- layer-2 epilogue: channel k, point columns [pbeg, pend)
-      mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
+      const int nh = min(NT, ((NT >> 1) + 15) & ~15);
+      const int pbeg = fgroup ? nh : 0, pend = fgroup ? NT : nh;
+      if (RING) {
+        // group g waits for ITS half (the second half only exists when the item has more than nh points)
+        if (pbeg < pend) { mbar_wait_relaxed(fgroup ? &bars->d2_full1 : &bars->d2_full, ph_d2); ph_d2 ^= 1; }
+      } else {
+        mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
+      }
       tc_fence_after();
       const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
       uint8_t* dst = sA2[b] + (k >> 3) * plane2 + (k & 7) * 2;
       float ts = 0.f, tss = 0.f, ta2 = 0.f;
-      const int nh = min(NT, ((NT >> 1) + 15) & ~15);
-      const int pbeg = fgroup ? nh : 0, pend = fgroup ? NT : nh;
+      const uint32_t d2_base = RING ? tmem + lane_base + kTmemD2Ring - (uint32_t)pbeg : tmem + lane_base + kTmemD2;
       for (int g16 = pbeg; g16 < pend; g16 += 16) {
         uint32_t r[16];
-        tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
+        tmem_ld16(d2_base + g16, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -289,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         }
       }
       tc_fence_before();
+      if (RING && fgroup == 0 && nh < NT) mbar_arrive(&bars->d2_empty);   // the region may take the second half now
       if (MODE == MODE_STATS2) {
         st_s += (double)ts; st_ss += (double)tss;
       } else {
@@ -328,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       uint32_t ph_full[2] = {0, 0};
+      uint32_t unit = 0;                             // RING: running count of accumulator half-tiles
       const int C3 = P.nchunk * 128;
       for (int li = 0; li < n_local; ++li) {
         const int it = it_begin + li;
@@ -344,10 +367,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           float m = -INFINITY;
           for (int h = 0; h < 2; ++h) {
             if (Nh[h] == 0) continue;
-            mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+            const uint32_t slot = RING ? unit % kRingSlots : (uint32_t)h;
+            if (RING) {
+              mbar_wait_relaxed(&bars->acc_full[slot], (unit / kRingSlots) & 1u);
+              ++unit;
+            } else {
+              mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+            }
             tc_fence_after();
             const int off = h ? N0 : 0;
-            const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
+            const uint32_t tbase = tmem + lane_base + (RING ? slot * kRingSlotCols : (h ? kTmemAcc1 : kTmemAcc0));
             // software pipeline: the load of the next group is in flight while this one is reduced
             uint32_t ra[16], rb[16];
             int g16 = bgroup * 16;
@@ -364,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
               }
             }
             tc_fence_before();
-            mbar_arrive(&bars->acc_empty[h]);
+            mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
           }
           atomicMax(P.zext + (size_t)cloud * C3 + j * 128 + e, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
 
@@ -420,6 +449,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           }
           __syncwarp();
         }
+      } else if (RING) {
+        // ---- ring variant: 3 accumulator slots, layer 2 in two point-halves through one TMEM region ----
+        uint32_t unit = 0, ph_d2e = 0;
+        int l2_stage = 0;                          // of the item being prepared: 0 nothing issued, 1 first half, 2 all
+        auto l2_ring = [&](int li, bool block) {
+          const int it = it_begin + li;
+          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+          const int NT = (nvalid + 15) & ~15;
+          const int N0 = min(NT, ((NT >> 1) + 15) & ~15), N1 = NT - N0;
+          const uint64_t bd = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
+          if (l2_stage == 0) {
+            if (!block && !__all_sync(0xffffffffu, mbar_try_wait(&bars->a1_full, ph_a1))) return;
+            mbar_wait(&bars->a1_full, ph_a1); ph_a1 ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t idesc = make_idesc(128, N0, 0, 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_raw(tmem + kTmemD2Ring, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd, ks * 2 * plane1),
+                             idesc, ks > 0);
+              mma_commit_raw(&bars->d2_full);
+            }
+            __syncwarp();
+            l2_stage = N1 > 0 ? 1 : 2;
+          }
+          if (l2_stage == 1) {
+            if (!block && !__all_sync(0xffffffffu, mbar_try_wait(&bars->d2_empty, ph_d2e))) return;
+            mbar_wait(&bars->d2_empty, ph_d2e); ph_d2e ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t idesc = make_idesc(128, N1, 0, 0);
+              const uint64_t bd1 = desc_advance(bd, N0 * 16);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_raw(tmem + kTmemD2Ring, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd1, ks * 2 * plane1),
+                             idesc, ks > 0);
+              mma_commit_raw(&bars->d2_full1);
+            }
+            __syncwarp();
+            l2_stage = 2;
+          }
+        };
+        l2_ring(0, true);
+        for (int li = 0; li < n_local; ++li) {
+          const int it = it_begin + li;
+          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
+          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
+          const int NT = (nvalid + 15) & ~15;
+          const int N0 = min(NT, ((NT >> 1) + 15) & ~15), N1 = NT - N0;
+          const int b = li & 1;
+          l2_stage = 0;                            // from here on it describes item li + 1
+          mbar_wait(&bars->a2_full[b], (ph_a2f >> b) & 1u); ph_a2f ^= 1u << b;
+          tc_fence_after();
+          const uint64_t b0_desc = make_desc(smem_u32(sA2[b]), plane2, 128);
+          const uint64_t b1_desc = desc_advance(b0_desc, N0 * 16);
+          const uint32_t idesc0 = make_idesc(128, N0, 0, 0), idesc1 = make_idesc(128, N1 > 0 ? N1 : 16, 0, 0);
+          for (int j = 0; j < P.nchunk; ++j) {
+            mbar_wait(&bars->w3_full[stage], (ph_w3f >> stage) & 1u); ph_w3f ^= 1u << stage;
+            const uint64_t a_desc = make_desc(smem_u32(sW3 + (size_t)stage * kW3ChunkBytes), kPlaneW2, 128);
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && N1 == 0) break;
+              const uint32_t slot = unit % kRingSlots, par = ((unit / kRingSlots) & 1u) ^ 1u;
+              ++unit;
+              mbar_wait(&bars->acc_empty[slot], par);     // the first pass over the slots falls through (parity trick)
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t bdesc = h ? b1_desc : b0_desc;
+                const uint32_t idesc = h ? idesc1 : idesc0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  mma_bf16_raw(tmem + slot * kRingSlotCols, desc_advance(a_desc, ks * 2 * kPlaneW2),
+                               desc_advance(bdesc, ks * 2 * plane2), idesc, ks > 0);
+                mma_commit_raw(&bars->acc_full[slot]);
+              }
+              __syncwarp();
+            }
+            mma_commit(&bars->w3_empty[stage]);
+            if (++stage == P.nstages) stage = 0;
+            // layer 2 of the next item, half by half, probed after every chunk and forced after the last one
+            if (li + 1 < n_local && l2_stage < 2) l2_ring(li + 1, j == P.nchunk - 1);
+          }
+          mma_commit(&bars->a2_empty[b]);
+        }
+        (void)ph_acce0; (void)ph_acce1;
       } else {
       issue_l2(0);
       for (int li = 0; li < n_local; ++li) {
