@@ -263,14 +263,22 @@ bool fwd_ring_enabled() {
 
 template <int MODE>
 int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
-  constexpr bool kHasRing = MODE != convfwd::MODE_STATS2;
-  const bool ring = kHasRing && fwd_ring_enabled();
-  auto* kern = convfwd::conv_stack_fwd_kernel<MODE, 0>;
-  if (ring) kern = convfwd::conv_stack_fwd_kernel<MODE, kHasRing ? 1 : 0>;
-  AN3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tag = MODE == convfwd::MODE_STATS2 ? PROF_CONV_STATS2 : PROF_CONV_FULL;
+  if constexpr (MODE != convfwd::MODE_STATS2) {
+    if (fwd_ring_enabled()) {
+      AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+      prof_mark(tag, true, st);
+      convfwd::conv_stack_fwd_kernel<MODE, 1><<<grid, convfwd::kThreads, smem, st>>>(P);
+      prof_mark(tag, false, st);
+      AN3D_LAUNCH_CHECK();
+      return AN3D_OK;
+    }
+  }
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
   prof_mark(tag, true, st);
-  kern<<<grid, convfwd::kThreads, smem, st>>>(P);
+  convfwd::conv_stack_fwd_kernel<MODE><<<grid, convfwd::kThreads, smem, st>>>(P);
   prof_mark(tag, false, st);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
