@@ -72,7 +72,7 @@ def _check(a, b, tol, bounds, rows=None):
 # tolerance for the rounding-level properties, tolerance under a coordinate shift, (min fraction of pairs with stable
 # bins, min fraction of those that must match).  bf16: batch sizes on either side of the tensor-core FC threshold
 # compute some FC layers in different precisions, so the bound is the bf16 mode's own parity bound.
-BOUNDS = {"fp32": (2e-4, 2e-3, (0.98, 0.99)), "bf16": (1e-1, 1e-1, (0.7, 0.9))}
+BOUNDS = {"fp32": (2e-4, 2e-3, (0.95, 0.97)), "bf16": (1e-1, 1e-1, (0.6, 0.85))}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
