@@ -252,27 +252,36 @@ BnIo bn_io(const Model& m, const PlanF32& p, const float* params, float* state, 
   return io;
 }
 
-// AN3D_FWD_RING=1 selects the experimental three-slot accumulator ring of the full passes (conv_fwd_bf16.cuh); read once.
-bool fwd_ring_enabled() {
-  static const bool on = [] {
+// AN3D_FWD_RING selects an experimental variant of the full passes (conv_fwd_bf16.cuh): bit 0 = three-slot accumulator
+// ring, bit 1 = early slot release.  Read once; 0 / unset = the measured default.
+int fwd_variant() {
+  static const int v = [] {
     const char* e = getenv("AN3D_FWD_RING");
-    return e != nullptr && e[0] == '1';
+    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
   }();
-  return on;
+  return v;
+}
+
+template <int MODE, int VAR>
+int launch_fused_variant(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  prof_mark(PROF_CONV_FULL, true, st);
+  convfwd::conv_stack_fwd_kernel<MODE, VAR><<<grid, convfwd::kThreads, smem, st>>>(P);
+  prof_mark(PROF_CONV_FULL, false, st);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
 }
 
 template <int MODE>
 int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
   const int tag = MODE == convfwd::MODE_STATS2 ? PROF_CONV_STATS2 : PROF_CONV_FULL;
   if constexpr (MODE != convfwd::MODE_STATS2) {
-    if (fwd_ring_enabled()) {
-      AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-      prof_mark(tag, true, st);
-      convfwd::conv_stack_fwd_kernel<MODE, 1><<<grid, convfwd::kThreads, smem, st>>>(P);
-      prof_mark(tag, false, st);
-      AN3D_LAUNCH_CHECK();
-      return AN3D_OK;
+    switch (fwd_variant()) {
+      case 1: return launch_fused_variant<MODE, 1>(P, grid, smem, st);
+      case 2: return launch_fused_variant<MODE, 2>(P, grid, smem, st);
+      case 3: return launch_fused_variant<MODE, 3>(P, grid, smem, st);
+      default: break;
     }
   }
   AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -30,7 +30,7 @@ constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
 constexpr uint32_t kPlaneW2 = 128 * 16;   // plane stride of the weight images (rows = 128 channels)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;
-// RING variant (template parameter, experimental, off by default -- selected with AN3D_FWD_RING=1): THREE layer-3
+// RING variant (template parameter VAR bit 0, experimental, off by default -- AN3D_FWD_RING=1, 2 or 3): THREE layer-3
 // accumulator slots of 128 columns (the MMA warp may run two half-tiles ahead of the max-reduction warps; with two
 // slots the drain + handshake latency of one half, ~800 cycles, exceeds the ~420 cycles the other half's MMAs take
 // and the tensor pipe idles), and the layer-2 accumulator delivered in two point-halves through ONE 128-column
@@ -141,9 +141,12 @@ __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nv
   }
 }
 
-template <int MODE, int RING = 0>
+// VAR: bit 0 = accumulator ring (above); bit 1 = early slot release: the max-reduction warps hand an accumulator
+// half back to the MMA warp as soon as their last TMEM load of it has landed in registers, before reducing it.
+template <int MODE, int VAR = 0>
 __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
-  static_assert(!RING || MODE != MODE_STATS2, "the ring variant only exists for the full passes");
+  constexpr bool RING = (VAR & 1) != 0, EARLY = (VAR & 2) != 0;
+  static_assert(VAR == 0 || MODE != MODE_STATS2, "the variants only exist for the full passes");
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
   const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
@@ -381,19 +384,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
             uint32_t ra[16], rb[16];
             int g16 = bgroup * 16;
             if (g16 < Nh[h]) tmem_ld16(tbase + g16, ra);
+            bool released = false;
             for (; g16 < Nh[h]; g16 += 64) {
               tmem_ld_wait();
               const int g2 = g16 + 32;
               if (g2 < Nh[h]) tmem_ld16(tbase + g2, rb);
+              else if (EARLY) {                      // no load of this half is outstanding or still to be issued
+                tc_fence_before();
+                mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
+                released = true;
+              }
               reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, m);
               if (g2 < Nh[h]) {
                 tmem_ld_wait();
                 if (g2 + 32 < Nh[h]) tmem_ld16(tbase + g2 + 32, ra);
+                else if (EARLY) {
+                  tc_fence_before();
+                  mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
+                  released = true;
+                }
                 reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, m);
               }
             }
-            tc_fence_before();
-            mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
+            if (!EARLY || !released) {               // (a warp with no column group of this half still has to arrive)
+              tc_fence_before();
+              mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
+            }
           }
           atomicMax(P.zext + (size_t)cloud * C3 + j * 128 + e, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
 

@@ -1,6 +1,6 @@
 """A/B a library switch that is read from the environment (e.g. AN3D_FWD_RING=1) on the GPU box.
 
-    python tools/ab_env.py AN3D_FWD_RING=1 [--workload c3] [--tests tests/test_gpu_conv_stack.py ...]
+    python tools/ab_env.py AN3D_FWD_RING=1 [--workload c3]      # 1 = accumulator ring, 2 = early slot release, 3 = both [--tests tests/test_gpu_conv_stack.py ...]
 
 Runs, in separate processes (the library reads its switches once): the given GPU tests with the switch ON (a variant
 that is not parity-green is not worth timing), then `bench.py` with the switch OFF and ON, and prints ms/step, the
