@@ -1,5 +1,6 @@
 // fp32 parity path: forward pass of get_model (models/tp8.py:135-158) with CUDA-core kernels.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels_f32.cuh"
 #include "bf16_path.cuh"
@@ -31,6 +32,51 @@ static BnView bn_view(const Model& m, const PlanF32& p, const float* params, flo
   v.acc1 = p.bn.acc1 + sl;
   v.ch = ch;
   return v;
+}
+
+// ---- experimental, off by default (AN3D_TWO_STREAMS=1): the two siamese branches of a conv stage on two streams ----
+// The branches of a stage are independent and touch disjoint scratch ([stage][branch] buffers), so the ~10 small
+// launches around one branch's persistent kernels (moments, folds, statistics, pool finalize; ~75 us per stage and
+// branch) can run under the other branch's persistent kernels, which leave threads and registers free on every SM.
+// Fork / join with events, so the pattern is also legal inside a stream capture.  The side stream and events are
+// created on first use: run one eager step before capturing a graph (Engine._capture does).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+static SideStream* side_stream() {
+  static SideStream per_device[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& x = per_device[dev];
+  if (!x.ok) {
+    if (cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    x.ok = true;
+  }
+  return &x;
+}
+static bool two_streams_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AN3D_TWO_STREAMS");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+static int conv_stage_two_streams(SideStream* ss, const Model& m, const PlanF32& p, int s, const float* const pcs[2],
+                                  const float* const center[2], const float* const angle[2], const float* params,
+                                  float* state, bool training, float decay, cudaStream_t st) {
+  AN3D_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+  AN3D_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  const int r0 = conv_stack_forward_bf16(m, p, s, 0, pcs[0], center[0], angle ? angle[0] : nullptr, params, state, training,
+                                         decay, st);
+  const int r1 = conv_stack_forward_bf16(m, p, s, 1, pcs[1], center[1], angle ? angle[1] : nullptr, params, state, training,
+                                         decay, ss->stream);
+  AN3D_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));      // always join: a capture must not end with a dangling fork
+  AN3D_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
+  return r0 != AN3D_OK ? r0 : r1;
 }
 
 // batch statistics of Z[R,C] (two-pass, tf.nn.moments) or shadows -> scale/shift; EMA update
@@ -261,7 +307,14 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
     }
     const float* mk1[2] = {masks[0], masks[1]};
     const float* mk2[2] = {masks[2], masks[3]};
+    SideStream* ss = two_streams_enabled() ? side_stream() : nullptr;
+    const float* const ctr_mu[2] = {p.mu[0], p.mu[1]};
+    const float* const ctr_c1[2] = {c1[0], c1[1]};
+    const float* const ctr_c2[2] = {c2[0], c2[1]};
+    const float* const ang2[2] = {p.ang[0], p.ang[1]};
     // stage 1 (tp8.py:106-109)
+    if (ss) AN3D_TRY(conv_stage_two_streams(ss, m, p, S1, pcs, ctr_mu, nullptr, params, state, training, bn_decay, st));
+    else
     for (int br = 0; br < 2; ++br)
       AN3D_TRY(conv_stack_forward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, params, state, training, bn_decay, st));
     const float* g1[2] = {p.g[S1][0], p.g[S1][1]};
@@ -271,6 +324,8 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
       AN3D_LAUNCH_CHECK();
     }
     // stage 2 (tp8.py:113-118)
+    if (ss) AN3D_TRY(conv_stage_two_streams(ss, m, p, S2, pcs, ctr_c1, nullptr, params, state, training, bn_decay, st));
+    else
     for (int br = 0; br < 2; ++br)
       AN3D_TRY(conv_stack_forward_bf16(m, p, S2, br, pcs[br], c1[br], nullptr, params, state, training, bn_decay, st));
     const float* g2[2] = {p.g[S2][0], p.g[S2][1]};
@@ -281,6 +336,8 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
       AN3D_LAUNCH_CHECK();
     }
     // canonicalise + final embedding (tp8.py:122-130)
+    if (ss) AN3D_TRY(conv_stage_two_streams(ss, m, p, EMB, pcs, ctr_c2, ang2, params, state, training, bn_decay, st));
+    else
     for (int br = 0; br < 2; ++br)
       AN3D_TRY(conv_stack_forward_bf16(m, p, EMB, br, pcs[br], c2[br], p.ang[br], params, state, training, bn_decay, st));
   } else {
