@@ -20,6 +20,7 @@ ERR_NAMES = {0: "AN3D_OK", -1: "AN3D_ERR_INVALID", -2: "AN3D_ERR_UNSUPPORTED", -
 TRAINING = 1
 PRECISION_FP32 = 0
 PRECISION_BF16 = 2
+WEIGHTS_PREPARED = 4
 
 
 class Arch(C.Structure):

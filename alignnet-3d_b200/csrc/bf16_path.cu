@@ -416,17 +416,22 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
     AN3D_LAUNCH_CHECK();
   }
-  fold_l1_kernel<<<1, 64, 0, st>>>(q.moments[s][br], (double)M, params + L1.w, params + L1.b, io1, training ? 1 : 0, decay,
-                                   q.w1f[s][br], q.c1f[s][br]);
-  AN3D_LAUNCH_CHECK();
+  const bool prepared = p.prepared && !training;   // inference with unchanged parameters: the folds below are still valid
+  if (!prepared) {
+    fold_l1_kernel<<<1, 64, 0, st>>>(q.moments[s][br], (double)M, params + L1.w, params + L1.b, io1, training ? 1 : 0, decay,
+                                     q.w1f[s][br], q.c1f[s][br]);
+    AN3D_LAUNCH_CHECK();
+  }
   if (training) {
     AN3D_TRY(launch_fused<convfwd::MODE_STATS2>(P, grid, smem, st));
     stats2_from_gram1_kernel<<<8, 128, 0, st>>>(params + L2.w, q.gram1[s][br], q.stats2[s][br]);
     AN3D_LAUNCH_CHECK();
   }
-  fold_acc_kernel<<<1, 128, 0, st>>>(q.stats2[s][br], (double)M, params + L2.b, io2, 128, training ? 1 : 0, decay, 0,
-                                     q.t2f[s][br]);
-  AN3D_LAUNCH_CHECK();
+  if (!prepared) {
+    fold_acc_kernel<<<1, 128, 0, st>>>(q.stats2[s][br], (double)M, params + L2.b, io2, 128, training ? 1 : 0, decay, 0,
+                                       q.t2f[s][br]);
+    AN3D_LAUNCH_CHECK();
+  }
   AN3D_CUDA_CHECK(cudaMemsetAsync(q.zext[s][br], 0, (size_t)B * C3 * sizeof(uint32_t), st));
   if (training) AN3D_TRY(launch_fused<convfwd::MODE_FULL_TRAIN>(P, grid, smem, st));
   else AN3D_TRY(launch_fused<convfwd::MODE_FULL_EVAL>(P, grid, smem, st));
@@ -448,9 +453,11 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
                                                            q.stats3[s][br]);
     AN3D_LAUNCH_CHECK();
   }
-  fold_acc_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.stats3[s][br], (double)M, params + L3.b, io3, C3, training ? 1 : 0,
-                                                    decay, 0, nullptr);
-  AN3D_LAUNCH_CHECK();
+  if (!prepared) {
+    fold_acc_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.stats3[s][br], (double)M, params + L3.b, io3, C3, training ? 1 : 0,
+                                                      decay, 0, nullptr);
+    AN3D_LAUNCH_CHECK();
+  }
   const int64_t ldg = s == EMB ? 2 * C3 : C3;
   const int64_t tot = (int64_t)B * C3;
   pool_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q.zext[s][br], B, C3, io3.gamma, params + L3.b,

@@ -163,6 +163,7 @@ struct PlanBf16 {
 struct PlanF32 {
   int B = 0, N = 0;
   bool bf16 = false;                        // AN3D_PRECISION_BF16: conv stacks and large FC GEMMs on the tensor cores
+  bool prepared = false;                    // AN3D_WEIGHTS_PREPARED (bf16 inference): folded BN / weight images are reused
   int64_t M = 0;  // rows per branch = B*N
   float* pin[3][2];                         // stage input points [M,3]
   float* z[3][AN3D_MAX_LAYERS][2];          // pre-BN conv outputs [M,C]

@@ -187,7 +187,7 @@ static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const fl
         bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
                                                                     v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
         AN3D_LAUNCH_CHECK();
-      } else {
+      } else if (!p.prepared) {
         AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
       }
       psc = v.scale;
@@ -245,7 +245,7 @@ static int mlp_forward_pair(const Model& m, const PlanF32& p, int s, const float
           bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
                                                                       v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
           AN3D_LAUNCH_CHECK();
-        } else {
+        } else if (!p.prepared) {
           AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
         }
         psc[br] = v.scale;
@@ -269,11 +269,14 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   }
   const bool training = (flags & AN3D_TRAINING) != 0;
   const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
-  if (bf16) AN3D_TRY(pack_weights_bf16(m, p, params, st));
+  p.prepared = bf16 && !training && (flags & AN3D_WEIGHTS_PREPARED) != 0;
+  if (bf16 && !p.prepared) AN3D_TRY(pack_weights_bf16(m, p, params, st));
   const int nb = m.nb;
   const int64_t M = p.M;
-  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
-  AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));
+  if (!p.prepared) {   // (the reduction scratch only feeds batch statistics and the eval-mode finalize kernels)
+    AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));
+  }
   const float* masks[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (training) {
     for (int i = 0; i < 5; ++i) {

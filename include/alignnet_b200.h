@@ -64,7 +64,12 @@ typedef struct an3d_ctx an3d_ctx;
 enum {
   AN3D_TRAINING = 1,        /* is_training=True: batch statistics, EMA update, dropout (tf_util.py:476-488,572) */
   AN3D_PRECISION_FP32 = 0,  /* CUDA-core fp32 everywhere: the <=1e-4 parity mode               */
-  AN3D_PRECISION_BF16 = 2   /* bf16 tcgen05 tensor-core GEMMs with fp32 accumulation (fast mode) */
+  AN3D_PRECISION_BF16 = 2,  /* bf16 tcgen05 tensor-core GEMMs with fp32 accumulation (fast mode) */
+  /* Inference only (ignored with AN3D_TRAINING and in fp32 mode; not part of the workspace size).  The caller
+   * asserts that the previous an3d_forward on THIS workspace ran in inference mode with the SAME params and
+   * bn_state: the folded BN scales / shifts and the packed weight images it left in the workspace are reused and
+   * the ~40 launches that derive them are skipped.  The library cannot check the assertion. */
+  AN3D_WEIGHTS_PREPARED = 4
 };
 
 /* The eight tensors of end_points (models/tp8.py:146-156).  Centers/translations [B,3],
