@@ -152,7 +152,9 @@ def test_c3_training_step_properties():
         lg.append(float(ec.train_step_graph(dev, lr=0.001, bn_decay=0.5)[0].cpu()))
     torch.cuda.synchronize()
     assert eb.step == 3
-    np.testing.assert_allclose(lg, le, rtol=5e-2)
+    # the two trajectories start from identical parameters and drift apart through the noisy gradients (see above)
+    for a, b, tol in zip(lg, le, (3e-2, 6e-2, 8e-2)):
+        assert abs(a - b) <= tol * abs(b), (lg, le)
     assert np.isfinite(le).all() and np.isfinite(lg).all()
     p0 = torch.from_numpy(ea._flatten(ea.params_layout, params)).cuda()
     de, dg = eb.params - p0, ec.params - p0
