@@ -21,6 +21,7 @@ TRAINING = 1
 PRECISION_FP32 = 0
 PRECISION_BF16 = 2
 WEIGHTS_PREPARED = 4
+DETERMINISTIC = 8
 
 
 class Arch(C.Structure):

@@ -304,14 +304,12 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   }
   // ---- wgrad3: sparse part + Gram on the tensor cores, dense correction on CUDA cores ----
   {
-    convbwd::Wg3Params W;
-    W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
-    W.gidx = p.gidx[s][br]; W.dyext = q.dyext; W.s3 = sc3;
     // (the Gram matrix A2^T A2 was computed on the tensor cores by the forward pass)
     prof_mark(PROF_BWD_T1, true, st);
     // sparse part T1 = A2^T S: gather-scale-accumulate on CUDA cores (1/N of the dense FLOPs)
     convbwd::T1Params T;
-    T.a2_img = W.a2_img; T.img_bytes = W.img_bytes; T.gidx = W.gidx; T.dyext = W.dyext; T.s3 = W.s3; T.B = B; T.N = N;
+    T.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); T.img_bytes = (uint32_t)q.img_bytes;
+    T.gidx = p.gidx[s][br]; T.dyext = q.dyext; T.s3 = sc3; T.B = B; T.N = N;
     T.PC = q.PC; T.npc = q.npc; T.C3 = C3; T.n_items = n_items; T.t1 = grads + L3.w;
     // 1024 resident threads per SM: one CTA of 1024 channels, or two of <= 512
     const int tr = std::max(1, std::min(n_items, (sms / 4) * (C3 <= 512 ? 2 : 1)));

@@ -68,6 +68,28 @@ __global__ void moments_kernel(const float* pcs, const float* center, const floa
   }
 }
 
+// Fixed-order sums of per-CTA partial results: out[r][c] = sum_p parts[p][r][c] (p ascending), so the cross-CTA
+// reductions of the statistics passes are bit-reproducible (fp32 atomics would add in arrival order).
+__global__ void sum_parts_kernel(const float* parts, int nparts, int rows, int cols_in, int cols_out, float* out,
+                                 double* extra /* optional [rows]: column `cols_out` of the parts, summed in fp64 */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols_out) {
+    const int r = i / cols_out, c = i - r * cols_out;
+    const float* src = parts + (size_t)r * cols_in + c;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) acc += src[(size_t)p * rows * cols_in];   // (loads are independent: unrolling overlaps them)
+    out[i] = acc;
+  } else if (extra && i < rows * cols_out + rows) {
+    const int r = i - rows * cols_out;
+    const float* src = parts + (size_t)r * cols_in + cols_out;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) acc += (double)src[(size_t)p * rows * cols_in];
+    extra[r] = acc;
+  }
+}
+
 struct BnIo {
   const float *gamma, *beta;
   float *state_mean, *state_var;
@@ -252,43 +274,38 @@ BnIo bn_io(const Model& m, const PlanF32& p, const float* params, float* state, 
   return io;
 }
 
-// AN3D_FWD_RING selects an experimental variant of the full passes (conv_fwd_bf16.cuh): bit 0 = three-slot accumulator
-// ring, bit 1 = early slot release.  Read once; 0 / unset = the measured default.
-int fwd_variant() {
-  static const int v = [] {
-    const char* e = getenv("AN3D_FWD_RING");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
-  }();
-  return v;
-}
-
-template <int MODE, int VAR>
-int launch_fused_variant(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
-  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int MODE>
+int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
   prof_mark(PROF_CONV_FULL, true, st);
-  convfwd::conv_stack_fwd_kernel<MODE, VAR><<<grid, convfwd::kThreads, smem, st>>>(P);
+  convfwd::conv_stack_fwd_kernel<MODE><<<grid, convfwd::kThreads, smem, st>>>(P);
   prof_mark(PROF_CONV_FULL, false, st);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }
 
-template <int MODE>
-int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t st) {
-  const int tag = MODE == convfwd::MODE_STATS2 ? PROF_CONV_STATS2 : PROF_CONV_FULL;
-  if constexpr (MODE != convfwd::MODE_STATS2) {
-    switch (fwd_variant()) {
-      case 1: return launch_fused_variant<MODE, 1>(P, grid, smem, st);
-      case 2: return launch_fused_variant<MODE, 2>(P, grid, smem, st);
-      case 3: return launch_fused_variant<MODE, 3>(P, grid, smem, st);
-      default: break;
-    }
+// layer-2 batch statistics pass: a light, latency-bound kernel -- as many CTAs per SM as fit
+int launch_stats2(convfwd::Params P, int sms, float* gram1_out, cudaStream_t st) {
+  const size_t smem = convfwd::stats2_smem_bytes(P.PC);
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t cached_smem = 0;
+  static int cached_per_sm = 1;
+  if (cached_smem != smem) {     // (host-side query: cached, the launch sits on the step's critical path when not graph-replayed)
+    int q = 1;
+    AN3D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, convfwd::conv_stats2_kernel, convfwd::kStatsThreads, smem));
+    cached_per_sm = std::max(1, std::min(q, (int)(512 / convfwd::kStatsTmemCols)));
+    cached_smem = smem;
   }
-  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stack_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-  prof_mark(tag, true, st);
-  convfwd::conv_stack_fwd_kernel<MODE><<<grid, convfwd::kThreads, smem, st>>>(P);
-  prof_mark(tag, false, st);
+  const int per_sm = cached_per_sm;
+  const int grid = std::max(1, std::min(std::min(P.n_items, sms * per_sm), kMaxParts1));
+  P.item_begin_stride = (P.n_items + grid - 1) / grid;
+  const int nparts = (P.n_items + P.item_begin_stride - 1) / P.item_begin_stride;   // CTAs that own items (and write a slot)
+  prof_mark(PROF_CONV_STATS2, true, st);
+  convfwd::conv_stats2_kernel<<<grid, convfwd::kStatsThreads, smem, st>>>(P);
+  prof_mark(PROF_CONV_STATS2, false, st);
+  AN3D_LAUNCH_CHECK();
+  sum_parts_kernel<<<(64 * 80 + 255) / 256, 256, 0, st>>>(P.gram1, nparts, 64, 80, 80, gram1_out, nullptr);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }
@@ -339,6 +356,10 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
     }
   }
   if (training) {
+    for (int br = 0; br < 2; ++br) {
+      q->gram1_parts[br] = a.take<float>((int64_t)kMaxParts1 * 64 * 80);
+      q->gram_parts[br] = a.take<float>((int64_t)kMaxParts * 128 * 132);
+    }
     int64_t c3max = 0;
     for (int s = 0; s < 3; ++s) {
       const int C3 = m.conv[s].back().cout;
@@ -399,9 +420,9 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   P.w1f = q.w1f[s][br]; P.c1f = q.c1f[s][br]; P.w2t_img = q.w2t[s]; P.s2 = io2.scale; P.t2f = q.t2f[s][br];
   P.w3t_img = q.w3t[s][br]; P.nchunk = C3 / 128;
   P.nstages = convfwd::smem_bytes(q.PC, 3) <= (size_t)kMaxSmem ? 3 : 2;
-  P.zext = q.zext[s][br]; P.gram1 = q.gram1[s][br]; P.stats3 = q.stats3[s][br];
-  P.a2_img = training ? q.a2img[s][br] : nullptr; P.sa2 = training ? q.sa2[s][br] : nullptr;
-  P.idx_mask = q.idx_mask;
+  P.zext = q.zext[s][br]; P.gram1 = q.gram1_parts[br];
+  P.a2_img = training ? q.a2img[s][br] : nullptr;
+  P.idx_mask = q.idx_mask; P.not15 = ~15u;
   const size_t smem = convfwd::smem_bytes(q.PC, P.nstages);
   if (smem > (size_t)kMaxSmem) {
     set_error("conv_stack_forward_bf16: tile needs %zu bytes of shared memory", smem);
@@ -410,8 +431,6 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
 
   if (training) {
     AN3D_CUDA_CHECK(cudaMemsetAsync(q.moments[s][br], 0, 16 * sizeof(double), st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram1[s][br], 0, 64 * 80 * sizeof(float), st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.sa2[s][br], 0, 128 * sizeof(double), st));
     const int mb = (int)std::min<int64_t>((M + 255) / 256, 4 * sms);
     moments_kernel<<<mb, 256, 0, st>>>(pcs, center, angle, N, M, q.moments[s][br]);
     AN3D_LAUNCH_CHECK();
@@ -423,7 +442,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     AN3D_LAUNCH_CHECK();
   }
   if (training) {
-    AN3D_TRY(launch_fused<convfwd::MODE_STATS2>(P, grid, smem, st));
+    AN3D_TRY(launch_stats2(P, sms, q.gram1[s][br], st));
     stats2_from_gram1_kernel<<<8, 128, 0, st>>>(params + L2.w, q.gram1[s][br], q.stats2[s][br]);
     AN3D_LAUNCH_CHECK();
   }
@@ -437,16 +456,18 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
   else AN3D_TRY(launch_fused<convfwd::MODE_FULL_EVAL>(P, grid, smem, st));
   if (training) {
     // Gram matrix of the saved layer-2 activations on the tensor cores -> layer-3 BN statistics
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gram[s][br], 0, 128 * 128 * sizeof(float), st));
-    convbwd::Wg3Params W;
+    convbwd::Gram2Params W;
     W.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); W.img_bytes = (uint32_t)q.img_bytes;
-    W.gidx = nullptr; W.dyext = nullptr; W.s3 = nullptr; W.B = B; W.N = N; W.PC = q.PC; W.npc = q.npc; W.C3 = 0;
-    W.n_items = P.n_items; W.gW3 = nullptr; W.gram = q.gram[s][br];
-    const int nranges = std::max(1, std::min(P.n_items, sms));
+    W.N = N; W.PC = q.PC; W.npc = q.npc; W.n_items = P.n_items; W.parts = q.gram_parts[br];
+    const int nranges = std::max(1, std::min(std::min(P.n_items, sms), kMaxParts));
     W.items_per_cta = (P.n_items + nranges - 1) / nranges;
-    const size_t gsmem = convbwd::wg3_smem_bytes(q.PC);
-    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    convbwd::wgrad3_kernel<<<dim3(nranges, 1), convbwd::kWg3Threads, gsmem, st>>>(W);
+    const int nparts = (P.n_items + W.items_per_cta - 1) / W.items_per_cta;
+    const size_t gsmem = convbwd::gram2_smem_bytes(q.PC);
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    convbwd::gram2_kernel<<<nranges, convbwd::kGram2Threads, gsmem, st>>>(W);
+    AN3D_LAUNCH_CHECK();
+    sum_parts_kernel<<<(128 * 128 + 128 + 255) / 256, 256, 0, st>>>(q.gram_parts[br], nparts, 128, convbwd::kGram2PartCols, 128,
+                                                                    q.gram[s][br], q.sa2[s][br]);
     AN3D_LAUNCH_CHECK();
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(gw3_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGwSmem));
     gw3_stats_kernel<<<C3 / 32, kGwThreads, kGwSmem, st>>>(params + L3.w, q.gram[s][br], q.sa2[s][br], C3, q.gw[s][br],

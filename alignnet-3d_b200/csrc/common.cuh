@@ -41,6 +41,7 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
 enum ProfTag { PROF_CONV_STATS2 = 0, PROF_CONV_FULL = 1, PROF_BWD_T1 = 2, PROF_BWD_DGRAD3 = 3, PROF_BWD_L2 = 4,
                PROF_FC = 5, PROF_NTAGS = 8 };
 void prof_mark(int tag, bool begin, cudaStream_t st);
+bool prof_active();
 
 // One linear layer (1x1 conv or FC).  Weights are stored as the reference stores them:
 // [Cin, Cout] row-major (conv kernels [1,1,Cin,Cout] / [1,3,1,Cout], FC [Cin,Cout]).
@@ -123,6 +124,8 @@ struct BnScratch {
 
 // Extra buffers of the bf16 tcgen05 path (conv stacks); FC layers, loss and the inter-stage
 // glue reuse the PlanF32 buffers.
+constexpr int kMaxParts1 = 640, kMaxParts = 160;   // CTAs of the statistics / Gram passes (>= SMs x CTAs per SM)
+
 struct PlanBf16 {
   int PC = 0, npc = 0;                      // points per work item (multiple of 16) and items per cloud
   uint32_t idx_mask = 0;                    // low mantissa bits carrying the arg-max point index
@@ -135,6 +138,8 @@ struct PlanBf16 {
   double* stats2[3][2];                     // sum / sum-of-squares of the raw layer-2 accumulator [128][2]
   double* stats3[3][2];                     // same for layer 3 [C3][2]
   float* gram1[3][2];                       // [64][80] Gram matrix + column sums of the layer-1 activations (layer-2 BN statistics)
+  float* gram1_parts[2];                    // per branch: [kMaxParts1][64*80] per-CTA partial sums (added in CTA order)
+  float* gram_parts[2];                     // per branch: [kMaxParts][128*132] per-CTA partial Gram matrices + column sums
   uint32_t* zext[3][2];                     // packed pooled extreme [B][C3]
   __nv_bfloat16* a2img[3][2];               // saved layer-2 activations (training): per item the A2 smem tile image
   int64_t img_bytes = 0;                    // bytes of one item image (16 planes)
@@ -163,6 +168,7 @@ struct PlanBf16 {
 struct PlanF32 {
   int B = 0, N = 0;
   bool bf16 = false;                        // AN3D_PRECISION_BF16: conv stacks and large FC GEMMs on the tensor cores
+  bool deterministic = false;               // AN3D_DETERMINISTIC: no split-K fp32 reductions in inference FC layers
   bool prepared = false;                    // AN3D_WEIGHTS_PREPARED (bf16 inference): folded BN / weight images are reused
   int64_t M = 0;  // rows per branch = B*N
   float* pin[3][2];                         // stage input points [M,3]

@@ -7,7 +7,8 @@
 //     wgrad3 = A2^T S + sa2 (x) p' + (G2 W3) diag(q)          S = sparse s3*dy3, G2 = A2^T A2 (Gram)
 //     da2    = S (W3)^T + u + A2 Gq                           Gq = W3 diag(q) W3^T, u = W3 p'
 // Kernels here:
-//   wgrad3_kernel : T1 = A2^T S and the Gram matrix, contraction over points (MN-major operands)
+//   gram2_kernel  : the Gram matrix A2^T A2 and the column sums, contraction over points (MN-major operands)
+//   t1_sparse_kernel : T1 = A2^T S, the sparse part of wgrad3
 //   dgrad3_kernel : da2 -> dy2 (ReLU mask) + BN2 backward sums, per cloud
 //   bwd_l2_kernel : dz2 -> wgrad2, da1 -> dy1 + BN1 backward sums
 // A2 / dy2 tiles travel between kernels as the exact shared-memory plane images (bulk copies).
@@ -26,190 +27,116 @@ constexpr uint32_t kWHalfBytes = 128 * 64 * 2;   // one [128 rows][64 k] weight 
 constexpr uint32_t kPlaneW = 2048;
 
 // =============================================================================================
-// wgrad3: T1[k, c] = sum_pt a2[pt, k] * S[pt, c]   (+ Gram[k, k'] = sum_pt a2[pt,k] a2[pt,k'])
+// gram2: Gram[k, k'] = sum_pt a2[pt,k] a2[pt,k']  and  sa2[k] = sum_pt a2[pt,k]  over the saved A2 tile images of one
+// (stage, branch): the layer-3 BN statistics of the forward pass and the dense part of wgrad3.  Contraction over
+// points with MN-major operands straight from the images; the column sums ride along as a 129th output column (a
+// constant 'ones' plane appended to every image buffer in shared memory), so nothing but the tensor cores ever
+// touches the activations.  HBM-bound (it streams every image once): three images in flight per SM.
 // =============================================================================================
-struct Wg3Params {
+struct Gram2Params {
   const uint8_t* a2_img;
   uint32_t img_bytes;
-  const int32_t* gidx;   // [B][C3] arg row (index within the cloud)
-  const float* dyext;    // [B][C3] gradient at the arg row (ReLU-masked)
-  const float* s3;       // [C3] BN scale
-  int B, N, PC, npc, C3, n_items, items_per_cta;
-  float* gW3;            // [128][C3]
-  float* gram;           // [128][128]
+  int N, PC, npc, n_items, items_per_cta;
+  float* parts;          // [CTA][128][132]: this CTA's Gram matrix (columns 0..127) and column sums (column 128)
 };
-constexpr int kWg3Threads = 192;
-constexpr int kWg3SlotsPerPass = 6;      // 6 x 64 channels + 128 Gram columns = 512 TMEM columns
+constexpr int kGram2PartCols = 132;
+constexpr int kGram2Threads = 192;       // warps 0-3 flush, warp 4 MMA, warp 5 loader
+constexpr int kGram2Bufs = 3;
+constexpr uint32_t kGram2Cols = 144;     // 128 Gram columns + the column sums + 15 zero columns
 
-inline size_t wg3_smem_bytes(int PC) { return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 256; }
+inline size_t gram2_smem_bytes(int PC) { return kGram2Bufs * 18 * (size_t)plane_stride(PC) + 256; }
 
-struct Wg3Bars {
-  uint64_t a2_full[2], a2_empty[2], sd_full[2], sd_empty[2], done;
+struct Gram2Bars {
+  uint64_t full[kGram2Bufs], empty[kGram2Bufs], done;
   uint32_t tmem_base;
 };
 
-static __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_kernel(const Wg3Params P) {
+static __global__ void __launch_bounds__(kGram2Threads, 1) gram2_kernel(const Gram2Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
-  const uint32_t sd_bytes = 8 * plane;
-  uint8_t* sA2[2] = {smem, smem + P.img_bytes};
-  uint8_t* sSd[2] = {smem + 2 * P.img_bytes, smem + 2 * P.img_bytes + sd_bytes};
-  Wg3Bars* bars = reinterpret_cast<Wg3Bars*>(smem + 2 * P.img_bytes + 2 * sd_bytes);
+  const uint32_t buf_bytes = 18 * plane;
+  Gram2Bars* bars = reinterpret_cast<Gram2Bars*>(smem + kGram2Bufs * buf_bytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.items_per_cta);
   const int it_end = min(P.n_items, it_begin + P.items_per_cta);
   const int n_local = it_end - it_begin;
-  const int pass = blockIdx.y;
-  const int c0 = pass * kWg3SlotsPerPass * 64;
-  const int nslots = min(kWg3SlotsPerPass, (P.C3 - c0) / 64);
-  const bool do_gram = pass == 0;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_empty[i], 1);
-      mbar_init(&bars->sd_full[i], 64); mbar_init(&bars->sd_empty[i], 1);
-    }
+    for (int i = 0; i < kGram2Bufs; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->done, 1);
     fence_barrier_init();
   }
-  for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kWg3Threads * 16) *reinterpret_cast<uint4*>(sSd[0] + i) = make_uint4(0, 0, 0, 0);
-  if (warp == 4) tmem_alloc(&bars->tmem_base, 512);
+  // planes 16 / 17 of every buffer: channel 128 = 1 for every row, channels 129..143 = 0 (padding rows of an image
+  // hold zero activations, so a one there adds nothing)
+  for (int i = tid; i < kGram2Bufs * 2 * P.PC; i += kGram2Threads) {
+    const int bidx = i / (2 * P.PC), r = i - bidx * 2 * P.PC;
+    const int pl = r / P.PC, row = r - pl * P.PC;
+    *reinterpret_cast<uint4*>(smem + bidx * buf_bytes + (16 + pl) * plane + row * 16) =
+        make_uint4(pl == 0 ? 0x00003f80u : 0u, 0, 0, 0);
+  }
+  if (warp == 4) tmem_alloc(&bars->tmem_base, 256);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < 2) {
-    // ---- scatter threads: one channel of the current 64-channel slot each.  The (arg row, weight) pairs of
-    // the NEXT item are loaded into registers while the current item is scattered, so the global-load
-    // latency never sits between two MMAs.
-    const int t = tid;
-    int prev_off[2] = {-1, -1};
-    uint32_t ph_e[2] = {1, 1};
-    int g = 0;
-    int cur_idx[kWg3SlotsPerPass], nxt_idx[kWg3SlotsPerPass];
-    float cur_w[kWg3SlotsPerPass], nxt_w[kWg3SlotsPerPass];
-    auto fetch = [&](int li, int (&ix)[kWg3SlotsPerPass], float (&wv)[kWg3SlotsPerPass]) {
-      const int cloud = (it_begin + li) / P.npc;
-#pragma unroll
-      for (int s = 0; s < kWg3SlotsPerPass; ++s) {
-        if (s < nslots) {
-          const int c = c0 + s * 64 + t;
-          ix[s] = P.gidx[(size_t)cloud * P.C3 + c];
-          wv[s] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
-        }
-      }
-    };
-    if (n_local > 0) fetch(0, cur_idx, cur_w);
-    for (int li = 0; li < n_local; ++li) {
-      const int it = it_begin + li;
-      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-      const int p0 = pchunk * P.PC;
-      const int nvalid = min(P.PC, P.N - p0);
-      if (li + 1 < n_local) fetch(li + 1, nxt_idx, nxt_w);
-#pragma unroll
-      for (int s = 0; s < kWg3SlotsPerPass; ++s) {
-        if (s >= nslots) break;
-        const int sb = g & 1;
-        mbar_wait(&bars->sd_empty[sb], ph_e[sb]); ph_e[sb] ^= 1;
-        if (prev_off[sb] >= 0) *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + prev_off[sb]) = __float2bfloat16_rn(0.f);
-        const int row = cur_idx[s] - p0;
-        const float w = cur_w[s];
-        if (row >= 0 && row < nvalid && w != 0.f) {
-          const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(sSd[sb] + off) = __float2bfloat16_rn(w);
-          prev_off[sb] = off;
-        } else {
-          prev_off[sb] = -1;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->sd_full[sb]);
-        ++g;
-      }
-#pragma unroll
-      for (int s = 0; s < kWg3SlotsPerPass; ++s) { cur_idx[s] = nxt_idx[s]; cur_w[s] = nxt_w[s]; }
-    }
-  } else if (warp == 4) {
+  if (warp == 4) {
     if (n_local > 0) {
-      uint32_t ph_a2[2] = {0, 0}, ph_sd[2] = {0, 0};
-      int g = 0;
+      const uint32_t idesc = make_idesc(128, kGram2Cols, 1, 1);
+      uint32_t ph = 0;
       for (int li = 0; li < n_local; ++li) {
         const int it = it_begin + li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
         const int NT = (nvalid + 15) & ~15;
-        const int b = li & 1;
-        mbar_wait(&bars->a2_full[b], ph_a2[b]); ph_a2[b] ^= 1;
+        const int b = li % kGram2Bufs;
+        mbar_wait(&bars->full[b], (ph >> b) & 1u); ph ^= 1u << b;
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA2[b]);
-        if (do_gram) {
-          const uint32_t idesc = make_idesc(128, 128, 1, 1);
-          for (int ks = 0; ks < NT / 16; ++ks) {
-            const uint64_t d = make_desc(a_base + ks * 256, 128, plane);
-            mma_bf16(tmem + 384, d, d, idesc, (li > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        const uint32_t idesc = make_idesc(128, 64, 1, 1);
-        for (int s = 0; s < nslots; ++s, ++g) {
-          const int sb = g & 1;
-          mbar_wait(&bars->sd_full[sb], ph_sd[sb]); ph_sd[sb] ^= 1;
-          tc_fence_after();
-          const uint32_t s_base = smem_u32(sSd[sb]);
+        if (elect_one()) {
+          const uint64_t d = make_desc(smem_u32(smem + b * buf_bytes), 128, plane);
           for (int ks = 0; ks < NT / 16; ++ks)
-            mma_bf16(tmem + s * 64, make_desc(a_base + ks * 256, 128, plane), make_desc(s_base + ks * 256, 128, plane),
-                     idesc, (li > 0 || ks > 0) ? 1u : 0u);
-          mma_commit(&bars->sd_empty[sb]);
+            mma_bf16_raw(tmem, desc_advance(d, ks * 256), desc_advance(d, ks * 256), idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          mma_commit_raw(&bars->empty[b]);
+          if (li == n_local - 1) mma_commit_raw(&bars->done);
         }
-        mma_commit(&bars->a2_empty[b]);
+        __syncwarp();
       }
-      mma_commit(&bars->done);
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      uint32_t ph_e[2] = {1, 1};
+      uint32_t ph_e = (1u << kGram2Bufs) - 1u;
       for (int li = 0; li < n_local; ++li) {
-        const int b = li & 1;
-        mbar_wait(&bars->a2_empty[b], ph_e[b]); ph_e[b] ^= 1;
-        mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
-        bulk_copy_g2s(sA2[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
+        const int b = li % kGram2Bufs;
+        mbar_wait_relaxed(&bars->empty[b], (ph_e >> b) & 1u); ph_e ^= 1u << b;
+        mbar_arrive_expect_tx(&bars->full[b], P.img_bytes);
+        bulk_copy_g2s(smem + b * buf_bytes, P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->full[b]);
       }
     }
-  }
-  // ---- epilogue: TMEM -> vector reductions into the gradient buffers (lanes = k) ----
-  if (warp < 4 && n_local > 0) {
-    mbar_wait(&bars->done, 0);
+  } else if (n_local > 0) {
+    // ---- flush: TMEM -> vector reductions (lanes = k) ----
+    mbar_wait_relaxed(&bars->done, 0);
     tc_fence_after();
     const int k = tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int s = 0; s < nslots; ++s) {
-      for (int g16 = 0; g16 < 64; g16 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_base + s * 64 + g16, r);
-        tmem_ld_wait();
-        float* dst = P.gW3 + (size_t)k * P.C3 + c0 + s * 64 + g16;
+    float* row = P.parts + ((size_t)blockIdx.x * 128 + k) * kGram2PartCols;
+    for (int g16 = 0; g16 < 128; g16 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + lane_base + g16, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                     __uint_as_float(r[j + 3]));
-      }
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(row + g16 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
     }
-    if (do_gram) {
-      for (int g16 = 0; g16 < 128; g16 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_base + 384 + g16, r);
-        tmem_ld_wait();
-        float* dst = P.gram + (size_t)k * 128 + g16;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                     __uint_as_float(r[j + 3]));
-      }
-    }
+    uint32_t r[16];
+    tmem_ld16(tmem + lane_base + 128, r);
+    tmem_ld_wait();
+    *reinterpret_cast<float4*>(row + 128) = make_float4(__uint_as_float(r[0]), 0.f, 0.f, 0.f);
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
 // =============================================================================================

@@ -1,19 +1,30 @@
 // Fused PointNet conv stack (3 -> 64 -> 128 -> C3, BN + ReLU folded, max-pool) for sm_100a.
 //
-// One persistent CTA per SM walks a contiguous range of work items (item = one cloud, or one
-// <=256-point chunk of a cloud).  Per item:
-//   front-end warps : recentre/rotate the points, layer 1 (K = 3, CUDA-core FFMA) -> bf16 A1 tile in
-//                     shared memory; after the layer-2 MMA, TMEM -> BN affine + ReLU -> bf16 A2 tile
-//   MMA thread      : tcgen05.mma  D2[128 ch, pts] = W2^T A1^T   (K = 64)
-//                     tcgen05.mma  D3[128 ch, pts] = W3^T[chunk] A2^T  (K = 128) per 128-channel chunk,
-//                     accumulators in TMEM, two point-halves double-buffered against the epilogue
-//   back-end warps  : TMEM -> per-channel running max over the cloud's points (one thread owns one
-//                     channel, so the max-pool and the BN statistics need no cross-thread reduction)
+// conv_stack_fwd_kernel: one persistent CTA per SM walks a contiguous range of work items (item = one cloud, or
+// one <=256-point chunk of a cloud).  Per item:
+//   front-end warps : recentre/rotate the points, layer 1 (K = 3, CUDA-core FFMA) -> bf16 A1 tile in shared
+//                     memory; after the layer-2 MMA, TMEM -> BN affine + ReLU -> bf16 A2 tile
+//   MMA warp        : tcgen05.mma  D2[pts, 128 ch] = A1 W2        (K = 64; POINT-major: lane = point)
+//                     tcgen05.mma  D3[128 ch, pts] = W3^T[chunk] A2^T (K = 128; CHANNEL-major) per 128-channel
+//                     chunk, accumulators in TMEM, two point-halves double-buffered against the epilogue
+//   back-end warps  : TMEM -> per-channel running max over the cloud's points (one thread owns one channel, so
+//                     the max-pool needs no cross-thread reduction)
 //   loader thread   : bulk async copies (TMA unit) of the pre-packed W2^T / W3^T images
-// Accumulators are channel-major (TMEM lane = output channel, column = point): the weights are the
-// MMA "A" operand, the activations the "B" operand.  W3 is sign-folded with sign(gamma) at pack time
-// so that the pooled extreme of the raw accumulator is always a max (BN + ReLU are monotone).
+// The two layers use opposite accumulator orientations on purpose.  Layer 3 is channel-major (weights = MMA "A"
+// operand) so that the max over points is a per-thread reduction.  Layer 2 is point-major (activations = MMA "A"
+// operand; the very same shared-memory images serve both roles) so that its epilogue thread owns one POINT and
+// writes the next layer's operand tile in 16-byte pieces (8 channels of one point are contiguous in the plane
+// layout): ~3 instructions per element instead of ~7 with 2-byte stores.  The kernel is bound by instruction
+// issue, not by the tensor pipe or TMEM bandwidth (profiles/r2_tmem_microbench.txt: >= 600 B/clk/SM of TMEM
+// read-back is available), so instruction count per accumulator element is what the design minimises.
+// W3 is sign-folded with sign(gamma) at pack time so that the pooled extreme of the raw accumulator is always a
+// max (BN + ReLU are monotone).
+//
+// conv_stats2_kernel: layer-2 BATCH statistics without running layer 2 (see below); a light kernel, several CTAs
+// per SM.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -29,20 +40,9 @@ constexpr uint32_t kW2Bytes = 128 * 64 * 2;
 constexpr uint32_t kW3ChunkBytes = 128 * 128 * 2;
 constexpr uint32_t kPlaneW2 = 128 * 16;   // plane stride of the weight images (rows = 128 channels)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;
-// RING variant (template parameter VAR bit 0, experimental, off by default -- AN3D_FWD_RING=1, 2 or 3): THREE layer-3
-// accumulator slots of 128 columns (the MMA warp may run two half-tiles ahead of the max-reduction warps; with two
-// slots the drain + handshake latency of one half, ~800 cycles, exceeds the ~420 cycles the other half's MMAs take
-// and the tensor pipe idles), and the layer-2 accumulator delivered in two point-halves through ONE 128-column
-// region (512 TMEM columns do not hold 3 slots + a 256-column layer-2 tile).
-constexpr uint32_t kRingSlots = 3, kRingSlotCols = 128, kTmemD2Ring = 384;
+constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;   // D2: two point-major tiles of 128 columns
 
-// MODE_STATS2: layer-2 BATCH statistics without running layer 2.  With z2 = a1 W2 (bias apart),
-//   sum_p z2[p,c] = (sum_p a1[p,:]) . w_c        sum_p z2[p,c]^2 = w_c^T (A1^T A1) w_c
-// so the pass only computes layer 1 and accumulates the 64 x 64 Gram matrix of its (bf16) activations plus their
-// column sums on the tensor cores (contraction over points, MN-major operands straight from the A1 tile, one extra
-// 'ones' plane) -- no per-item accumulator read-back at all.
-enum Mode { MODE_STATS2 = 0, MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
+enum Mode { MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
 
 struct Params {
   const float* pcs;       // [B, N, 3] raw points of this branch
@@ -61,20 +61,20 @@ struct Params {
   int nchunk;             // C3 / 128
   int nstages;            // W3 ring depth (2 or 3)
   uint32_t* zext;         // [B][C3] ordered-uint packed max of the raw layer-3 accumulator
-  float* gram1;           // MODE_STATS2: [64][80] += A1^T [A1 | 1 | 0]  (Gram matrix and column sums of the bf16 layer-1
-                          // activations over all points; gives the layer-2 batch statistics in closed form)
-  double* stats3;         // [C3][2]   same for layer 3 (sign-folded)
+  float* gram1;           // stats2 kernel: [CTA][64][80] = A1^T [A1 | 1 | 0] over the CTA's items (Gram matrix and column
+                          // sums of the bf16 layer-1 activations; gives the layer-2 batch statistics in closed form)
   __nv_bfloat16* a2_img;  // optional: per item, the A2 tile exactly as staged in shared memory (16 planes),
                           // saved for the backward kernels (bulk store, TMA unit)
-  double* sa2;            // optional [128]: column sums of the (bf16-rounded) layer-2 activations
   uint32_t idx_mask;      // low mantissa bits that carry the arg-max point index (training)
+  uint32_t not15;         // ~15u, passed through a register on purpose: `(x & reg) | imm` is ONE LOP3, while
+                          // `(x & imm) | imm` costs two -- and this expression runs once per accumulator element
 };
 
 __host__ __device__ inline uint32_t plane_stride(int rows) { return (uint32_t)rows * 16u + 16u; }
 
 inline size_t smem_bytes(int PC, int nstages) {
   const size_t a2 = 16 * (size_t)plane_stride(PC);
-  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,s2,t2f*/ + 2 * kMaxPC * 16 /*raw points*/ +
+  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,bn2*/ + 2 * kMaxPC * 16 /*raw points*/ +
          256 /*barriers*/ + 128;
 }
 
@@ -101,10 +101,8 @@ struct Barriers {
   uint64_t d2_full;
   uint64_t a2_full[2];
   uint64_t a2_empty[2];
-  uint64_t acc_full[3];   // [2] only in the RING variant
-  uint64_t acc_empty[3];
-  uint64_t d2_full1;      // RING: second point-half of the layer-2 accumulator
-  uint64_t d2_empty;      // RING: the first half has been drained (128 arrivals: front-end group 0)
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
   uint32_t tmem_base;
   float xf[16];  // per-item transform (double-buffered): cx, cy, cz, cos, sin
 };
@@ -114,14 +112,14 @@ struct Barriers {
 // element, the group's base index is spliced in only if the group wins.
 template <int MODE>
 __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nvalid, int p0, uint32_t idx_mask,
-                                             float& m) {
+                                             uint32_t not15, float& m) {
   float gm = -INFINITY;
   if (col0 + 16 <= nvalid) {
     // three-input max (FMNMX3): 8 instead of 16 max instructions per group
 #pragma unroll
     for (int q = 0; q < 16; q += 2) {
       if (MODE == MODE_FULL_TRAIN)
-        gm = fmax3(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q), __uint_as_float((r[q + 1] & ~15u) | (uint32_t)(q + 1)));
+        gm = fmax3(gm, __uint_as_float((r[q] & not15) | (uint32_t)q), __uint_as_float((r[q + 1] & not15) | (uint32_t)(q + 1)));
       else
         gm = fmax3(gm, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
     }
@@ -129,7 +127,7 @@ __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nv
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       if (col0 + q < nvalid) {
-        if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & ~15u) | (uint32_t)q));
+        if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & not15) | (uint32_t)q));
         else gm = fmaxf(gm, __uint_as_float(r[q]));
       }
     }
@@ -141,12 +139,39 @@ __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nv
   }
 }
 
-// VAR: bit 0 = accumulator ring (above); bit 1 = early slot release: the max-reduction warps hand an accumulator
-// half back to the MMA warp as soon as their last TMEM load of it has landed in registers, before reducing it.
-template <int MODE, int VAR = 0>
+// item geometry shared by all roles
+struct Item {
+  int cloud, p0, nvalid, NT;
+};
+__device__ __forceinline__ Item item_of(const Params& P, int it) {
+  Item I;
+  I.cloud = it / P.npc;
+  const int pchunk = it - I.cloud * P.npc;
+  I.p0 = pchunk * P.PC;
+  I.nvalid = min(P.PC, P.N - I.p0);
+  I.NT = (I.nvalid + 15) & ~15;
+  return I;
+}
+
+// 8 channels of layer 1 for one point -> one 16-byte chunk of the A1 tile
+__device__ __forceinline__ uint4 layer1_chunk(const float4 raw, float cx, float cy, float cz, float cs, float sn,
+                                              const float (&w1x)[8], const float (&w1y)[8], const float (&w1z)[8],
+                                              const float (&c1r)[8]) {
+  uint4 q = make_uint4(0, 0, 0, 0);
+  if (raw.w != 0.f) {
+    const float x0 = raw.x - cx, y0 = raw.y - cy, z = raw.z - cz;
+    const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j]))), 0.f);
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  }
+  return q;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
-  constexpr bool RING = (VAR & 1) != 0, EARLY = (VAR & 2) != 0;
-  static_assert(VAR == 0 || MODE != MODE_STATS2, "the variants only exist for the full passes");
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
   const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
@@ -156,9 +181,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   uint8_t* sW3 = sW2 + kW2Bytes;
   float* sW1f = reinterpret_cast<float*>(sW3 + (size_t)P.nstages * kW3ChunkBytes);  // [3][64]
   float* sC1f = sW1f + 192;
-  float* sS2 = sC1f + 64;
-  float* sT2f = sS2 + 128;
-  float4* sRaw = reinterpret_cast<float4*>(sT2f + 128);      // [2][kMaxPC] raw points (w = 1 for real points)
+  float4* sBn2 = reinterpret_cast<float4*>(sC1f + 64);       // [64] channel pairs: (scale, shift) of 2c, (scale, shift) of 2c+1
+  float4* sRaw = sBn2 + 64;                                  // [2][kMaxPC] raw points (w = 1 for real points)
   Barriers* bars = reinterpret_cast<Barriers*>(sRaw + 2 * kMaxPC);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -177,18 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_init(&bars->acc_full[i], 1);
       mbar_init(&bars->acc_empty[i], 256);
     }
-    if (RING) {
-      mbar_init(&bars->acc_full[2], 1);
-      mbar_init(&bars->acc_empty[2], 256);
-      mbar_init(&bars->d2_full1, 1);
-      mbar_init(&bars->d2_empty, kFrontThreads / 2);
-    }
     fence_barrier_init();
   }
   for (int i = tid; i < 192; i += kThreads) sW1f[i] = P.w1f[i];
   for (int i = tid; i < 64; i += kThreads) sC1f[i] = P.c1f[i];
-  if (MODE != MODE_STATS2)
-    for (int i = tid; i < 128; i += kThreads) { sS2[i] = P.s2[i]; sT2f[i] = P.t2f[i]; }
+  for (int i = tid; i < 64; i += kThreads) sBn2[i] = make_float4(P.s2[2 * i], P.t2f[2 * i], P.s2[2 * i + 1], P.t2f[2 * i + 1]);
   if (warp == 8) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -197,34 +214,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
 
   if ((warp >= 4 && warp < 8) || warp >= 14) {
     // ================================ front-end ================================
-    // 8 warps: layer 1 with one thread per point; layer-2 epilogue with two warps per TMEM lane quarter, each
-    // taking half of the point columns.  (The front end, not the tensor pipe, paces the narrow stages.)
+    // 8 warps.  Layer 1: warp g owns channels 8g..8g+7 for all points.  Layer-2 epilogue: warp (quarter, half)
+    // reads TMEM lanes [32 quarter, +32) = points of a 128-point tile, and 64 of the 128 channel columns.
     const int fgroup = warp >= 14 ? 1 : 0;
-    const int k = (warp & 3) * 32 + lane;          // channel of the layer-2 epilogue (TMEM lane)
-    const int f = fgroup * 128 + k;                // 0..255: point slot of layer 1
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int quarter = warp & 3;
+    const int f = fgroup * 128 + quarter * 32 + lane;   // 0..255: point slot of the raw-point staging
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
-    double st_s = 0.0, st_ss = 0.0, st_a2 = 0.0;
     const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
     // register prefetch of the next item's transform (thread 0) and point (thread f owns point f):
     // the global-load latency is paid behind the current item's work instead of in front of a barrier
     float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
     auto prefetch = [&](int li) {
-      const int it = it_begin + li;
-      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-      const int p0 = pchunk * P.PC;
-      const int nvalid = min(P.PC, P.N - p0);
-      const int64_t row0 = (int64_t)cloud * P.N + p0;
+      const Item I = item_of(P, it_begin + li);
+      const int64_t row0 = (int64_t)I.cloud * P.N + I.p0;
       if (f == 0) {
-        pf_c[0] = P.center[cloud * 3]; pf_c[1] = P.center[cloud * 3 + 1]; pf_c[2] = P.center[cloud * 3 + 2];
-        pf_ang = P.angle ? P.angle[cloud] : 0.f;
+        pf_c[0] = P.center[I.cloud * 3]; pf_c[1] = P.center[I.cloud * 3 + 1]; pf_c[2] = P.center[I.cloud * 3 + 2];
+        pf_ang = P.angle ? P.angle[I.cloud] : 0.f;
       }
-      if (f < nvalid) {
+      if (f < I.nvalid) {
         const float* src = P.pcs + (row0 + f) * 3;
         pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
       }
     };
-    const int fg8 = fgroup * 4 + (warp & 3);       // channel group (A1 plane) of this warp in layer 1
+    const int fg8 = fgroup * 4 + quarter;          // channel group (A1 plane) of this warp in layer 1
     float w1x[8], w1y[8], w1z[8], c1r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -233,12 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
-      const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-      const int p0 = pchunk * P.PC;
-      const int nvalid = min(P.PC, P.N - p0);
-      const int NT = (nvalid + 15) & ~15;
+      const Item I = item_of(P, it);
+      const int nvalid = I.nvalid, NT = I.NT;
       const int b = li & 1;
-      (void)cloud;
       if (li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
@@ -256,164 +266,102 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
       // ---- layer 1: y = relu(W1f^T p' + c1f).  Warp g of the 8 front-end warps owns channels 8g..8g+7 (= plane g
-      // of the A1 tile) for ALL points: its 32 folded weights live in registers (the thread-per-point form spent
-      // 4 shared-memory loads per channel on them), lanes walk consecutive points, so the raw-point loads and the
-      // 16-byte tile stores are conflict-free.
-      for (int p = lane; p < NT; p += 32) {
-        const float4 raw = sRaw[b * kMaxPC + p];
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (raw.w != 0.f) {
-          const float x0 = raw.x - cx, y0 = raw.y - cy, z = raw.z - cz;
-          const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j]))), 0.f);
-          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-          q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-        }
-        *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) = q;
-        if (MODE == MODE_STATS2 && fg8 == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
-          *reinterpret_cast<uint4*>(sA1 + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sA1 + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
-        }
-      }
+      // of the A1 tile) for ALL points: its 32 folded weights live in registers, lanes walk consecutive points, so
+      // the raw-point loads and the 16-byte tile stores are conflict-free.
+      for (int p = lane; p < NT; p += 32)
+        *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) =
+            layer1_chunk(sRaw[b * kMaxPC + p], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
-      if (MODE == MODE_STATS2) continue;   // the Gram MMAs need no per-item epilogue
-      // ---- layer-2 epilogue: channel k, point columns [pbeg, pend)
-      const int nh = min(NT, ((NT >> 1) + 15) & ~15);
-      const int pbeg = fgroup ? nh : 0, pend = fgroup ? NT : nh;
-      if (RING) {
-        // group g waits for ITS half (the second half only exists when the item has more than nh points)
-        if (pbeg < pend) { mbar_wait_relaxed(fgroup ? &bars->d2_full1 : &bars->d2_full, ph_d2); ph_d2 ^= 1; }
-      } else {
-        mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
-      }
+      // ---- layer-2 epilogue: this thread owns the points  t*128 + 32*quarter + lane  and 64 channels
+      mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
       tc_fence_after();
-      const float sc = MODE == MODE_STATS2 ? 0.f : sS2[k], sh = MODE == MODE_STATS2 ? 0.f : sT2f[k];
-      uint8_t* dst = sA2[b] + (k >> 3) * plane2 + (k & 7) * 2;
-      float ts = 0.f, tss = 0.f, ta2 = 0.f;
-      const uint32_t d2_base = RING ? tmem + lane_base + kTmemD2Ring - (uint32_t)pbeg : tmem + lane_base + kTmemD2;
-      for (int g16 = pbeg; g16 < pend; g16 += 16) {
-        uint32_t r[16];
-        tmem_ld16(d2_base + g16, r);
-        tmem_ld_wait();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int prow = t * 128 + quarter * 32;     // warp-uniform
+        if (prow >= NT) break;
+        const int p = prow + lane;
+        const bool real = p < nvalid;
+        uint8_t* dst = sA2[b] + (size_t)(fgroup * 8) * plane2 + p * 16;
+        const uint32_t tb = tmem + lane_base + kTmemD2 + (uint32_t)t * 128u + (uint32_t)fgroup * 64u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int p = g16 + j;
-          const float acc = __uint_as_float(r[j]);
-          if (MODE == MODE_STATS2) {
-            if (p < nvalid) { ts += acc; tss = fmaf(acc, acc, tss); }
-          } else {
-            const float v = p < nvalid ? fmaxf(fmaf(acc, sc, sh), 0.f) : 0.f;
-            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-            *reinterpret_cast<__nv_bfloat16*>(dst + p * 16) = hb;
-            if (MODE == MODE_FULL_TRAIN) ta2 += __bfloat162float(hb);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld32(tb + h * 32, r);
+          tmem_ld_wait();
+          if (p < NT) {
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 bn = sBn2[fgroup * 32 + h * 16 + c8 * 4 + j];      // broadcast: channels 2c, 2c+1
+                const float v0 = fmaxf(fmaf(__uint_as_float(r[c8 * 8 + 2 * j]), bn.x, bn.y), 0.f);
+                const float v1 = fmaxf(fmaf(__uint_as_float(r[c8 * 8 + 2 * j + 1]), bn.z, bn.w), 0.f);
+                o[j] = real ? pack_bf16x2(v0, v1) : 0u;
+              }
+              *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + c8) * plane2) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
           }
         }
       }
       tc_fence_before();
-      if (RING && fgroup == 0 && nh < NT) mbar_arrive(&bars->d2_empty);   // the region may take the second half now
-      if (MODE == MODE_STATS2) {
-        st_s += (double)ts; st_ss += (double)tss;
-      } else {
-        st_a2 += (double)ta2;
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->a2_full[b]);
-        if (save_a2) {
-          asm volatile("bar.sync 2, 256;" ::: "memory");      // every front-end thread has written + fenced
-          if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, sA2[b], a2_bytes);
-        }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->a2_full[b]);
+      if (save_a2) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");      // every front-end thread has written + fenced
+        if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, sA2[b], a2_bytes);
       }
     }
     if (save_a2 && f == 0) bulk_wait_read_all();
-    if (MODE == MODE_FULL_TRAIN && P.sa2 && n_local > 0) atomicAdd(P.sa2 + k, st_a2);
-    if (MODE == MODE_STATS2 && n_local > 0 && k < 64) {
-      // Gram accumulator of the whole item range: lanes = layer-1 channel k, 80 columns (64 channels, sums, pad)
-      mbar_wait_relaxed(&bars->d2_full, 0);
-      tc_fence_after();
-      const int cbeg = fgroup ? 48 : 0, cend = fgroup ? 80 : 48;
-      for (int g16 = cbeg; g16 < cend; g16 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_base + kTmemD2 + g16, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(P.gram1 + k * 80 + g16 + j, __uint_as_float(r[j]));
-      }
-      tc_fence_before();
-    }
-    (void)st_s; (void)st_ss;
   } else if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ================================ back-end =================================
     // two warps per TMEM lane quarter (warps w and w+10 with equal w%4): the 16-column groups of every
     // accumulator half are dealt alternately to the two, which halves the latency of draining a half --
-    // the MMA thread can only refill a half once it is drained, so this latency paces the tensor pipe.
-    if (MODE != MODE_STATS2) {
-      const int bgroup = warp < 4 ? 0 : 1;
-      const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
-      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      uint32_t ph_full[2] = {0, 0};
-      uint32_t unit = 0;                             // RING: running count of accumulator half-tiles
-      const int C3 = P.nchunk * 128;
-      for (int li = 0; li < n_local; ++li) {
-        const int it = it_begin + li;
-        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-        const int p0 = pchunk * P.PC;
-        const int nvalid = min(P.PC, P.N - p0);
-        const int NT = (nvalid + 15) & ~15;
-        int N0 = ((NT >> 1) + 15) & ~15;
-        if (N0 > NT) N0 = NT;
-        const int Nh[2] = {N0, NT - N0};
+    // the MMA thread can only refill a half once it is drained.
+    const int bgroup = warp < 4 ? 0 : 1;
+    const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph_full[2] = {0, 0};
+    const int C3 = P.nchunk * 128;
+    const uint32_t not15 = P.not15;
+    for (int li = 0; li < n_local; ++li) {
+      const Item I = item_of(P, it_begin + li);
+      const int nvalid = I.nvalid, NT = I.NT, p0 = I.p0;
+      int N0 = ((NT >> 1) + 15) & ~15;
+      if (N0 > NT) N0 = NT;
+      const int Nh[2] = {N0, NT - N0};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j >= P.nchunk) break;
-          float m = -INFINITY;
-          for (int h = 0; h < 2; ++h) {
-            if (Nh[h] == 0) continue;
-            const uint32_t slot = RING ? unit % kRingSlots : (uint32_t)h;
-            if (RING) {
-              mbar_wait_relaxed(&bars->acc_full[slot], (unit / kRingSlots) & 1u);
-              ++unit;
-            } else {
-              mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
-            }
-            tc_fence_after();
-            const int off = h ? N0 : 0;
-            const uint32_t tbase = tmem + lane_base + (RING ? slot * kRingSlotCols : (h ? kTmemAcc1 : kTmemAcc0));
-            // software pipeline: the load of the next group is in flight while this one is reduced
-            uint32_t ra[16], rb[16];
-            int g16 = bgroup * 16;
-            if (g16 < Nh[h]) tmem_ld16(tbase + g16, ra);
-            bool released = false;
-            for (; g16 < Nh[h]; g16 += 64) {
+      for (int j = 0; j < 8; ++j) {
+        if (j >= P.nchunk) break;
+        float m = -INFINITY;
+        for (int h = 0; h < 2; ++h) {
+          if (Nh[h] == 0) continue;
+          mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+          tc_fence_after();
+          const int off = h ? N0 : 0;
+          const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
+          // software pipeline: the load of the next group is in flight while this one is reduced
+          uint32_t ra[16], rb[16];
+          int g16 = bgroup * 16;
+          if (g16 < Nh[h]) tmem_ld16(tbase + g16, ra);
+          for (; g16 < Nh[h]; g16 += 64) {
+            tmem_ld_wait();
+            const int g2 = g16 + 32;
+            if (g2 < Nh[h]) tmem_ld16(tbase + g2, rb);
+            reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, not15, m);
+            if (g2 < Nh[h]) {
               tmem_ld_wait();
-              const int g2 = g16 + 32;
-              if (g2 < Nh[h]) tmem_ld16(tbase + g2, rb);
-              else if (EARLY) {                      // no load of this half is outstanding or still to be issued
-                tc_fence_before();
-                mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
-                released = true;
-              }
-              reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, m);
-              if (g2 < Nh[h]) {
-                tmem_ld_wait();
-                if (g2 + 32 < Nh[h]) tmem_ld16(tbase + g2 + 32, ra);
-                else if (EARLY) {
-                  tc_fence_before();
-                  mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
-                  released = true;
-                }
-                reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, m);
-              }
-            }
-            if (!EARLY || !released) {               // (a warp with no column group of this half still has to arrive)
-              tc_fence_before();
-              mbar_arrive(&bars->acc_empty[RING ? slot : (uint32_t)h]);
+              if (g2 + 32 < Nh[h]) tmem_ld16(tbase + g2 + 32, ra);
+              reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, not15, m);
             }
           }
-          atomicMax(P.zext + (size_t)cloud * C3 + j * 128 + e, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
-
+          tc_fence_before();
+          mbar_arrive(&bars->acc_empty[h]);
         }
+        uint32_t* zp = P.zext + (size_t)I.cloud * C3 + j * 128 + e;
+        // the two warps of a lane quarter hold partial maxima of the same channel: always combine atomically
+        atomicMax(zp, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
       }
     }
   } else if (warp == 8) {
@@ -425,138 +373,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       int stage = 0;
       mbar_wait(&bars->w2_full, 0);
       const uint64_t w2_desc = make_desc(smem_u32(sW2), kPlaneW2, 128);
+      // layer 2, point-major: D2[tile t][pt, ch] = A1[128 pts of tile t][64] * W2^T[128 ch][64]^T.  Tile 1 exists when
+      // the item has more than 128 points; its MMA reads 128 rows whatever NT is (rows beyond the item are other
+      // planes' bytes: finite or not, they only reach accumulator lanes nobody reads).
       auto issue_l2 = [&](int li) {
-        const int it = it_begin + li;
-        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-        const int NT = (nvalid + 15) & ~15;
+        const Item I = item_of(P, it_begin + li);
         mbar_wait(&bars->a1_full, ph_a1); ph_a1 ^= 1;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t idesc = make_idesc(128, NT, 0, 0);
-          const uint64_t bd = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
+          const uint32_t idesc = make_idesc(128, 128, 0, 0);
+          const uint64_t ad = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            mma_bf16_raw(tmem + kTmemD2, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd, ks * 2 * plane1), idesc,
+            mma_bf16_raw(tmem + kTmemD2, desc_advance(ad, ks * 2 * plane1), desc_advance(w2_desc, ks * 2 * kPlaneW2), idesc,
                          ks > 0);
+          if (I.NT > 128) {
+            const uint64_t ad1 = desc_advance(ad, 128 * 16);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_raw(tmem + kTmemD2 + 128, desc_advance(ad1, ks * 2 * plane1), desc_advance(w2_desc, ks * 2 * kPlaneW2),
+                           idesc, ks > 0);
+          }
           mma_commit_raw(&bars->d2_full);
         }
         __syncwarp();
       };
-      if (MODE == MODE_STATS2) {
-        const uint32_t idesc = make_idesc(128, 80, 1, 1);
-        uint32_t ph = 0;
-        for (int li = 0; li < n_local; ++li) {
-          const int it = it_begin + li;
-          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-          const int NT = (nvalid + 15) & ~15;
-          (void)cloud;
-          mbar_wait(&bars->a1_full, ph); ph ^= 1;
-          tc_fence_after();
-          if (elect_one()) {
-            // contraction over the item's points: both operands are the A1 tile read MN-major (rows = points)
-            const uint64_t d = make_desc(smem_u32(sA2[li & 1]), 128, plane1);
-            for (int ks = 0; ks < NT / 16; ++ks)
-              mma_bf16_raw(tmem + kTmemD2, desc_advance(d, ks * 256), desc_advance(d, ks * 256), idesc,
-                           (li > 0 || ks > 0) ? 1u : 0u);
-            mma_commit_raw(&bars->a2_empty[li & 1]);
-            if (li == n_local - 1) mma_commit_raw(&bars->d2_full);
-          }
-          __syncwarp();
-        }
-      } else if (RING) {
-        // ---- ring variant: 3 accumulator slots, layer 2 in two point-halves through one TMEM region ----
-        uint32_t unit = 0, ph_d2e = 0;
-        int l2_stage = 0;                          // of the item being prepared: 0 nothing issued, 1 first half, 2 all
-        auto l2_ring = [&](int li, bool block) {
-          const int it = it_begin + li;
-          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-          const int NT = (nvalid + 15) & ~15;
-          const int N0 = min(NT, ((NT >> 1) + 15) & ~15), N1 = NT - N0;
-          const uint64_t bd = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
-          if (l2_stage == 0) {
-            if (!block && !__all_sync(0xffffffffu, mbar_try_wait(&bars->a1_full, ph_a1))) return;
-            mbar_wait(&bars->a1_full, ph_a1); ph_a1 ^= 1;
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t idesc = make_idesc(128, N0, 0, 0);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_bf16_raw(tmem + kTmemD2Ring, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd, ks * 2 * plane1),
-                             idesc, ks > 0);
-              mma_commit_raw(&bars->d2_full);
-            }
-            __syncwarp();
-            l2_stage = N1 > 0 ? 1 : 2;
-          }
-          if (l2_stage == 1) {
-            if (!block && !__all_sync(0xffffffffu, mbar_try_wait(&bars->d2_empty, ph_d2e))) return;
-            mbar_wait(&bars->d2_empty, ph_d2e); ph_d2e ^= 1;
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t idesc = make_idesc(128, N1, 0, 0);
-              const uint64_t bd1 = desc_advance(bd, N0 * 16);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_bf16_raw(tmem + kTmemD2Ring, desc_advance(w2_desc, ks * 2 * kPlaneW2), desc_advance(bd1, ks * 2 * plane1),
-                             idesc, ks > 0);
-              mma_commit_raw(&bars->d2_full1);
-            }
-            __syncwarp();
-            l2_stage = 2;
-          }
-        };
-        l2_ring(0, true);
-        for (int li = 0; li < n_local; ++li) {
-          const int it = it_begin + li;
-          const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-          const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-          const int NT = (nvalid + 15) & ~15;
-          const int N0 = min(NT, ((NT >> 1) + 15) & ~15), N1 = NT - N0;
-          const int b = li & 1;
-          l2_stage = 0;                            // from here on it describes item li + 1
-          mbar_wait(&bars->a2_full[b], (ph_a2f >> b) & 1u); ph_a2f ^= 1u << b;
-          tc_fence_after();
-          const uint64_t b0_desc = make_desc(smem_u32(sA2[b]), plane2, 128);
-          const uint64_t b1_desc = desc_advance(b0_desc, N0 * 16);
-          const uint32_t idesc0 = make_idesc(128, N0, 0, 0), idesc1 = make_idesc(128, N1 > 0 ? N1 : 16, 0, 0);
-          for (int j = 0; j < P.nchunk; ++j) {
-            mbar_wait(&bars->w3_full[stage], (ph_w3f >> stage) & 1u); ph_w3f ^= 1u << stage;
-            const uint64_t a_desc = make_desc(smem_u32(sW3 + (size_t)stage * kW3ChunkBytes), kPlaneW2, 128);
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && N1 == 0) break;
-              const uint32_t slot = unit % kRingSlots, par = ((unit / kRingSlots) & 1u) ^ 1u;
-              ++unit;
-              mbar_wait(&bars->acc_empty[slot], par);     // the first pass over the slots falls through (parity trick)
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t bdesc = h ? b1_desc : b0_desc;
-                const uint32_t idesc = h ? idesc1 : idesc0;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                  mma_bf16_raw(tmem + slot * kRingSlotCols, desc_advance(a_desc, ks * 2 * kPlaneW2),
-                               desc_advance(bdesc, ks * 2 * plane2), idesc, ks > 0);
-                mma_commit_raw(&bars->acc_full[slot]);
-              }
-              __syncwarp();
-            }
-            mma_commit(&bars->w3_empty[stage]);
-            if (++stage == P.nstages) stage = 0;
-            // layer 2 of the next item, half by half, probed after every chunk and forced after the last one
-            if (li + 1 < n_local && l2_stage < 2) l2_ring(li + 1, j == P.nchunk - 1);
-          }
-          mma_commit(&bars->a2_empty[b]);
-        }
-        (void)ph_acce0; (void)ph_acce1;
-      } else {
       issue_l2(0);
       for (int li = 0; li < n_local; ++li) {
-        const int it = it_begin + li;
-        const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
-        const int nvalid = min(P.PC, P.N - pchunk * P.PC);
-        const int NT = (nvalid + 15) & ~15;
+        const Item I = item_of(P, it_begin + li);
+        const int NT = I.NT;
         int N0 = ((NT >> 1) + 15) & ~15;
         if (N0 > NT) N0 = NT;
         const int N1 = NT - N0;
@@ -604,30 +449,177 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         }
         mma_commit(&bars->a2_empty[b]);
       }
-      }
     }
   } else {
     // ================================ weight loader ============================
     if (lane == 0 && n_local > 0) {
       mbar_arrive_expect_tx(&bars->w2_full, kW2Bytes);
       bulk_copy_g2s(sW2, P.w2t_img, kW2Bytes, &bars->w2_full);
-      if (MODE != MODE_STATS2) {
-        uint32_t ph_e[3] = {1, 1, 1};
-        const int total = n_local * P.nchunk;
-        for (int q = 0; q < total; ++q) {
-          const int stage = q % P.nstages;
-          mbar_wait_relaxed(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
-          mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
-          bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
-                        P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,
-                        &bars->w3_full[stage]);
-        }
+      uint32_t ph_e[3] = {1, 1, 1};
+      const int total = n_local * P.nchunk;
+      for (int q = 0; q < total; ++q) {
+        const int stage = q % P.nstages;
+        mbar_wait_relaxed(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
+        mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
+        bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
+                      P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,
+                      &bars->w3_full[stage]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+}
+
+// =============================================================================================================
+// Layer-2 BATCH statistics without running layer 2.  With z2 = a1 W2 (bias apart),
+//   sum_p z2[p,c] = (sum_p a1[p,:]) . w_c        sum_p z2[p,c]^2 = w_c^T (A1^T A1) w_c
+// so the pass only computes layer 1 and accumulates the 64 x 64 Gram matrix of its (bf16) activations plus their
+// column sums on the tensor cores (contraction over points, MN-major operands straight from the A1 tile, one extra
+// 'ones' plane) -- no per-item accumulator read-back at all.  The kernel is latency-bound (load points -> layer 1 ->
+// a handful of MMAs per item), so it is built small -- 9 warps, 128 TMEM columns, two 10-plane tiles of shared
+// memory -- and several CTAs share an SM.
+// =============================================================================================================
+constexpr int kStatsThreads = 288;       // warps 0-7 layer 1, warp 8 MMA
+constexpr uint32_t kStatsTmemCols = 128;
+
+// The Gram MMA is issued with M = 128 (lane = channel): its A operand spans 16 planes from the tile's start although a
+// tile has 10 (channels 80..127 are don't-care accumulator lanes).  The bytes it reads there must merely EXIST inside
+// the CTA's allocation -- the second tile plus 6 more planes' worth, which also hold the small arrays.
+inline size_t stats2_smem_bytes(int PC) {
+  const size_t tail = 1024 + 2 * (size_t)PC * 16 + 128;
+  return 20 * (size_t)plane_stride(PC) + std::max(tail, 6 * (size_t)plane_stride(PC));
+}
+
+struct StatsBars {
+  uint64_t a1_full[2], a1_empty[2], done;
+  uint32_t tmem_base;
+  float xf[16];
+};
+
+static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t plane1 = plane_stride(P.PC);
+  const uint32_t a1_bytes = 10 * plane1;                 // 8 planes of channels + the 'ones' plane + a zero plane
+  uint8_t* sA1[2] = {smem, smem + a1_bytes};
+  float* sW1f = reinterpret_cast<float*>(smem + 2 * a1_bytes);   // [3][64]
+  float* sC1f = sW1f + 192;
+  float4* sRaw = reinterpret_cast<float4*>(sC1f + 64);           // [2][PC]
+  StatsBars* bars = reinterpret_cast<StatsBars*>(sRaw + 2 * P.PC);
+
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
+  const int it_end = min(P.n_items, it_begin + P.item_begin_stride);
+  const int n_local = it_end - it_begin;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a1_full[i], 256); mbar_init(&bars->a1_empty[i], 1); }
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 192; i += kStatsThreads) sW1f[i] = P.w1f[i];
+  for (int i = tid; i < 64; i += kStatsThreads) sC1f[i] = P.c1f[i];
+  if (warp == 8) tmem_alloc(&bars->tmem_base, kStatsTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < 8) {
+    const int f = tid;                              // 0..255: point slot of the raw-point staging
+    const int g = warp;                             // channel group (A1 plane) of this warp
+    float w1x[8], w1y[8], w1z[8], c1r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w1x[j] = sW1f[g * 8 + j]; w1y[j] = sW1f[64 + g * 8 + j]; w1z[j] = sW1f[128 + g * 8 + j]; c1r[j] = sC1f[g * 8 + j];
+    }
+    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
+    auto prefetch = [&](int li) {
+      const Item I = item_of(P, it_begin + li);
+      const int64_t row0 = (int64_t)I.cloud * P.N + I.p0;
+      if (f == 0) {
+        pf_c[0] = P.center[I.cloud * 3]; pf_c[1] = P.center[I.cloud * 3 + 1]; pf_c[2] = P.center[I.cloud * 3 + 2];
+        pf_ang = P.angle ? P.angle[I.cloud] : 0.f;
+      }
+      if (f < I.nvalid) {
+        const float* src = P.pcs + (row0 + f) * 3;
+        pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
+      }
+    };
+    uint32_t ph_e[2] = {0, 0};
+    if (n_local > 0) prefetch(0);
+    for (int li = 0; li < n_local; ++li) {
+      const Item I = item_of(P, it_begin + li);
+      const int nvalid = I.nvalid, NT = I.NT;
+      const int b = li & 1;
+      if (li >= 2) { mbar_wait_relaxed(&bars->a1_empty[b], ph_e[b]); ph_e[b] ^= 1; }
+      if (f == 0) {
+        float sn = 0.f, cs = 1.f;
+        if (P.angle) sincosf(pf_ang, &sn, &cs);
+        float* xf = bars->xf + b * 8;
+        xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
+      }
+      if (f < NT) sRaw[b * P.PC + f] = f < nvalid ? make_float4(pf_p[0], pf_p[1], pf_p[2], 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* xfr = bars->xf + b * 8;
+      const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
+      if (li + 1 < n_local) prefetch(li + 1);
+      for (int p = lane; p < NT; p += 32) {
+        const float4 raw = sRaw[b * P.PC + p];
+        *reinterpret_cast<uint4*>(sA1[b] + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+        if (g == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
+          *reinterpret_cast<uint4*>(sA1[b] + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sA1[b] + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->a1_full[b]);
+    }
+    if (n_local > 0 && warp < 4) {
+      // Gram accumulator of the whole item range: lanes = layer-1 channel k (64 of them: warps 0, 1 hold real
+      // rows; M = 128 leaves lanes 64..127 as the products of the ones / zero planes), 80 columns
+      mbar_wait_relaxed(&bars->done, 0);
+      tc_fence_after();
+      if (warp < 2) {
+        const int k = tid;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (int g16 = 0; g16 < 80; g16 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + g16, r);
+          tmem_ld_wait();
+          // this CTA's partial sums go to its own slot; a second kernel adds the slots in CTA order (bit-reproducible)
+          float* dst = P.gram1 + (size_t)blockIdx.x * (64 * 80) + k * 80 + g16;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (n_local > 0) {
+    const uint32_t idesc = make_idesc(128, 80, 1, 1);
+    uint32_t ph[2] = {0, 0};
+    for (int li = 0; li < n_local; ++li) {
+      const Item I = item_of(P, it_begin + li);
+      const int b = li & 1;
+      mbar_wait(&bars->a1_full[b], ph[b]); ph[b] ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        // contraction over the item's points: both operands are the A1 tile read MN-major (rows = points)
+        const uint64_t d = make_desc(smem_u32(sA1[b]), 128, plane1);
+        for (int ks = 0; ks < I.NT / 16; ++ks)
+          mma_bf16_raw(tmem, desc_advance(d, ks * 256), desc_advance(d, ks * 256), idesc, (li > 0 || ks > 0) ? 1u : 0u);
+        mma_commit_raw(&bars->a1_empty[b]);
+        if (li == n_local - 1) mma_commit_raw(&bars->done);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, kStatsTmemCols);
 }
 
 }  // namespace convfwd

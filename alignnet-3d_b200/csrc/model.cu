@@ -17,6 +17,8 @@ struct ProfState {
 };
 static ProfState g_prof;
 
+bool prof_active() { return g_prof.on; }
+
 void prof_mark(int tag, bool begin, cudaStream_t st) {
   if (!g_prof.on) return;
   cudaEvent_t e;

@@ -77,13 +77,16 @@ class Layout:
 
 class Engine:
     def __init__(self, arch: _lib.Arch, device: Optional[str] = None, precision: str = "fp32", seed: int = 0,
-                 allocate: bool = True, cache_eval_weights: bool = False):
-        """cache_eval_weights (experimental, off by default; AN3D_EVAL_CACHE=1 turns it on): bf16 inference calls after
-        the first one on unchanged parameters pass AN3D_WEIGHTS_PREPARED and skip the ~40 launches that fold the BN
-        layers and pack the weight images.  Every Engine method that changes parameters or BN state invalidates the
-        cache; code that writes `engine.params` / `engine.bn_state` directly must call `params_changed()`."""
+                 allocate: bool = True, cache_eval_weights: bool = True, deterministic: bool = False):
+        """cache_eval_weights (on by default; AN3D_EVAL_CACHE=0 turns it off): bf16 inference calls after the first
+        one on unchanged parameters pass AN3D_WEIGHTS_PREPARED and skip the ~40 launches that fold the BN layers and
+        pack the weight images (c2 on B200: 0.588 -> 0.501 ms, profiles/r2_ab_switches.txt).  Every Engine method that
+        changes parameters or BN state invalidates the cache; code that writes `engine.params` / `engine.bn_state`
+        directly must call `params_changed()`."""
         self.lib = _lib.load()
-        self.cache_eval_weights = bool(cache_eval_weights) or os.environ.get("AN3D_EVAL_CACHE") == "1"
+        # AN3D_DETERMINISTIC: bit-reproducible inference too (training-mode forwards always are); see the C header
+        self.deterministic = bool(deterministic) or os.environ.get("AN3D_DETERMINISTIC") == "1"
+        self.cache_eval_weights = bool(cache_eval_weights) and os.environ.get("AN3D_EVAL_CACHE") != "0"
         self._pversion = 0                       # bumped whenever params / bn_state may have changed
         self._prepared: Dict[Tuple[int, int, int], int] = {}
         self.arch = arch
@@ -207,7 +210,13 @@ class Engine:
         key = (B, N, flags)
         ws = self._ws.get(key)
         if ws is None:
-            self._ws.clear()   # one live workspace: large shapes would otherwise pile up
+            # one live workspace: large shapes would otherwise pile up.  Captured graphs keep their own reference to
+            # the workspace they baked in (see _capture), so eviction here never frees memory a replay touches; what
+            # lives INSIDE the evicted workspace -- the cached inference folds -- is forgotten with it.
+            self._ws.clear()
+            self._prepared.clear()
+            for k in [k for k in getattr(self, "_graphs", {}) if k[0] == "fwd-lean"]:
+                del self._graphs[k]
             ws = torch.empty(self.workspace_bytes(B, N, flags) + 256, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
@@ -254,7 +263,7 @@ class Engine:
         self._check_input(pcs2, (B, N, 3))
         flags = self.pflag | (_lib.TRAINING if is_training else 0)
         ws = self._workspace(B, N, flags)
-        call_flags = flags
+        call_flags = flags | (_lib.DETERMINISTIC if self.deterministic else 0)
         if is_training:
             self._pversion += 1                  # the moving averages change
         elif self.cache_eval_weights and self.pflag == _lib.PRECISION_BF16:
@@ -335,14 +344,17 @@ class Engine:
         """Returns (graph, outputs, fresh).  The first call runs `fn` once for real (workspace allocation,
         kernel attributes) and then captures it; `fresh` tells the caller that this call's work is already done."""
         if key in self._graphs:
-            g, out = self._graphs[key]
+            g, out, _held = self._graphs[key]
             return g, out, False
         out = fn()
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = fn()
-        self._graphs[key] = (g, out)
+        # the graph bakes in raw pointers of the workspace and output buffers live at capture time: hold them for
+        # the graph's lifetime, whatever `_workspace` / `_outputs` evict later
+        held = (list(self._ws.values()), list(self._out.values()))
+        self._graphs[key] = (g, out, held)
         return g, out, True
 
     def forward_graph(self, pcs1: torch.Tensor, pcs2: torch.Tensor) -> Dict[str, torch.Tensor]:

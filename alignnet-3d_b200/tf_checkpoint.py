@@ -16,8 +16,9 @@ PARITY UNPINNED for this row: no TensorFlow-written checkpoint is available offl
 released weights are an external download, README.md:92), so reader and writer are validated against each other and
 against hand-built blocks (tests/test_tf_checkpoint.py), not against a file produced by TensorFlow.  The reader
 accepts what a real Saver emits beyond what the writer produces: several data blocks, shared key prefixes, snappy-
-compressed blocks, unknown proto fields, and the doubled-scope EMA names TF creates inside `tf.cond`
-(`<scope>/bn/<scope>/bn/moments/Squeeze/ExponentialMovingAverage`).
+compressed blocks, unknown proto fields, and the EMA shadow names TF's slot creator produces
+(`<variable scope>/bn/<op name>/ExponentialMovingAverage`, see `tf_ema_key`: the second siamese branch reads
+`siamese/X/bn/siamese_1/X/bn/moments/Squeeze/ExponentialMovingAverage`).
 """
 from __future__ import annotations
 
@@ -403,18 +404,33 @@ def write_checkpoint(prefix: str, tensors: Dict[str, np.ndarray], block_size: in
         fh.write(bytes(data))
 
 
+def tf_ema_key(name: str) -> str:
+    """The key TensorFlow gives the EMA shadow the engine calls `name` [TF-sem, slot_creator.create_zeros_slot inside
+    tf.train.ExponentialMovingAverage.apply]: `<current VARIABLE scope>/<primary tensor's OP name>/ExponentialMovingAverage`.
+    The variable scope of the second siamese branch is still `siamese/...` (tp8.py:142 re-enters it with AUTO_REUSE),
+    only its NAME scope -- hence the op name of the batch moment -- is uniquified to `siamese_1/...`:
+        branch 1: siamese/X/bn/siamese/X/bn/moments/Squeeze/ExponentialMovingAverage
+        branch 2: siamese/X/bn/siamese_1/X/bn/moments/Squeeze/ExponentialMovingAverage
+        head    : fc1/bn/fc1/bn/moments/Squeeze/ExponentialMovingAverage"""
+    marker = "/bn/moments/"
+    if marker not in name:
+        return name
+    scope = name[:name.index(marker)] + "/bn/"
+    if scope.startswith("siamese_1/"):
+        scope = "siamese/" + scope[len("siamese_1/"):]
+    return scope + name
+
+
 def _lookup(ckpt: Dict[str, np.ndarray], name: str) -> Optional[np.ndarray]:
-    """Variable by the reference graph's name; EMA shadows also under TF's doubled-scope spelling."""
+    """Variable by the reference graph's name; EMA shadows under TF's spelling (`tf_ema_key`), under the engine's own
+    (files written by earlier versions of this module), or under any unique key that ends with the op-name part."""
     if name in ckpt:
         return ckpt[name]
-    marker = "/bn/moments/"
-    if marker in name:
-        scope = name[:name.index(marker)] + "/bn/"
-        doubled = scope + name
-        if doubled in ckpt:
-            return ckpt[doubled]
-        tail = name[name.index(marker):]
-        hits = [k for k in ckpt if k.endswith(tail) and k.startswith(scope)]
+    if "/bn/moments/" in name:
+        key = tf_ema_key(name)
+        if key in ckpt:
+            return ckpt[key]
+        hits = [k for k in ckpt if k.endswith("/" + name)]
         if len(hits) == 1:
             return ckpt[hits[0]]
     return None
@@ -456,7 +472,7 @@ def load_into_engine(engine, prefix: str, strict: bool = True) -> Dict[str, List
         engine.adam_v.copy_(torch.from_numpy(engine._flatten(engine.params_layout, v)))
     if "Variable" in ckpt:                                   # global step (train.py:195)
         engine.step = int(ckpt["Variable"])
-    used = set(params) | set(state)
+    used = set(params) | set(state) | {tf_ema_key(k) for k in state}
     return dict(missing=missing, unused=[k for k in ckpt if k not in used and not k.endswith(("/Adam", "/Adam_1"))
                                          and k not in ("Variable", "beta1_power", "beta2_power")])
 
@@ -471,7 +487,7 @@ def save_from_engine(engine, prefix: str, beta1: float = 0.9, beta2: float = 0.9
             kw = 3 if name.endswith("conv1/weights") else 1
             a = a.reshape(1, kw, cin // kw, cout)
         tensors[name] = a.astype(np.float32)
-    tensors.update({k: v.astype(np.float32) for k, v in engine.get_state().items()})
+    tensors.update({tf_ema_key(k): v.astype(np.float32) for k, v in engine.get_state().items()})
     m = engine._unflatten(engine.params_layout, engine.adam_m.cpu().numpy())
     v = engine._unflatten(engine.params_layout, engine.adam_v.cpu().numpy())
     for name in m:

@@ -418,7 +418,7 @@ def run_ours(args, wl):
             "clocks": clocks,
             "kernel_ms_by_tag": {str(i): ms_tags[i] / args.steps for i in range(8) if n_tags[i]},
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(wl)
         print(json.dumps(line))
     if world > 1:
@@ -434,6 +434,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (A/B runs of a kernel switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the stream instead of replaying a CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -69,7 +69,12 @@ enum {
    * asserts that the previous an3d_forward on THIS workspace ran in inference mode with the SAME params and
    * bn_state: the folded BN scales / shifts and the packed weight images it left in the workspace are reused and
    * the ~40 launches that derive them are skipped.  The library cannot check the assertion. */
-  AN3D_WEIGHTS_PREPARED = 4
+  AN3D_WEIGHTS_PREPARED = 4,
+  /* Bit-reproducible forward pass (not part of the workspace size).  Training-mode forwards always are: every
+   * cross-CTA fp32 sum of the pass goes through per-CTA partial slots added in a fixed order, and no FC layer splits K
+   * across CTAs.  Inference additionally splits K of under-filled FC launches with fp32 reductions (+9 % at B=1024);
+   * this flag turns that off, so two inference calls on the same inputs return identical bits. */
+  AN3D_DETERMINISTIC = 8
 };
 
 /* The eight tensors of end_points (models/tp8.py:146-156).  Centers/translations [B,3],

@@ -1,0 +1,89 @@
+"""Run-to-run reproducibility of the bf16 fast mode (the mode bench.py times).
+
+Round 1 measured a gradient cosine of only 0.979 between two identical c3 steps: fp32 atomics added the per-CTA
+partial sums of the BN statistics (Gram matrices) and the split-K slices of the 3- / 103-wide FC layers in arrival
+order, a last-bit difference moved a bf16 rounding or an arg-max downstream, and the model is discontinuous there.
+Now every cross-CTA fp32 sum of the forward pass goes through per-CTA slots added in a fixed order
+(`sum_parts_kernel`), training never splits K, and the remaining atomics of the forward are fp64 sums that are
+rounded to fp32 afterwards (order-dependent in the 16th digit only) or exact (`atomicMax`).  So:
+  * two training forwards on the same inputs return IDENTICAL bits (outputs, loss, moving averages);
+  * the backward still reduces weight gradients with fp32 atomics, but nothing discrete depends on them: gradient
+    cosine >= 0.9999 (measured: 1 - 1e-9), every tensor within 1e-4 of its max;
+  * inference is bit-reproducible with Engine(deterministic=True) / AN3D_DETERMINISTIC (no split-K reductions)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import arch as A
+from helpers import OUTPUT_KEYS, engine_arch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def _dev(batch):
+    return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).cuda() for k, v in batch.items()}
+
+
+def _engines(n, **kw):
+    from alignnet_b200 import engine
+    arch = A.Arch()
+    params, state = A.randomize_for_test(arch, A.init_params(arch, 70), A.init_state(arch), 71)
+    out = []
+    for _ in range(n):
+        e = engine.Engine(engine_arch(arch), "cuda:0", "bf16", **kw)
+        e.set_params(params)
+        e.set_state(state)
+        out.append(e)
+    return out
+
+
+@pytest.mark.parametrize("B,N", [(4096, 200), (96, 512)])
+def test_training_step_is_reproducible(B, N):
+    from alignnet_b200 import synth
+    dev = _dev(synth.make_batch_fast(B, N, seed=72))
+    runs = []
+    for e in _engines(2):
+        ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.5, None, seed=5)
+        loss = e.backward(dev["pcs1"], dev["pcs2"], dev, ep)
+        torch.cuda.synchronize()
+        runs.append(({k: ep[k].clone() for k in OUTPUT_KEYS}, loss.clone(), e.bn_state.clone(), e.grads.clone()))
+    (ep_a, l_a, s_a, g_a), (ep_b, l_b, s_b, g_b) = runs
+    for k in OUTPUT_KEYS:
+        assert torch.equal(ep_a[k], ep_b[k]), k                         # bit for bit
+    assert torch.equal(s_a, s_b)                                        # moving averages
+    assert float(l_a[0]) == float(l_b[0])
+    cos = float(torch.dot(g_a.double(), g_b.double()) / (g_a.double().norm() * g_b.double().norm()))
+    rel = float((g_a - g_b).abs().max() / g_a.abs().max())
+    print(f"B={B} N={N}: gradient cosine between two runs 1 - {1 - cos:.2e}, max |diff| / max |g| = {rel:.2e}")
+    assert cos >= 0.9999 and rel <= 1e-4, (cos, rel)
+
+
+def test_optimiser_trajectories_stay_together():
+    """Three optimiser steps on two engines: same losses to 1e-5, parameters within a few ulps of the update size."""
+    from alignnet_b200 import synth
+    dev = _dev(synth.make_batch_fast(1024, 200, seed=73))
+    ea, eb = _engines(2)
+    la = [float(ea.train_step(dev, lr=1e-3, bn_decay=0.5, seed=i)[0].cpu()) for i in range(3)]
+    lb = [float(eb.train_step(dev, lr=1e-3, bn_decay=0.5, seed=i)[0].cpu()) for i in range(3)]
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-5 * abs(b), (la, lb)
+    assert float((ea.params - eb.params).abs().max()) <= 1e-5
+
+
+def test_deterministic_inference_flag():
+    from alignnet_b200 import synth
+    dev = _dev(synth.make_batch_fast(1024, 200, seed=74))
+    outs = []
+    for e in _engines(2, deterministic=True):
+        ep = e.forward(dev["pcs1"], dev["pcs2"], False)
+        ep = e.forward(dev["pcs1"], dev["pcs2"], False)                 # second call: cached folds
+        torch.cuda.synchronize()
+        outs.append({k: ep[k].clone() for k in OUTPUT_KEYS})
+    for k in OUTPUT_KEYS:
+        assert torch.equal(outs[0][k], outs[1][k]), k

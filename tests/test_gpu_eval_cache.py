@@ -1,11 +1,6 @@
-"""GPU tests of the switches that are OFF by default because they were written after the round's GPU budget ran out
-(DESIGN section 9).  They run only with AN3D_RUN_EXPERIMENTAL=1 so that the default `-m gpu` suite holds nothing
-unmeasured:
-
-    AN3D_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
-    AN3D_RUN_EXPERIMENTAL=1 AN3D_FWD_RING=3 python -m pytest tests/test_gpu_conv_stack.py tests/test_gpu_bf16.py -m gpu -q
-    AN3D_RUN_EXPERIMENTAL=1 AN3D_TWO_STREAMS=1 python -m pytest tests/test_gpu_bf16.py -m gpu -q
-"""
+"""GPU tests of the inference weight cache (Engine(cache_eval_weights=True), the default; flag AN3D_WEIGHTS_PREPARED of the
+C ABI) and of the lifetime rules around it: cached folds live inside the workspace, captured graphs bake workspace
+pointers in, and the engine keeps one live workspace per shape."""
 import os
 
 import numpy as np
@@ -15,8 +10,7 @@ import torch
 from oracle import arch as A
 from helpers import OUTPUT_KEYS, engine_arch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AN3D_RUN_EXPERIMENTAL") != "1", reason="experimental switches: opt-in")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -49,7 +43,7 @@ def test_eval_weight_cache_matches_uncached_and_invalidates():
     arch = A.Arch()
     params, state = A.randomize_for_test(arch, A.init_params(arch, 5), A.init_state(arch), 6)
     dev = _dev(synth.make_batch_fast(256, 200, seed=9))
-    plain = engine.Engine(engine_arch(arch), "cuda:0", "bf16")
+    plain = engine.Engine(engine_arch(arch), "cuda:0", "bf16", cache_eval_weights=False)
     cached = engine.Engine(engine_arch(arch), "cuda:0", "bf16", cache_eval_weights=True)
     for e in (plain, cached):
         e.set_params(params); e.set_state(state)
@@ -84,3 +78,44 @@ def test_eval_weight_cache_matches_uncached_and_invalidates():
     ref3 = _snap(plain.forward(dev["pcs1"], dev["pcs2"], False))
     got4 = _snap(cached.forward(dev["pcs1"], dev["pcs2"], False))
     _close(got4, ref3)
+
+
+def test_workspace_eviction_forgets_cached_folds_and_keeps_graphs_alive():
+    """The engine keeps ONE live workspace: a call with another batch size evicts it.  The cached folds lived inside the
+    evicted workspace, so the next call on the old shape must re-derive them (it used to pass AN3D_WEIGHTS_PREPARED on
+    fresh, uninitialised memory); and a graph captured on the old workspace must stay replayable (it used to replay on
+    memory returned to the allocator)."""
+    from alignnet_b200 import engine, synth
+    arch = A.Arch()
+    params, state = A.randomize_for_test(arch, A.init_params(arch, 25), A.init_state(arch), 26)
+    big, small = _dev(synth.make_batch_fast(192, 200, seed=19)), _dev(synth.make_batch_fast(48, 200, seed=20))
+    plain = engine.Engine(engine_arch(arch), "cuda:0", "bf16", cache_eval_weights=False)
+    cached = engine.Engine(engine_arch(arch), "cuda:0", "bf16")
+    for e in (plain, cached):
+        e.set_params(params); e.set_state(state)
+    ref_big = _snap(plain.forward(big["pcs1"], big["pcs2"], False))
+    ref_small = _snap(plain.forward(small["pcs1"], small["pcs2"], False))
+    cached.forward(big["pcs1"], big["pcs2"], False)
+    _close(_snap(cached.forward(big["pcs1"], big["pcs2"], False)), ref_big)          # prepared call
+    g_big = _snap(cached.forward_graph(big["pcs1"], big["pcs2"]))                     # lean graph on the big workspace
+    _close(g_big, ref_big)
+    _close(_snap(cached.forward(small["pcs1"], small["pcs2"], False)), ref_small)    # evicts the big workspace
+    # scribble over whatever the allocator hands out next: freed-and-reused memory would show
+    junk = [torch.full((64 << 20,), float("nan"), device="cuda") for _ in range(4)]
+    torch.cuda.synchronize()
+    _close(_snap(cached.forward(big["pcs1"], big["pcs2"], False)), ref_big)          # fresh workspace: folds re-derived
+    _close(_snap(cached.forward(big["pcs1"], big["pcs2"], False)), ref_big)
+    _close(_snap(cached.forward_graph(big["pcs1"], big["pcs2"])), ref_big)
+    _close(_snap(cached.forward_graph(big["pcs1"], big["pcs2"])), ref_big)
+    del junk
+    # a training graph captured before an eval call of another shape keeps replaying on its own workspace
+    tr = engine.Engine(engine_arch(arch), "cuda:0", "bf16")
+    tr.set_params(params); tr.set_state(state)
+    l0 = float(tr.train_step_graph(big, lr=1e-3, bn_decay=0.5)[0].cpu())
+    tr.forward(small["pcs1"], small["pcs2"], False)
+    junk = [torch.full((64 << 20,), float("nan"), device="cuda") for _ in range(4)]
+    l1 = float(tr.train_step_graph(big, lr=1e-3, bn_decay=0.5)[0].cpu())
+    l2 = float(tr.train_step_graph(big, lr=1e-3, bn_decay=0.5)[0].cpu())
+    del junk
+    assert np.isfinite([l0, l1, l2]).all() and abs(l1 - l0) < 0.5 * max(1.0, abs(l0)), (l0, l1, l2)
+    assert torch.isfinite(tr.params).all()

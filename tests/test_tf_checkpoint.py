@@ -75,6 +75,23 @@ def test_doubled_scope_ema_names_are_found():
     assert T._lookup({"other": v}, name) is None
 
 
+def test_ema_shadow_keys_follow_tf_slot_creator_rule():
+    """[TF-sem] ExponentialMovingAverage.apply -> slot_creator.create_zeros_slot names the shadow
+    `<current variable scope>/<op name of the averaged tensor>/ExponentialMovingAverage`.  The second siamese branch
+    re-enters variable scope `siamese` (tp8.py:142, AUTO_REUSE) -- only its name scope becomes `siamese_1`."""
+    b1 = "siamese/transformer1/embedding/conv1/bn/moments/Squeeze/ExponentialMovingAverage"
+    b2 = "siamese_1/transformer2/mlp/fc2/bn/moments/Squeeze_1/ExponentialMovingAverage"
+    hd = "fc1/bn/moments/Squeeze/ExponentialMovingAverage"
+    assert T.tf_ema_key(b1) == "siamese/transformer1/embedding/conv1/bn/" + b1
+    assert T.tf_ema_key(b2) == "siamese/transformer2/mlp/fc2/bn/" + b2          # variable scope stays `siamese/`
+    assert T.tf_ema_key(hd) == "fc1/bn/" + hd
+    assert T.tf_ema_key("siamese_1/embedding/conv1/bn/gamma") == "siamese_1/embedding/conv1/bn/gamma"   # not a shadow
+    v = np.ones(4, np.float32)
+    assert T._lookup({T.tf_ema_key(b2): v}, b2) is v                 # a reference checkpoint's key for a branch-2 shadow
+    assert T._lookup({"siamese_1/transformer2/mlp/fc2/bn/" + b2: v}, b2) is v   # files of this module's first version
+    assert T._lookup({"x/" + b2: v, "y/" + b2: v}, b2) is None       # ambiguous suffix matches are refused
+
+
 def test_bad_files_are_rejected(tmp_path):
     p = tmp_path / "x.index"
     p.write_bytes(b"\0" * 100)
@@ -97,6 +114,10 @@ def test_engine_export_import_round_trip(tmp_path):
     ck = T.read_checkpoint(prefix)
     assert ck["siamese/transformer1/embedding/conv1/weights"].shape == (1, 3, 1, 64)      # TF kernel shape
     assert ck["fc3/weights"].shape == (256, 103) and int(ck["Variable"]) == 2
+    # shadows are written under TensorFlow's keys (both branches under variable scope `siamese/`)
+    assert "siamese/embedding/conv3/bn/siamese_1/embedding/conv3/bn/moments/Squeeze/ExponentialMovingAverage" in ck
+    assert "fc2/bn/fc2/bn/moments/Squeeze_1/ExponentialMovingAverage" in ck
+    assert not any(k.startswith("siamese_1/") and k.endswith("ExponentialMovingAverage") for k in ck)
     b = engine.Engine(engine.shipped_arch(), "cuda:0", "fp32", seed=99)
     info = T.load_into_engine(b, prefix)
     assert info["missing"] == [] and info["unused"] == []
