@@ -68,25 +68,45 @@ __global__ void moments_kernel(const float* pcs, const float* center, const floa
   }
 }
 
-// Fixed-order sums of per-CTA partial results: out[r][c] = sum_p parts[p][r][c] (p ascending), so the cross-CTA
-// reductions of the statistics passes are bit-reproducible (fp32 atomics would add in arrival order).
-__global__ void sum_parts_kernel(const float* parts, int nparts, int rows, int cols_in, int cols_out, float* out,
-                                 double* extra /* optional [rows]: column `cols_out` of the parts, summed in fp64 */) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < rows * cols_out) {
-    const int r = i / cols_out, c = i - r * cols_out;
+// Fixed-shape sums of per-CTA partial results: out[r][c] = sum_p parts[p][r][c].  The cross-CTA reductions of the
+// statistics passes are bit-reproducible this way (fp32 atomics would add in arrival order).  Block = 32 elements x 8
+// part-lanes: lane l adds the parts p = l, l + 8, ... in ascending order, the eight lane sums are then added in lane
+// order -- a fixed tree, whatever the schedule.  `extra` (optional, [rows]) receives column `cols_out` of the parts,
+// summed the same way in fp64.
+constexpr int kSumLanes = 8;
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float* parts, int nparts, int rows, int cols_in, int cols_out,
+                                                        float* out, double* extra) {
+  __shared__ double sm[kSumLanes][32];
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31), l = threadIdx.x >> 5;
+  const int n_main = rows * cols_out, n_all = n_main + (extra ? rows : 0);
+  double acc = 0.0;
+  if (e < n_all) {
+    const bool is_extra = e >= n_main;
+    const int r = is_extra ? e - n_main : e / cols_out, c = is_extra ? cols_out : e - r * cols_out;
     const float* src = parts + (size_t)r * cols_in + c;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < nparts; ++p) acc += src[(size_t)p * rows * cols_in];   // (loads are independent: unrolling overlaps them)
-    out[i] = acc;
-  } else if (extra && i < rows * cols_out + rows) {
-    const int r = i - rows * cols_out;
-    const float* src = parts + (size_t)r * cols_in + cols_out;
-    double acc = 0.0;
-#pragma unroll 8
-    for (int p = 0; p < nparts; ++p) acc += (double)src[(size_t)p * rows * cols_in];
-    extra[r] = acc;
+    const size_t stride = (size_t)rows * cols_in;
+    if (is_extra) {
+#pragma unroll 4
+      for (int p = l; p < nparts; p += kSumLanes) acc += (double)src[p * stride];
+    } else {
+      float a = 0.f;
+#pragma unroll 4
+      for (int p = l; p < nparts; p += kSumLanes) a += src[p * stride];     // (independent loads: unrolling overlaps them)
+      acc = (double)a;
+    }
+  }
+  sm[l][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (l == 0 && e < n_all) {
+    if (e >= n_main) {
+      double t = 0.0;
+      for (int i = 0; i < kSumLanes; ++i) t += sm[i][threadIdx.x];
+      extra[e - n_main] = t;
+    } else {
+      float t = 0.f;
+      for (int i = 0; i < kSumLanes; ++i) t += (float)sm[i][threadIdx.x];
+      out[e] = t;
+    }
   }
 }
 
@@ -305,7 +325,7 @@ int launch_stats2(convfwd::Params P, int sms, float* gram1_out, cudaStream_t st)
   convfwd::conv_stats2_kernel<<<grid, convfwd::kStatsThreads, smem, st>>>(P);
   prof_mark(PROF_CONV_STATS2, false, st);
   AN3D_LAUNCH_CHECK();
-  sum_parts_kernel<<<(64 * 80 + 255) / 256, 256, 0, st>>>(P.gram1, nparts, 64, 80, 80, gram1_out, nullptr);
+  sum_parts_kernel<<<(64 * 80 + 31) / 32, 256, 0, st>>>(P.gram1, nparts, 64, 80, 80, gram1_out, nullptr);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }
@@ -466,7 +486,7 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     convbwd::gram2_kernel<<<nranges, convbwd::kGram2Threads, gsmem, st>>>(W);
     AN3D_LAUNCH_CHECK();
-    sum_parts_kernel<<<(128 * 128 + 128 + 255) / 256, 256, 0, st>>>(q.gram_parts[br], nparts, 128, convbwd::kGram2PartCols, 128,
+    sum_parts_kernel<<<(128 * 128 + 128 + 31) / 32, 256, 0, st>>>(q.gram_parts[br], nparts, 128, convbwd::kGram2PartCols, 128,
                                                                     q.gram[s][br], q.sa2[s][br]);
     AN3D_LAUNCH_CHECK();
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(gw3_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGwSmem));

@@ -108,7 +108,7 @@ static __global__ void __launch_bounds__(kGram2Threads, 1) gram2_kernel(const Gr
       uint32_t ph_e = (1u << kGram2Bufs) - 1u;
       for (int li = 0; li < n_local; ++li) {
         const int b = li % kGram2Bufs;
-        mbar_wait_relaxed(&bars->empty[b], (ph_e >> b) & 1u); ph_e ^= 1u << b;
+        mbar_wait_sleep(&bars->empty[b], (ph_e >> b) & 1u, 128u); ph_e ^= 1u << b;
         mbar_arrive_expect_tx(&bars->full[b], P.img_bytes);
         bulk_copy_g2s(smem + b * buf_bytes, P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->full[b]);
       }

@@ -107,6 +107,16 @@ struct Barriers {
   float xf[16];  // per-item transform (double-buffered): cx, cy, cz, cos, sin
 };
 
+// (x & mask) | Q as ONE LOP3: the immediate has to sit in the instruction's second source slot and the mask in a
+// register (ptxas emits an AND and an OR for the C expression, whichever way it is written: 23 % of the kernel's
+// instructions were those two).  Runs once per accumulator element of the training pass.
+template <int Q>
+__device__ __forceinline__ float tag4(uint32_t x, uint32_t mask) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(d) : "r"(x), "n"(Q), "r"(mask));   // (a & c) | b
+  return __uint_as_float(d);
+}
+
 // Running max over one 16-column group of an accumulator row.  Training mode carries the arg-max point
 // index in the low mantissa bits: the column-in-group (an immediate) goes into the low 4 bits of every
 // element, the group's base index is spliced in only if the group wins.
@@ -116,12 +126,14 @@ __device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nv
   float gm = -INFINITY;
   if (col0 + 16 <= nvalid) {
     // three-input max (FMNMX3): 8 instead of 16 max instructions per group
+    if (MODE == MODE_FULL_TRAIN) {
+#define AN3D_TAGGED_PAIR(Q) gm = fmax3(gm, tag4<Q>(r[Q], not15), tag4<Q + 1>(r[Q + 1], not15));
+      AN3D_TAGGED_PAIR(0) AN3D_TAGGED_PAIR(2) AN3D_TAGGED_PAIR(4) AN3D_TAGGED_PAIR(6)
+      AN3D_TAGGED_PAIR(8) AN3D_TAGGED_PAIR(10) AN3D_TAGGED_PAIR(12) AN3D_TAGGED_PAIR(14)
+#undef AN3D_TAGGED_PAIR
+    } else {
 #pragma unroll
-    for (int q = 0; q < 16; q += 2) {
-      if (MODE == MODE_FULL_TRAIN)
-        gm = fmax3(gm, __uint_as_float((r[q] & not15) | (uint32_t)q), __uint_as_float((r[q + 1] & not15) | (uint32_t)(q + 1)));
-      else
-        gm = fmax3(gm, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
+      for (int q = 0; q < 16; q += 2) gm = fmax3(gm, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
     }
   } else {
 #pragma unroll
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
   const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
   const uint32_t a2_bytes = 16 * plane2;
-  uint8_t* sA2[2] = {smem, smem + a2_bytes};
+  auto a2buf = [&](int b) { return smem + (size_t)b * a2_bytes; };   // (no pointer array: it would live in local memory)
   uint8_t* sW2 = smem + 2 * a2_bytes;
   uint8_t* sW3 = sW2 + kW2Bytes;
   float* sW1f = reinterpret_cast<float*>(sW3 + (size_t)P.nstages * kW3ChunkBytes);  // [3][64]
@@ -220,21 +232,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     const int quarter = warp & 3;
     const int f = fgroup * 128 + quarter * 32 + lane;   // 0..255: point slot of the raw-point staging
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t ph_d2 = 0, ph_a2e[2] = {0, 0};
+    uint32_t ph_d2 = 0, ph_a2e = 0;     // (phase bits in one scalar: an array indexed by li & 1 would live in local memory)
     const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
     // register prefetch of the next item's transform (thread 0) and point (thread f owns point f):
     // the global-load latency is paid behind the current item's work instead of in front of a barrier
-    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
+    float pf_c0 = 0.f, pf_c1 = 0.f, pf_c2 = 0.f, pf_ang = 0.f, pf_p0 = 0.f, pf_p1 = 0.f, pf_p2 = 0.f;
     auto prefetch = [&](int li) {
       const Item I = item_of(P, it_begin + li);
       const int64_t row0 = (int64_t)I.cloud * P.N + I.p0;
       if (f == 0) {
-        pf_c[0] = P.center[I.cloud * 3]; pf_c[1] = P.center[I.cloud * 3 + 1]; pf_c[2] = P.center[I.cloud * 3 + 2];
+        pf_c0 = P.center[I.cloud * 3]; pf_c1 = P.center[I.cloud * 3 + 1]; pf_c2 = P.center[I.cloud * 3 + 2];
         pf_ang = P.angle ? P.angle[I.cloud] : 0.f;
       }
       if (f < I.nvalid) {
         const float* src = P.pcs + (row0 + f) * 3;
-        pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
+        pf_p0 = src[0]; pf_p1 = src[1]; pf_p2 = src[2];
       }
     };
     const int fg8 = fgroup * 4 + quarter;          // channel group (A1 plane) of this warp in layer 1
@@ -249,18 +261,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const Item I = item_of(P, it);
       const int nvalid = I.nvalid, NT = I.NT;
       const int b = li & 1;
-      if (li >= 2) { mbar_wait_relaxed(&bars->a2_empty[b], ph_a2e[b]); ph_a2e[b] ^= 1; }
+      if (li >= 2) { mbar_wait_sleep(&bars->a2_empty[b], (ph_a2e >> b) & 1u); ph_a2e ^= 1u << b; }   // (a whole item of slack)
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
-      uint8_t* sA1 = sA2[b];
+      uint8_t* sA1 = a2buf(b);
       if (f == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(pf_ang, &sn, &cs);
         float* xf = bars->xf + (li & 1) * 8;
-        xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
+        xf[0] = pf_c0; xf[1] = pf_c1; xf[2] = pf_c2; xf[3] = cs; xf[4] = sn;
       }
       // the prefetched raw point of thread f goes to shared memory: layer 1 below is organised by channel group
-      if (f < NT) sRaw[b * kMaxPC + f] = f < nvalid ? make_float4(pf_p[0], pf_p[1], pf_p[2], 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < NT) sRaw[b * kMaxPC + f] = f < nvalid ? make_float4(pf_p0, pf_p1, pf_p2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* xfr = bars->xf + (li & 1) * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         if (prow >= NT) break;
         const int p = prow + lane;
         const bool real = p < nvalid;
-        uint8_t* dst = sA2[b] + (size_t)(fgroup * 8) * plane2 + p * 16;
+        uint8_t* dst = a2buf(b) + (size_t)(fgroup * 8) * plane2 + p * 16;
         const uint32_t tb = tmem + lane_base + kTmemD2 + (uint32_t)t * 128u + (uint32_t)fgroup * 64u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_arrive(&bars->a2_full[b]);
       if (save_a2) {
         asm volatile("bar.sync 2, 256;" ::: "memory");      // every front-end thread has written + fenced
-        if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, sA2[b], a2_bytes);
+        if (f == 0) bulk_copy_s2g(reinterpret_cast<uint8_t*>(P.a2_img) + (size_t)it * a2_bytes, a2buf(b), a2_bytes);
       }
     }
     if (save_a2 && f == 0) bulk_wait_read_all();
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     const int bgroup = warp < 4 ? 0 : 1;
     const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph_full[2] = {0, 0};
+    uint32_t ph_full = 0;
     const int C3 = P.nchunk * 128;
     const uint32_t not15 = P.not15;
     for (int li = 0; li < n_local; ++li) {
@@ -330,29 +342,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int nvalid = I.nvalid, NT = I.NT, p0 = I.p0;
       int N0 = ((NT >> 1) + 15) & ~15;
       if (N0 > NT) N0 = NT;
-      const int Nh[2] = {N0, NT - N0};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j >= P.nchunk) break;
+#pragma unroll 1     // (unrolled eight times the kernel was 226 KB of SASS: instruction-cache misses on every role switch)
+      for (int j = 0; j < P.nchunk; ++j) {
         float m = -INFINITY;
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
-          if (Nh[h] == 0) continue;
-          mbar_wait_relaxed(&bars->acc_full[h], ph_full[h]); ph_full[h] ^= 1;
+          const int nh = h ? NT - N0 : N0;
+          if (nh == 0) continue;
+          mbar_wait_relaxed(&bars->acc_full[h], (ph_full >> h) & 1u); ph_full ^= 1u << h;
           tc_fence_after();
           const int off = h ? N0 : 0;
           const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
           // software pipeline: the load of the next group is in flight while this one is reduced
           uint32_t ra[16], rb[16];
           int g16 = bgroup * 16;
-          if (g16 < Nh[h]) tmem_ld16(tbase + g16, ra);
-          for (; g16 < Nh[h]; g16 += 64) {
+          if (g16 < nh) tmem_ld16(tbase + g16, ra);
+          for (; g16 < nh; g16 += 64) {
             tmem_ld_wait();
             const int g2 = g16 + 32;
-            if (g2 < Nh[h]) tmem_ld16(tbase + g2, rb);
+            if (g2 < nh) tmem_ld16(tbase + g2, rb);
             reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, not15, m);
-            if (g2 < Nh[h]) {
+            if (g2 < nh) {
               tmem_ld_wait();
-              if (g2 + 32 < Nh[h]) tmem_ld16(tbase + g2 + 32, ra);
+              if (g2 + 32 < nh) tmem_ld16(tbase + g2 + 32, ra);
               reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, not15, m);
             }
           }
@@ -382,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         tc_fence_after();
         if (elect_one()) {
           const uint32_t idesc = make_idesc(128, 128, 0, 0);
-          const uint64_t ad = make_desc(smem_u32(sA2[li & 1]), plane1, 128);
+          const uint64_t ad = make_desc(smem_u32(a2buf(li & 1)), plane1, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             mma_bf16_raw(tmem + kTmemD2, desc_advance(ad, ks * 2 * plane1), desc_advance(w2_desc, ks * 2 * kPlaneW2), idesc,
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         const int b = li & 1;
         mbar_wait(&bars->a2_full[b], (ph_a2f >> b) & 1u); ph_a2f ^= 1u << b;
         tc_fence_after();
-        const uint64_t b0_desc = make_desc(smem_u32(sA2[b]), plane2, 128);
+        const uint64_t b0_desc = make_desc(smem_u32(a2buf(b)), plane2, 128);
         const uint64_t b1_desc = desc_advance(b0_desc, N0 * 16);
         const uint32_t idesc0 = make_idesc(128, N0, 0, 0), idesc1 = make_idesc(128, N1 > 0 ? N1 : 16, 0, 0);
         bool l2_pending = li + 1 < n_local;
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const int total = n_local * P.nchunk;
       for (int q = 0; q < total; ++q) {
         const int stage = q % P.nstages;
-        mbar_wait_relaxed(&bars->w3_empty[stage], ph_e[stage]); ph_e[stage] ^= 1;
+        mbar_wait_sleep(&bars->w3_empty[stage], ph_e[stage], 128u); ph_e[stage] ^= 1;
         mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
         bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
                       P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,
@@ -502,7 +514,7 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane1 = plane_stride(P.PC);
   const uint32_t a1_bytes = 10 * plane1;                 // 8 planes of channels + the 'ones' plane + a zero plane
-  uint8_t* sA1[2] = {smem, smem + a1_bytes};
+  auto a1buf = [&](int b) { return smem + (size_t)b * a1_bytes; };
   float* sW1f = reinterpret_cast<float*>(smem + 2 * a1_bytes);   // [3][64]
   float* sC1f = sW1f + 192;
   float4* sRaw = reinterpret_cast<float4*>(sC1f + 64);           // [2][PC]
@@ -534,17 +546,17 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
     for (int j = 0; j < 8; ++j) {
       w1x[j] = sW1f[g * 8 + j]; w1y[j] = sW1f[64 + g * 8 + j]; w1z[j] = sW1f[128 + g * 8 + j]; c1r[j] = sC1f[g * 8 + j];
     }
-    float pf_c[3] = {0.f, 0.f, 0.f}, pf_ang = 0.f, pf_p[3] = {0.f, 0.f, 0.f};
+    float pf_c0 = 0.f, pf_c1 = 0.f, pf_c2 = 0.f, pf_ang = 0.f, pf_p0 = 0.f, pf_p1 = 0.f, pf_p2 = 0.f;
     auto prefetch = [&](int li) {
       const Item I = item_of(P, it_begin + li);
       const int64_t row0 = (int64_t)I.cloud * P.N + I.p0;
       if (f == 0) {
-        pf_c[0] = P.center[I.cloud * 3]; pf_c[1] = P.center[I.cloud * 3 + 1]; pf_c[2] = P.center[I.cloud * 3 + 2];
+        pf_c0 = P.center[I.cloud * 3]; pf_c1 = P.center[I.cloud * 3 + 1]; pf_c2 = P.center[I.cloud * 3 + 2];
         pf_ang = P.angle ? P.angle[I.cloud] : 0.f;
       }
       if (f < I.nvalid) {
         const float* src = P.pcs + (row0 + f) * 3;
-        pf_p[0] = src[0]; pf_p[1] = src[1]; pf_p[2] = src[2];
+        pf_p0 = src[0]; pf_p1 = src[1]; pf_p2 = src[2];
       }
     };
     uint32_t ph_e[2] = {0, 0};
@@ -553,24 +565,24 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
       const Item I = item_of(P, it_begin + li);
       const int nvalid = I.nvalid, NT = I.NT;
       const int b = li & 1;
-      if (li >= 2) { mbar_wait_relaxed(&bars->a1_empty[b], ph_e[b]); ph_e[b] ^= 1; }
+      if (li >= 2) { mbar_wait_sleep(&bars->a1_empty[b], ph_e[b], 128u); ph_e[b] ^= 1; }
       if (f == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(pf_ang, &sn, &cs);
         float* xf = bars->xf + b * 8;
-        xf[0] = pf_c[0]; xf[1] = pf_c[1]; xf[2] = pf_c[2]; xf[3] = cs; xf[4] = sn;
+        xf[0] = pf_c0; xf[1] = pf_c1; xf[2] = pf_c2; xf[3] = cs; xf[4] = sn;
       }
-      if (f < NT) sRaw[b * P.PC + f] = f < nvalid ? make_float4(pf_p[0], pf_p[1], pf_p[2], 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < NT) sRaw[b * P.PC + f] = f < nvalid ? make_float4(pf_p0, pf_p1, pf_p2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* xfr = bars->xf + b * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
       for (int p = lane; p < NT; p += 32) {
         const float4 raw = sRaw[b * P.PC + p];
-        *reinterpret_cast<uint4*>(sA1[b] + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+        *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
         if (g == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
-          *reinterpret_cast<uint4*>(sA1[b] + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sA1[b] + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a1buf(b) + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a1buf(b) + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
         }
       }
       fence_proxy_async_smem();
@@ -608,7 +620,7 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
       tc_fence_after();
       if (elect_one()) {
         // contraction over the item's points: both operands are the A1 tile read MN-major (rows = points)
-        const uint64_t d = make_desc(smem_u32(sA1[b]), 128, plane1);
+        const uint64_t d = make_desc(smem_u32(a1buf(b)), 128, plane1);
         for (int ks = 0; ks < I.NT / 16; ++ks)
           mma_bf16_raw(tmem, desc_advance(d, ks * 256), desc_advance(d, ks * 256), idesc, (li > 0 || ks > 0) ? 1u : 0u);
         mma_commit_raw(&bars->a1_empty[b]);

@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// for waiters with slack of microseconds (a producer running a whole work item ahead, a weight loader): poll, then
+// sleep.  Measured on the forward conv kernel (profiles/r2_ncu_fwd_emb.txt): the hinted try_wait above returns after
+// ~70 cycles, not after its hint, so eight warps parked on one barrier still issued 27 % of the kernel's instructions.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 256u) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---- cp.async (LDGSTS): 4-byte asynchronous global -> shared copies, completion by commit groups --------
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");

@@ -47,3 +47,31 @@ def allreduce_grads(flat_grads: torch.Tensor) -> float:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
         return 1.0 / dist.get_world_size()
     return 1.0
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pins this process (and the threads it creates later: pinned-memory allocation, copy submission, NCCL proxy) to
+    the CPUs of the NUMA node its GPU hangs off, so that the per-step host staging buffers are allocated and touched
+    next to the PCIe root of the GPU they feed.  With 8 ranks on a two-socket box the default placement puts half of
+    the ranks' staging memory on the far socket (SCALE_r01: end-to-end scaling 0.943 at 8 ranks against 0.980 for
+    device-resident inputs).  Best effort: returns a description of what was done, never raises."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return f"gpu {local_rank} ({bus}): no NUMA information"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"gpu {local_rank} ({bus}): node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {local_rank} ({bus}): bound to NUMA node {node} ({len(allowed)} cpus)"
+    except Exception as e:   # containers without sysfs, exotic topologies
+        return f"gpu {local_rank}: not bound ({type(e).__name__}: {e})"

@@ -228,32 +228,47 @@ def cpu_baseline_sample(wl, budget_s=12.0):
                       "restatement of the reference TF1 graph (TensorFlow 1.8 not installable here)"}
 
 
-def run_ours(args, wl):
+class Ctx:
+    """Process-wide state of one bench run (rank layout, device, library handle)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as ge
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.rank == 0:
+            ge.build()
+        torch.cuda.set_device(self.local)
+        self.numa = None
+        if self.world > 1:
+            from alignnet_b200 import dist as an3d_dist
+            self.numa = an3d_dist.bind_to_gpu_numa_node(self.local)    # before any pinned allocation / NCCL thread exists
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
+            dist.barrier()
+        if self.rank != 0:
+            ge.build()
+        from alignnet_b200 import _lib
+        self.lib = _lib.load()
+        self.dev = torch.device(f"cuda:{self.local}")
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+
+
+def measure(ctx, wl, precision, steps, warmup, no_graph=False, tags=True):
+    """Times one workload: `steps` device-timed steps with HBM-resident inputs (L2 flushed in between), the tagged
+    kernels on the same number of eager steps, and the end-to-end loop with pinned-host inputs.  Returns a dict."""
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as ge
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        ge.build()
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        dist.barrier()
-    if rank != 0:
-        ge.build()
-    from alignnet_b200 import _lib, engine, synth
-    lib = _lib.load()
+    from alignnet_b200 import engine, synth
+    rank, world, dev, lib, flush = ctx.rank, ctx.world, ctx.dev, ctx.lib, ctx.flush
     B, N, train = wl["B"], wl["N"], wl["train"]
-    dev = torch.device(f"cuda:{local}")
-    eng = engine.Engine(engine.shipped_arch(), str(dev), args.precision, seed=0)
+    eng = engine.Engine(engine.shipped_arch(), str(dev), precision, seed=0)
     host = synth.make_batch_fast(B, N, seed=1234 + (2 if train else 1) + rank)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     resident = {k: t.to(dev) for k, t in pinned.items()}
     staging = {k: torch.empty_like(t, device=dev) for k, t in pinned.items()}
     staging2 = {k: torch.empty_like(t, device=dev) for k, t in pinned.items()}     # second buffer set: double-buffered H2D
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     in_keys = list(host.keys()) if train else ["pcs1", "pcs2"]
     h2d_bytes = sum(pinned[k].numel() * 4 for k in in_keys)
     out_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
@@ -261,15 +276,14 @@ def run_ours(args, wl):
     loss_host = torch.empty(20, dtype=torch.float32).pin_memory()
 
     def allreduce(g):
-        if world > 1:
-            dist.all_reduce(g)
-            return 1.0 / world
-        return 1.0
+        dist.all_reduce(g)
+        return 1.0 / world
 
     # eval-mode forward needs populated BN shadows (zero-initialised shadows are degenerate, quirk Q7):
     # ten training-mode forwards with decay 0.5 fill them.
-    for i in range(10):
-        eng.forward(resident["pcs1"], resident["pcs2"], True, 0.5, None, seed=i)
+    if not train:
+        for i in range(10):
+            eng.forward(resident["pcs1"], resident["pcs2"], True, 0.5, None, seed=i)
     torch.cuda.synchronize()
 
     ar = allreduce if world > 1 else None
@@ -277,10 +291,10 @@ def run_ours(args, wl):
     def step(batch):
         """One step through the engine's public API; CUDA-graph replay unless --no-graph."""
         if train:
-            if args.no_graph:
+            if no_graph:
                 return eng.train_step(batch, lr=0.005, bn_decay=0.5, allreduce=ar)
             return eng.train_step_graph(batch, lr=0.005, bn_decay=0.5, allreduce=ar)
-        if args.no_graph:
+        if no_graph:
             return eng.forward(batch["pcs1"], batch["pcs2"], False)
         return eng.forward_graph(batch["pcs1"], batch["pcs2"])
 
@@ -303,10 +317,10 @@ def run_ours(args, wl):
     copy_stream = torch.cuda.Stream(device=dev)
     sets = [staging, staging2]
 
-    def e2e_pipelined(steps):
+    def e2e_pipelined(n):
         """The serving / training loop a user of the API writes: step i computes on buffer set i % 2 while the pinned
         host batch of step i + 1 is copied into the other set on a copy stream.  EVERY step's H2D copy and D2H read of
-        the result is issued inside the timed region; the region is one CUDA-event bracket over all `steps` steps
+        the result is issued inside the timed region; the region is one CUDA-event bracket over all `n` steps
         (per-step working set >> L2, so no flush is needed between them)."""
         main = torch.cuda.current_stream()
         ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -328,8 +342,8 @@ def run_ours(args, wl):
         e0.record()
         copy_stream.wait_event(e0)
         issue_copy(0)
-        for i in range(steps):
-            if i + 1 < steps:
+        for i in range(n):
+            if i + 1 < n:
                 issue_copy(i + 1)
             main.wait_event(ready[i % 2])
             out = step(sets[i % 2])
@@ -346,11 +360,9 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    d2h_bytes = 80 if train else B * 16
-
-    def timed(fn, steps):
+    def timed(fn, n):
         total = 0.0
-        for _ in range(steps):
+        for _ in range(n):
             flush.fill_(1)                                   # evict L2 between timed iterations (untimed)
             if world > 1:
                 dist.barrier()
@@ -366,58 +378,107 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step(resident)
         step_e2e()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_total = timed(lambda: step(resident), args.steps)
-    # per-kernel device times: CUDA events cannot bracket kernels inside a replayed graph, so the tagged kernels
-    # are timed on the same number of EAGER steps of the same workload right after the timed region
-    launches0 = lib.an3d_launch_count()
-    lib.an3d_profile_begin()
-    timed(lambda: step_eager(resident), args.steps)
-    ms_tags, n_tags = (C.c_float * 8)(), (C.c_int32 * 8)()
-    lib.an3d_profile_end(C.byref(ms_tags), C.byref(n_tags))
-    launches = (lib.an3d_launch_count() - launches0) // args.steps
+    ms_total = timed(lambda: step(resident), steps)
+    res = dict(B=B, N=N, train=train, precision=precision, steps=steps, ms_per_step=ms_total / steps,
+               value=B * world * steps / (ms_total * 1e-3), h2d_bytes=h2d_bytes, d2h_bytes=80 if train else B * 16,
+               allreduce_in_graph=getattr(eng, "_ar_in_graph", None))
+    if tags:
+        # per-kernel device times: CUDA events cannot bracket kernels inside a replayed graph, so the tagged kernels
+        # are timed on the same number of EAGER steps of the same workload right after the timed region (the library
+        # serialises the two branch streams while it profiles)
+        launches0 = lib.an3d_launch_count()
+        lib.an3d_profile_begin()
+        timed(lambda: step_eager(resident), steps)
+        ms_tags, n_tags = (C.c_float * 8)(), (C.c_int32 * 8)()
+        lib.an3d_profile_end(C.byref(ms_tags), C.byref(n_tags))
+        res["launches"] = int((lib.an3d_launch_count() - launches0) // steps)
+        res["ms_tags"] = {str(i): ms_tags[i] / steps for i in range(8) if n_tags[i]}
     for k_ in in_keys:                      # capture the graph of the second buffer set outside the timed region
         staging2[k_].copy_(pinned[k_], non_blocking=True)
     step(staging2)
     torch.cuda.synchronize()
     e2e_pipelined(2)
-    ms_e2e = e2e_pipelined(args.steps)
+    ms_e2e = e2e_pipelined(steps)
+    res["e2e_value"] = B * world * steps / (ms_e2e * 1e-3)
+    del eng, resident, staging, staging2
+    torch.cuda.empty_cache()
+    return res
+
+
+def config_entry(r, pk, world):
+    """One entry of the `configs` sub-object: a BASELINE.json config other than the headline one, measured in the
+    same run with the same method."""
+    e = {"batch_per_gpu": r["B"], "num_points": r["N"], "mode": "train" if r["train"] else "eval", "dtype": r["precision"],
+         "n_gpus": world, "steps": r["steps"], "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "pairs/s",
+         "e2e": {"value": r["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d_bytes"],
+                 "d2h_bytes_per_step": r["d2h_bytes"]},
+         "whole_step_tensor_frac": r["value"] / world * flops_per_pair(r["N"], r["train"]) / (pk["bf16_sustained"] * 1e12)}
+    if r["precision"] != "bf16":
+        e["whole_step_tensor_frac"] = None        # the fp32 parity mode runs on CUDA cores: not held to the bf16 roofline
+    return e
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    ctx = Ctx()
+    rank, world = ctx.rank, ctx.world
+    B, N, train = wl["B"], wl["N"], wl["train"]
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+    r = measure(ctx, wl, args.precision, args.steps, max(args.warmup, 3), no_graph=args.no_graph, tags=True)
     clocks = sampler.stop() if rank == 0 else None
+
+    # The other BASELINE.json configs, measured in the same run (every rank takes part: the training ones all-reduce):
+    # c2 (eval forward), the fp32 parity mode on the headline workload, and -- at the GPU counts BASELINE names for
+    # them -- c4 (4 GPUs) / c5 (8 GPUs) with their real global batch.
+    extra = {}
+    if args.workload == DEFAULT_WORKLOAD and args.precision == "bf16" and not args.no_configs:
+        short = max(5, args.steps // 2)
+        extra["c2"] = measure(ctx, WORKLOADS["c2"], "bf16", short, 3, tags=False)
+        extra["c3_fp32"] = measure(ctx, WORKLOADS["c3"], "fp32", 3, 3, tags=False)
+        if world == 4:
+            extra["c4"] = measure(ctx, WORKLOADS["c4"], "bf16", short, 3, tags=False)
+        if world == 8:
+            extra["c5"] = measure(ctx, WORKLOADS["c5"], "bf16", short, 3, tags=False)
 
     if rank == 0:
         pk = peaks()
-        pairs = B * world
-        value = pairs * args.steps / (ms_total * 1e-3)
-        e2e_value = pairs * args.steps / (ms_e2e * 1e-3)
+        value, e2e_value = r["value"], r["e2e_value"]
         # dominant kernel: conv-stack full pass (tag 1): 6 launches per step (3 stages x 2 branches)
-        k_ms = ms_tags[1] / max(1, args.steps)
+        k_ms = r["ms_tags"].get("1", 0.0)
         k_flops = B * emb_full_flops_per_pair(N)
         achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         line = {
             "metric": "point-cloud pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "num_points": N, "mode": "train" if train else "eval",
                        "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
                        "launch": "eager stream launches" if args.no_graph else "CUDA-graph replay of the step (Engine.train_step_graph / forward_graph)",
+                       "collective": None if world == 1 else ("one NCCL all-reduce of the flat fp32 gradient per step, " +
+                                                              ("captured inside the step graph" if r["allreduce_in_graph"] else "issued between two graph segments")),
+                       "host_binding": ctx.numa,
                        "e2e": "pinned host batch -> H2D every step (double-buffered on a copy stream, overlapped with the previous step) -> step -> D2H of the result; one event bracket over all steps",
                        "whole_step_tensor_frac": value / world * flops_per_pair(N, train) / (pk["bf16_sustained"] * 1e12)},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": r["d2h_bytes"]},
+            "gpu_launches": r["launches"],
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_sustained"], "traffic": measured_traffic() if train else None,
+                         "traffic_source": "constant from the committed ncu --set full capture (profiles/), not measured in this run",
                          "kernel": "conv_stack_fwd_kernel (full pass), 6 launches/step", "kernel_ms_per_step": k_ms,
                          "peak_source": pk["source"] + ", sustained bf16"},
             "clocks": clocks,
-            "kernel_ms_by_tag": {str(i): ms_tags[i] / args.steps for i in range(8) if n_tags[i]},
+            "kernel_ms_by_tag": r["ms_tags"],
         }
+        if extra:
+            line["configs"] = {k: config_entry(v, pk, world) for k, v in extra.items()}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(wl)
         print(json.dumps(line))
@@ -434,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the `configs` sub-object)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (A/B runs of a kernel switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the stream instead of replaying a CUDA graph")
     args = ap.parse_args()

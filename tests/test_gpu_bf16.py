@@ -258,10 +258,12 @@ def test_bf16_train_step_runs_and_learns():
     e = make_engine(arch, A.init_params(arch, 0), A.init_state(arch))
     batch = to_dev(synth.make_batch_fast(64, 200, seed=77))
     losses = []
-    for i in range(12):
-        losses.append(float(e.train_step(batch, lr=0.002, bn_decay=0.5, seed=i)[0].cpu()))
+    for i in range(60):
+        losses.append(float(e.train_step(batch, lr=0.001, bn_decay=0.5, seed=i)[0].cpu()))
     assert np.isfinite(losses).all()
-    assert min(losses[3:]) < losses[0], losses          # (run-to-run noise of a bf16 step is ~1 % of the loss)
+    # Adam's first steps overshoot on a 64-pair batch; over 60 steps the fixed batch is being fitted
+    # (convergence against the fp32 mode: tests/test_gpu_convergence.py)
+    assert max(losses) < 3 * losses[0] and np.mean(losses[-10:]) < 0.9 * losses[0], losses
 
 
 def test_graph_replay_matches_eager_steps():

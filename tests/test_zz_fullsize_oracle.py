@@ -8,7 +8,7 @@
     autograd.  (fwd+bwd through torch autograd at B=4096 holds ~60 GB of [M,1024] activations on the host, so the
     gradient check is the B=1024 one; the loss at B=4096 covers the [B,B] loss couplings at full size.)
   * the c4 / c5 cloud sizes N=512 / N=1024 (B=64) end to end, eval and training, both precisions.
-Oracle cost on 8 host cores: ~8 s (fp64 eval, B=1024), ~16 s (fp32 fwd+bwd, B=1024), ~25 s (fp32 forward, B=4096).
+Oracle cost on 8 host cores: ~8 s (fp64 eval, B=1024), ~2 x 16 s (fp32 fwd+bwd with and without the bf16 rounding model, B=1024), ~25 s (fp32 forward, B=4096).
 Measured numbers are printed (run with -s) and written to gpurun_out/parity_fullsize.json when that directory exists.
 The file name sorts last on purpose: these are the slowest GPU tests."""
 import json
@@ -172,6 +172,14 @@ def test_c2_size_training_step_vs_oracle_autograd():
     nb = arch.num_bins
     loss_ref, ep_ref, grads_ref, _ = TR.loss_and_grads(batch, arch, params, state, 0.5, masks, dtype=torch.float32)
     ep_ref = {k: v.astype(np.float64) for k, v in ep_ref.items()}
+    # the yardstick for the bf16 mode: the SAME oracle with the engine's rounding points (bf16 operands of every conv
+    # layer after the first) -- how far bf16 arithmetic alone moves the gradient of this (discontinuous) loss
+    TR.SIM_BF16 = True
+    try:
+        _, _, grads_sim, _ = TR.loss_and_grads(batch, arch, params, state, 0.5, masks, dtype=torch.float32)
+    finally:
+        TR.SIM_BF16 = False
+    _, cos_sim = _grad_report(grads_sim, grads_ref)
     dev, dm = _dev(batch), _dev(masks)
     out = {}
     for prec in ("fp32", "bf16"):
@@ -196,9 +204,12 @@ def test_c2_size_training_step_vs_oracle_autograd():
     frac, emax, emean, lv, cos_all, worst_cos, worst_rel = out["bf16"]
     assert frac > 0.6 and emax < BF16_MAX_TRAIN and emean < BF16_MEAN_TRAIN, (frac, emax, emean)
     assert abs(lv - loss_ref) <= 3e-2 * max(1.0, abs(loss_ref)), (lv, loss_ref)
-    # bf16 gradients at a batch where the rounding noise averages out: direction of every significant tensor and
-    # of the whole gradient (thresholds from the measured values, profiles/r2_parity_fullsize.json)
-    assert cos_all > 0.9 and worst_cos > 0.8, (cos_all, worst_cos)
+    # bf16 gradients: this loss is discontinuous in roundings (arg-max bins, class targets built from sample 0's decoded
+    # angle -- quirk Q4, max-pool rows), so bf16 arithmetic alone moves its gradient: the oracle's own rounding model
+    # sits at cosine ~0.82 from the fp32 oracle here (7 % of the bins flip).  The engine must be no further away than
+    # that model (measured 0.84 vs 0.82); what the distance means for training is tests/test_gpu_convergence.py.
+    _note("c2size_train_bf16_rounding_model", grad_cos_all_vs_fp32_oracle=cos_sim)
+    assert cos_all > 0.75 and cos_all >= cos_sim - 0.05 and worst_cos > 0.6, (cos_all, cos_sim, worst_cos)
 
 
 def test_c3_training_forward_and_loss_vs_oracle():

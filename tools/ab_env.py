@@ -19,7 +19,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def run_bench(env, workload, steps, warmup):
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--workload", workload, "--steps", str(steps), "--warmup",
-                        str(warmup), "--no-cpu-baseline"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+                        str(warmup), "--no-cpu-baseline", "--no-configs"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode != 0 or not lines:
         raise RuntimeError(f"bench failed (rc={r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
