@@ -309,15 +309,16 @@ int launch_fused(const convfwd::Params& P, int grid, size_t smem, cudaStream_t s
 int launch_stats2(convfwd::Params P, int sms, float* gram1_out, cudaStream_t st) {
   const size_t smem = convfwd::stats2_smem_bytes(P.PC);
   AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static size_t cached_smem = 0;
-  static int cached_per_sm = 1;
-  if (cached_smem != smem) {     // (host-side query: cached, the launch sits on the step's critical path when not graph-replayed)
-    int q = 1;
-    AN3D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, convfwd::conv_stats2_kernel, convfwd::kStatsThreads, smem));
-    cached_per_sm = std::max(1, std::min(q, (int)(512 / convfwd::kStatsTmemCols)));
-    cached_smem = smem;
-  }
-  const int per_sm = cached_per_sm;
+  // (without the carve-out preference the driver sizes shared memory for ONE block of this kernel per SM: the first
+  // version of this launch ran 148 CTAs although two fit)
+  AN3D_CUDA_CHECK(cudaFuncSetAttribute(convfwd::conv_stats2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+  // CTAs per SM from the kernel's own footprint (shared memory + 1 KB reserved per block, 288 threads, 72 registers,
+  // 128 TMEM columns).  cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for this kernel on B200 although two
+  // blocks fit (86.9 KB each at 208 points per item), so the launch does its own arithmetic; if the hardware disagrees
+  // the surplus CTAs simply queue.
+  const int by_smem = (int)((228 * 1024) / (smem + 1024)), by_regs = 65536 / (convfwd::kStatsThreads * 72);
+  const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), (int)(512 / convfwd::kStatsTmemCols)));
   const int grid = std::max(1, std::min(std::min(P.n_items, sms * per_sm), kMaxParts1));
   P.item_begin_stride = (P.n_items + grid - 1) / grid;
   const int nparts = (P.n_items + P.item_begin_stride - 1) / P.item_begin_stride;   // CTAs that own items (and write a slot)

@@ -192,17 +192,25 @@ static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Param
   const int c = tid;                       // blockDim.x == C3 (<= 1024)
   const float s3c = P.s3[c];
   const bool one_item_per_cloud = P.npc == 1;      // the common case: no integer division per item
-  auto fetch = [&](int li, float& w, int& row) {
-    w = 0.f; row = -1;
+  // The look-ahead ring holds the RAW loaded values (gradient at the arg row, arg row): anything computed from them at
+  // fetch time -- the validity test used to be -- makes the thread wait for the load it has just issued, and the ring
+  // buys nothing (ncu: 45 % of this kernel's stall samples sat on these two loads).
+  auto fetch = [&](int li, float& dy, int& idx) {
+    dy = 0.f; idx = -1;
     if (li < n_local) {
       const int it = it_begin + li;
       const int cloud = one_item_per_cloud ? it : it / P.npc;
-      const int pchunk = one_item_per_cloud ? 0 : it - cloud * P.npc;
-      const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
-      const float wv = s3c * P.dyext[(size_t)cloud * P.C3 + c];
-      const int r = P.gidx[(size_t)cloud * P.C3 + c] - p0;
-      if (r >= 0 && r < nvalid && wv != 0.f) { w = wv; row = r; }
+      dy = P.dyext[(size_t)cloud * P.C3 + c];
+      idx = P.gidx[(size_t)cloud * P.C3 + c];
     }
+  };
+  auto resolve = [&](int li, float dy, int idx, float& w, int& row) {
+    const int it = it_begin + li;
+    const int pchunk = one_item_per_cloud ? 0 : it - (it / P.npc) * P.npc;
+    const int p0 = pchunk * P.PC, nvalid = min(P.PC, P.N - p0);
+    const int r = idx - p0;
+    w = s3c * dy;
+    row = (r >= 0 && r < nvalid && w != 0.f) ? r : -1;
   };
   float acc[32];
 #pragma unroll
@@ -220,8 +228,9 @@ static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Param
       const int li = li0 + u;
       if (li >= n_local) break;
       const int st = li % kT1Stages;
-      const float w0 = wq[u];
-      const int r0 = rq[u];
+      float w0;
+      int r0;
+      resolve(li, wq[u], rq[u], w0, r0);
       fetch(li + kT1Look, wq[u], rq[u]);
       // refill the stage drained one iteration ago (every warp has arrived on its `empty` barrier by now, or will shortly)
       if (tid == 0 && li >= 1 && li - 1 + kT1Stages < n_local) {
@@ -391,6 +400,10 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     const int nhc_t = nhc >> 1;
     int cur_idx[kMaxHcT], nxt_idx[kMaxHcT];
     float cur_w[kMaxHcT], nxt_w[kMaxHcT];
+    float s3r[kMaxHcT];        // BN3 scale of this thread's channels: loaded once, not once per item
+#pragma unroll
+    for (int h = 0; h < kMaxHcT; ++h) s3r[h] = h < nhc_t ? P.s3[(2 * h + team) * 64 + t] : 0.f;
+    // the prefetched values stay RAW until they are used: a multiply at fetch time would wait for the load just issued
     auto fetch = [&](int li, int (&ix)[kMaxHcT], float (&wv)[kMaxHcT]) {
       const int cloud = (it_begin + li) / P.npc;
 #pragma unroll
@@ -398,7 +411,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         if (h < nhc_t) {
           const int c = (2 * h + team) * 64 + t;
           ix[h] = P.gidx[(size_t)cloud * P.C3 + c];
-          wv[h] = P.s3[c] * P.dyext[(size_t)cloud * P.C3 + c];
+          wv[h] = P.dyext[(size_t)cloud * P.C3 + c];
         }
       }
     };
@@ -416,7 +429,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         mbar_wait(&bars->sd_empty[team], ph_e); ph_e ^= 1;
         if (prev_off >= 0) *reinterpret_cast<__nv_bfloat16*>(sS + prev_off) = __float2bfloat16_rn(0.f);
         const int row = cur_idx[h] - p0;
-        const float w = cur_w[h];
+        const float w = s3r[h] * cur_w[h];
         if (row >= 0 && row < nvalid && w != 0.f) {
           const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(sS + off) = __float2bfloat16_rn(w);

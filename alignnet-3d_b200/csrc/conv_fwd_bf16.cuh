@@ -119,35 +119,38 @@ __device__ __forceinline__ float tag4(uint32_t x, uint32_t mask) {
 
 // Running max over one 16-column group of an accumulator row.  Training mode carries the arg-max point
 // index in the low mantissa bits: the column-in-group (an immediate) goes into the low 4 bits of every
-// element, the group's base index is spliced in only if the group wins.
+// element, the group's base index is spliced in only if the group wins.  The back-end warps are the kernel's
+// critical resource (two per scheduler, ~80 % busy in the ncu samples), so this routine is written for them:
+// two independent max chains per group (a single chain of eight dependent 3-input maxima left the warp waiting on
+// its own previous instruction), the padding columns of a cloud's last group overwritten with -FLT_MAX by sixteen
+// predicated moves instead of a 16-way branchy tail, masks hoisted into registers by the caller.
 template <int MODE>
-__device__ __forceinline__ void reduce_group(const uint32_t* r, int col0, int nvalid, int p0, uint32_t idx_mask,
+__device__ __forceinline__ void reduce_group(uint32_t* r, int col0, int nvalid, int p0, uint32_t keep_mask,
                                              uint32_t not15, float& m) {
-  float gm = -INFINITY;
-  if (col0 + 16 <= nvalid) {
-    // three-input max (FMNMX3): 8 instead of 16 max instructions per group
-    if (MODE == MODE_FULL_TRAIN) {
-#define AN3D_TAGGED_PAIR(Q) gm = fmax3(gm, tag4<Q>(r[Q], not15), tag4<Q + 1>(r[Q + 1], not15));
-      AN3D_TAGGED_PAIR(0) AN3D_TAGGED_PAIR(2) AN3D_TAGGED_PAIR(4) AN3D_TAGGED_PAIR(6)
-      AN3D_TAGGED_PAIR(8) AN3D_TAGGED_PAIR(10) AN3D_TAGGED_PAIR(12) AN3D_TAGGED_PAIR(14)
-#undef AN3D_TAGGED_PAIR
-    } else {
+  const int k = nvalid - col0;                     // warp-uniform; < 16 only in the last group of a cloud
+  if (k < 16) {
 #pragma unroll
-      for (int q = 0; q < 16; q += 2) gm = fmax3(gm, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if (col0 + q < nvalid) {
-        if (MODE == MODE_FULL_TRAIN) gm = fmaxf(gm, __uint_as_float((r[q] & not15) | (uint32_t)q));
-        else gm = fmaxf(gm, __uint_as_float(r[q]));
-      }
-    }
+    for (int q = 1; q < 16; ++q)
+      if (q >= k) r[q] = 0xff7fffffu;              // -FLT_MAX: loses against every real accumulator (k >= 1 always)
   }
+  float g0, g1;
   if (MODE == MODE_FULL_TRAIN) {
-    if (gm > m) m = __uint_as_float((__float_as_uint(gm) & ~(idx_mask & ~15u)) | (uint32_t)(p0 + col0));
+    g0 = fmax3(tag4<0>(r[0], not15), tag4<1>(r[1], not15), tag4<2>(r[2], not15));
+    g1 = fmax3(tag4<8>(r[8], not15), tag4<9>(r[9], not15), tag4<10>(r[10], not15));
+    g0 = fmax3(g0, tag4<3>(r[3], not15), tag4<4>(r[4], not15));
+    g1 = fmax3(g1, tag4<11>(r[11], not15), tag4<12>(r[12], not15));
+    g0 = fmax3(g0, tag4<5>(r[5], not15), tag4<6>(r[6], not15));
+    g1 = fmax3(g1, tag4<13>(r[13], not15), tag4<14>(r[14], not15));
+    const float gm = fmax3(g0, g1, fmaxf(tag4<7>(r[7], not15), tag4<15>(r[15], not15)));
+    if (gm > m) m = __uint_as_float((__float_as_uint(gm) & keep_mask) | (uint32_t)(p0 + col0));
   } else {
-    m = fmaxf(m, gm);
+    g0 = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+    g1 = fmax3(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]));
+    g0 = fmax3(g0, __uint_as_float(r[3]), __uint_as_float(r[4]));
+    g1 = fmax3(g1, __uint_as_float(r[11]), __uint_as_float(r[12]));
+    g0 = fmax3(g0, __uint_as_float(r[5]), __uint_as_float(r[6]));
+    g1 = fmax3(g1, __uint_as_float(r[13]), __uint_as_float(r[14]));
+    m = fmax3(m, fmax3(g0, g1, __uint_as_float(r[7])), __uint_as_float(r[15]));
   }
 }
 
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     uint32_t ph_full = 0;
     const int C3 = P.nchunk * 128;
     const uint32_t not15 = P.not15;
+    const uint32_t keep_mask = ~(P.idx_mask & ~15u);     // clears the group-index bits of the winning element
     for (int li = 0; li < n_local; ++li) {
       const Item I = item_of(P, it_begin + li);
       const int nvalid = I.nvalid, NT = I.NT, p0 = I.p0;
@@ -361,11 +365,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
             tmem_ld_wait();
             const int g2 = g16 + 32;
             if (g2 < nh) tmem_ld16(tbase + g2, rb);
-            reduce_group<MODE>(ra, off + g16, nvalid, p0, P.idx_mask, not15, m);
+            reduce_group<MODE>(ra, off + g16, nvalid, p0, keep_mask, not15, m);
             if (g2 < nh) {
               tmem_ld_wait();
               if (g2 + 32 < nh) tmem_ld16(tbase + g2 + 32, ra);
-              reduce_group<MODE>(rb, off + g2, nvalid, p0, P.idx_mask, not15, m);
+              reduce_group<MODE>(rb, off + g2, nvalid, p0, keep_mask, not15, m);
             }
           }
           tc_fence_before();

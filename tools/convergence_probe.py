@@ -16,6 +16,8 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--points", type=int, default=200)
 ap.add_argument("--lr", type=float, default=0.001)
 ap.add_argument("--pool", type=int, default=16, help="distinct training batches cycled through")
+ap.add_argument("--every", type=int, default=200, help="evaluate every this many steps")
+ap.add_argument("--runs", default="fp32:0,bf16:0,fp32:1,bf16:1", help="precision:dropout-seed-offset list")
 a = ap.parse_args()
 ge.build()
 from alignnet_b200 import engine, synth, evaluation
@@ -25,20 +27,24 @@ train = [dev(synth.make_batch_fast(a.batch, a.points, seed=1000 + i)) for i in r
 val_host = synth.make_batch_fast(1024, a.points, seed=999)
 val = dev(val_host)
 out = {}
-for prec in ("fp32", "bf16"):
-    e = engine.Engine(engine.shipped_arch(), "cuda:0", prec, seed=3)
-    losses = []
-    for t in range(a.steps):
-        losses.append(float(e.train_step(train[t % a.pool], lr=a.lr, bn_decay=0.5, seed=t)[0].cpu()))
+
+
+def evaluate(e):
     ep = e.forward(val["pcs1"], val["pcs2"], False)
     vloss = float(e.loss(val, ep)[0].cpu())
-    pa = e.pred_angles(ep).cpu().numpy()
-    pt = ep["pred_translations"].cpu().numpy()
-    terr = np.linalg.norm(pt[:, :2] - val_host["translations"][:, :2], axis=1)
-    aerr = np.abs((pa - val_host["rel_angles"][:, 0] + np.pi) % (2 * np.pi) - np.pi)
-    out[prec] = dict(loss_first=losses[:5], loss_last=float(np.mean(losses[-20:])), val_loss=vloss,
-                     t_err_mean=float(terr.mean()), t_err_med=float(np.median(terr)), a_err_mean_deg=float(np.degrees(aerr.mean())),
-                     a_err_med_deg=float(np.degrees(np.median(aerr))), t_lt_10cm=float((terr < 0.1).mean()),
-                     t_lt_20cm=float((terr < 0.2).mean()), a_lt_5deg=float((aerr < np.radians(5)).mean()),
-                     a_lt_10deg=float((aerr < np.radians(10)).mean()), traj=[float(np.mean(losses[i:i + 20])) for i in range(0, a.steps, 20)])
-    print(prec, json.dumps(out[prec]))
+    ev = evaluation.evaluate(ep["pred_translations"], e.pred_angles(ep), val_host["translations"], val_host["rel_angles"],
+                             ep["pred_s2_pc1centers"], val_host["pc1_centers"], accept_inverted_angle=True)
+    return dict(val_loss=round(vloss, 5), t_mean=round(ev["mean_dist_translation"], 4), a_mean_deg=round(ev["mean_dist_angle"], 2),
+                t_levels=[round(x, 3) for x in ev["corr_levels_translation"]], a_levels=[round(x, 3) for x in ev["corr_levels_angles"]])
+
+
+for run in a.runs.split(","):
+    prec, off = run.split(":")
+    e = engine.Engine(engine.shipped_arch(), "cuda:0", prec, seed=3)
+    losses, hist = [], []
+    for t in range(a.steps):
+        losses.append(float(e.train_step(train[t % a.pool], lr=a.lr, bn_decay=0.5, seed=t + 100000 * int(off))[0].cpu()))
+        if (t + 1) % a.every == 0:
+            hist.append(dict(step=t + 1, train_loss=round(float(np.mean(losses[-20:])), 5), **evaluate(e)))
+            print(run, json.dumps(hist[-1]), flush=True)
+    out[run] = hist
