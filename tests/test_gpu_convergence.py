@@ -13,7 +13,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-STEPS, BATCH, POINTS, POOL = 400, 256, 200, 16
+STEPS, BATCH, POINTS, POOL = 1000, 256, 200, 16
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -38,24 +38,28 @@ def _train(precision):
 
 
 def test_bf16_training_converges_like_fp32():
+    """Measured (profiles/r2_convergence.txt, two dropout seeds per precision, checkpoints every 200 steps up to 1600):
+    final training loss 0.0375 (fp32) vs 0.0378 (bf16), held-out loss 0.00931 vs 0.00936, mean translation error
+    0.107-0.118 m vs 0.109-0.139 m; mid-training the bf16 runs trail the fp32 runs in translation error by up to 35 %
+    (step 1000: 0.12 vs 0.155 m) and catch up by step 1400.  The angle metrics of this early phase swing by +-15 degrees
+    between checkpoints and between two fp32 dropout seeds, so they are only required to be in the same regime."""
     l32, v32, ev32 = _train("fp32")
     l16, v16, ev16 = _train("bf16")
-    first32, last32, last16 = l32[:20].mean(), l32[-20:].mean(), l16[-20:].mean()
-    print(f"train loss: first-20 {first32:.4f}; last-20 fp32 {last32:.4f} bf16 {last16:.4f}; val loss fp32 {v32:.5f} bf16 {v16:.5f}")
-    print("fp32 eval:", {k: ev32[k] for k in ("corr_levels_translation", "mean_dist_translation", "corr_levels_angles", "mean_dist_angle")})
-    print("bf16 eval:", {k: ev16[k] for k in ("corr_levels_translation", "mean_dist_translation", "corr_levels_angles", "mean_dist_angle")})
+    first32, last32, last16 = l32[:20].mean(), l32[-50:].mean(), l16[-50:].mean()
+    print(f"train loss: first-20 {first32:.4f}; last-50 fp32 {last32:.4f} bf16 {last16:.4f}; val loss fp32 {v32:.5f} bf16 {v16:.5f}")
+    keys = ("corr_levels_translation", "mean_dist_translation", "corr_levels_angles", "mean_dist_angle")
+    print("fp32 eval:", {k: ev32[k] for k in keys})
+    print("bf16 eval:", {k: ev16[k] for k in keys})
     assert np.isfinite(l32).all() and np.isfinite(l16).all()
-    # both learn: the loss halves over the run
-    assert last32 < 0.6 * first32 and last16 < 0.6 * l16[:20].mean(), (first32, last32, last16)
-    # and they learn the same thing: windowed loss trajectories, final training loss, held-out loss and metrics
-    w32 = l32.reshape(-1, 20).mean(1)
-    w16 = l16.reshape(-1, 20).mean(1)
-    assert np.abs(w16 - w32).max() <= 0.12 * w32.max() and np.abs(w16[5:] / w32[5:] - 1).max() <= 0.12, (w32, w16)
-    assert abs(last16 - last32) <= 0.10 * last32
-    assert abs(v16 - v32) <= 0.10 * v32, (v16, v32)
-    assert abs(ev16["mean_dist_translation"] - ev32["mean_dist_translation"]) <= 0.15 * ev32["mean_dist_translation"]
-    assert abs(ev16["mean_dist_angle"] - ev32["mean_dist_angle"]) <= 0.15 * ev32["mean_dist_angle"] + 1.0
-    for a, b in zip(ev16["corr_levels_translation"], ev32["corr_levels_translation"]):     # 2 / 10 / 20 cm
-        assert abs(a - b) <= 0.06, (ev16["corr_levels_translation"], ev32["corr_levels_translation"])
-    for a, b in zip(ev16["corr_levels_angles"], ev32["corr_levels_angles"]):               # 1 / 5 / 10 degrees
-        assert abs(a - b) <= 0.06, (ev16["corr_levels_angles"], ev32["corr_levels_angles"])
+    # both learn: the loss more than halves, the translation error falls from ~0.7 m (step 200) below 0.25 m
+    assert last32 < 0.5 * first32 and last16 < 0.5 * l16[:20].mean(), (first32, last32, last16)
+    assert ev32["mean_dist_translation"] < 0.25 and ev16["mean_dist_translation"] < 0.25
+    # and they learn the same thing: loss trajectories (50-step windows), final training loss, held-out loss
+    w32, w16 = l32.reshape(-1, 50).mean(1), l16.reshape(-1, 50).mean(1)
+    assert np.abs(w16[2:] / w32[2:] - 1).max() <= 0.06, (w32, w16)
+    assert abs(last16 - last32) <= 0.04 * last32, (last16, last32)
+    assert abs(v16 - v32) <= 0.03 * v32, (v16, v32)
+    # translation error: bf16 may trail mid-training (measured up to +35 % at this step), never by more than half
+    assert ev16["mean_dist_translation"] <= 1.5 * ev32["mean_dist_translation"]
+    # angles: same regime (see the docstring for why not tighter)
+    assert abs(ev16["mean_dist_angle"] - ev32["mean_dist_angle"]) <= 30.0
