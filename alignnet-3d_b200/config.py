@@ -187,6 +187,14 @@ def validate(cfg: NameSpace) -> None:
         raise ValueError("training.loss.options.soft_angle_classes=true is not implemented")
     if cfg.data.num_channels != 3:
         raise ValueError("data.num_channels must be 3")
+    if cfg.training.has("optimizer") and cfg.training.optimizer.has("optimizer") \
+            and cfg.training.optimizer.optimizer != "adam":
+        raise ValueError(f"training.optimizer.optimizer={cfg.training.optimizer.optimizer!r} is not implemented (only "
+                         "'adam'; the reference's momentum branch, train.py:211-212, is selected by no shipped config)")
+    if cfg.evaluation.has("special") and cfg.evaluation.special.mode != "timings":
+        raise ValueError(f"evaluation.special.mode={cfg.evaluation.special.mode!r} is not implemented: 'icp' (the Open3D "
+                         "baselines, icp.py:150) and 'held' (evaluate_held, evaluation.py:49) are outside the hot path; "
+                         "'timings' (train.py:553-559) is")
 
 
 def arch_from_config(cfg: NameSpace) -> "_lib.Arch":

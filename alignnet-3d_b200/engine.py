@@ -373,9 +373,11 @@ class Engine:
             g.replay()
         return out
 
-    def _advance_step(self) -> None:
+    def _advance_step(self, seed_base: int = 0) -> None:
+        """step_dev += 1; seed_dev = seed_base + step_dev (one thread, inside the captured graph).  `seed_base` is baked
+        into the graph: data-parallel ranks pass rank << 40 so that the shards do not share dropout masks."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.an3d_step_advance(self.step_dev.data_ptr(), self.seed_dev.data_ptr(), 0, stream),
+        _lib.check(self.lib.an3d_step_advance(self.step_dev.data_ptr(), self.seed_dev.data_ptr(), int(seed_base), stream),
                    "an3d_step_advance")
 
     def _adam_step_dev(self, lr: float, grad_scale: float, beta1=0.9, beta2=0.999, eps=1e-8) -> None:
@@ -385,7 +387,8 @@ class Engine:
                                                self.adam_v.data_ptr(), self.params.numel(), lr, self.step_dev.data_ptr(),
                                                grad_scale, beta1, beta2, eps, stream), "an3d_adam_step_dev")
 
-    def train_step_graph(self, batch: Dict[str, torch.Tensor], lr: float, bn_decay: float, allreduce=None) -> torch.Tensor:
+    def train_step_graph(self, batch: Dict[str, torch.Tensor], lr: float, bn_decay: float, allreduce=None,
+                         seed_salt: int = 0) -> torch.Tensor:
         """`Engine.train_step` replayed as CUDA graphs over the caller's STATIC batch buffers.  Without an
         all-reduce the whole step is one graph; with one (data parallel) the graph is split around the collective:
         [advance step, forward, loss + backward] -> all-reduce (eager, NCCL) -> [Adam]."""
@@ -394,8 +397,10 @@ class Engine:
         ptrs = tuple(batch[k].data_ptr() for k in sorted(batch))
         shape = tuple(batch["pcs1"].shape)
 
+        salt = int(seed_salt) << 40
+
         def fwd_bwd():
-            self._advance_step()
+            self._advance_step(salt)
             ep = self.forward(batch["pcs1"], batch["pcs2"], True, bn_decay, None, seed_on_device=True)
             return self.backward(batch["pcs1"], batch["pcs2"], batch, ep)
 
@@ -409,7 +414,7 @@ class Engine:
                 scale = 1.0 if allreduce is None else float(allreduce(self.grads))
                 self._adam_step_dev(lr, scale)
                 return loss
-            key = ("train" if allreduce is None else "train-ar", ptrs, shape, float(lr), float(bn_decay), self.pflag)
+            key = ("train" if allreduce is None else "train-ar", ptrs, shape, float(lr), float(bn_decay), self.pflag, salt)
             try:
                 g, loss, fresh = self._capture(key, whole)
                 if allreduce is not None:
@@ -423,7 +428,7 @@ class Engine:
             if not fresh:
                 g.replay()
         else:
-            g1, loss, fresh = self._capture(("train-a", ptrs, shape, float(bn_decay), self.pflag), fwd_bwd)
+            g1, loss, fresh = self._capture(("train-a", ptrs, shape, float(bn_decay), self.pflag, salt), fwd_bwd)
             if not fresh:
                 g1.replay()
             scale = float(allreduce(self.grads))

@@ -9,9 +9,12 @@ last epoch) and output files: `<logdir>/config.json`, `<logdir>/out.log`, `<logd
 eval_180.json, pred_*.npy}` (train.py:399-407,487-543, evaluation.py:274-287), `<logdir>/model.ckpt.*` and
 `<logdir>/model-<epoch>.*` in TensorFlow's checkpoint format (`alignnet_b200.tf_checkpoint`, train.py:316-322).
 Differences, all deliberate: there is no TensorBoard writer, `--refineICP` runs the batched device ICP of `alignnet_b200.icp` instead of the
-authors' Open3D fork (row N4, parity unpinned; `--use_old_results` is accepted and ignored), and the
+authors' Open3D fork (row N4, parity unpinned), and the
 val/test split of the synthetic sets (evaluation.py:161-162: idx >= 1000) is computed here and passed to the device
-evaluation.  One process per GPU; under torchrun the gradient all-reduce is the only collective."""
+evaluation.  `evaluation.special.mode == "timings"` is the reference's own benchmark harness (train.py:553-559): batch 32,
+no restore, ten evaluation passes, `Timing bs=32: <seconds per pair>`.  `training.pretraining.model` is restored like the
+reference does (all variables except the global step, then an initial evaluation, train.py:276-293).  One process per GPU;
+under torchrun every rank reads only its shard of each batch and the gradient all-reduce is the only collective."""
 from __future__ import annotations
 
 import argparse
@@ -63,27 +66,41 @@ def save_checkpoint(eng: E.Engine, prefix: str) -> None:
     tf_checkpoint.save_from_engine(eng, prefix)
 
 
-def load_checkpoint(eng: E.Engine, prefix: str) -> None:
-    """saver.restore (train.py:250-293); also reads checkpoints written by the reference itself."""
+def load_checkpoint(eng: E.Engine, prefix: str, restore_step: bool = True) -> None:
+    """saver.restore (train.py:250-293); also reads checkpoints written by the reference itself.  With
+    `restore_step=False` everything but the global step is taken (the pre-training restore, train.py:277-281)."""
+    step = eng.step
     tf_checkpoint.load_into_engine(eng, prefix)
+    if not restore_step:
+        eng.step = step
 
 
 def train_one_epoch(cfg, eng: E.Engine, train_idxs: List[int], epoch: int, rank: int, world: int) -> float:
-    """train.py:337-393: shuffle, load + jitter each batch, one optimiser step per batch."""
+    """train.py:337-393: shuffle, load + jitter each batch, one optimiser step per batch.  The step is replayed as a CUDA
+    graph over static batch buffers (what bench.py measures); a new lr / bn_decay plateau captures a new graph.  Data
+    parallel: every rank draws the SAME permutation (seeded with the epoch) and reads only its contiguous slice of each
+    global batch, so an epoch is a partition of the training set and the host IO is not multiplied by the world size."""
     idxs = list(train_idxs)
-    np.random.shuffle(idxs)
+    if world > 1:
+        np.random.RandomState(1000003 * (epoch + 1)).shuffle(idxs)
+    else:
+        np.random.shuffle(idxs)                                  # the reference's global-RNG draw (train.py:341)
     bs = cfg.training.batch_size
     nb_epoch = len(train_idxs) // bs
     lo, hi = D.shard_bounds(bs, rank, world)
+    mine = [i for b in range(nb_epoch) for i in idxs[b * bs + lo:b * bs + hi]]
     loss_sum, n = 0.0, 0
     allreduce = D.allreduce_grads if world > 1 else None
-    loader = provider.Prefetcher(cfg.data.basepath, idxs, bs, cfg.model.num_points, jitter=True, device=str(eng.device))
+    loader = provider.Prefetcher(cfg.data.basepath, mine, hi - lo, cfg.model.num_points, jitter=True, device=str(eng.device))
+    static = None
     for batch in loader:
-        if world > 1:
-            batch = {k: v[lo:hi].contiguous() for k, v in batch.items()}
+        if static is None:
+            static = {k: torch.empty_like(v) for k, v in batch.items()}
+        for k, v in batch.items():
+            static[k].copy_(v)
         lr = schedules.learning_rate(cfg, eng.step, nb_epoch)
         bn_d = schedules.bn_decay(cfg, eng.step, nb_epoch)
-        loss = eng.train_step(batch, lr=lr, bn_decay=bn_d, allreduce=allreduce)
+        loss = eng.train_step_graph(static, lr=lr, bn_decay=bn_d, allreduce=allreduce, seed_salt=rank)
         loss_sum += float(loss[0].cpu())
         n += 1
     mean = loss_sum / max(n, 1)
@@ -91,11 +108,12 @@ def train_one_epoch(cfg, eng: E.Engine, train_idxs: List[int], epoch: int, rank:
     return mean
 
 
-def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int, refine_icp: bool = False, its: int = 30,
-                   icp_method: str = "p2p") -> Dict:
+def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch, refine_icp: bool = False, its: int = 30,
+                   icp_method: str = "p2p", use_old_results: bool = False, do_timings: bool = False) -> Dict:
     """train.py:396-545: eval-mode forward over the validation split, host decode of the angles (quirk Q1), the
     eval.json metrics with and without accepting the 180-degree flip."""
     eval_dir = f"{cfg.logging.logdir}/val/eval{str(epoch).zfill(6)}"
+    base_eval_dir = eval_dir
     if refine_icp:                                               # train.py:401-402
         eval_dir = f'{eval_dir}/refined_{icp_method}{"_" + str(its) if int(its) != 30 else ""}'
     if os.path.isdir(eval_dir):                                  # keep earlier results (train.py:404-405)
@@ -107,9 +125,12 @@ def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int, refine_i
     bs = cfg.training.batch_size
     num_batches = int(np.ceil(len(val_idxs) / bs))
     keep: Dict[str, list] = {k: [] for k in ("pred_translations", "pred_angles", "pred_s1_pc1centers", "pred_s1_pc2centers",
-                                             "pred_s2_pc1centers", "pred_s2_pc2centers", "gt_translations", "gt_angles",
-                                             "gt_pc1centers")}
-    loss_sum, t_exec = 0.0, []
+                                             "pred_s2_pc1centers", "pred_s2_pc2centers", "pred_s2_pc1angles",
+                                             "pred_s2_pc2angles", "gt_translations", "gt_angles", "gt_pc1centers")}
+    old = None
+    if use_old_results:                                          # train.py:421-424: predictions of an earlier run
+        old = {k: np.load(f"{base_eval_dir}/{k}.npy") for k in ("pred_translations", "pred_angles", "pred_s2_pc1centers")}
+    loss_sum, t_exec, num_full_batches = 0.0, [], 0
     for b in range(num_batches):
         chunk = list(val_idxs[b * bs:(b + 1) * bs])
         valid = len(chunk)
@@ -122,14 +143,23 @@ def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int, refine_i
         pa = eng.pred_angles(ep)
         torch.cuda.synchronize()
         t_exec.append((time.time() - t0) / bs)
-        loss_sum += float(loss[0].cpu())
+        if valid == bs:                                          # the padded last batch is not counted (train.py:459-460)
+            loss_sum += float(loss[0].cpu())
+            num_full_batches += 1
         pt, pang = ep["pred_translations"][:valid].cpu().numpy(), pa[:valid].cpu().numpy()
+        a1 = eng.decode_angles(ep["pred_pc1angle_logits"], False)[:valid].cpu().numpy()
+        a2 = eng.decode_angles(ep["pred_pc2angle_logits"], False)[:valid].cpu().numpy()
         centers = {k: ep[k][:valid].cpu().numpy() for k in ("pred_s1_pc1centers", "pred_s1_pc2centers", "pred_s2_pc1centers",
                                                             "pred_s2_pc2centers")}
         if refine_icp:                                           # train.py:463-484, the whole batch in one launch
             full1 = [np.load(f"{cfg.data.basepath}/pointcloud1/{str(i).zfill(8)}.npy")[:, :3] for i in chunk[:valid]]
             full2 = [np.load(f"{cfg.data.basepath}/pointcloud2/{str(i).zfill(8)}.npy")[:, :3] for i in chunk[:valid]]
-            inits = np.stack([icp.get_mat_angle(pt[i], float(pang[i]), centers["pred_s2_pc1centers"][i]) for i in range(valid)])
+            if old is not None:                                  # train.py:464-465
+                sl = slice(b * bs, b * bs + valid)
+                inits = np.stack([icp.get_mat_angle(old["pred_translations"][sl][i], float(np.ravel(old["pred_angles"][sl][i])[0]),
+                                                    old["pred_s2_pc1centers"][sl][i]) for i in range(valid)])
+            else:
+                inits = np.stack([icp.get_mat_angle(pt[i], float(pang[i]), centers["pred_s2_pc1centers"][i]) for i in range(valid)])
             t1 = time.time()
             refined, _ = icp.refine(full1, full2, inits, radius=0.1, its=int(its), device=str(eng.device))
             t_exec[-1] += (time.time() - t1) / max(valid, 1)
@@ -138,25 +168,31 @@ def eval_one_epoch(cfg, eng: E.Engine, val_idxs: List[int], epoch: int, refine_i
             centers["pred_s2_pc1centers"] = np.zeros_like(centers["pred_s2_pc1centers"])       # rotation about the origin now
         keep["pred_translations"].append(pt)
         keep["pred_angles"].append(pang[:, None])
+        keep["pred_s2_pc1angles"].append(a1[:, None])
+        keep["pred_s2_pc2angles"].append(a2[:, None])
         for k, v in centers.items():
             keep[k].append(v)
         keep["gt_translations"].append(batch["translations"][:valid].cpu().numpy())
         keep["gt_angles"].append(batch["rel_angles"][:valid].cpu().numpy())
         keep["gt_pc1centers"].append(batch["pc1_centers"][:valid].cpu().numpy())
-    arr = {k: np.concatenate(v, axis=0).astype(np.float64) for k, v in keep.items()}
+    arr = {k: np.concatenate(v, axis=0).astype(np.float32) for k, v in keep.items()}      # float32 like train.py:408-419
+    mean_time = float(np.sum(t_exec) * bs / max(len(val_idxs), 1))                        # train.py:502
+    if do_timings:                                               # train.py:504-505: the reference's benchmark harness
+        print(f"Timing bs={bs}: {mean_time}")
+        return {"mean_time": mean_time}
     is_test = _is_test(cfg, list(val_idxs))
     result = {}
     for inverted in (False, True):
         d = evaluation.evaluate(arr["pred_translations"], arr["pred_angles"], arr["gt_translations"], arr["gt_angles"],
-                                arr["pred_s2_pc1centers"], arr["gt_pc1centers"], is_test, inverted, float(np.mean(t_exec)),
+                                arr["pred_s2_pc1centers"], arr["gt_pc1centers"], is_test, inverted, mean_time,
                                 device=str(eng.device))
         with open(f'{eval_dir}/eval{"_180" if inverted else ""}.json', "w") as fh:
             json.dump(d, fh)
         result["eval_180" if inverted else "eval"] = d
     for k in ("pred_translations", "pred_angles", "pred_s1_pc1centers", "pred_s1_pc2centers", "pred_s2_pc1centers",
-              "pred_s2_pc2centers"):
+              "pred_s2_pc2centers", "pred_s2_pc1angles", "pred_s2_pc2angles"):                 # train.py:534-543
         np.save(f"{eval_dir}/{k}.npy", arr[k])
-    logger.info("val mean loss: %f" % (loss_sum / max(num_batches, 1)))
+    logger.info("val mean loss: %f" % (loss_sum / num_full_batches if num_full_batches > 0 else 0.0))   # train.py:501
     logger.info("val corr_levels %s (180: %s)" % (result["eval"]["corr_levels"], result["eval_180"]["corr_levels"]))
     return result
 
@@ -180,27 +216,52 @@ def main(argv=None) -> Dict:
     val_idxs = provider.get_data_files(f"{cfg.data.basepath}/split/val.txt")
     device = f"cuda:{local}"
     torch.cuda.set_device(local)
+    timings = cfg.evaluation.has("special") and cfg.evaluation.special.mode == "timings"
+    if timings:                                                  # train.py:553-559
+        cfg.training.__dict__["batch_size"] = 32
     eng = E.Engine(C.arch_from_config(cfg), device, flags.precision, seed=0)
     start_epoch = 0
     ckpt = f"{cfg.logging.logdir}/model.ckpt"
-    eval_only = flags.operation == "eval_only"
+    eval_only = flags.operation == "eval_only" or timings
+    nb_epoch = max(1, len(train_idxs) // cfg.training.batch_size)
     if eval_only:
-        path = f"{cfg.logging.logdir}/model-{int(flags.eval_epoch)}"
-        load_checkpoint(eng, path if os.path.isfile(path + ".index") else ckpt)
         start_epoch = int(flags.eval_epoch)
-    elif os.path.isfile(ckpt + ".index"):                        # resume (train.py:267-270)
+        if not flags.use_old_results and not timings:            # train.py:250-264
+            path = f"{cfg.logging.logdir}/model-{int(flags.eval_epoch)}"
+            if not os.path.isfile(path + ".index"):
+                raise FileNotFoundError(path + ".index")
+            load_checkpoint(eng, path)
+            if eng.step % nb_epoch != 0 or eng.step // nb_epoch - 1 != int(flags.eval_epoch):
+                raise ValueError(f"{path}: global step {eng.step} is not the end of epoch {flags.eval_epoch} "
+                                 f"({nb_epoch} batches per epoch)")
+        logger.info(f"Evaluating at epoch {start_epoch}")
+    elif os.path.isfile(ckpt + ".index"):                        # resume (train.py:267-275)
         load_checkpoint(eng, ckpt)
-        start_epoch = eng.step // max(1, len(train_idxs) // cfg.training.batch_size)
+        if eng.step % nb_epoch != 0:
+            raise ValueError(f"{ckpt}: global step {eng.step} is not a multiple of {nb_epoch} batches per epoch")
+        start_epoch = eng.step // nb_epoch
+        logger.info(f"Continuing training at epoch {start_epoch}")
+    elif cfg.training.pretraining.model != "":                   # train.py:276-293
+        pre = cfg.training.pretraining.model
+        if not os.path.isfile(pre + ".index"):
+            raise FileNotFoundError(pre + ".index")
+        load_checkpoint(eng, pre, restore_step=False)
+        assert eng.step == 0
+        logger.info(f"Pre-trained weights loaded from {pre}, starting initial evaluation")
+        if rank == 0:
+            eval_one_epoch(cfg, eng, val_idxs, "pretr")
+        logger.info("Initial evaluation finished")
     last = {}
     for epoch in range(start_epoch, cfg.training.num_epochs):
-        nb_epoch = max(1, len(train_idxs) // cfg.training.batch_size)
         logger.info("**** EPOCH %03d ****    lr: %.8f, bn_decay: %.8f" % (epoch, schedules.learning_rate(cfg, eng.step, nb_epoch),
                                                                            schedules.bn_decay(cfg, eng.step, nb_epoch)))
         if not eval_only:
             train_one_epoch(cfg, eng, train_idxs, epoch, rank, world)
         if rank == 0:
-            last = eval_one_epoch(cfg, eng, val_idxs, epoch, refine_icp=bool(flags.refineICP), its=int(flags.its),
-                                  icp_method=flags.refineICPmethod)
+            for _ in range(10 if timings else 1):                # train.py:305-307
+                last = eval_one_epoch(cfg, eng, val_idxs, epoch, refine_icp=bool(flags.refineICP), its=int(flags.its),
+                                      icp_method=flags.refineICPmethod, use_old_results=bool(flags.use_old_results),
+                                      do_timings=timings)
         if eval_only:
             break
         was_last = epoch == cfg.training.num_epochs - 1

@@ -28,8 +28,8 @@ def test_dp_gradients_and_parameters_agree_across_ranks():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
-    print(r.stdout[-4000:])
-    print(r.stderr[-4000:])
+    print(r.stdout[-6000:])
+    print(r.stderr[-2000:])
     assert r.returncode == 0
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     rep = json.loads(line)
