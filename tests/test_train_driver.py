@@ -46,6 +46,9 @@ def test_train_then_eval_only_round_trip(tmp_path):
                 "val/eval000001/eval_180.json", "val/eval000001/pred_translations.npy", "val/eval000001/pred_angles.npy",
                 "val/eval000001/pred_s2_pc1centers.npy"):
         assert (logdir / rel).exists(), rel
+    for k in ("pred_translations", "pred_angles", "pred_s2_pc1angles", "pred_s2_pc2angles", "pred_s1_pc2centers"):
+        a = np.load(logdir / f"val/eval000001/{k}.npy")          # train.py:408-419,534-543: float32, [n,3] / [n,1]
+        assert a.dtype == np.float32 and a.shape[0] == 6, (k, a.dtype, a.shape)
     d = json.load(open(logdir / "val/eval000001/eval.json"))
     assert d["num"] == 6 and set(d) >= {"corr_levels", "eval_5m", "val", "test", "reg_eval", "mean_time"}
     assert last["eval"]["num"] == 6
@@ -76,3 +79,54 @@ def test_train_then_eval_only_round_trip(tmp_path):
     assert (rdir / "eval.json").exists() and ref["eval"]["num"] == 6
     assert not np.load(rdir / "pred_s2_pc1centers.npy").any()
     assert np.isfinite(np.load(rdir / "pred_translations.npy")).all() and np.isfinite(np.load(rdir / "pred_angles.npy")).all()
+
+    # eval_only asserts that the requested epoch's checkpoint exists (train.py:251) instead of falling back
+    C.reset_config()
+    with pytest.raises(FileNotFoundError):
+        train.main(["eval_only", "--config", cfg_path, "--eval_epoch", "7", "--precision", "fp32"])
+    # --use_old_results (train.py:421-424,464-465): ICP seeded from the stored predictions, no checkpoint needed
+    C.reset_config()
+    np.random.seed(11)
+    old = train.main(["eval_only", "--config", cfg_path, "--eval_epoch", "1", "--precision", "fp32", "--refineICP", "--use_old_results"])
+    assert old["eval"]["num"] == 6
+
+    # pre-training restore (train.py:276-293): all variables but the global step, then an initial evaluation
+    cfg = json.load(open(cfg_path))
+    cfg["training"]["pretraining"] = {"model": str(logdir / "model-1")}
+    cfg["training"]["num_epochs"] = 1
+    pre_path = tmp_path / "TinyPre.json"
+    pre_path.write_text(json.dumps(cfg))
+    C.reset_config()
+    np.random.seed(5)
+    train.main(["train", "--config", str(pre_path), "--precision", "fp32"])
+    pre_dir = tmp_path / "logs" / "TinyPre"
+    assert (pre_dir / "val/eval0pretr/eval.json").exists()                                 # 'pretr'.zfill(6)
+    first_eval = np.load(pre_dir / "val/eval0pretr/pred_translations.npy")
+    assert np.abs(first_eval - pred_a).max() < 0.2                                         # the restored weights, not a fresh init
+    assert int(tf_checkpoint.read_checkpoint(str(pre_dir / "model-0"))["Variable"]) == 3   # the step restarted at 0
+    cfg["training"]["pretraining"] = {"model": str(tmp_path / "nope")}
+    pre_path.write_text(json.dumps(cfg))
+    C.reset_config()
+    shutil.rmtree(pre_dir)
+    with pytest.raises(FileNotFoundError):
+        train.main(["train", "--config", str(pre_path), "--precision", "fp32"])
+
+    # the reference's own benchmark harness (train.py:553-559): batch 32, no restore, ten passes, seconds per pair
+    cfg = json.load(open(cfg_path))
+    cfg["evaluation"] = {"special": {"mode": "timings"}}
+    t_path = tmp_path / "TinyTimings.json"
+    t_path.write_text(json.dumps(cfg))
+    C.reset_config()
+    res = train.main(["eval_only", "--config", str(t_path), "--precision", "bf16"])
+    assert res["mean_time"] > 0
+    # what the engine does not implement is rejected, not ignored
+    for bad in ({"evaluation": {"special": {"mode": "icp"}}}, {"training": {"optimizer": {"optimizer": "momentum"}}}):
+        cfg = json.load(open(cfg_path))
+        for k, v in bad.items():
+            cfg.setdefault(k, {}).update(v)
+        b_path = tmp_path / "TinyBad.json"
+        b_path.write_text(json.dumps(cfg))
+        C.reset_config()
+        with pytest.raises(ValueError):
+            train.main(["train", "--config", str(b_path), "--precision", "fp32"])
+    C.reset_config()
