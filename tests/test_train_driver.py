@@ -98,11 +98,15 @@ def test_train_then_eval_only_round_trip(tmp_path):
     pre_path.write_text(json.dumps(cfg))
     C.reset_config()
     np.random.seed(5)
+    train.main(["eval_only", "--config", cfg_path, "--eval_epoch", "1", "--precision", "fp32"])
+    want = np.load(logdir / "val/eval000001/pred_translations.npy")      # model-1's predictions under this seed's resampling draws
+    C.reset_config()
+    np.random.seed(5)
     train.main(["train", "--config", str(pre_path), "--precision", "fp32"])
     pre_dir = tmp_path / "logs" / "TinyPre"
     assert (pre_dir / "val/eval0pretr/eval.json").exists()                                 # 'pretr'.zfill(6)
     first_eval = np.load(pre_dir / "val/eval0pretr/pred_translations.npy")
-    assert np.abs(first_eval - pred_a).max() < 0.2                                         # the restored weights, not a fresh init
+    np.testing.assert_allclose(first_eval, want, atol=1e-4)                                # the restored weights, not a fresh init
     assert int(tf_checkpoint.read_checkpoint(str(pre_dir / "model-0"))["Variable"]) == 3   # the step restarted at 0
     cfg["training"]["pretraining"] = {"model": str(tmp_path / "nope")}
     pre_path.write_text(json.dumps(cfg))
