@@ -34,6 +34,11 @@ namespace convfwd {
 using namespace umma;
 
 constexpr int kThreads = 576;          // warps 0-3 / 10-13 back-end, 4-7 / 14-17 front-end, 8 MMA, 9 weight loader
+// Back-end warps per TMEM lane quarter.  The max-reduction is ALU-pipe bound (LOP3 and FMNMX3 issue at half rate; the
+// microbenchmark drains 112 columns in 621 cycles with 8 warps and in 490 with 16), but a third warp per quarter
+// (704 threads, register cap 80 instead of 96, spills in the front end) made the kernel SLOWER on B200:
+// 1.114 -> 1.212 ms per c3 step.  Two it is.
+constexpr int kBackWarpsPerQuarter = 2;
 constexpr int kFrontThreads = 256;
 constexpr int kMaxPC = 256;            // points per item
 constexpr uint32_t kW2Bytes = 128 * 64 * 2;
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       mbar_init(&bars->a2_full[i], kFrontThreads);
       mbar_init(&bars->a2_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1);
-      mbar_init(&bars->acc_empty[i], 256);
+      mbar_init(&bars->acc_empty[i], kBackWarpsPerQuarter * 128);
     }
     fence_barrier_init();
   }
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if ((warp >= 4 && warp < 8) || warp >= 14) {
+  if ((warp >= 4 && warp < 8) || (warp >= 14 && warp < 18)) {
     // ================================ front-end ================================
     // 8 warps.  Layer 1: warp g owns channels 8g..8g+7 for all points.  Layer-2 epilogue: warp (quarter, half)
     // reads TMEM lanes [32 quarter, +32) = points of a 128-point tile, and 64 of the 128 channel columns.
@@ -331,9 +336,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     if (save_a2 && f == 0) bulk_wait_read_all();
   } else if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ================================ back-end =================================
-    // two warps per TMEM lane quarter (warps w and w+10 with equal w%4): the 16-column groups of every
-    // accumulator half are dealt alternately to the two, which halves the latency of draining a half --
-    // the MMA thread can only refill a half once it is drained.
+    // kBackWarpsPerQuarter warps per TMEM lane quarter (warps with equal w%4): the 16-column groups of every accumulator
+    // half are dealt round-robin to them -- the MMA thread can only refill a half once it is drained.
     const int bgroup = warp < 4 ? 0 : 1;
     const int e = (warp & 3) * 32 + lane;          // channel within the 128-channel chunk
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -358,17 +362,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           const int off = h ? N0 : 0;
           const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
           // software pipeline: the load of the next group is in flight while this one is reduced
+          constexpr int kStride = 16 * kBackWarpsPerQuarter;
           uint32_t ra[16], rb[16];
           int g16 = bgroup * 16;
           if (g16 < nh) tmem_ld16(tbase + g16, ra);
-          for (; g16 < nh; g16 += 64) {
+          for (; g16 < nh; g16 += 2 * kStride) {
             tmem_ld_wait();
-            const int g2 = g16 + 32;
+            const int g2 = g16 + kStride;
             if (g2 < nh) tmem_ld16(tbase + g2, rb);
             reduce_group<MODE>(ra, off + g16, nvalid, p0, keep_mask, not15, m);
             if (g2 < nh) {
               tmem_ld_wait();
-              if (g2 + 32 < nh) tmem_ld16(tbase + g2 + 32, ra);
+              if (g2 + kStride < nh) tmem_ld16(tbase + g2 + kStride, ra);
               reduce_group<MODE>(rb, off + g2, nvalid, p0, keep_mask, not15, m);
             }
           }
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           mbar_arrive(&bars->acc_empty[h]);
         }
         uint32_t* zp = P.zext + (size_t)I.cloud * C3 + j * 128 + e;
-        // the two warps of a lane quarter hold partial maxima of the same channel: always combine atomically
+        // the warps of a lane quarter hold partial maxima of the same channel: always combine atomically
         atomicMax(zp, to_ordered(__float_as_uint(m)));   // zext pre-zeroed
       }
     }
