@@ -293,6 +293,24 @@ __global__ void assemble_s2_grad_kernel(const float* dlg, const float* dc2, cons
 
 }  // namespace
 
+// the two branches of a conv stage backward: independent (their own scratch, parameter gradients accumulate with
+// reductions), so branch 1 runs on the side stream and its ~8 small launches hide under branch 0's persistent kernels
+template <typename F>
+static int two_branches(cudaStream_t st, F&& run) {
+  SideStream* ss = two_streams_enabled() ? side_stream() : nullptr;
+  if (!ss) {
+    AN3D_TRY(run(0, st));
+    return run(1, st);
+  }
+  AN3D_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+  AN3D_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  const int r0 = run(0, st);
+  const int r1 = run(1, ss->stream);
+  AN3D_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));      // always join: a capture must not end with a dangling fork
+  AN3D_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
+  return r0 != AN3D_OK ? r0 : r1;
+}
+
 int backward_impl(const Model& m, const float* params, const float* pcs1, const float* pcs2, const an3d_labels* labels,
                   const an3d_outputs* out, int B, int N, int flags, float* grads, float* loss_out, void* workspace,
                   int64_t workspace_bytes, cudaStream_t st) {
@@ -330,23 +348,25 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
     const int c2w = m.conv[S2].back().cout, c1w = m.conv[S1].back().cout;
     float* const dO[2] = {p.dout, p.dout_b};
     float* const dGs[2] = {p.dg, p.dg_b};
-    for (int br = 0; br < 2; ++br) {
-      AN3D_CUDA_CHECK(cudaMemsetAsync(p.dang[br], 0, sizeof(float) * B, st));
+    AN3D_TRY(two_branches(st, [&](int br, cudaStream_t s2) -> int {
+      AN3D_CUDA_CHECK(cudaMemsetAsync(p.dang[br], 0, sizeof(float) * B, s2));
       AN3D_TRY(conv_stack_backward_bf16(m, p, EMB, br, pcs[br], c2o[br], p.ang[br], p.dfeat + (int64_t)br * c_emb,
-                                        2 * c_emb, params, grads, true, p.dc2[br], p.dang[br], st));
-      assemble_s2_grad_kernel<<<w_blocks, 128, 0, st>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], dO[br],
+                                        2 * c_emb, params, grads, true, p.dc2[br], p.dang[br], s2));
+      assemble_s2_grad_kernel<<<w_blocks, 128, 0, s2>>>(dlg[br], p.dc2[br], p.dang[br], p.angk[br], ds1c[br], dO[br],
                                                         p.dc1[br], B, nb);
       AN3D_LAUNCH_CHECK();
-    }
+      return AN3D_OK;
+    }));
     {
       const float* x[2] = {p.g[S2][0], p.g[S2][1]};
       const float* dOut[2] = {dO[0], dO[1]};
       const float* mk[2] = {masks[2], masks[3]};
       AN3D_TRY(mlp_backward_pair(m, p, S2, x, c2w, dOut, params, grads, dGs, c2w, mk, st));
     }
-    for (int br = 0; br < 2; ++br)
-      AN3D_TRY(conv_stack_backward_bf16(m, p, S2, br, pcs[br], c1o[br], nullptr, dGs[br], c2w, params, grads, true,
-                                        p.dc1[br], nullptr, st));
+    AN3D_TRY(two_branches(st, [&](int br, cudaStream_t s2) -> int {
+      return conv_stack_backward_bf16(m, p, S2, br, pcs[br], c1o[br], nullptr, dGs[br], c2w, params, grads, true, p.dc1[br],
+                                      nullptr, s2);
+    }));
     {
       // stage 1: d(delta1) = dc1 (tp8.py:109); its input p - mean(p) carries no parameter gradient
       const float* x[2] = {p.g[S1][0], p.g[S1][1]};
@@ -354,9 +374,10 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
       const float* mk[2] = {masks[0], masks[1]};
       AN3D_TRY(mlp_backward_pair(m, p, S1, x, c1w, dOut, params, grads, dGs, c1w, mk, st));
     }
-    for (int br = 0; br < 2; ++br)
-      AN3D_TRY(conv_stack_backward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, dGs[br], c1w, params, grads, false,
-                                        nullptr, nullptr, st));
+    AN3D_TRY(two_branches(st, [&](int br, cudaStream_t s2) -> int {
+      return conv_stack_backward_bf16(m, p, S1, br, pcs[br], p.mu[br], nullptr, dGs[br], c1w, params, grads, false, nullptr,
+                                      nullptr, s2);
+    }));
     return AN3D_OK;
   }
   for (int br = 0; br < 2; ++br) {

@@ -133,7 +133,8 @@ __global__ void wgrad3_dense_kernel(const float* gw, const double* sa2, const fl
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128 * C3) return;
   const int k = i / C3, c = i - k * C3;
-  gW3[i] += (float)sa2[k] * coef3[C3 + c] + coef3[c] * gw[i];
+  // (a reduction, not `+=`: the other branch's kernels and the sparse part T1 add into the same weights concurrently)
+  atomicAdd(gW3 + i, (float)sa2[k] * coef3[C3 + c] + coef3[c] * gw[i]);
 }
 
 // BN backward coefficients of layers 2 / 1 from (sum dy, sum dy*xhat)
@@ -264,6 +265,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
                              const float* angle, const float* dG, int64_t lddg, const float* params, float* grads,
                              bool want_input_grad, float* dcenter, float* dangle, cudaStream_t st) {
   const PlanBf16& q = p.bf;
+  const BwdScratch& w = q.bw[br];
   const int B = p.B, N = p.N;
   const int64_t M = p.M;
   const Lin &L1 = m.conv[s][0], &L2 = m.conv[s][1], &L3 = m.conv[s][2];
@@ -283,23 +285,23 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
   const int64_t ldg = s == EMB ? 2 * C3 : C3;
 
   // ---- layer 3: pooled gradient -> BN3 coefficients ----
-  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red3, 0, 2 * (size_t)C3 * sizeof(double), st));
-  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red2, 0, 256 * sizeof(double), st));
-  AN3D_CUDA_CHECK(cudaMemsetAsync(q.red1, 0, 128 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(w.red3, 0, 2 * (size_t)C3 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(w.red2, 0, 256 * sizeof(double), st));
+  AN3D_CUDA_CHECK(cudaMemsetAsync(w.red1, 0, 128 * sizeof(double), st));
   {
     const int bchunk = 16;
     dim3 grid((C3 + 127) / 128, (B + bchunk - 1) / bchunk);
     pool_bwd_prep_kernel<<<grid, 128, 0, st>>>(dG, lddg, p.g[s][br], ldg, q.zext[s][br], B, C3, gamma3, params + L3.b, mean3,
-                                               inv3, q.idx_mask, q.dyext, q.red3, bchunk);
+                                               inv3, q.idx_mask, w.dyext, w.red3, bchunk);
     AN3D_LAUNCH_CHECK();
-    bwd3_coeff_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(q.red3, C3, (double)M, sc3, inv3, mean3, params + L3.b,
-                                                        grads + poff(L3.bn), grads + poff(L3.bn) + C3, q.coef3);
+    bwd3_coeff_kernel<<<(C3 + 127) / 128, 128, 0, st>>>(w.red3, C3, (double)M, sc3, inv3, mean3, params + L3.b,
+                                                        grads + poff(L3.bn), grads + poff(L3.bn) + C3, w.coef3);
     AN3D_LAUNCH_CHECK();
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.gq_f32, 0, 128 * 128 * sizeof(float), st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(q.uvec, 0, 128 * sizeof(float), st));
-    gq_partial_kernel<<<dim3(4, 4, C3 / 64), 256, 0, st>>>(params + L3.w, q.coef3, C3, q.gq_f32, q.uvec);
+    AN3D_CUDA_CHECK(cudaMemsetAsync(w.gq_f32, 0, 128 * 128 * sizeof(float), st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(w.uvec, 0, 128 * sizeof(float), st));
+    gq_partial_kernel<<<dim3(4, 4, C3 / 64), 256, 0, st>>>(params + L3.w, w.coef3, C3, w.gq_f32, w.uvec);
     AN3D_LAUNCH_CHECK();
-    gq_pack_kernel<<<64, 256, 0, st>>>(q.gq_f32, q.gq);
+    gq_pack_kernel<<<64, 256, 0, st>>>(w.gq_f32, w.gq);
     AN3D_LAUNCH_CHECK();
   }
   // ---- wgrad3: sparse part + Gram on the tensor cores, dense correction on CUDA cores ----
@@ -309,7 +311,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     // sparse part T1 = A2^T S: gather-scale-accumulate on CUDA cores (1/N of the dense FLOPs)
     convbwd::T1Params T;
     T.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); T.img_bytes = (uint32_t)q.img_bytes;
-    T.gidx = p.gidx[s][br]; T.dyext = q.dyext; T.s3 = sc3; T.B = B; T.N = N;
+    T.gidx = p.gidx[s][br]; T.dyext = w.dyext; T.s3 = sc3; T.B = B; T.N = N;
     T.PC = q.PC; T.npc = q.npc; T.C3 = C3; T.n_items = n_items; T.t1 = grads + L3.w;
     // 1024 resident threads per SM: one CTA of 1024 channels, or two of <= 512
     const int tr = std::max(1, std::min(n_items, (sms / 4) * (C3 <= 512 ? 2 : 1)));
@@ -319,16 +321,16 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     convbwd::t1_sparse_kernel<<<dim3(tr, 4), convbwd::t1_threads(C3), tsmem, st>>>(T);
     prof_mark(PROF_BWD_T1, false, st);
     AN3D_LAUNCH_CHECK();
-    wgrad3_dense_kernel<<<(128 * C3 + 255) / 256, 256, 0, st>>>(q.gw[s][br], q.sa2[s][br], q.coef3, C3, grads + L3.w);
+    wgrad3_dense_kernel<<<(128 * C3 + 255) / 256, 256, 0, st>>>(q.gw[s][br], q.sa2[s][br], w.coef3, C3, grads + L3.w);
     AN3D_LAUNCH_CHECK();
   }
   // ---- dgrad3 -> dy2 images + BN2 backward sums ----
   {
     convbwd::Dg3Params D;
-    D.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); D.dy2_img = reinterpret_cast<uint8_t*>(q.dy2img);
-    D.img_bytes = (uint32_t)q.img_bytes; D.gidx = p.gidx[s][br]; D.dyext = q.dyext; D.s3 = sc3; D.gq_img = q.gq;
-    D.w3n_img = q.w3n[s]; D.uvec = q.uvec; D.gamma2 = gamma2; D.beta2 = beta2; D.B = B; D.N = N; D.PC = q.PC; D.npc = q.npc;
-    D.C3 = C3; D.n_items = n_items; D.red2 = q.red2;
+    D.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); D.dy2_img = reinterpret_cast<uint8_t*>(w.dy2img);
+    D.img_bytes = (uint32_t)q.img_bytes; D.gidx = p.gidx[s][br]; D.dyext = w.dyext; D.s3 = sc3; D.gq_img = w.gq;
+    D.w3n_img = q.w3n[s]; D.uvec = w.uvec; D.gamma2 = gamma2; D.beta2 = beta2; D.B = B; D.N = N; D.PC = q.PC; D.npc = q.npc;
+    D.C3 = C3; D.n_items = n_items; D.red2 = w.red2;
     const int grid = std::min(n_items, sms);
     D.items_per_cta = (n_items + grid - 1) / grid;
     const size_t smem = convbwd::dg3_smem_bytes(q.PC);
@@ -338,20 +340,20 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     convbwd::dgrad3_kernel<<<grid, convbwd::kDg3Threads, smem, st>>>(D);
     prof_mark(PROF_BWD_DGRAD3, false, st);
     AN3D_LAUNCH_CHECK();
-    bn_bwd_coeff_kernel<<<1, 128, 0, st>>>(q.red2, 128, (double)M, grads + poff(L2.bn), grads + poff(L2.bn) + 128, q.coef2);
+    bn_bwd_coeff_kernel<<<1, 128, 0, st>>>(w.red2, 128, (double)M, grads + poff(L2.bn), grads + poff(L2.bn) + 128, w.coef2);
     AN3D_LAUNCH_CHECK();
   }
   // ---- layer 2 backward -> wgrad2, dy1 + BN1 backward sums ----
   {
     convbwd::L2Params P2;
-    P2.pcs = pcs; P2.center = center; P2.angle = angle; P2.dy2_img = reinterpret_cast<const uint8_t*>(q.dy2img);
+    P2.pcs = pcs; P2.center = center; P2.angle = angle; P2.dy2_img = reinterpret_cast<const uint8_t*>(w.dy2img);
     P2.img_bytes = (uint32_t)q.img_bytes; P2.B = B; P2.N = N; P2.PC = q.PC; P2.npc = q.npc; P2.n_items = n_items;
     const int grid = std::min(n_items, sms);
     P2.items_per_cta = (n_items + grid - 1) / grid;
     P2.w1f = q.w1f[s][br]; P2.c1f = q.c1f[s][br]; P2.W1 = params + L1.w; P2.b1 = params + L1.b; P2.mean1 = mean1;
     P2.inv1 = inv1; P2.gamma1 = gamma1; P2.beta1 = beta1; P2.w2t_img = q.w2t[s]; P2.w2p_img = q.w2p[s];
-    P2.b2 = params + L2.b; P2.mean2 = mean2; P2.inv2 = inv2; P2.s2 = sc2; P2.coef2 = q.coef2; P2.gW2 = grads + L2.w;
-    P2.l1sums = q.l1sums; P2.red1 = q.red1;
+    P2.b2 = params + L2.b; P2.mean2 = mean2; P2.inv2 = inv2; P2.s2 = sc2; P2.coef2 = w.coef2; P2.gW2 = grads + L2.w;
+    P2.l1sums = w.l1sums; P2.red1 = w.red1;
     const size_t smem = convbwd::l2_smem_bytes(q.PC);
     if (smem > (size_t)kMaxSmem) { set_error("bwd_l2 tile too large"); return AN3D_ERR_UNSUPPORTED; }
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::bwd_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -359,14 +361,14 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     convbwd::bwd_l2_kernel<<<grid, convbwd::kL2Threads, smem, st>>>(P2);
     prof_mark(PROF_BWD_L2, false, st);
     AN3D_LAUNCH_CHECK();
-    bn_bwd_coeff_kernel<<<1, 64, 0, st>>>(q.red1, 64, (double)M, grads + poff(L1.bn), grads + poff(L1.bn) + 64, q.coef1);
+    bn_bwd_coeff_kernel<<<1, 64, 0, st>>>(w.red1, 64, (double)M, grads + poff(L1.bn), grads + poff(L1.bn) + 64, w.coef1);
     AN3D_LAUNCH_CHECK();
   }
   // ---- layer 1 backward (CUDA cores) ----
   {
     const int ipb = std::max(1, (n_items + 4 * sms - 1) / (4 * sms));     // ~4 blocks per SM, wgrad1 atomics once per block
-    bwd_l1_finish_kernel<<<(n_items + ipb - 1) / ipb, 256, 0, st>>>(pcs, center, angle, q.l1sums, N, q.PC, q.npc, n_items, ipb,
-                                                                  params + L1.w, params + L1.b, mean1, inv1, sc1, q.coef1,
+    bwd_l1_finish_kernel<<<(n_items + ipb - 1) / ipb, 256, 0, st>>>(pcs, center, angle, w.l1sums, N, q.PC, q.npc, n_items, ipb,
+                                                                  params + L1.w, params + L1.b, mean1, inv1, sc1, w.coef1,
                                                                   grads + L1.w, dcenter, dangle, want_input_grad ? 1 : 0);
     AN3D_LAUNCH_CHECK();
   }

@@ -388,19 +388,21 @@ void plan_bf16(const Model& m, int B, int N, int flags, Arena& a, PlanBf16* q) {
       q->w3n[s] = a.take<__nv_bfloat16>((int64_t)C3 * 128);
       q->w2p[s] = a.take<__nv_bfloat16>(128 * 128);
     }
-    q->dyext = a.take<float>((int64_t)B * c3max);
-    q->red3 = a.take<double>(2 * c3max);
-    q->coef3 = a.take<float>(4 * c3max);
-    q->gq = a.take<__nv_bfloat16>(128 * 128);
-    q->gq_f32 = a.take<float>(128 * 128);
-    q->uvec = a.take<float>(128);
-    q->t1 = a.take<float>(128 * c3max);
-    q->dy2img = a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2));
-    q->red2 = a.take<double>(256);
-    q->coef2 = a.take<float>(256);
-    q->l1sums = a.take<float>((int64_t)B * q->npc * 256);
-    q->red1 = a.take<double>(128);
-    q->coef1 = a.take<float>(128);
+    for (int br = 0; br < 2; ++br) {
+      BwdScratch& w = q->bw[br];
+      w.dyext = a.take<float>((int64_t)B * c3max);
+      w.red3 = a.take<double>(2 * c3max);
+      w.coef3 = a.take<float>(4 * c3max);
+      w.gq = a.take<__nv_bfloat16>(128 * 128);
+      w.gq_f32 = a.take<float>(128 * 128);
+      w.uvec = a.take<float>(128);
+      w.dy2img = a.take<__nv_bfloat16>((int64_t)B * q->npc * (q->img_bytes / 2));
+      w.red2 = a.take<double>(256);
+      w.coef2 = a.take<float>(256);
+      w.l1sums = a.take<float>((int64_t)B * q->npc * 256);
+      w.red1 = a.take<double>(128);
+      w.coef1 = a.take<float>(128);
+    }
   }
 }
 

@@ -124,6 +124,22 @@ struct BnScratch {
 
 // Extra buffers of the bf16 tcgen05 path (conv stacks); FC layers, loss and the inter-stage
 // glue reuse the PlanF32 buffers.
+// Backward scratch of ONE siamese branch (the two branches of a stage run on two streams, so each has its own).
+struct BwdScratch {
+  float* dyext = nullptr;                   // [B, C3max] gradient at the pooled arg rows (after the ReLU mask)
+  double* red3 = nullptr;                   // [2][C3max] sum dy, sum dy*xhat of layer 3
+  float* coef3 = nullptr;                   // [4][C3max]: q, p', (unused), (unused)
+  __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
+  float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
+  float* uvec = nullptr;                    // [128]
+  __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
+  double* red2 = nullptr;                   // [128][2]
+  float* coef2 = nullptr;                   // [128][2]  m0, m1
+  float* l1sums = nullptr;                  // [items][64][4]: sum_p dy1 * (1, x, y, z) per item and channel
+  double* red1 = nullptr;                   // [64][2]
+  float* coef1 = nullptr;                   // [64][2]
+};
+
 constexpr int kMaxParts1 = 640, kMaxParts = 160;   // CTAs of the statistics / Gram passes (>= SMs x CTAs per SM)
 
 struct PlanBf16 {
@@ -145,23 +161,11 @@ struct PlanBf16 {
   int64_t img_bytes = 0;                    // bytes of one item image (16 planes)
   double* sa2[3][2];                        // column sums of a2 [128]
   // ---- backward scratch (training) ----
+  BwdScratch bw[2];                         // per branch
   __nv_bfloat16* w3n[3];                    // W3 (unfolded) half-chunk images [C3/64][128 k][64 c], K-major in c
   __nv_bfloat16* w2p[3];                    // W2 padded to 128 rows, image [128 k1][128 k2]
-  float* dyext = nullptr;                   // [B, C3max] gradient at the pooled arg rows (after the ReLU mask)
-  double* red3 = nullptr;                   // [2][C3max] sum dy, sum dy*xhat of layer 3
-  float* coef3 = nullptr;                   // [4][C3max]: q, p', (unused), (unused)
-  __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
-  float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
-  float* uvec = nullptr;                    // [128]
   float* gram[3][2];                        // [128][128] a2^T a2 per (stage, branch): BN3 statistics and wgrad3
   float* gw[3][2];                          // [128][C3] gram * W3 (bf16-rounded weights), forward -> backward
-  float* t1 = nullptr;                      // [128][C3max] sparse part of wgrad3 (16-byte aligned scratch)
-  __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
-  double* red2 = nullptr;                   // [128][2]
-  float* coef2 = nullptr;                   // [128][2]  m0, m1
-  float* l1sums = nullptr;                  // [items][64][4]: sum_p dy1 * (1, x, y, z) per item and channel
-  double* red1 = nullptr;                   // [64][2]
-  float* coef1 = nullptr;                   // [64][2]
 };
 
 // Workspace plan of the fp32 (parity) path: everything the backward needs is materialised.
@@ -210,6 +214,15 @@ struct Ctx {
 };
 
 int check_device();
+
+// The two siamese branches of a stage on two streams (forward_f32.cu): fork / join with events, legal inside a capture.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream* side_stream();
+bool two_streams_enabled();
 
 }  // namespace an3d
 

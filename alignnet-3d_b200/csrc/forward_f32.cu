@@ -41,12 +41,7 @@ static BnView bn_view(const Model& m, const PlanF32& p, const float* params, flo
 // branch) can run under the other branch's persistent kernels, which leave threads and registers free on every SM.
 // Fork / join with events, so the pattern is also legal inside a stream capture.  The side stream and events are
 // created on first use: run one eager step before capturing a graph (Engine._capture does).
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
-};
-static SideStream* side_stream() {
+SideStream* side_stream() {
   static SideStream per_device[16];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
@@ -61,7 +56,7 @@ static SideStream* side_stream() {
 }
 // Per-kernel profiling (an3d_profile_begin) serialises the branches: an event pair around a kernel that shares the
 // device with the other branch's kernels would time the overlap, not the kernel.
-static bool two_streams_enabled() {
+bool two_streams_enabled() {
   static const bool on = [] {
     const char* e = getenv("AN3D_TWO_STREAMS");
     return !(e != nullptr && e[0] == '0');
