@@ -109,16 +109,17 @@ def main():
                 gs.append(local_grad(rep, shards[r], seed=100 + t))
             solo.grads.copy_(torch.stack(gs).sum(0))
             solo.adam_step(1e-3, grad_scale=1.0 / world)
-        # The two computations differ only through the backward's fp32 reductions (~1e-3 of the largest gradient
-        # element, tests/test_gpu_determinism.py).  Adam's first updates are sign-like (m / sqrt(v) = +-1 at t = 1), so a
-        # gradient element at that noise level can move its weight by +lr here and -lr there: the bound is 2 lr per
-        # step for any weight, and all but a small fraction of the weights agree to 1e-5.
-        diff = (solo.params - p_dp).abs()
-        d, frac = float(diff.max()), float((diff > 1e-5).float().mean())
-        moved = float((solo.params - fresh().params).abs().max())
-        report["dp_vs_replicas_params_max_abs"], report["dp_vs_replicas_frac_above_1e-5"] = d, frac
-        report["params_moved_max_abs"] = moved
-        assert d <= 2 * K * 1e-3 * 1.05 and frac <= 0.05 and moved > 1e-3, (d, frac, moved)
+        # The two computations differ only through the backward's fp32 reductions (1e-3 of the LARGEST gradient element,
+        # tests/test_gpu_determinism.py -- i.e. tens of percent of a typical small one).  Adam normalises every element,
+        # so small, noisy elements move their weights by comparable amounts in slightly different directions: the
+        # bounds are 2 lr per step for any weight and the direction of the whole K-step update (measured: cos 0.99).
+        p0 = fresh().params
+        u_solo, u_dp = (solo.params - p0).double(), (p_dp - p0).double()
+        d = float((u_solo - u_dp).abs().max())
+        cos = float(torch.dot(u_solo, u_dp) / (u_solo.norm() * u_dp.norm()))
+        report["dp_vs_replicas_params_max_abs"], report["dp_vs_replicas_update_cos"] = d, cos
+        report["params_moved_max_abs"] = float(u_solo.abs().max())
+        assert d <= 2 * K * 1e-3 * 1.05 and cos >= 0.9 and float(u_solo.abs().max()) > 1e-3, (d, cos)
         print(json.dumps(report))
     dist.barrier()
     dist.destroy_process_group()
