@@ -4,7 +4,7 @@
 
 #include "kernels_f32.cuh"
 #include "bf16_path.cuh"
-#include "fc_gemm_bf16.cuh"
+#include "fc2_gemm.cuh"
 
 namespace an3d {
 
@@ -140,107 +140,84 @@ static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, c
   return AN3D_OK;
 }
 
-// get_mlp (models/tp8.py:75-82).  x: [B, cin] with leading dim ldx, already activated.
-static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const float* x, int64_t ldx, const float* params,
-                       float* state, bool training, float decay, const float* mask, cudaStream_t st) {
-  const bool head = s == HEAD;
-  const float *psc = nullptr, *psh = nullptr;
-  const size_t nl = m.fc[s].size();
-  for (size_t l = 0; l < nl; ++l) {
-    const Lin& L = m.fc[s][l];
-    GemmArgs g;
-    g.A = x; g.lda = ldx; g.B = params + L.w; g.ldb = L.cout; g.C = p.fz[s][l][br]; g.ldc = L.cout;
-    g.M = p.B; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
-    if (l == nl - 1 && training && mask) {
-      g.pro_mask = mask;
-      g.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
+// bf16 mode: the weight images of every FC layer, once per forward (fc2_gemm.cuh); the backward reuses them
+static int pack_fc_weights(const Model& m, const PlanF32& p, const float* params, cudaStream_t st) {
+  for (int s = 0; s < 3; ++s)
+    for (size_t l = 0; l < m.fc[s].size(); ++l) {
+      const Lin& L = m.fc[s][l];
+      fc2::PackArgs a;
+      a.src = params + L.w; a.ld = L.cout; a.rows = L.cin; a.cols = L.cout; a.dst = p.fcw[s][l];
+      AN3D_TRY(fc2::pack(a, st));
     }
-    fcgemm::Params f;
-    f.A = g.A; f.lda = g.lda; f.a_mn = 0; f.B = g.B; f.ldb = g.ldb; f.b_mn = 1; f.C = g.C; f.ldc = g.ldc;
-    f.M = g.M; f.N = g.N; f.K = g.K; f.bias = g.bias; f.pro_scale = g.pro_scale; f.pro_shift = g.pro_shift;
-    f.pro_mask = g.pro_mask; f.pro_mask_scale = g.pro_mask_scale; f.ksplit = 1; f.accumulate = 0;
-    bool fused_stats = false;
-    if (p.bf16 && fcgemm::usable(f)) {
-      if (L.bn >= 0 && training) {   // column sums of z and z^2 come out of the GEMM epilogue
-        BnView v = bn_view(m, p, params, state, head, br, L.bn);
-        f.stat_sum = v.acc0;
-        f.stat_sq = v.acc1;
-        fused_stats = true;
-      }
-      // few output tiles (inference batches): split K so that the launch fills the SMs.  Never in training mode and
-      // not under AN3D_DETERMINISTIC: the K slices meet in fp32 reductions, whose order is not reproducible.
-      if (!fused_stats && !training && !p.deterministic) {
-        const int tiles = ((f.M + 127) / 128) * ((f.N + 127) / 128);
-        const int ks = std::min(f.K / 128, 148 / tiles);
-        if (ks > 1) {
-          f.ksplit = ks;
-          AN3D_CUDA_CHECK(cudaMemsetAsync(f.C, 0, sizeof(float) * (size_t)f.M * f.ldc, st));
-        }
-      }
-      AN3D_TRY(fcgemm::launch(f, st));
-    } else {
-      AN3D_TRY(launch_gemm(g, false, false, st));
-    }
-    if (L.bn >= 0) {
-      BnView v = bn_view(m, p, params, state, head, br, L.bn);
-      if (fused_stats) {
-        bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
-                                                                    v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
-        AN3D_LAUNCH_CHECK();
-      } else if (!p.prepared) {
-        AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
-      }
-      psc = v.scale;
-      psh = v.shift;
-    }
-    x = p.fz[s][l][br];
-    ldx = L.cout;
-  }
   return AN3D_OK;
 }
 
-// get_mlp for BOTH siamese branches of stage s in the bf16 mode: every layer is one launch of the tcgen05 GEMM with
-// the two branches as a batch of two problems (same weights; their own input, BN prologue, statistics, mask, output).
-static int mlp_forward_pair(const Model& m, const PlanF32& p, int s, const float* const x_in[2], int64_t ldx_in,
-                            const float* params, float* state, bool training, float decay, const float* const mask[2],
-                            cudaStream_t st) {
+// get_mlp (models/tp8.py:75-82) for one branch (nbr = 1: the head, or the fp32 mode) or for BOTH siamese branches of
+// stage s at once (bf16 mode: every layer is one launch of the GEMM with the two branches as a batch of two problems --
+// same weights; their own input, BN prologue, statistics, mask, output).  x: [B, cin] with leading dim ldx, already
+// activated.  In bf16 mode each layer is: pack the input (BN affine + ReLU + dropout of the producing layer applied on
+// the way) into its bf16 image -> tcgen05 GEMM fed by bulk copies, BN column statistics fused into the epilogue.
+static int mlp_forward_n(const Model& m, const PlanF32& p, int s, int nbr, int br0, const float* const x_in[2], int64_t ldx_in,
+                         const float* params, float* state, bool training, float decay, const float* const mask[2],
+                         cudaStream_t st) {
+  const bool head = s == HEAD;
   const float* x[2] = {x_in[0], x_in[1]};
   int64_t ldx = ldx_in;
   const float *psc[2] = {nullptr, nullptr}, *psh[2] = {nullptr, nullptr};
   const size_t nl = m.fc[s].size();
   for (size_t l = 0; l < nl; ++l) {
     const Lin& L = m.fc[s][l];
-    fcgemm::Params f[2];
-    bool fused_stats = L.bn >= 0 && training;
-    for (int br = 0; br < 2; ++br) {
-      fcgemm::Params& q = f[br];
-      q.A = x[br]; q.lda = ldx; q.a_mn = 0; q.B = params + L.w; q.ldb = L.cout; q.b_mn = 1; q.C = p.fz[s][l][br]; q.ldc = L.cout;
-      q.M = p.B; q.N = L.cout; q.K = L.cin; q.bias = params + L.b; q.pro_scale = psc[br]; q.pro_shift = psh[br];
-      if (l == nl - 1 && training && mask[br]) {
-        q.pro_mask = mask[br];
-        q.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
-      }
-      q.ksplit = 1; q.accumulate = 0;
-      if (fused_stats) {
-        BnView v = bn_view(m, p, params, state, false, br, L.bn);
-        q.stat_sum = v.acc0;
-        q.stat_sq = v.acc1;
-      }
-    }
-    if (!fused_stats && !training && !p.deterministic) {   // (see mlp_forward)
-      const int tiles = 2 * ((f[0].M + 127) / 128) * ((f[0].N + 127) / 128);
-      const int ks = std::min(f[0].K / 128, 148 / tiles);
-      if (ks > 1) {
-        for (int br = 0; br < 2; ++br) {
-          f[br].ksplit = ks;
-          AN3D_CUDA_CHECK(cudaMemsetAsync(f[br].C, 0, sizeof(float) * (size_t)f[br].M * f[br].ldc, st));
+    const bool fused_stats = p.bf16 && L.bn >= 0 && training;
+    if (p.bf16) {
+      fc2::PackArgs pa[2];
+      fc2::Params f[2];
+      for (int i = 0; i < nbr; ++i) {
+        const int br = br0 + i;
+        pa[i].src = x[i]; pa[i].ld = ldx; pa[i].rows = p.B; pa[i].cols = L.cin; pa[i].scale = psc[i]; pa[i].shift = psh[i];
+        if (l == nl - 1 && training && mask[i]) {
+          pa[i].mask = mask[i];
+          pa[i].mask_scale = 1.0f / m.arch.keep_prob[s];
+        }
+        pa[i].dst = p.fcx[s][l][br];
+        fc2::Params& q = f[i];
+        q.A.g = p.fcx[s][l][br]; q.A.rows = p.B; q.A.cols = L.cin; q.a_mn = 0;
+        q.B.g = p.fcw[s][l]; q.B.rows = L.cin; q.B.cols = L.cout; q.b_mn = 1;
+        q.C = p.fz[s][l][br]; q.ldc = L.cout; q.M = p.B; q.N = L.cout; q.K = L.cin; q.bias = params + L.b;
+        q.zero_page = p.zero_page;
+        if (fused_stats) {   // column sums of z and z^2 come out of the GEMM epilogue
+          BnView v = bn_view(m, p, params, state, head, br, L.bn);
+          q.stat_sum = v.acc0;
+          q.stat_sq = v.acc1;
         }
       }
+      AN3D_TRY(fc2::pack(pa[0], st, nbr == 2 ? &pa[1] : nullptr));
+      // few output tiles (inference batches): split K so that the launch fills the SMs.  Never in training mode and
+      // not under AN3D_DETERMINISTIC: the K slices meet in fp32 reductions, whose order is not reproducible.
+      if (!fused_stats && !training && !p.deterministic) {
+        const int tiles = nbr * ((p.B + 127) / 128) * ((L.cout + 127) / 128);
+        const int ks = std::min(L.cin / 128, 148 / tiles);
+        if (ks > 1) {
+          for (int i = 0; i < nbr; ++i) {
+            f[i].ksplit = ks;
+            AN3D_CUDA_CHECK(cudaMemsetAsync(f[i].C, 0, sizeof(float) * (size_t)p.B * L.cout, st));
+          }
+        }
+      }
+      AN3D_TRY(fc2::launch(f[0], st, nbr == 2 ? &f[1] : nullptr));
+    } else {
+      GemmArgs g;
+      g.A = x[0]; g.lda = ldx; g.B = params + L.w; g.ldb = L.cout; g.C = p.fz[s][l][br0]; g.ldc = L.cout;
+      g.M = p.B; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc[0]; g.pro_shift = psh[0];
+      if (l == nl - 1 && training && mask[0]) {
+        g.pro_mask = mask[0];
+        g.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
+      }
+      AN3D_TRY(launch_gemm(g, false, false, st));
     }
-    AN3D_TRY(fcgemm::launch(f[0], st, &f[1]));
-    for (int br = 0; br < 2; ++br) {
+    for (int i = 0; i < nbr; ++i) {
+      const int br = br0 + i;
       if (L.bn >= 0) {
-        BnView v = bn_view(m, p, params, state, false, br, L.bn);
+        BnView v = bn_view(m, p, params, state, head, br, L.bn);
         if (fused_stats) {
           bn_finalize_sums_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / p.B, v.gamma, v.beta, v.state_mean,
                                                                       v.state_var, v.mean, v.inv, v.scale, v.shift, v.ch, decay);
@@ -248,14 +225,27 @@ static int mlp_forward_pair(const Model& m, const PlanF32& p, int s, const float
         } else if (!p.prepared) {
           AN3D_TRY(bn_forward(v, p.fz[s][l][br], p.B, training, decay, st));
         }
-        psc[br] = v.scale;
-        psh[br] = v.shift;
+        psc[i] = v.scale;
+        psh[i] = v.shift;
       }
-      x[br] = p.fz[s][l][br];
+      x[i] = p.fz[s][l][br];
     }
     ldx = L.cout;
   }
   return AN3D_OK;
+}
+
+static int mlp_forward(const Model& m, const PlanF32& p, int s, int br, const float* x, int64_t ldx, const float* params,
+                       float* state, bool training, float decay, const float* mask, cudaStream_t st) {
+  const float* xs[2] = {x, nullptr};
+  const float* ms[2] = {mask, nullptr};
+  return mlp_forward_n(m, p, s, 1, br, xs, ldx, params, state, training, decay, ms, st);
+}
+
+static int mlp_forward_pair(const Model& m, const PlanF32& p, int s, const float* const x_in[2], int64_t ldx_in,
+                            const float* params, float* state, bool training, float decay, const float* const mask[2],
+                            cudaStream_t st) {
+  return mlp_forward_n(m, p, s, 2, 0, x_in, ldx_in, params, state, training, decay, mask, st);
 }
 
 int forward_impl(const Model& m, const float* params, float* state, const float* pcs1, const float* pcs2, int B, int N,
@@ -271,7 +261,11 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
   p.prepared = bf16 && !training && (flags & AN3D_WEIGHTS_PREPARED) != 0;
   p.deterministic = (flags & AN3D_DETERMINISTIC) != 0;
-  if (bf16 && !p.prepared) AN3D_TRY(pack_weights_bf16(m, p, params, st));
+  if (bf16 && !p.prepared) {
+    AN3D_TRY(pack_weights_bf16(m, p, params, st));
+    AN3D_CUDA_CHECK(cudaMemsetAsync(p.zero_page, 0, 2048, st));
+    AN3D_TRY(pack_fc_weights(m, p, params, st));
+  }
   const int nb = m.nb;
   const int64_t M = p.M;
   if (!p.prepared) {   // (the reduction scratch only feeds batch statistics and the eval-mode finalize kernels)

@@ -50,6 +50,22 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
         max_fc_ch = std::max<int64_t>(max_fc_ch, m.fc[s][l].cin);
       }
   }
+  for (int s = 0; s < 3; ++s)
+    for (int l = 0; l <= AN3D_MAX_LAYERS; ++l) {
+      p->fcw[s][l] = nullptr;
+      p->fcx[s][l][0] = p->fcx[s][l][1] = nullptr;
+    }
+  if (bf16) {
+    for (int s = 0; s < 3; ++s) {
+      const int nbr = s == HEAD ? 1 : 2;
+      for (size_t l = 0; l < m.fc[s].size(); ++l) {
+        const Lin& L = m.fc[s][l];
+        p->fcw[s][l] = a.take<__nv_bfloat16>(fc_image_elems(L.cin, L.cout));
+        for (int br = 0; br < nbr; ++br) p->fcx[s][l][br] = a.take<__nv_bfloat16>(fc_image_elems(B, L.cin));
+      }
+    }
+    p->zero_page = a.take<__nv_bfloat16>(1024);
+  }
   // dropout masks: s1/b0, s1/b1, s2/b0, s2/b1, head; width = last hidden FC width of the stage
   for (int i = 0; i < 5; ++i) {
     const int s = i < 2 ? S1 : (i < 4 ? S2 : HEAD);
@@ -84,6 +100,8 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     p->dout = a.take<float>((int64_t)B * (3 + 2 * m.nb));
     p->dbias_acc = a.take<double>(std::max<int64_t>(std::max(max_conv_ch, max_fc_ch), 3 + 2 * m.nb));
     if (bf16) {
+      for (int br = 0; br < 2; ++br)
+        p->fcdz[br] = a.take<__nv_bfloat16>(fc_image_elems(B, (int)std::max<int64_t>(max_fc_ch, 3 + 2 * m.nb)));
       p->dfc_b[0] = a.take<float>((int64_t)B * max_fc_ch);
       p->dfc_b[1] = a.take<float>((int64_t)B * max_fc_ch);
       p->dg_b = a.take<float>((int64_t)B * max_c3);
