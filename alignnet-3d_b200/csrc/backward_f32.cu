@@ -5,7 +5,7 @@
 #include "kernels_f32.cuh"
 #include "loss.cuh"
 #include "bf16_path.cuh"
-#include "fc_gemm_bf16.cuh"
+#include "fc2_gemm.cuh"
 
 namespace an3d {
 
@@ -49,27 +49,52 @@ int bn_relu_backward(const BnRef& v, const float* Z, int R, const float* dA, int
   return AN3D_OK;
 }
 
+// bf16 mode: the operands of an FC layer's backward GEMMs as plane-major bf16 images (fc2_gemm.cuh): the layer's input
+// activations and weights were packed by the forward pass, the gradient image is packed here.
+struct FcImages {
+  const __nv_bfloat16* x = nullptr;     // [R, cin]  input activations (forward)
+  const __nv_bfloat16* w = nullptr;     // [cin, cout] weights (forward)
+  __nv_bfloat16* dz = nullptr;          // [R, cout] scratch for the gradient image
+};
+
+// wgrad (grads.W += X^T dZ, split-K with reductions) and dgrad (dX = dZ W^T) of one FC layer on the tensor cores, for
+// one branch or for the two siamese branches as one batched launch each.
+static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2], const float* const dZ[2], float* gradW,
+                            float* const dX[2], int64_t lddx, cudaStream_t st) {
+  fc2::PackArgs pa[2];
+  fc2::Params w[2], d[2];
+  for (int i = 0; i < nbr; ++i) {
+    pa[i].src = dZ[i]; pa[i].ld = L.cout; pa[i].rows = R; pa[i].cols = L.cout; pa[i].dst = img[i].dz;
+    fc2::Params& f = w[i];
+    f.A.g = img[i].x; f.A.rows = R; f.A.cols = L.cin; f.a_mn = 1;          // contraction over the batch rows
+    f.B.g = img[i].dz; f.B.rows = R; f.B.cols = L.cout; f.b_mn = 1;
+    f.C = gradW; f.ldc = L.cout; f.M = L.cin; f.N = L.cout; f.K = R; f.accumulate = 1;
+    const int tiles = nbr * ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
+    f.ksplit = std::max(1, std::min((R + 255) / 256, (296 + tiles - 1) / tiles));   // fill the SMs: wgrad has few output tiles
+    fc2::Params& g = d[i];
+    g.A.g = img[i].dz; g.A.rows = R; g.A.cols = L.cout; g.a_mn = 0;
+    g.B.g = img[i].w; g.B.rows = L.cin; g.B.cols = L.cout; g.b_mn = 0;    // rows = output index (cin), cols = K (cout)
+    g.C = dX[i]; g.ldc = lddx; g.M = R; g.N = L.cin; g.K = L.cout;
+  }
+  AN3D_TRY(fc2::pack(pa[0], st, nbr == 2 ? &pa[1] : nullptr));
+  AN3D_TRY(fc2::launch(w[0], st, nbr == 2 ? &w[1] : nullptr));
+  if (dX[0]) AN3D_TRY(fc2::launch(d[0], st, nbr == 2 ? &d[1] : nullptr));
+  return AN3D_OK;
+}
+
 // Z = pro(X) W + b.  Given dZ [R,cout] (dense, ld = cout):
 //   grads.W += pro(X)^T dZ ; grads.b += colsum(dZ) ; dX = dZ W^T (if dX != nullptr).
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
                     float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
-                    int64_t lddx, double* bias_acc, cudaStream_t st, bool bf16 = false) {
+                    int64_t lddx, double* bias_acc, cudaStream_t st, const FcImages* img = nullptr) {
+  const bool bf16 = img != nullptr;
   bool wgrad_done = false, dgrad_done = false;
   if (bf16) {
-    fcgemm::Params f;
-    f.A = X; f.lda = ldx; f.a_mn = 1; f.B = dZ; f.ldb = L.cout; f.b_mn = 1; f.C = grads + L.w; f.ldc = L.cout;
-    f.M = L.cin; f.N = L.cout; f.K = R; f.bias = nullptr; f.pro_scale = psc; f.pro_shift = psh; f.pro_mask = pmask;
-    f.pro_mask_scale = pmask_scale; f.accumulate = 1;
-    const int tiles = ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
-    f.ksplit = std::max(1, std::min((R + 255) / 256, (296 + tiles - 1) / tiles));   // fill the SMs: wgrad has few output tiles
-    if (fcgemm::usable(f)) { AN3D_TRY(fcgemm::launch(f, st)); wgrad_done = true; }
-    if (dX) {
-      fcgemm::Params d;
-      d.A = dZ; d.lda = L.cout; d.a_mn = 0; d.B = params + L.w; d.ldb = L.cout; d.b_mn = 0; d.C = dX; d.ldc = lddx;
-      d.M = R; d.N = L.cin; d.K = L.cout; d.bias = nullptr; d.pro_scale = nullptr; d.pro_shift = nullptr; d.pro_mask = nullptr;
-      d.pro_mask_scale = 1.f; d.ksplit = 1; d.accumulate = 0;
-      if (fcgemm::usable(d)) { AN3D_TRY(fcgemm::launch(d, st)); dgrad_done = true; }
-    }
+    const FcImages im[2] = {*img, FcImages()};
+    const float* dz[2] = {dZ, nullptr};
+    float* dx[2] = {dX, nullptr};
+    AN3D_TRY(fc_backward_bf16(L, R, 1, im, dz, grads + L.w, dx, lddx, st));
+    wgrad_done = dgrad_done = true;
   }
   if (!wgrad_done) {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
     GemmArgs g;
@@ -178,8 +203,10 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
       dX = dIn;
       lddx = lddin;
     }
+    FcImages im;
+    im.x = p.fcx[s][l][br]; im.w = p.fcw[s][l]; im.dz = p.fcdz[0];
     AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st,
-                             p.bf16));
+                             p.bf16 ? &im : nullptr));
     dZ = dX;
     cur ^= 1;
   }
@@ -206,39 +233,17 @@ int mlp_backward_pair(const Model& m, const PlanF32& p, int s, const float* cons
       AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], R, dZ[br], L.cout, dropped ? mask[br] : nullptr, ms,
                                 const_cast<float*>(dZ[br]), L.cout, st));
     }
-    fcgemm::Params w[2], d[2];
     float* dX[2];
     int64_t lddx;
     for (int br = 0; br < 2; ++br) {
-      const float *X, *psc = nullptr, *psh = nullptr, *pm = nullptr;
-      int64_t lx;
       if (l > 0) {
-        const Lin& P = m.fc[s][l - 1];
-        X = p.fz[s][l - 1][br];
-        lx = P.cout;
-        const int64_t sl = m.bn_slot_off(false, br, P.bn);
-        psc = p.bn.scale + sl;
-        psh = p.bn.shift + sl;
-        if (l == nl - 1) pm = mask[br];
         dX[br] = scratch[br][cur];
         lddx = L.cin;
       } else {
-        X = x[br];
-        lx = ldx;
         dX[br] = dIn[br];
         lddx = lddin;
       }
-      fcgemm::Params& f = w[br];
-      f.A = X; f.lda = lx; f.a_mn = 1; f.B = dZ[br]; f.ldb = L.cout; f.b_mn = 1; f.C = grads + L.w; f.ldc = L.cout;
-      f.M = L.cin; f.N = L.cout; f.K = R; f.pro_scale = psc; f.pro_shift = psh; f.pro_mask = pm;
-      f.pro_mask_scale = mask[br] ? 1.0f / m.arch.keep_prob[s] : 1.f; f.accumulate = 1;
-      const int tiles = 2 * ((L.cin + 127) / 128) * ((L.cout + 127) / 128);
-      f.ksplit = std::max(1, std::min((R + 255) / 256, (296 + tiles - 1) / tiles));
-      fcgemm::Params& g = d[br];
-      g.A = dZ[br]; g.lda = L.cout; g.a_mn = 0; g.B = params + L.w; g.ldb = L.cout; g.b_mn = 0; g.C = dX[br]; g.ldc = lddx;
-      g.M = R; g.N = L.cin; g.K = L.cout; g.ksplit = 1; g.accumulate = 0;
     }
-    AN3D_TRY(fcgemm::launch(w[0], st, &w[1]));
     if (L.bn < 0) {   // only a bias that does not feed a batch-statistics BN has a non-zero gradient
       for (int br = 0; br < 2; ++br) {
         AN3D_CUDA_CHECK(cudaMemsetAsync(p.dbias_acc, 0, sizeof(double) * L.cout, st));
@@ -249,7 +254,11 @@ int mlp_backward_pair(const Model& m, const PlanF32& p, int s, const float* cons
         AN3D_LAUNCH_CHECK();
       }
     }
-    AN3D_TRY(fcgemm::launch(d[0], st, &d[1]));
+    FcImages img[2];
+    for (int br = 0; br < 2; ++br) {
+      img[br].x = p.fcx[s][l][br]; img[br].w = p.fcw[s][l]; img[br].dz = p.fcdz[br];
+    }
+    AN3D_TRY(fc_backward_bf16(L, R, 2, img, dZ, grads + L.w, dX, lddx, st));
     dZ[0] = dX[0];
     dZ[1] = dX[1];
     cur ^= 1;

@@ -185,7 +185,6 @@ struct PlanF32 {
   __nv_bfloat16* fcx[3][AN3D_MAX_LAYERS + 1][2];   // input activations of FC layer l of stage s, per branch (head: [0])
   __nv_bfloat16* fcw[3][AN3D_MAX_LAYERS + 1];      // weights of FC layer l of stage s
   __nv_bfloat16* fcdz[2] = {nullptr, nullptr};     // gradient wrt the current layer's output, per branch (training)
-  __nv_bfloat16* zero_page = nullptr;              // 2 KB of zeros: source of operand planes that do not exist
   float* mask[5];                           // dropout keep masks [B, width]
   float* mu[2];                             // centroids [B,3]
   float* ang[2];                            // decoded stage-2 yaw [B]
@@ -214,8 +213,8 @@ struct PlanF32 {
 
 int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* p);
 
-// elements of the plane-major bf16 image of a [rows, cols] matrix (fc2_gemm.cuh): rows padded to 128, cols to 8
-inline int64_t fc_image_elems(int rows, int cols) { return (int64_t)((cols + 7) >> 3) * ((rows + 127) & ~127) * 8; }
+// elements of the bf16 block image of a [rows, cols] matrix (fc2_gemm.cuh): whole 128 x 128 blocks
+inline int64_t fc_image_elems(int rows, int cols) { return (int64_t)((rows + 127) >> 7) * ((cols + 127) >> 7) * 16384; }
 
 struct Ctx {
   Model model;

@@ -1,6 +1,6 @@
 // FC layers of the bf16 path, second generation: bf16 operand IMAGES in global memory, fetched by the TMA unit.
 //
-//   C[i, j] (+)= sum_k A(i,k) * B(j,k)  (+ bias[j])        tile 128 x 128, K in blocks of 64
+//   C[i, j] (+)= sum_k A(i,k) * B(j,k)  (+ bias[j])        tile 128 x 128, K in blocks of 128
 //
 // Round 1's FC GEMM converted fp32 operands on loader warps: every CTA re-read and re-converted its fp32 A and B tiles
 // (268 MB through L2 for the 4096 x 2048 x 512 head layer, 66 us = 0.05 of the tensor peak) and the register-staged
@@ -9,13 +9,15 @@
 // also applies the BN affine + ReLU + dropout mask of the producing layer -- and each image serves every role of that
 // matrix (activations: forward + wgrad; weights: forward + dgrad; gradients: wgrad + dgrad):
 //
-//   image of X[R rows][C cols]:  chunk c8 = C/8 planes, plane c8 holds for every row r the 16 bytes X[r][8 c8 .. 8 c8 + 7]
-//                                at  (c8 * Rpad + r) * 16,  Rpad = R rounded up to 128, zero padded in both directions.
+//   image of X[R rows][C cols]:  blocks of 128 rows x 128 columns, block (rb, cb) at (rb * ncb + cb) * 32 KB; inside a block
+//                                16 planes (8 columns each) of 128 rows x 16 bytes:  ((c8 % 16) * 128 + r % 128) * 16.
+//                                Zero padded to whole blocks.
 //
-// A 128 x 64 K-major operand tile is then 8 contiguous 2 KB pieces, a 64 x 128 MN-major tile 16 pieces of 1 KB: plain
-// 1-D bulk copies (cp.async.bulk) straight into the un-swizzled shared-memory layout of umma.cuh, issued by ONE thread
-// through a 6-stage mbarrier ring.  No loader warps, no conversions, no bounds logic (planes that do not exist are
-// fetched from a page of zeros).
+// A block IS the un-swizzled shared-memory operand tile of umma.cuh -- K-major (rows = M / N index, planes = K chunks) and
+// MN-major (rows = K index, planes = M / N chunks) alike -- so every operand tile of a 128-wide K block is ONE 32 KB bulk
+// copy (cp.async.bulk, TMA unit) issued by one thread through a 3-stage mbarrier ring.  No loader warps, no
+// conversions, no bounds logic.  (A first version with 1-2 KB pieces per plane spent 0.7 us per K block just issuing
+// its 24 copies: profiles/r2_fc_launches.txt.)
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -28,10 +30,10 @@ using namespace umma;
 struct Image {
   const __nv_bfloat16* g = nullptr;
   int rows = 0, cols = 0;
-  __host__ __device__ int rows_pad() const { return (rows + 127) & ~127; }
-  __host__ __device__ int chunks() const { return (cols + 7) >> 3; }
+  __host__ __device__ int row_blocks() const { return (rows + 127) >> 7; }
+  __host__ __device__ int col_blocks() const { return (cols + 127) >> 7; }
+  __host__ __device__ const __nv_bfloat16* block(int rb, int cb) const { return g + ((int64_t)rb * col_blocks() + cb) * 16384; }
 };
-inline int64_t image_elems(int rows, int cols) { return (int64_t)((cols + 7) >> 3) * ((rows + 127) & ~127) * 8; }
 
 // ---------------------------------------------------------------------------------------------
 // packing: fp32 matrix (+ optional BN affine + ReLU, + optional dropout mask) -> bf16 image.  One thread per
@@ -49,15 +51,16 @@ struct PackArgs {
 
 static __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a0, const PackArgs a1) {
   const PackArgs a = blockIdx.z ? a1 : a0;
-  const int rows_pad = (a.rows + 127) & ~127, chunks = (a.cols + 7) >> 3;
+  const int rows_pad = (a.rows + 127) & ~127, chunks = ((a.cols + 127) & ~127) >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows_pad * chunks) return;
-  // consecutive threads walk the chunks of one row: the fp32 reads are coalesced (the 16-byte writes stride by a plane)
-  const int r = (int)(i / chunks), c8 = (int)(i - (int64_t)r * chunks);
+  // consecutive threads walk the rows of one chunk: every lane reads one full 32-byte sector of its row, and the warp's
+  // 16-byte writes are contiguous (the other order wrote 16 bytes per 2 KB: 15 us for a 4096 x 512 pair)
+  const int c8 = (int)(i / rows_pad), r = (int)(i - (int64_t)c8 * rows_pad);
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = 0.f;
-  if (r < a.rows) {
+  if (r < a.rows && c8 * 8 < a.cols) {
     const float* p = a.src + (int64_t)r * a.ld + c8 * 8;
     const int n = min(8, a.cols - c8 * 8);
     const bool vec = n == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
@@ -86,7 +89,9 @@ static __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a0, con
   uint4 out;
   out.x = *reinterpret_cast<uint32_t*>(&b0); out.y = *reinterpret_cast<uint32_t*>(&b1);
   out.z = *reinterpret_cast<uint32_t*>(&b2); out.w = *reinterpret_cast<uint32_t*>(&b3);
-  *reinterpret_cast<uint4*>(a.dst + ((int64_t)c8 * rows_pad + r) * 8) = out;
+  const int ncb = chunks >> 4;
+  const int64_t blk = (int64_t)(r >> 7) * ncb + (c8 >> 4);
+  *reinterpret_cast<uint4*>(a.dst + blk * 16384 + ((c8 & 15) * 128 + (r & 127)) * 8) = out;
 }
 
 // one launch packs one matrix, or two of identical shape (the two siamese branches)
@@ -95,7 +100,7 @@ static int pack(const PackArgs& a, cudaStream_t st, const PackArgs* b = nullptr)
     set_error("fc2::pack: batched matrices must have identical shapes");
     return AN3D_ERR_INVALID;
   }
-  const int64_t total = (int64_t)((a.rows + 127) & ~127) * ((a.cols + 7) >> 3);
+  const int64_t total = (int64_t)((a.rows + 127) & ~127) * (((a.cols + 127) & ~127) >> 3);
   dim3 grid((unsigned)((total + 255) / 256), 1, b ? 2 : 1);
   pack_kernel<<<grid, 256, 0, st>>>(a, b ? *b : a);
   AN3D_LAUNCH_CHECK();
@@ -115,45 +120,22 @@ struct Params {
   int accumulate = 0;                       // reductions even with ksplit == 1
   double* stat_sum = nullptr;               // optional [N]: += column sums of C (bias included); needs ksplit == 1
   double* stat_sq = nullptr;                // optional [N]: += column sums of C^2
-  const __nv_bfloat16* zero_page = nullptr; // >= 2 KB of zeros
   int c_vec = 1;                            // set by launch(): 16-byte vector access legal for C
 };
 
 constexpr int kThreads = 192;                 // warps 0-3 epilogue, 4 TMA issuer, 5 MMA
-constexpr int kStages = 6;
-constexpr uint32_t kPlaneK = 128 * 16 + 16;   // K-major tile: 8 planes x 128 rows
-constexpr uint32_t kPlaneMN = 64 * 16 + 16;   // MN-major tile: 16 planes x 64 rows
-constexpr uint32_t kTileBytes = 16 * kPlaneMN > 8 * kPlaneK ? 16 * kPlaneMN : 8 * kPlaneK;
-constexpr uint32_t kTileStride = (kTileBytes + 127) & ~127u;
-constexpr uint32_t kTxBytes = 2 * 16384;      // both operand tiles of a K block: 8 x 2 KB or 16 x 1 KB each
-constexpr size_t kSmemBytes = 2 * kStages * (size_t)kTileStride + 256;
-static_assert(kStages * kTileStride >= 128 * 129 * 4, "the statistics transpose tile reuses the A ring");
+constexpr int kStages = 3;
+constexpr int kKBlock = 128;
+constexpr uint32_t kPlane = 128 * 16;         // plane stride inside a block (both majors)
+constexpr uint32_t kTileBytes = 16 * kPlane;  // 32 KB
+constexpr uint32_t kTxBytes = 2 * kTileBytes; // both operand tiles of a K block
+constexpr size_t kSmemBytes = 2 * kStages * (size_t)kTileBytes + 256;
+static_assert(kStages * kTileBytes >= 128 * 129 * 4, "the statistics transpose tile reuses the A ring");
 
 struct Bars {
   uint64_t full[kStages], empty[kStages], done;
   uint32_t tmem_base;
 };
-
-// the pieces of one operand tile for the K block starting at k0 (mn0 = first M / N index of the CTA's tile)
-__device__ __forceinline__ void issue_tile(const Image& X, int mn_major, int mn0, int k0, uint8_t* dst, uint64_t* bar,
-                                           const __nv_bfloat16* zero_page) {
-  const int rp = X.rows_pad(), nch = X.chunks();
-  if (mn_major) {
-#pragma unroll 4
-    for (int pl = 0; pl < 16; ++pl) {
-      const int c8 = (mn0 >> 3) + pl;
-      const __nv_bfloat16* src = c8 < nch ? X.g + ((int64_t)c8 * rp + k0) * 8 : zero_page;
-      bulk_copy_g2s(dst + pl * kPlaneMN, src, 1024, bar);
-    }
-  } else {
-#pragma unroll 4
-    for (int pl = 0; pl < 8; ++pl) {
-      const int c8 = (k0 >> 3) + pl;
-      const __nv_bfloat16* src = c8 < nch ? X.g + ((int64_t)c8 * rp + mn0) * 8 : zero_page;
-      bulk_copy_g2s(dst + pl * kPlaneK, src, 2048, bar);
-    }
-  }
-}
 
 // Two problems of identical shape (the two siamese branches of one FC layer: same weights, their own activations,
 // statistics and output) can share a launch: blockIdx.z = batch * ksplit + k-slice.
@@ -162,14 +144,14 @@ static __global__ void __launch_bounds__(kThreads, 1) fc2_gemm_kernel(const Para
   const Params& P = bz ? P1 : P0;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kTileStride;
-  Bars* bars = reinterpret_cast<Bars*>(smem + 2 * kStages * kTileStride);
+  uint8_t* sB = smem + kStages * kTileBytes;
+  Bars* bars = reinterpret_cast<Bars*>(smem + 2 * kStages * kTileBytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128;
   int kchunk = (P.K + P.ksplit - 1) / P.ksplit;
-  kchunk = (kchunk + 63) & ~63;
+  kchunk = (kchunk + kKBlock - 1) & ~(kKBlock - 1);
   const int kbeg = kz * kchunk, kend = min(P.K, kbeg + kchunk);
-  const int nkb = kend > kbeg ? (kend - kbeg + 63) / 64 : 0;
+  const int nkb = kend > kbeg ? (kend - kbeg + kKBlock - 1) / kKBlock : 0;
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -189,9 +171,10 @@ static __global__ void __launch_bounds__(kThreads, 1) fc2_gemm_kernel(const Para
         const int st = kb % kStages;
         mbar_wait(&bars->empty[st], (ph >> st) & 1u); ph ^= 1u << st;
         mbar_arrive_expect_tx(&bars->full[st], kTxBytes);
-        const int k0 = kbeg + kb * 64;
-        issue_tile(P.A, P.a_mn, i0, k0, sA + st * kTileStride, &bars->full[st], P.zero_page);
-        issue_tile(P.B, P.b_mn, j0, k0, sB + st * kTileStride, &bars->full[st], P.zero_page);
+        const int kblk = (kbeg >> 7) + kb, ib = i0 >> 7, jb = j0 >> 7;
+        // K-major: block (row block = M / N tile, column block = K block); MN-major: block (K block, M / N tile)
+        bulk_copy_g2s(sA + st * kTileBytes, P.a_mn ? P.A.block(kblk, ib) : P.A.block(ib, kblk), kTileBytes, &bars->full[st]);
+        bulk_copy_g2s(sB + st * kTileBytes, P.b_mn ? P.B.block(kblk, jb) : P.B.block(jb, kblk), kTileBytes, &bars->full[st]);
       }
     }
   } else if (warp == 5) {
@@ -201,12 +184,12 @@ static __global__ void __launch_bounds__(kThreads, 1) fc2_gemm_kernel(const Para
       const int st = kb % kStages;
       mbar_wait(&bars->full[st], (ph >> st) & 1u); ph ^= 1u << st;
       tc_fence_after();
-      const uint32_t a_base = smem_u32(sA + st * kTileStride), b_base = smem_u32(sB + st * kTileStride);
+      const uint32_t a_base = smem_u32(sA + st * kTileBytes), b_base = smem_u32(sB + st * kTileBytes);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = P.a_mn ? make_desc(a_base + ks * 256, 128, kPlaneMN) : make_desc(a_base + ks * 2 * kPlaneK, kPlaneK, 128);
-          const uint64_t bd = P.b_mn ? make_desc(b_base + ks * 256, 128, kPlaneMN) : make_desc(b_base + ks * 2 * kPlaneK, kPlaneK, 128);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = P.a_mn ? make_desc(a_base + ks * 256, 128, kPlane) : make_desc(a_base + ks * 2 * kPlane, kPlane, 128);
+          const uint64_t bd = P.b_mn ? make_desc(b_base + ks * 256, 128, kPlane) : make_desc(b_base + ks * 2 * kPlane, kPlane, 128);
           mma_bf16_raw(tmem, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
         }
         mma_commit_raw(&bars->empty[st]);
@@ -285,7 +268,7 @@ static int launch(Params p, cudaStream_t st, const Params* p1 = nullptr) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   auto check = [&](const Params& q) {
     const int a_rows = q.a_mn ? q.K : q.M, a_cols = q.a_mn ? q.M : q.K, b_rows = q.b_mn ? q.K : q.N, b_cols = q.b_mn ? q.N : q.K;
-    return q.M > 0 && q.N > 0 && q.K > 0 && q.A.g && q.B.g && q.C && q.zero_page && q.A.rows == a_rows && q.A.cols == a_cols &&
+    return q.M > 0 && q.N > 0 && q.K > 0 && q.A.g && q.B.g && q.C && q.A.rows == a_rows && q.A.cols == a_cols &&
            q.B.rows == b_rows && q.B.cols == b_cols && !(q.stat_sum && q.ksplit > 1);
   };
   Params q = p1 ? *p1 : p;

@@ -183,7 +183,6 @@ static int mlp_forward_n(const Model& m, const PlanF32& p, int s, int nbr, int b
         q.A.g = p.fcx[s][l][br]; q.A.rows = p.B; q.A.cols = L.cin; q.a_mn = 0;
         q.B.g = p.fcw[s][l]; q.B.rows = L.cin; q.B.cols = L.cout; q.b_mn = 1;
         q.C = p.fz[s][l][br]; q.ldc = L.cout; q.M = p.B; q.N = L.cout; q.K = L.cin; q.bias = params + L.b;
-        q.zero_page = p.zero_page;
         if (fused_stats) {   // column sums of z and z^2 come out of the GEMM epilogue
           BnView v = bn_view(m, p, params, state, head, br, L.bn);
           q.stat_sum = v.acc0;
@@ -263,7 +262,6 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
   p.deterministic = (flags & AN3D_DETERMINISTIC) != 0;
   if (bf16 && !p.prepared) {
     AN3D_TRY(pack_weights_bf16(m, p, params, st));
-    AN3D_CUDA_CHECK(cudaMemsetAsync(p.zero_page, 0, 2048, st));
     AN3D_TRY(pack_fc_weights(m, p, params, st));
   }
   const int nb = m.nb;

@@ -64,7 +64,6 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
         for (int br = 0; br < nbr; ++br) p->fcx[s][l][br] = a.take<__nv_bfloat16>(fc_image_elems(B, L.cin));
       }
     }
-    p->zero_page = a.take<__nv_bfloat16>(1024);
   }
   // dropout masks: s1/b0, s1/b1, s2/b0, s2/b1, head; width = last hidden FC width of the stage
   for (int i = 0; i < 5; ++i) {

@@ -2,7 +2,7 @@
 // bf16 tensor-core path with a caller-supplied upstream gradient, so the backward kernels can be
 // checked against autograd without the (discontinuous) rest of the model in between.
 #include "bf16_path.cuh"
-#include "fc_gemm_bf16.cuh"
+#include "fc2_gemm.cuh"
 
 using namespace an3d;
 
@@ -51,9 +51,25 @@ extern "C" int an3d_selftest_fc_gemm(const float* a, int64_t lda, int32_t a_mn, 
     return AN3D_ERR_INVALID;
   }
   AN3D_TRY(check_device());
-  fcgemm::Params f;
-  f.A = a; f.lda = lda; f.a_mn = a_mn; f.B = b; f.ldb = ldb; f.b_mn = b_mn; f.C = c; f.ldc = ldc; f.M = m; f.N = n; f.K = k;
-  f.bias = bias; f.pro_scale = pro_scale; f.pro_shift = pro_shift; f.pro_mask = pro_mask; f.pro_mask_scale = pro_mask_scale;
-  f.ksplit = ksplit; f.accumulate = accumulate; f.stat_sum = stat_sum; f.stat_sq = stat_sq;
-  return fcgemm::launch(f, (cudaStream_t)stream);
+  // the caller's fp32 operands (either major, optional BN + ReLU + mask prologue on A) are packed into the bf16 plane-major
+  // images the GEMM consumes, exactly as the model code does; the temporaries live for the duration of this call
+  cudaStream_t st = (cudaStream_t)stream;
+  const int a_rows = a_mn ? k : m, a_cols = a_mn ? m : k, b_rows = b_mn ? k : n, b_cols = b_mn ? n : k;
+  __nv_bfloat16 *ia = nullptr, *ib = nullptr;
+  AN3D_CUDA_CHECK(cudaMalloc(&ia, sizeof(__nv_bfloat16) * fc_image_elems(a_rows, a_cols)));
+  AN3D_CUDA_CHECK(cudaMalloc(&ib, sizeof(__nv_bfloat16) * fc_image_elems(b_rows, b_cols)));
+  fc2::PackArgs pa, pb;
+  pa.src = a; pa.ld = lda; pa.rows = a_rows; pa.cols = a_cols; pa.scale = pro_scale; pa.shift = pro_shift; pa.mask = pro_mask;
+  pa.mask_scale = pro_mask_scale; pa.dst = ia;
+  pb.src = b; pb.ld = ldb; pb.rows = b_rows; pb.cols = b_cols; pb.dst = ib;
+  int rc = fc2::pack(pa, st);
+  if (rc == AN3D_OK) rc = fc2::pack(pb, st);
+  fc2::Params f;
+  f.A.g = ia; f.A.rows = a_rows; f.A.cols = a_cols; f.a_mn = a_mn; f.B.g = ib; f.B.rows = b_rows; f.B.cols = b_cols; f.b_mn = b_mn;
+  f.C = c; f.ldc = ldc; f.M = m; f.N = n; f.K = k; f.bias = bias; f.ksplit = ksplit; f.accumulate = accumulate;
+  f.stat_sum = stat_sum; f.stat_sq = stat_sq;
+  if (rc == AN3D_OK) rc = fc2::launch(f, st);
+  cudaStreamSynchronize(st);
+  cudaFree(ia); cudaFree(ib);
+  return rc;
 }
