@@ -34,15 +34,54 @@ BnRef bn_ref(const Model& m, const PlanF32& p, float* grads, bool head, int br, 
   return v;
 }
 
-// dA (grad wrt post-activation, post-dropout) -> dZ (grad wrt pre-BN), written to dZ (may alias dA).
+// bn_bwd_apply_kernel for the bf16 FC path: dZ goes straight into the bf16 block image the wgrad / dgrad GEMMs read
+// (fc2_gemm.cuh) -- one thread per (row, 8-column chunk), padding written as zeros -- instead of to an fp32 matrix that
+// a pack kernel would then re-read.
+static __global__ void __launch_bounds__(256) bn_bwd_apply_img_kernel(ColArgs a, __nv_bfloat16* img, double inv_rows) {
+  const int rows_pad = (a.R + 127) & ~127, chunks = ((a.C + 127) & ~127) >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows_pad * chunks) return;
+  const int c8 = (int)(i / rows_pad), r = (int)(i - (int64_t)c8 * rows_pad);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c8 * 8 + e;
+    float out = 0.f;
+    if (r < a.R && c < a.C) {
+      const float z = a.Z[(int64_t)r * a.ldz + c];
+      float dy = a.dA[(int64_t)r * a.ldd + c];
+      if (a.mask) dy *= a.mask[(int64_t)r * a.ldd + c] * a.mask_scale;
+      if (!(fmaf(z, a.scale[c], a.shift[c]) > 0.f)) dy = 0.f;
+      const float xhat = (z - a.mean[c]) * a.inv[c];
+      const float m0 = (float)(a.acc0[c] * inv_rows), m1 = (float)(a.acc1[c] * inv_rows);
+      out = a.scale[c] * (dy - m0 - xhat * m1);
+    }
+    v[e] = out;
+  }
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]),
+                 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+  o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+  const int64_t blk = (int64_t)(r >> 7) * (chunks >> 4) + (c8 >> 4);
+  *reinterpret_cast<uint4*>(img + blk * 16384 + ((c8 & 15) * 128 + (r & 127)) * 8) = o;
+}
+
+// dA (grad wrt post-activation, post-dropout) -> dZ (grad wrt pre-BN), written to dZ (may alias dA) -- or, with `img`,
+// to the bf16 block image of dZ only.
 int bn_relu_backward(const BnRef& v, const float* Z, int R, const float* dA, int64_t ldd, const float* mask,
-                     float mask_scale, float* dZ, int64_t ldo, cudaStream_t st) {
+                     float mask_scale, float* dZ, int64_t ldo, cudaStream_t st, __nv_bfloat16* img = nullptr) {
   ColArgs a;
   a.Z = Z; a.ldz = v.ch; a.R = R; a.C = v.ch; a.mean = v.mean; a.inv = v.inv; a.scale = v.scale; a.shift = v.shift;
   a.dA = dA; a.ldd = ldd; a.mask = mask; a.mask_scale = mask_scale; a.acc0 = v.acc0; a.acc1 = v.acc1;
   AN3D_TRY(launch_col_reduce(a, COL_DY, st));
-  const int64_t total = (int64_t)R * v.ch;
-  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, dZ, ldo, 1.0 / R);
+  if (img) {
+    const int64_t total = (int64_t)((R + 127) & ~127) * (((v.ch + 127) & ~127) >> 3);
+    bn_bwd_apply_img_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, img, 1.0 / R);
+  } else {
+    const int64_t total = (int64_t)R * v.ch;
+    bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, dZ, ldo, 1.0 / R);
+  }
   AN3D_LAUNCH_CHECK();
   bn_bwd_params_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, v.dgamma, v.dbeta, v.ch);
   AN3D_LAUNCH_CHECK();
@@ -55,12 +94,13 @@ struct FcImages {
   const __nv_bfloat16* x = nullptr;     // [R, cin]  input activations (forward)
   const __nv_bfloat16* w = nullptr;     // [cin, cout] weights (forward)
   __nv_bfloat16* dz = nullptr;          // [R, cout] scratch for the gradient image
+  bool dz_packed = false;               // the image already holds dZ (written by the BN backward)
 };
 
 // wgrad (grads.W += X^T dZ, split-K with reductions) and dgrad (dX = dZ W^T) of one FC layer on the tensor cores, for
 // one branch or for the two siamese branches as one batched launch each.
 static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2], const float* const dZ[2], float* gradW,
-                            float* const dX[2], int64_t lddx, cudaStream_t st) {
+                            float* const dX[2], int64_t lddx, cudaStream_t st, bool dz_packed = false) {
   fc2::PackArgs pa[2];
   fc2::Params w[2], d[2];
   for (int i = 0; i < nbr; ++i) {
@@ -76,7 +116,7 @@ static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2],
     g.B.g = img[i].w; g.B.rows = L.cin; g.B.cols = L.cout; g.b_mn = 0;    // rows = output index (cin), cols = K (cout)
     g.C = dX[i]; g.ldc = lddx; g.M = R; g.N = L.cin; g.K = L.cout;
   }
-  AN3D_TRY(fc2::pack(pa[0], st, nbr == 2 ? &pa[1] : nullptr));
+  if (!dz_packed) AN3D_TRY(fc2::pack(pa[0], st, nbr == 2 ? &pa[1] : nullptr));   // (the BN backward wrote the image itself)
   AN3D_TRY(fc2::launch(w[0], st, nbr == 2 ? &w[1] : nullptr));
   if (dX[0]) AN3D_TRY(fc2::launch(d[0], st, nbr == 2 ? &d[1] : nullptr));
   return AN3D_OK;
@@ -93,7 +133,7 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     const FcImages im[2] = {*img, FcImages()};
     const float* dz[2] = {dZ, nullptr};
     float* dx[2] = {dX, nullptr};
-    AN3D_TRY(fc_backward_bf16(L, R, 1, im, dz, grads + L.w, dx, lddx, st));
+    AN3D_TRY(fc_backward_bf16(L, R, 1, im, dz, grads + L.w, dx, lddx, st, img->dz_packed));
     wgrad_done = dgrad_done = true;
   }
   if (!wgrad_done) {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
@@ -181,7 +221,8 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
       // dZ currently holds dA (grad wrt this layer's post-activation); dropout only after the last hidden layer
       const bool dropped = (l == nl - 2) && mask;
       float* buf = const_cast<float*>(dZ);
-      AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], p.B, dZ, L.cout, dropped ? mask : nullptr, mask_scale, buf, L.cout, st));
+      AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], p.B, dZ, L.cout, dropped ? mask : nullptr, mask_scale, buf, L.cout, st,
+                                p.bf16 ? p.fcdz[0] : nullptr));
     }
     const float *X, *psc = nullptr, *psh = nullptr, *pm = nullptr;
     int64_t lx;
@@ -204,7 +245,7 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
       lddx = lddin;
     }
     FcImages im;
-    im.x = p.fcx[s][l][br]; im.w = p.fcw[s][l]; im.dz = p.fcdz[0];
+    im.x = p.fcx[s][l][br]; im.w = p.fcw[s][l]; im.dz = p.fcdz[0]; im.dz_packed = L.bn >= 0;
     AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st,
                              p.bf16 ? &im : nullptr));
     dZ = dX;
@@ -231,7 +272,7 @@ int mlp_backward_pair(const Model& m, const PlanF32& p, int s, const float* cons
       const bool dropped = (l == nl - 2) && mask[br];
       const float ms = mask[br] ? 1.0f / m.arch.keep_prob[s] : 1.f;
       AN3D_TRY(bn_relu_backward(v, p.fz[s][l][br], R, dZ[br], L.cout, dropped ? mask[br] : nullptr, ms,
-                                const_cast<float*>(dZ[br]), L.cout, st));
+                                const_cast<float*>(dZ[br]), L.cout, st, p.fcdz[br]));
     }
     float* dX[2];
     int64_t lddx;
@@ -258,7 +299,7 @@ int mlp_backward_pair(const Model& m, const PlanF32& p, int s, const float* cons
     for (int br = 0; br < 2; ++br) {
       img[br].x = p.fcx[s][l][br]; img[br].w = p.fcw[s][l]; img[br].dz = p.fcdz[br];
     }
-    AN3D_TRY(fc_backward_bf16(L, R, 2, img, dZ, grads + L.w, dX, lddx, st));
+    AN3D_TRY(fc_backward_bf16(L, R, 2, img, dZ, grads + L.w, dX, lddx, st, L.bn >= 0));
     dZ[0] = dX[0];
     dZ[1] = dX[1];
     cur ^= 1;
