@@ -42,21 +42,49 @@ static __global__ void __launch_bounds__(256) bn_bwd_apply_img_kernel(ColArgs a,
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows_pad * chunks) return;
   const int c8 = (int)(i / rows_pad), r = (int)(i - (int64_t)c8 * rows_pad);
+  const int c0 = c8 * 8;
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c8 * 8 + e;
-    float out = 0.f;
-    if (r < a.R && c < a.C) {
-      const float z = a.Z[(int64_t)r * a.ldz + c];
-      float dy = a.dA[(int64_t)r * a.ldd + c];
-      if (a.mask) dy *= a.mask[(int64_t)r * a.ldd + c] * a.mask_scale;
-      if (!(fmaf(z, a.scale[c], a.shift[c]) > 0.f)) dy = 0.f;
-      const float xhat = (z - a.mean[c]) * a.inv[c];
-      const float m0 = (float)(a.acc0[c] * inv_rows), m1 = (float)(a.acc1[c] * inv_rows);
-      out = a.scale[c] * (dy - m0 - xhat * m1);
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (r < a.R && c0 < a.C) {
+    const int n = min(8, a.C - c0);
+    float z[8], dy[8], mk[8];
+    const float* zp = a.Z + (int64_t)r * a.ldz + c0;
+    const float* dp = a.dA + (int64_t)r * a.ldd + c0;
+    const float* mp = a.mask ? a.mask + (int64_t)r * a.ldd + c0 : nullptr;
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    // lanes walk consecutive ROWS (the image's fast axis), so each lane owns one 32-byte sector of its row: read it with
+    // two 16-byte loads -- eight scalar loads per array made this kernel LSU-bound (22 us per launch)
+    if (n == 8 && al(zp) && al(dp) && (!mp || al(mp))) {
+      const float4 z0 = *reinterpret_cast<const float4*>(zp), z1 = *reinterpret_cast<const float4*>(zp + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(dp), d1 = *reinterpret_cast<const float4*>(dp + 4);
+      z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+      dy[0] = d0.x; dy[1] = d0.y; dy[2] = d0.z; dy[3] = d0.w; dy[4] = d1.x; dy[5] = d1.y; dy[6] = d1.z; dy[7] = d1.w;
+      if (mp) {
+        const float4 m0 = *reinterpret_cast<const float4*>(mp), m1 = *reinterpret_cast<const float4*>(mp + 4);
+        mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w; mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        z[e] = e < n ? zp[e] : 0.f;
+        dy[e] = e < n ? dp[e] : 0.f;
+        mk[e] = (mp && e < n) ? mp[e] : 0.f;
+      }
     }
-    v[e] = out;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < n) {
+        const int c = c0 + e;
+        float g = dy[e];
+        if (mp) g *= mk[e] * a.mask_scale;
+        const float sc = a.scale[c];
+        if (!(fmaf(z[e], sc, a.shift[c]) > 0.f)) g = 0.f;
+        const float xhat = (z[e] - a.mean[c]) * a.inv[c];
+        const float m0 = (float)(a.acc0[c] * inv_rows), m1 = (float)(a.acc1[c] * inv_rows);
+        v[e] = sc * (g - m0 - xhat * m1);
+      }
+    }
   }
   __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]),
                  b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
