@@ -99,60 +99,100 @@ __global__ void loss_sample_kernel(LossScratch s, SampleArgs a) {
     const double tot = block_sum(h, sm);
     if (threadIdx.x == 0) atomicAdd(s.sums + t, tot);
   }
-  // angle terms: class target, CE, selected residual prediction; both variants
+}
+
+// angle terms: class target, cross-entropy, selected residual prediction; both variants (target, target + pi).
+// One WARP per sample (the thread-per-sample form walked 100 logits with a 400-byte stride between lanes: 40 us at
+// B = 4096 on 32 SMs): lanes stride over the classes, so the logit rows are read coalesced; log-sum-exp once per
+// instance, kept in `lse` / `mxs` for the gradient kernel.
+__global__ void __launch_bounds__(256) loss_ce_kernel(LossScratch s, SampleArgs a) {
+  __shared__ double sm[8];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool on = i < a.B;
+  const int B = a.B, nb = a.nb;
+  float* lse_store = reinterpret_cast<float*>(s.S);          // [3][B] max, [3][B] 1 / sum exp  (S is otherwise unused)
   for (int inst = 0; inst < 3; ++inst) {
-    for (int v = 0; v < 2; ++v) {
-      double ce = 0.0;
-      if (on) {
-        const float* lg = a.logits[inst] + (int64_t)i * 2 * nb;
-        float target = inst < 2 ? a.ang_gt[inst][i] : (s.gt3[i] - s.pd[0]);  // class from column 0 (Q4)
-        if (v) target = target + kPi;
-        int cls;
-        float res;
-        angle2class(target, nb, &cls, &res);
-        cls = min(max(cls, 0), nb - 1);
-        float mx = lg[0];
-        for (int c = 1; c < nb; ++c) mx = fmaxf(mx, lg[c]);
-        float se = 0.f;
-        for (int c = 0; c < nb; ++c) se += expf(lg[c] - mx);
-        ce = (double)(logf(se) + mx - lg[cls]);
-        const int slot = (inst * 2 + v) * B + i;
-        s.cls[slot] = cls;
-        s.pred[slot] = lg[nb + cls];
-        if (inst < 2) s.lab[slot] = res / (kPi / (float)nb);
+    double ce[2] = {0.0, 0.0};
+    if (on) {
+      const float* lg = a.logits[inst] + (int64_t)i * 2 * nb;
+      float mx = -INFINITY;
+      for (int c = lane; c < nb; c += 32) mx = fmaxf(mx, lg[c]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float se = 0.f;
+      for (int c = lane; c < nb; c += 32) se += expf(lg[c] - mx);
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      if (lane == 0) {
+        lse_store[inst * B + i] = mx;
+        lse_store[(3 + inst) * B + i] = 1.0f / se;
+        for (int v = 0; v < 2; ++v) {
+          float target = inst < 2 ? a.ang_gt[inst][i] : (s.gt3[i] - s.pd[0]);  // class from column 0 (Q4)
+          if (v) target = target + kPi;
+          int cls;
+          float res;
+          angle2class(target, nb, &cls, &res);
+          cls = min(max(cls, 0), nb - 1);
+          ce[v] = (double)(logf(se) + mx - lg[cls]);
+          const int slot = (inst * 2 + v) * B + i;
+          s.cls[slot] = cls;
+          s.pred[slot] = lg[nb + cls];
+          if (inst < 2) s.lab[slot] = res / (kPi / (float)nb);
+        }
       }
-      const double tot = block_sum(ce, sm);
+    }
+    for (int v = 0; v < 2; ++v) {
+      // lanes other than 0 contribute zero: block_sum adds the per-warp values
+      const double tot = block_sum(ce[v], sm);
       if (threadIdx.x == 0) atomicAdd(s.sums + 5 + inst * 2 + v, tot);
     }
   }
 }
 
+// tf.mod for a positive modulus without fmodf's exact (and slow, iterative) remainder: one multiply by the reciprocal, one
+// fused multiply-add, two fix-ups.  Within an ulp of x of the exact value; used only inside the O(B^2) pair loop below, where
+// every term carries a weight of 1/B^2 (the O(B) class targets keep the exact form).
+__device__ __forceinline__ float floor_mod_fast(float x, float y, float inv_y) {
+  float r = fmaf(-floorf(x * inv_y), y, x);
+  if (r < 0.f) r += y;
+  if (r >= y) r -= y;
+  return r;
+}
+
 // pairwise residual loss: S_j = sum_i huber(pred_j - label_ij), G_j = sum_i huber'(.)
-__global__ void loss_pair_kernel(LossScratch s, int B, int nb, int ichunk) {
+// Block = 128 columns j x one chunk of `ichunk` rows i (staged in shared memory: every thread walks the same rows).
+__global__ void __launch_bounds__(128) loss_pair_kernel(LossScratch s, int B, int nb, int ichunk) {
   __shared__ double sm[8];
+  __shared__ float srow[256];
   const int iv = blockIdx.z, inst = iv >> 1, v = iv & 1;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = blockIdx.y * ichunk, i1 = min(B, i0 + ichunk);
+  const float* rows = inst < 2 ? s.lab + iv * B : s.gt3;
+  for (int i = threadIdx.x; i < i1 - i0; i += blockDim.x) srow[i] = rows[i0 + i];
+  __syncthreads();
   float S = 0.f, G = 0.f;
   if (j < B) {
     const float pred = s.pred[iv * B + j];
+    const int n = i1 - i0;
     if (inst < 2) {
-      const float* lab = s.lab + iv * B;
-      for (int i = i0; i < i1; ++i) {
-        const float d = pred - lab[i];
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const float d = pred - srow[i];
         S += huber(d, 1.0f);
         G += fminf(fmaxf(d, -1.0f), 1.0f);
       }
     } else {
-      const float pd = s.pd[j];
-      const float scale = kPi / (float)nb;
-      for (int i = i0; i < i1; ++i) {
-        float t = s.gt3[i] - pd;
-        if (v) t = t + kPi;
-        int cls;
-        float res;
-        angle2class(t, nb, &cls, &res);
-        const float d = pred - res / scale;
+      // stage-3 label of pair (i, j): residual of tf_angle2class(gt_i - pd_j [+ pi]) (quirk Q4), normalised by pi / nb
+      const float twopi = 2.0f * kPi, inv_twopi = 1.0f / twopi;
+      const float apc = twopi / (float)nb, inv_apc = (float)nb / twopi, half = apc / 2.0f;
+      const float inv_scale = (float)nb / kPi;
+      const float off = (v ? kPi : 0.f) - s.pd[j];
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const float angle = floor_mod_fast(srow[i] + off, twopi, inv_twopi);
+        const float shifted = floor_mod_fast(angle + half, twopi, inv_twopi);
+        const float c = floorf(shifted * inv_apc);
+        const float res = shifted - fmaf(c, apc, half);
+        const float d = fmaf(-res, inv_scale, pred);
         S += huber(d, 1.0f);
         G += fminf(fmaxf(d, -1.0f), 1.0f);
       }
@@ -202,14 +242,21 @@ __global__ void loss_final_kernel(LossScratch s, float* loss_out, int B, float e
   for (int i = 17; i < 20; ++i) loss_out[i] = 0.f;
 }
 
-__global__ void loss_grad_kernel(LossScratch s, const float* lg1, const float* lg2, const float* rem, float* dend,
-                                 int B, int nb, float esf, float af) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// d loss / d logits, one WARP per sample (coalesced rows; max and 1 / sum-exp come from loss_ce_kernel)
+__global__ void __launch_bounds__(256) loss_grad_kernel(LossScratch s, const float* lg1, const float* lg2, const float* rem,
+                                                        float* dend, int B, int nb, float esf, float af) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= B) return;
   const float* logits[3] = {lg1, lg2, rem};
   float* dl[3] = {dend + (int64_t)5 * B * 3, dend + (int64_t)5 * B * 3 + (int64_t)B * 2 * nb,
                   dend + (int64_t)5 * B * 3 + (int64_t)2 * B * 2 * nb};
+  const float* lse_store = reinterpret_cast<const float*>(s.S);
   const float invB = 1.0f / (float)B;
+  // stage-3 residual label depends on the decoded stage-2 yaws (Q4): d/d pd_j = w3*20*G_j/(B^2 * pi/nb),
+  // d a_r / d logit_r[nb + k_r] = pi/nb  ->  the pi/nb cancels.
+  const float gpd = af * invB * 20.0f * invB * invB * (float)s.G[(4 + s.sel[2]) * B + j];
+  const int k1 = s.k1[j], k2 = s.k2[j];
   for (int inst = 0; inst < 3; ++inst) {
     const int v = s.sel[inst];
     const int slot = (inst * 2 + v) * B + j;
@@ -217,22 +264,15 @@ __global__ void loss_grad_kernel(LossScratch s, const float* lg1, const float* l
     const float* lg = logits[inst] + (int64_t)j * 2 * nb;
     float* d = dl[inst] + (int64_t)j * 2 * nb;
     const int cls = s.cls[slot];
-    float mx = lg[0];
-    for (int c = 1; c < nb; ++c) mx = fmaxf(mx, lg[c]);
-    float se = 0.f;
-    for (int c = 0; c < nb; ++c) se += expf(lg[c] - mx);
-    const float inv_se = 1.0f / se;
-    for (int c = 0; c < nb; ++c) d[c] = w * invB * (expf(lg[c] - mx) * inv_se - (c == cls ? 1.f : 0.f));
-    for (int c = 0; c < nb; ++c) d[nb + c] = 0.f;
-    d[nb + cls] = w * 20.0f * invB * invB * (float)s.G[slot];
-  }
-  // stage-3 residual label depends on the decoded stage-2 yaws (Q4): d/d pd_j = w3*20*G_j/(B^2 * pi/nb),
-  // d a_r / d logit_r[nb + k_r] = pi/nb  ->  the pi/nb cancels.
-  {
-    const int v = s.sel[2];
-    const float gpd = af * invB * 20.0f * invB * invB * (float)s.G[(4 + v) * B + j];
-    dl[1][(int64_t)j * 2 * nb + nb + s.k2[j]] += gpd;
-    dl[0][(int64_t)j * 2 * nb + nb + s.k1[j]] -= gpd;
+    const float mx = lse_store[inst * B + j], inv_se = lse_store[(3 + inst) * B + j];
+    const float gres = w * 20.0f * invB * invB * (float)s.G[slot];
+    for (int c = lane; c < nb; c += 32) {
+      d[c] = w * invB * (expf(lg[c] - mx) * inv_se - (c == cls ? 1.f : 0.f));
+      float r = c == cls ? gres : 0.f;
+      if (inst == 1 && c == k2) r += gpd;
+      if (inst == 0 && c == k1) r -= gpd;
+      d[nb + c] = r;
+    }
   }
 }
 
@@ -281,6 +321,8 @@ int run_loss(const Model& m, const an3d_labels* lb, const an3d_outputs* out, int
   a.w_t3 = invB / 3.0f * invB;
   loss_sample_kernel<<<nblk, tb, 0, st>>>(s, a);
   AN3D_LAUNCH_CHECK();
+  loss_ce_kernel<<<(B + 7) / 8, 256, 0, st>>>(s, a);
+  AN3D_LAUNCH_CHECK();
   const int ichunk = 256;
   dim3 grid(nblk, (B + ichunk - 1) / ichunk, 6);
   loss_pair_kernel<<<grid, tb, 0, st>>>(s, B, nb, ichunk);
@@ -289,7 +331,7 @@ int run_loss(const Model& m, const an3d_labels* lb, const an3d_outputs* out, int
                                        m.arch.accept_inverted_angle);
   AN3D_LAUNCH_CHECK();
   if (dend) {
-    loss_grad_kernel<<<nblk, tb, 0, st>>>(s, out->pred_pc1angle_logits, out->pred_pc2angle_logits,
+    loss_grad_kernel<<<(B + 7) / 8, 256, 0, st>>>(s, out->pred_pc1angle_logits, out->pred_pc2angle_logits,
                                           out->pred_remaining_angle_logits, dend, B, nb, m.arch.early_stage_factor,
                                           m.arch.angle_factor);
     AN3D_LAUNCH_CHECK();
