@@ -558,7 +558,7 @@ constexpr uint32_t kL2AccWG = 448;                             // wgrad2 accumul
 
 inline size_t l2_smem_bytes(int PC) {
   return kL2Groups * (8 + 16) * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
-         kL2Groups * 256 * 3 * 4 + kL2Groups * 4 * 64 * 16 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
+         kL2Groups * 256 * 4 * 4 + kL2Groups * 4 * 64 * 16 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
 }
 
 struct L2Bars {
@@ -572,15 +572,17 @@ struct L2Bars {
 static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
-  uint8_t* sA1b[kL2Groups] = {smem, smem + 8 * plane};
-  uint8_t* sDZb[kL2Groups] = {smem + 16 * plane, smem + 32 * plane};
+  // (functions of the group index, not pointer arrays: a runtime-indexed array would live in local memory)
+  auto sA1b = [&](int g) { return smem + (size_t)g * 8 * plane; };
+  auto sDZb = [&](int g) { return smem + (size_t)(16 + 16 * g) * plane; };
   uint8_t* sW2T = smem + 48 * plane;
   uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
-  float* sPtsAll = reinterpret_cast<float*>(sW2P + 128 * 128 * 2);   // [groups][256][3] transformed points
-  float4* sRedAll = reinterpret_cast<float4*>(sPtsAll + kL2Groups * 768);   // [groups][4 parts][64]
-  float* sW1f = reinterpret_cast<float*>(sRedAll + kL2Groups * 256);   // 192
-  float* sC1f = sW1f + 192;      // 64
-  float* sW1 = sC1f + 64;        // 192
+  float4* sPtsAll = reinterpret_cast<float4*>(sW2P + 128 * 128 * 2);   // [groups][256] transformed points (x, y, z, -)
+  float4* sRedAll = sPtsAll + kL2Groups * 256;                          // [groups][4 parts][64]
+  // folded layer-1 weights as one float4 (wx, wy, wz, c) per channel: the recompute reads them with ONE broadcast
+  // load per channel instead of four (256 LDS per thread and item before)
+  float4* sW1f4 = sRedAll + kL2Groups * 256;                            // 64
+  float* sW1 = reinterpret_cast<float*>(sW1f4 + 64);                    // 192
   float* sL1 = sW1 + 192;        // b1, mean1, inv1, gamma1, beta1 : 5 x 64
   float* sL2 = sL1 + 320;        // cx2 (= (b2-mean2)*inv2), inv2, s2, m0, m1, spare : 6 x 128
   L2Bars* bars = reinterpret_cast<L2Bars*>(sL2 + 768);
@@ -599,9 +601,9 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
     }
     fence_barrier_init();
   }
-  for (int i = tid; i < 192; i += kL2Threads) { sW1f[i] = P.w1f[i]; sW1[i] = P.W1[i]; }
+  for (int i = tid; i < 192; i += kL2Threads) sW1[i] = P.W1[i];
   for (int i = tid; i < 64; i += kL2Threads) {
-    sC1f[i] = P.c1f[i];
+    sW1f4[i] = make_float4(P.w1f[i], P.w1f[64 + i], P.w1f[128 + i], P.c1f[i]);
     sL1[i] = P.b1[i]; sL1[64 + i] = P.mean1[i]; sL1[128 + i] = P.inv1[i]; sL1[192 + i] = P.gamma1[i]; sL1[256 + i] = P.beta1[i];
   }
   for (int i = tid; i < 128; i += kL2Threads) {
@@ -620,9 +622,9 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
     const int k = t & 127, half = t >> 7;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t kD = grp * kL2AccStride;
-    uint8_t* sA1 = sA1b[grp];
-    uint8_t* sDZ = sDZb[grp];
-    float* sPts = sPtsAll + grp * 768;
+    uint8_t* sA1 = sA1b(grp);
+    uint8_t* sDZ = sDZb(grp);
+    float4* sPts = sPtsAll + grp * 256;
     float4* sRed = sRedAll + grp * 256;
     int prev_it = -1;
     float* xf = bars->xf[grp];
@@ -678,14 +680,14 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         if (p < nvalid) {
           const float x0 = cur_p[0] - xf[0], y0 = cur_p[1] - xf[1], z = cur_p[2] - xf[2];
           const float x = x0 * xf[3] - y0 * xf[4], y = x0 * xf[4] + y0 * xf[3];
-          sPts[p * 3] = x; sPts[p * 3 + 1] = y; sPts[p * 3 + 2] = z;
+          sPts[p] = make_float4(x, y, z, 0.f);
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = c8 * 8 + j;
-              v[j] = fmaxf(fmaf(x, sW1f[c], fmaf(y, sW1f[64 + c], fmaf(z, sW1f[128 + c], sC1f[c]))), 0.f);
+              const float4 w = sW1f4[c8 * 8 + j];
+              v[j] = fmaxf(fmaf(x, w.x, fmaf(y, w.y, fmaf(z, w.z, w.w))), 0.f);
             }
             uint4 q;
             q.x = convfwd::pack_bf16x2(v[0], v[1]); q.y = convfwd::pack_bf16x2(v[2], v[3]);
@@ -693,7 +695,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
             *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = q;
           }
         } else {
-          sPts[p * 3] = 0.f; sPts[p * 3 + 1] = 0.f; sPts[p * 3 + 2] = 0.f;
+          sPts[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = make_uint4(0, 0, 0, 0);
         }
@@ -749,7 +751,8 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           for (int j = 0; j < 16; ++j) {
             const int p = g16 + j;
             if (p < nvalid) {
-              const float x = sPts[p * 3], y = sPts[p * 3 + 1], z = sPts[p * 3 + 2];
+              const float4 pt = sPts[p];
+              const float x = pt.x, y = pt.y, z = pt.z;
               const float z1 = fmaf(x, wx, fmaf(y, wy, fmaf(z, wz, b1)));
               const float dy = fmaf(g1, (z1 - mu1) * inv1, be1) > 0.f ? __uint_as_float(r[j]) : 0.f;
               s0 += dy;
@@ -802,10 +805,10 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         return (nvalid + 15) & ~15;
       };
       const uint64_t w2t_desc = make_desc(smem_u32(sW2T), kPlaneW, 128), w2p_desc = make_desc(smem_u32(sW2P), kPlaneW, 128);
-      const uint64_t a1k_desc[2] = {make_desc(smem_u32(sA1b[0]), plane, 128), make_desc(smem_u32(sA1b[1]), plane, 128)};
-      const uint64_t a1m_desc[2] = {make_desc(smem_u32(sA1b[0]), 128, plane), make_desc(smem_u32(sA1b[1]), 128, plane)};
-      const uint64_t dzk_desc[2] = {make_desc(smem_u32(sDZb[0]), plane, 128), make_desc(smem_u32(sDZb[1]), plane, 128)};
-      const uint64_t dzm_desc[2] = {make_desc(smem_u32(sDZb[0]), 128, plane), make_desc(smem_u32(sDZb[1]), 128, plane)};
+      const uint64_t a1k_desc[2] = {make_desc(smem_u32(sA1b(0)), plane, 128), make_desc(smem_u32(sA1b(1)), plane, 128)};
+      const uint64_t a1m_desc[2] = {make_desc(smem_u32(sA1b(0)), 128, plane), make_desc(smem_u32(sA1b(1)), 128, plane)};
+      const uint64_t dzk_desc[2] = {make_desc(smem_u32(sDZb(0)), plane, 128), make_desc(smem_u32(sDZb(1)), plane, 128)};
+      const uint64_t dzm_desc[2] = {make_desc(smem_u32(sDZb(0)), 128, plane), make_desc(smem_u32(sDZb(1)), 128, plane)};
       // every group of MMAs and its commits is issued from one elected region (see umma.cuh)
       auto issue_d2 = [&](int li) {
         const int g = li & 1;
@@ -861,7 +864,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         const int g = li & 1;
         mbar_wait_relaxed(&bars->dz_free[g], (uint32_t)(((li >> 1) & 1) ^ 1));
         mbar_arrive_expect_tx(&bars->dz_full[g], P.img_bytes);
-        bulk_copy_g2s(sDZb[g], P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[g]);
+        bulk_copy_g2s(sDZb(g), P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[g]);
       }
     }
   }
