@@ -298,8 +298,8 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   const uint32_t sd_bytes = 8 * plane;
-  uint8_t* sA2[2] = {smem, smem + P.img_bytes};
-  uint8_t* sSd[2] = {smem + 2 * P.img_bytes, smem + 2 * P.img_bytes + sd_bytes};
+  auto sA2 = [&](int i) { return smem + (size_t)i * P.img_bytes; };        // (not pointer arrays: see bwd_l2_kernel)
+  auto sSd = [&](int i) { return smem + 2 * (size_t)P.img_bytes + (size_t)i * sd_bytes; };
   uint8_t* sW = smem + 2 * P.img_bytes + 2 * sd_bytes;
   float* sU = reinterpret_cast<float*>(sW + 3 * kWHalfBytes);
   float* sBeta = sU + 128;
@@ -321,7 +321,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     for (int i = 0; i < 3; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     fence_barrier_init();
   }
-  for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kDg3Threads * 16) *reinterpret_cast<uint4*>(sSd[0] + i) = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kDg3Threads * 16) *reinterpret_cast<uint4*>(sSd(0) + i) = make_uint4(0, 0, 0, 0);
   if (tid < 128) {
     sU[tid] = P.uvec[tid];
     sBeta[tid] = P.beta2[tid];
@@ -340,7 +340,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     const int k = (warp & 3) * 32 + lane;
     const int half = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph_d[2] = {0, 0};
+    uint32_t ph_d = 0;                    // (phase bits in one scalar: an array indexed by li & 1 lives in local memory)
     double acc0 = 0.0, acc1 = 0.0;
     const float u = sU[k], beta = sBeta[k], ig = sIg[k];
     for (int li = 0; li < n_local; ++li) {
@@ -351,28 +351,29 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       const int nh = ((NT >> 1) + 15) & ~15;
       const int pbeg = half ? min(nh, NT) : 0, pend = half ? NT : min(nh, NT);
       const int b = li & 1;
-      mbar_wait_relaxed(&bars->d_full[b], ph_d[b]); ph_d[b] ^= 1;
+      mbar_wait_relaxed(&bars->d_full[b], (ph_d >> b) & 1u); ph_d ^= 1u << b;
       tc_fence_after();
-      uint8_t* col = sA2[b] + (k >> 3) * plane + (k & 7) * 2;
-      float s0 = 0.f, s1 = 0.f;
+      uint8_t* col = smem + (size_t)b * P.img_bytes + (k >> 3) * plane + (k & 7) * 2;
+      // sums for the BN2 backward: s0 = sum dy, s1 = sum dy * xhat with xhat = (a - beta) / gamma, accumulated as
+      // sa = sum dy * a (one FMA per element) and finished once per item
+      float s0 = 0.f, sa = 0.f;
       for (int g16 = pbeg; g16 < pend; g16 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + b * 256 + g16, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int p = g16 + j;
-          __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
+          __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + (g16 + j) * 16);
           const float a = __bfloat162float(*ptr);
-          float dy = 0.f;
-          if (p < nvalid && a > 0.f) dy = __uint_as_float(r[j]) + u;
+          const float dy = a > 0.f ? __uint_as_float(r[j]) + u : 0.f;   // (padding rows of the image hold a = 0)
           const __nv_bfloat16 hb = __float2bfloat16_rn(dy);
           const float dyr = __bfloat162float(hb);
           s0 += dyr;
-          s1 = fmaf(dyr, (a - beta) * ig, s1);
+          sa = fmaf(dyr, a, sa);
           *ptr = hb;
         }
       }
+      const float s1 = (sa - beta * s0) * ig;
       acc0 += (double)s0; acc1 += (double)s1;
       tc_fence_before();
       __syncwarp();
@@ -380,7 +381,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) {
-        bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, sA2[b], P.img_bytes);
+        bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, smem + (size_t)b * P.img_bytes, P.img_bytes);
         bulk_wait_read_all();
         mbar_arrive(&bars->a2_free[b]);
       }
@@ -415,7 +416,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         }
       }
     };
-    uint8_t* sS = sSd[team];
+    uint8_t* sS = sSd(team);
     if (n_local > 0) fetch(0, cur_idx, cur_w);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
@@ -464,8 +465,8 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
         const uint32_t d_tmem = tmem + b * 256;
-        const uint64_t a2_desc = make_desc(smem_u32(sA2[b]), plane, 128);
-        const uint64_t sd_desc0 = make_desc(smem_u32(sSd[0]), plane, 128), sd_desc1 = make_desc(smem_u32(sSd[1]), plane, 128);
+        const uint64_t a2_desc = make_desc(smem_u32(sA2(b)), plane, 128);
+        const uint64_t sd_desc0 = make_desc(smem_u32(sSd(0)), plane, 128), sd_desc1 = make_desc(smem_u32(sSd(1)), plane, 128);
         for (int r = 0; r < nring; ++r) {
           mbar_wait(&bars->w_full[st], (ph_w >> st) & 1u); ph_w ^= 1u << st;
           const uint64_t a_desc = make_desc(w_base + (uint32_t)st * kWHalfBytes, kPlaneW, 128);
@@ -513,7 +514,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         const int b = li & 1;
         mbar_wait_relaxed(&bars->a2_free[b], ph_f[b]); ph_f[b] ^= 1;
         mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
-        bulk_copy_g2s(sA2[b], P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
+        bulk_copy_g2s(sA2(b), P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
       }
     }
   }
@@ -718,12 +719,20 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           uint32_t r[16];
           tmem_ld16(tmem + lane_base + kD + g16, r);
           tmem_ld_wait();
+          if (g16 + 16 <= nvalid) {              // (warp-uniform; only an item's last group has padding rows)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int p = g16 + j;
-            __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
-            const float dz = p < nvalid ? fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)) : 0.f;
-            *ptr = __float2bfloat16_rn(dz);
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + (g16 + j) * 16);
+              *ptr = __float2bfloat16_rn(fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int p = g16 + j;
+              __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
+              const float dz = p < nvalid ? fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)) : 0.f;
+              *ptr = __float2bfloat16_rn(dz);
+            }
           }
         }
       }
@@ -738,11 +747,15 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         // group) combinations each take a quarter of the point columns
         const int k1 = k & 63;
         const float wx = sW1[k1], wy = sW1[64 + k1], wz = sW1[128 + k1];
-        const float b1 = sL1[k1], mu1 = sL1[64 + k1], inv1 = sL1[128 + k1], g1 = sL1[192 + k1], be1 = sL1[256 + k1];
+        const float b1 = sL1[k1], mu1 = sL1[64 + k1], inv1 = sL1[128 + k1];
         const int nq = ((NT >> 2) + 15) & ~15;
         const int part = (k >> 6) + 2 * half;
         const int pbeg = min(NT, part * nq), pend = part == 3 ? NT : min(NT, (part + 1) * nq);
         float s0 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+        // ReLU mask of layer 1 straight from the recomputed a1 tile (still intact: the next item's recompute waits for
+        // barrier A): one 2-byte load and a sign test instead of re-evaluating the layer and its BN per element.
+        // Padding rows hold a1 = 0, so they drop out without a bounds test.
+        const uint8_t* a1col = sA1 + (k1 >> 3) * plane + (k1 & 7) * 2;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
           tmem_ld16(tmem + lane_base + kD + g16, r);
@@ -750,16 +763,13 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int p = g16 + j;
-            if (p < nvalid) {
-              const float4 pt = sPts[p];
-              const float x = pt.x, y = pt.y, z = pt.z;
-              const float z1 = fmaf(x, wx, fmaf(y, wy, fmaf(z, wz, b1)));
-              const float dy = fmaf(g1, (z1 - mu1) * inv1, be1) > 0.f ? __uint_as_float(r[j]) : 0.f;
-              s0 += dy;
-              sx = fmaf(dy, x, sx);
-              sy = fmaf(dy, y, sy);
-              sz = fmaf(dy, z, sz);
-            }
+            const short a1bits = *reinterpret_cast<const short*>(a1col + p * 16);
+            const float dy = a1bits > 0 ? __uint_as_float(r[j]) : 0.f;
+            const float4 pt = sPts[p];
+            s0 += dy;
+            sx = fmaf(dy, pt.x, sx);
+            sy = fmaf(dy, pt.y, sy);
+            sz = fmaf(dy, pt.z, sz);
           }
         }
         sRed[part * 64 + k1] = make_float4(s0, sx, sy, sz);
