@@ -330,7 +330,7 @@ int conv_stack_backward_bf16(const Model& m, const PlanF32& p, int s, int br, co
     D.a2_img = reinterpret_cast<const uint8_t*>(q.a2img[s][br]); D.dy2_img = reinterpret_cast<uint8_t*>(w.dy2img);
     D.img_bytes = (uint32_t)q.img_bytes; D.gidx = p.gidx[s][br]; D.dyext = w.dyext; D.s3 = sc3; D.gq_img = w.gq;
     D.w3n_img = q.w3n[s]; D.uvec = w.uvec; D.gamma2 = gamma2; D.beta2 = beta2; D.B = B; D.N = N; D.PC = q.PC; D.npc = q.npc;
-    D.C3 = C3; D.n_items = n_items; D.red2 = w.red2;
+    D.C3 = C3; D.n_items = n_items; D.red2 = w.red2; D.wstages = convbwd::dg3_wstages(q.PC);
     const int grid = std::min(n_items, sms);
     D.items_per_cta = (n_items + grid - 1) / grid;
     const size_t smem = convbwd::dg3_smem_bytes(q.PC);

@@ -277,6 +277,7 @@ struct Dg3Params {
   const float* gamma2;           // [128]
   const float* beta2;            // [128]
   int B, N, PC, npc, C3, n_items, items_per_cta;
+  int wstages;                   // depth of the weight ring (3 or 4)
   double* red2;                  // [128][2] sum dy2, sum dy2 * xhat2
 };
 // warps 0-7 epilogue (two per TMEM lane quarter, each takes half of the point columns), warps 8-11 two scatter
@@ -285,12 +286,17 @@ constexpr int kDg3Threads = 480;
 constexpr int kDg3EpiThreads = 256;
 constexpr int kDg3MmaWarp = 12;
 
+// weight ring depth: the kernel is bound by the latency of this ring (every cloud re-streams all W3 half-chunks), and a
+// fourth 16 KB stage is what still fits next to two A2 tiles and two scatter tiles at 208 points per item
+inline int dg3_wstages(int PC) {
+  return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 4 * kWHalfBytes + 3 * 128 * 4 + 256 <= 227 * 1024 ? 4 : 3;
+}
 inline size_t dg3_smem_bytes(int PC) {
-  return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + 3 * kWHalfBytes + 3 * 128 * 4 + 256;
+  return 2 * 16 * (size_t)plane_stride(PC) + 2 * 8 * (size_t)plane_stride(PC) + dg3_wstages(PC) * kWHalfBytes + 3 * 128 * 4 + 256;
 }
 
 struct Dg3Bars {
-  uint64_t a2_full[2], a2_free[2], w_full[3], w_empty[3], sd_full[2], sd_empty[2], d_full[2], d_empty[2];
+  uint64_t a2_full[2], a2_free[2], w_full[4], w_empty[4], sd_full[2], sd_empty[2], d_full[2], d_empty[2];
   uint32_t tmem_base;
 };
 
@@ -301,7 +307,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   auto sA2 = [&](int i) { return smem + (size_t)i * P.img_bytes; };        // (not pointer arrays: see bwd_l2_kernel)
   auto sSd = [&](int i) { return smem + 2 * (size_t)P.img_bytes + (size_t)i * sd_bytes; };
   uint8_t* sW = smem + 2 * P.img_bytes + 2 * sd_bytes;
-  float* sU = reinterpret_cast<float*>(sW + 3 * kWHalfBytes);
+  float* sU = reinterpret_cast<float*>(sW + (size_t)P.wstages * kWHalfBytes);
   float* sBeta = sU + 128;
   float* sIg = sBeta + 128;
   Dg3Bars* bars = reinterpret_cast<Dg3Bars*>(sIg + 128);
@@ -318,7 +324,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       mbar_init(&bars->sd_full[i], 2); mbar_init(&bars->sd_empty[i], 1);      // one arrival per warp of the team
       mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], kDg3EpiThreads / 32);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     fence_barrier_init();
   }
   for (uint32_t i = tid * 16; i < 2 * sd_bytes; i += kDg3Threads * 16) *reinterpret_cast<uint4*>(sSd(0) + i) = make_uint4(0, 0, 0, 0);
@@ -489,18 +495,18 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
             if (r == nring - 1) mma_commit_raw(&bars->d_full[b]);
           }
           __syncwarp();
-          if (++st == 3) st = 0;
+          if (++st == P.wstages) st = 0;
         }
       }
     }
   } else if (warp == kDg3MmaWarp + 1) {
     if (lane == 0 && n_local > 0) {
-      uint32_t ph_e[3] = {1, 1, 1};
+      uint32_t ph_e = 0xfu;                 // one phase bit per stage
       int wq = 0;
       for (int li = 0; li < n_local; ++li) {
         for (int r = 0; r < nring; ++r, ++wq) {
-          const int st = wq % 3;
-          mbar_wait_relaxed(&bars->w_empty[st], ph_e[st]); ph_e[st] ^= 1;
+          const int st = wq % P.wstages;
+          mbar_wait_relaxed(&bars->w_empty[st], (ph_e >> st) & 1u); ph_e ^= 1u << st;
           mbar_arrive_expect_tx(&bars->w_full[st], kWHalfBytes);
           const __nv_bfloat16* src = r < 2 ? P.gq_img + (size_t)r * 8192 : P.w3n_img + (size_t)(r - 2) * 8192;
           bulk_copy_g2s(sW + (size_t)st * kWHalfBytes, src, kWHalfBytes, &bars->w_full[st]);
