@@ -86,7 +86,9 @@ static __global__ void __launch_bounds__(kGram2Threads, 1) gram2_kernel(const Gr
       const uint32_t idesc = make_idesc(128, kGram2Cols, 1, 1);
       uint32_t ph = 0;
       for (int li = 0; li < n_local; ++li) {
-        const int it = it_begin + li;
+        // the range is walked BACKWARDS: the forward kernel (same item partition) wrote the images in ascending order a
+        // moment ago, so the tail of every CTA's range is what may still sit in L2
+        const int it = it_end - 1 - li;
         const int cloud = it / P.npc, pchunk = it - cloud * P.npc;
         const int nvalid = min(P.PC, P.N - pchunk * P.PC);
         const int NT = (nvalid + 15) & ~15;
@@ -110,7 +112,7 @@ static __global__ void __launch_bounds__(kGram2Threads, 1) gram2_kernel(const Gr
         const int b = li % kGram2Bufs;
         mbar_wait_sleep(&bars->empty[b], (ph_e >> b) & 1u, 128u); ph_e ^= 1u << b;
         mbar_arrive_expect_tx(&bars->full[b], P.img_bytes);
-        bulk_copy_g2s(smem + b * buf_bytes, P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->full[b]);
+        bulk_copy_g2s(smem + b * buf_bytes, P.a2_img + (size_t)(it_end - 1 - li) * P.img_bytes, P.img_bytes, &bars->full[b]);
       }
     }
   } else if (n_local > 0) {
@@ -466,7 +468,6 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         const int NT = (nvalid + 15) & ~15;
         const int b = li & 1;
         (void)cloud;
-        mbar_wait(&bars->a2_full[b], (ph_a2 >> b) & 1u); ph_a2 ^= 1u << b;
         mbar_wait(&bars->d_empty[b], (ph_de >> b) & 1u); ph_de ^= 1u << b;
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
@@ -478,8 +479,12 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           const uint64_t a_desc = make_desc(w_base + (uint32_t)st * kWHalfBytes, kPlaneW, 128);
           uint64_t b_desc;
           const int sb = r & 1;
-          if (r < 2) {
-            b_desc = desc_advance(a2_desc, r * 8 * plane);
+          // ring order: the nhc scatter steps first, the two Gq steps last -- only those read the A2 tile, so its
+          // (HBM-latency) load hides behind the scatter steps instead of heading the item's dependency chain
+          const bool scatter_step = r < nhc;
+          if (!scatter_step) {
+            if (r == nhc) { mbar_wait(&bars->a2_full[b], (ph_a2 >> b) & 1u); ph_a2 ^= 1u << b; }
+            b_desc = desc_advance(a2_desc, (r - nhc) * 8 * plane);
           } else {
             mbar_wait(&bars->sd_full[sb], (ph_sd >> sb) & 1u); ph_sd ^= 1u << sb;
             b_desc = sb ? sd_desc1 : sd_desc0;
@@ -490,7 +495,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
             for (int ks = 0; ks < 4; ++ks)
               mma_bf16_raw(d_tmem, desc_advance(a_desc, ks * 2 * kPlaneW), desc_advance(b_desc, ks * 2 * plane), idesc,
                            (r > 0 || ks > 0) ? 1u : 0u);
-            if (r >= 2) mma_commit_raw(&bars->sd_empty[sb]);
+            if (scatter_step) mma_commit_raw(&bars->sd_empty[sb]);
             mma_commit_raw(&bars->w_empty[st]);
             if (r == nring - 1) mma_commit_raw(&bars->d_full[b]);
           }
@@ -508,17 +513,17 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           const int st = wq % P.wstages;
           mbar_wait_relaxed(&bars->w_empty[st], (ph_e >> st) & 1u); ph_e ^= 1u << st;
           mbar_arrive_expect_tx(&bars->w_full[st], kWHalfBytes);
-          const __nv_bfloat16* src = r < 2 ? P.gq_img + (size_t)r * 8192 : P.w3n_img + (size_t)(r - 2) * 8192;
+          const __nv_bfloat16* src = r < nhc ? P.w3n_img + (size_t)r * 8192 : P.gq_img + (size_t)(r - nhc) * 8192;
           bulk_copy_g2s(sW + (size_t)st * kWHalfBytes, src, kWHalfBytes, &bars->w_full[st]);
         }
       }
     }
   } else {
     if (lane == 0) {
-      uint32_t ph_f[2] = {1, 1};
+      uint32_t ph_f = 3u;
       for (int li = 0; li < n_local; ++li) {
         const int b = li & 1;
-        mbar_wait_relaxed(&bars->a2_free[b], ph_f[b]); ph_f[b] ^= 1;
+        mbar_wait_relaxed(&bars->a2_free[b], (ph_f >> b) & 1u); ph_f ^= 1u << b;
         mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
         bulk_copy_g2s(sA2(b), P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
       }
@@ -694,11 +699,11 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 w = sW1f4[c8 * 8 + j];
-              v[j] = fmaxf(fmaf(x, w.x, fmaf(y, w.y, fmaf(z, w.z, w.w))), 0.f);
+              v[j] = fmaf(x, w.x, fmaf(y, w.y, fmaf(z, w.z, w.w)));
             }
-            uint4 q;
-            q.x = convfwd::pack_bf16x2(v[0], v[1]); q.y = convfwd::pack_bf16x2(v[2], v[3]);
-            q.z = convfwd::pack_bf16x2(v[4], v[5]); q.w = convfwd::pack_bf16x2(v[6], v[7]);
+            uint4 q;   // (ReLU inside the conversion, as in the forward kernel: same bits)
+            q.x = convfwd::pack_bf16x2_relu(v[0], v[1]); q.y = convfwd::pack_bf16x2_relu(v[2], v[3]);
+            q.z = convfwd::pack_bf16x2_relu(v[4], v[5]); q.w = convfwd::pack_bf16x2_relu(v[6], v[7]);
             *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = q;
           }
         } else {
@@ -828,7 +833,6 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       // every group of MMAs and its commits is issued from one elected region (see umma.cuh)
       auto issue_d2 = [&](int li) {
         const int g = li & 1;
-        mbar_wait(&bars->a1_full[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, nt_of(li), 0, 0);
         if (elect_one()) {
@@ -840,10 +844,10 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         }
         __syncwarp();
       };
+      bool wg_started = false;
       auto issue_bwd = [&](int li) {
         const int g = li & 1;
         const int NT = nt_of(li);
-        mbar_wait(&bars->dz_ready[g], (uint32_t)((li >> 1) & 1));
         tc_fence_after();
         const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
@@ -852,7 +856,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           const uint64_t dzk = g ? dzk_desc[1] : dzk_desc[0];
           for (int ks = 0; ks < NT / 16; ++ks)
             mma_bf16_raw(tmem + kL2AccWG, desc_advance(dzm, ks * 256), desc_advance(a1m, ks * 256), idesc_w,
-                         (li > 0 || ks > 0) ? 1u : 0u);
+                         (wg_started || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             mma_bf16_raw(tmem + g * kL2AccStride, desc_advance(w2p_desc, ks * 2 * kPlaneW), desc_advance(dzk, ks * 2 * plane),
@@ -860,14 +864,17 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           mma_commit_raw(&bars->da_full[g]);
           mma_commit_raw(&bars->dz_free[g]);
         }
+        wg_started = true;
         __syncwarp();
       };
       // fixed service order D2(2q), D2(2q+1), BWD(2q), BWD(2q+1): consistent with each group's own sequence
       for (int q = 0; q < n_local; q += 2) {
+        mbar_wait(&bars->a1_full[0], (uint32_t)((q >> 1) & 1));
         issue_d2(q);
-        if (q + 1 < n_local) issue_d2(q + 1);
+        if (q + 1 < n_local) { mbar_wait(&bars->a1_full[1], (uint32_t)((q >> 1) & 1)); issue_d2(q + 1); }
+        mbar_wait(&bars->dz_ready[0], (uint32_t)((q >> 1) & 1));
         issue_bwd(q);
-        if (q + 1 < n_local) issue_bwd(q + 1);
+        if (q + 1 < n_local) { mbar_wait(&bars->dz_ready[1], (uint32_t)((q >> 1) & 1)); issue_bwd(q + 1); }
       }
       mma_commit(&bars->done);
     }

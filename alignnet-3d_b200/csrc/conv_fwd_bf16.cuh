@@ -92,6 +92,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// bf16x2(max(lo, 0), max(hi, 0)) in ONE conversion: the ReLU rides on the pack (cvt's .relu clamps negative results to
+// +0), which takes an FMNMX per element off the ALU pipe -- the pipe this kernel's front end is bound by.
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -183,9 +191,9 @@ __device__ __forceinline__ uint4 layer1_chunk(const float4 raw, float cx, float 
     const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j]))), 0.f);
-    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j])));
+    q.x = pack_bf16x2_relu(v[0], v[1]); q.y = pack_bf16x2_relu(v[2], v[3]);
+    q.z = pack_bf16x2_relu(v[4], v[5]); q.w = pack_bf16x2_relu(v[6], v[7]);
   }
   return q;
 }
@@ -309,19 +317,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           uint32_t r[32];
           tmem_ld32(tb + h * 32, r);
           tmem_ld_wait();
-          if (p < NT) {
+          // (padding rows of the tile are zeroed by a branch, not by a select per packed word: only the item's last
+          // warp diverges, and then only to eight stores)
+          if (real) {
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
               uint32_t o[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 bn = sBn2[fgroup * 32 + h * 16 + c8 * 4 + j];      // broadcast: channels 2c, 2c+1
-                const float v0 = fmaxf(fmaf(__uint_as_float(r[c8 * 8 + 2 * j]), bn.x, bn.y), 0.f);
-                const float v1 = fmaxf(fmaf(__uint_as_float(r[c8 * 8 + 2 * j + 1]), bn.z, bn.w), 0.f);
-                o[j] = real ? pack_bf16x2(v0, v1) : 0u;
+                o[j] = pack_bf16x2_relu(fmaf(__uint_as_float(r[c8 * 8 + 2 * j]), bn.x, bn.y),
+                                        fmaf(__uint_as_float(r[c8 * 8 + 2 * j + 1]), bn.z, bn.w));
               }
               *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + c8) * plane2) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+          } else if (p < NT) {
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8)
+              *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + c8) * plane2) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }
@@ -476,11 +489,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
     if (lane == 0 && n_local > 0) {
       mbar_arrive_expect_tx(&bars->w2_full, kW2Bytes);
       bulk_copy_g2s(sW2, P.w2t_img, kW2Bytes, &bars->w2_full);
-      uint32_t ph_e[3] = {1, 1, 1};
+      uint32_t ph_e = 7u;
       const int total = n_local * P.nchunk;
       for (int q = 0; q < total; ++q) {
         const int stage = q % P.nstages;
-        mbar_wait_sleep(&bars->w3_empty[stage], ph_e[stage], 128u); ph_e[stage] ^= 1;
+        mbar_wait_sleep(&bars->w3_empty[stage], (ph_e >> stage) & 1u, 128u); ph_e ^= 1u << stage;
         mbar_arrive_expect_tx(&bars->w3_full[stage], kW3ChunkBytes);
         bulk_copy_g2s(sW3 + (size_t)stage * kW3ChunkBytes,
                       P.w3t_img + (size_t)(q % P.nchunk) * (kW3ChunkBytes / 2), kW3ChunkBytes,
@@ -568,13 +581,13 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
         pf_p0 = src[0]; pf_p1 = src[1]; pf_p2 = src[2];
       }
     };
-    uint32_t ph_e[2] = {0, 0};
+    uint32_t ph_e = 0;
     if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li) {
       const Item I = item_of(P, it_begin + li);
       const int nvalid = I.nvalid, NT = I.NT;
       const int b = li & 1;
-      if (li >= 2) { mbar_wait_sleep(&bars->a1_empty[b], ph_e[b], 128u); ph_e[b] ^= 1; }
+      if (li >= 2) { mbar_wait_sleep(&bars->a1_empty[b], (ph_e >> b) & 1u, 128u); ph_e ^= 1u << b; }
       if (f == 0) {
         float sn = 0.f, cs = 1.f;
         if (P.angle) sincosf(pf_ang, &sn, &cs);
@@ -621,11 +634,11 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
     }
   } else if (n_local > 0) {
     const uint32_t idesc = make_idesc(128, 80, 1, 1);
-    uint32_t ph[2] = {0, 0};
+    uint32_t ph = 0;
     for (int li = 0; li < n_local; ++li) {
       const Item I = item_of(P, it_begin + li);
       const int b = li & 1;
-      mbar_wait(&bars->a1_full[b], ph[b]); ph[b] ^= 1;
+      mbar_wait(&bars->a1_full[b], (ph >> b) & 1u); ph ^= 1u << b;
       tc_fence_after();
       if (elect_one()) {
         // contraction over the item's points: both operands are the A1 tile read MN-major (rows = points)
