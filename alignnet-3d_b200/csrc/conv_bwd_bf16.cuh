@@ -23,6 +23,14 @@ namespace convbwd {
 using namespace umma;
 using convfwd::plane_stride;
 
+// -DAN3D_TIMELINE: CTA 0 of dgrad3 / bwd_l2 stamps clock64() at its roles' hand-over points and prints one line per item
+// (tools/build_variants.sh ... -DAN3D_TIMELINE; read with tools/prof_step.py).  Never defined in the shipped build.
+#ifdef AN3D_TIMELINE
+static __device__ long long g_tl[12][64];
+#define TL(slot, li) do { if (blockIdx.x == 0 && (li) < 64) g_tl[slot][li] = clock64(); } while (0)
+#else
+#define TL(slot, li) do { } while (0)
+#endif
 constexpr uint32_t kWHalfBytes = 128 * 64 * 2;   // one [128 rows][64 k] weight image
 constexpr uint32_t kPlaneW = 2048;
 
@@ -360,6 +368,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       const int pbeg = half ? min(nh, NT) : 0, pend = half ? NT : min(nh, NT);
       const int b = li & 1;
       mbar_wait_relaxed(&bars->d_full[b], (ph_d >> b) & 1u); ph_d ^= 1u << b;
+      if (tid == 0) TL(0, li);
       tc_fence_after();
       uint8_t* col = smem + (size_t)b * P.img_bytes + (k >> 3) * plane + (k & 7) * 2;
       // sums for the BN2 backward: s0 = sum dy, s1 = sum dy * xhat with xhat = (a - beta) / gamma, accumulated as
@@ -383,14 +392,17 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       }
       const float s1 = (sa - beta * s0) * ig;
       acc0 += (double)s0; acc1 += (double)s1;
+      if (tid == 0) TL(1, li);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->d_empty[b]);
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) {
+        TL(2, li);
         bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, smem + (size_t)b * P.img_bytes, P.img_bytes);
         bulk_wait_read_all();
+        TL(3, li);
         mbar_arrive(&bars->a2_free[b]);
       }
     }
@@ -469,6 +481,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
         const int b = li & 1;
         (void)cloud;
         mbar_wait(&bars->d_empty[b], (ph_de >> b) & 1u); ph_de ^= 1u << b;
+        if (lane == 0) TL(4, li);
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, NT, 0, 0);
         const uint32_t d_tmem = tmem + b * 256;
@@ -483,7 +496,11 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           // (HBM-latency) load hides behind the scatter steps instead of heading the item's dependency chain
           const bool scatter_step = r < nhc;
           if (!scatter_step) {
-            if (r == nhc) { mbar_wait(&bars->a2_full[b], (ph_a2 >> b) & 1u); ph_a2 ^= 1u << b; }
+            if (r == nhc) {
+              if (lane == 0) TL(5, li);
+              mbar_wait(&bars->a2_full[b], (ph_a2 >> b) & 1u); ph_a2 ^= 1u << b;
+              if (lane == 0) TL(6, li);
+            }
             b_desc = desc_advance(a2_desc, (r - nhc) * 8 * plane);
           } else {
             mbar_wait(&bars->sd_full[sb], (ph_sd >> sb) & 1u); ph_sd ^= 1u << sb;
@@ -524,6 +541,7 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       for (int li = 0; li < n_local; ++li) {
         const int b = li & 1;
         mbar_wait_relaxed(&bars->a2_free[b], (ph_f >> b) & 1u); ph_f ^= 1u << b;
+        TL(7, li);
         mbar_arrive_expect_tx(&bars->a2_full[b], P.img_bytes);
         bulk_copy_g2s(sA2(b), P.a2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->a2_full[b]);
       }
@@ -532,6 +550,15 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   tc_fence_before();
   __syncthreads();
   if (warp == kDg3MmaWarp) tmem_dealloc(tmem, 512);
+#ifdef AN3D_TIMELINE
+  if (blockIdx.x == 0 && tid == 0) {
+    const long long t0 = g_tl[7][0];
+    for (int li = 0; li < min(n_local, 64); ++li)
+      printf("DG3 C3=%d li=%d load_issue=%lld mma_start=%lld gq_wait=%lld a2_full=%lld d_full=%lld epi_end=%lld store_issue=%lld store_read=%lld\n",
+             P.C3, li, g_tl[7][li] - t0, g_tl[4][li] - t0, g_tl[5][li] - t0, g_tl[6][li] - t0, g_tl[0][li] - t0, g_tl[1][li] - t0,
+             g_tl[2][li] - t0, g_tl[3][li] - t0);
+  }
+#endif
 }
 
 // =============================================================================================
@@ -684,6 +711,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       // barrier B: xf visible; sRed has been flushed before this item's dy1 phase rewrites it
       if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (t == 0) TL(0, li);
       const float cur_p[3] = {pf_p[0], pf_p[1], pf_p[2]};
       if (li + kL2Groups < n_local) prefetch(li + kL2Groups);
       // ---- recompute a1 (layer 1), one thread per point ----
@@ -712,11 +740,14 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(sA1 + c8 * plane + p * 16) = make_uint4(0, 0, 0, 0);
         }
       }
+      if (t == 0) TL(1, li);
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full[grp]);
       // ---- dz2 from the raw layer-2 accumulator (xhat2) and dy2 ----
       mbar_wait_relaxed(&bars->d2_full[grp], ph);
+      if (t == 0) TL(2, li);
       mbar_wait_relaxed(&bars->dz_full[grp], ph);
+      if (t == 0) TL(3, li);
       tc_fence_after();
       {
         // dz = s2 (dy - m0 - xhat m1), xhat = acc*inv2 + cx   ==   dy*cA + cB + acc*cC
@@ -747,11 +778,13 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           }
         }
       }
+      if (t == 0) TL(4, li);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bars->dz_ready[grp]);
       // ---- dy1 = da1 * [a1 > 0], BN1 backward sums (channels k1 < 64 only) ----
       mbar_wait_relaxed(&bars->da_full[grp], ph);
+      if (t == 0) TL(5, li);
       tc_fence_after();
       {
         // accumulator rows 64..127 duplicate rows 0..63: channel k1 = k & 63, and the four (lane half, warp
@@ -788,6 +821,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         r0 += (double)s0;
         r1 += (double)(inv1 * (wx * sx + wy * sy + wz * sz + (b1 - mu1) * s0));
       }
+      if (t == 0) TL(6, li);
       tc_fence_before();
     }
     if (n_local > 0) {
@@ -894,6 +928,15 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
   tc_fence_before();
   __syncthreads();
   if (warp == kL2MmaWarp) tmem_dealloc(tmem, 512);
+#ifdef AN3D_TIMELINE
+  if (blockIdx.x == 0 && tid == 0) {
+    const long long t0 = g_tl[0][0];
+    for (int li = 0; li < min(n_local, 64); ++li)
+      printf("L2 li=%d start=%lld a1_done=%lld d2_full=%lld dz_full=%lld dz_done=%lld da_full=%lld dy1_done=%lld\n", li,
+             g_tl[0][li] - t0, g_tl[1][li] - t0, g_tl[2][li] - t0, g_tl[3][li] - t0, g_tl[4][li] - t0, g_tl[5][li] - t0,
+             g_tl[6][li] - t0);
+  }
+#endif
 }
 
 }  // namespace convbwd

@@ -163,7 +163,13 @@ __device__ __forceinline__ float floor_mod_fast(float x, float y, float inv_y) {
 __global__ void __launch_bounds__(128) loss_pair_kernel(LossScratch s, int B, int nb, int ichunk) {
   __shared__ double sm[8];
   __shared__ float srow[256];
+  // the two stage-3 variants cost ~3x the others per pair: they go FIRST (blocks are dispatched in ascending z), so the
+  // tail of the grid is made of the light blocks
+#ifdef AN3D_LOSS_OLD_ORDER
   const int iv = blockIdx.z, inst = iv >> 1, v = iv & 1;
+#else
+  const int iv = 5 - (int)blockIdx.z, inst = iv >> 1, v = iv & 1;
+#endif
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = blockIdx.y * ichunk, i1 = min(B, i0 + ichunk);
   const float* rows = inst < 2 ? s.lab + iv * B : s.gt3;
