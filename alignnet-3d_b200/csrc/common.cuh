@@ -132,7 +132,7 @@ struct BwdScratch {
   __nv_bfloat16* gq = nullptr;              // Gq image, two K halves [2][128][64]
   float* gq_f32 = nullptr;                  // [128][128] fp32 accumulation of Gq
   float* uvec = nullptr;                    // [128]
-  __nv_bfloat16* dy2img = nullptr;          // per item image of dy2 (same format as a2img)
+  __nv_bfloat16* dy2img = nullptr;          // per item image of dy2, TRANSPOSED (convbwd::dy2_img_bytes; fits the a2img size)
   double* red2 = nullptr;                   // [128][2]
   float* coef2 = nullptr;                   // [128][2]  m0, m1
   float* l1sums = nullptr;                  // [items][64][4]: sum_p dy1 * (1, x, y, z) per item and channel

@@ -11,7 +11,12 @@
 //   t1_sparse_kernel : T1 = A2^T S, the sparse part of wgrad3
 //   dgrad3_kernel : da2 -> dy2 (ReLU mask) + BN2 backward sums, per cloud
 //   bwd_l2_kernel : dz2 -> wgrad2, da1 -> dy1 + BN1 backward sums
-// A2 / dy2 tiles travel between kernels as the exact shared-memory plane images (bulk copies).
+// A2 tiles travel between kernels as the exact shared-memory plane images (bulk copies).  dy2 travels TRANSPOSED
+// (dy2_img_bytes below): the accumulators of dgrad3 / bwd_l2 are channel-major (thread = channel, registers = consecutive
+// points), so an image whose 16-byte chunks hold 8 consecutive POINTS of one channel is written and re-read with 16-byte
+// accesses, where the forward layout (chunk = 8 channels of one point) costs a 2-byte access per element.  Both kernels
+// are bound by shared-memory bandwidth (the MMAs' operand reads alone take ~45 % of it), not by issue slots or the tensor
+// pipe (profiles/r2_timeline_bwd.txt), so the epilogues' access width is what matters.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -32,6 +37,11 @@ static __device__ long long g_tl[12][64];
 #define TL(slot, li) do { } while (0)
 #endif
 constexpr uint32_t kWHalfBytes = 128 * 64 * 2;   // one [128 rows][64 k] weight image
+// Transposed tile image [point block of 8][128 channels][8 points] bf16: element (pt, k) at (pt / 8) * 2048 + k * 16 +
+// (pt % 8) * 2.  As an MMA operand it is K-major for a contraction over points (rows = channels; LBO = 2048, SBO = 128)
+// and MN-major for a contraction over channels (rows = K = channels, MN = points; LBO = 128, SBO = 2048).
+constexpr uint32_t kTPlane = 2048;
+__host__ __device__ inline uint32_t dy2_img_bytes(int PC) { return (uint32_t)(PC / 8) * kTPlane; }
 constexpr uint32_t kPlaneW = 2048;
 
 // =============================================================================================
@@ -272,7 +282,8 @@ static __global__ void __launch_bounds__(1024, 1) t1_sparse_kernel(const T1Param
 }
 
 // =============================================================================================
-// dgrad3: da2^T[k, pt] = Gq a2^T + u + W3 S^T ; dy2 = da2 * [a2 > 0] ; sums for the BN2 backward
+// dgrad3: da2^T[k, pt] = Gq a2^T + u + W3 S^T ; dy2 = da2 * [a2 > 0] (written as the transposed image) ; sums for the
+// BN2 backward
 // =============================================================================================
 struct Dg3Params {
   const uint8_t* a2_img;
@@ -306,7 +317,7 @@ inline size_t dg3_smem_bytes(int PC) {
 }
 
 struct Dg3Bars {
-  uint64_t a2_full[2], a2_free[2], w_full[4], w_empty[4], sd_full[2], sd_empty[2], d_full[2], d_empty[2];
+  uint64_t a2_full[2], a2_free[2], w_full[4], w_empty[4], sd_full[2], sd_empty[4], d_full[2], d_empty[2];
   uint32_t tmem_base;
 };
 
@@ -327,11 +338,13 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   const int n_local = it_end - it_begin;
   const int nhc = P.C3 / 64;           // even: C3 is a multiple of 128
   const int nring = 2 + nhc;
+  const uint32_t dy2_bytes = dy2_img_bytes(P.PC);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_free[i], 1);
-      mbar_init(&bars->sd_full[i], 2); mbar_init(&bars->sd_empty[i], 1);      // one arrival per warp of the team
+      mbar_init(&bars->a2_full[i], 1); mbar_init(&bars->a2_free[i], kDg3EpiThreads / 32);
+      mbar_init(&bars->sd_full[i], 2);                                       // one arrival per warp of the team
+      mbar_init(&bars->sd_empty[2 * i], 1); mbar_init(&bars->sd_empty[2 * i + 1], 1);
       mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], kDg3EpiThreads / 32);
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
@@ -370,24 +383,45 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       mbar_wait_relaxed(&bars->d_full[b], (ph_d >> b) & 1u); ph_d ^= 1u << b;
       if (tid == 0) TL(0, li);
       tc_fence_after();
-      uint8_t* col = smem + (size_t)b * P.img_bytes + (k >> 3) * plane + (k & 7) * 2;
+      const uint8_t* col = smem + (size_t)b * P.img_bytes + (k >> 3) * plane + (k & 7) * 2;
+      uint8_t* gout = P.dy2_img + (size_t)it * dy2_bytes + (size_t)k * 16;
       // sums for the BN2 backward: s0 = sum dy, s1 = sum dy * xhat with xhat = (a - beta) / gamma, accumulated as
       // sa = sum dy * a (one FMA per element) and finished once per item
       float s0 = 0.f, sa = 0.f;
-      for (int g16 = pbeg; g16 < pend; g16 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_base + b * 256 + g16, r);
-        tmem_ld_wait();
+      // 16 points per step; the TMEM load of the next step is in flight while this one is processed
+      auto step = [&](const uint32_t (&r)[16], int g16) {
+        uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + (g16 + j) * 16);
-          const float a = __bfloat162float(*ptr);
-          const float dy = a > 0.f ? __uint_as_float(r[j]) + u : 0.f;   // (padding rows of the image hold a = 0)
-          const __nv_bfloat16 hb = __float2bfloat16_rn(dy);
-          const float dyr = __bfloat162float(hb);
-          s0 += dyr;
-          sa = fmaf(dyr, a, sa);
-          *ptr = hb;
+        for (int j = 0; j < 16; j += 2) {
+          const float a0 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(col + (g16 + j) * 16));
+          const float a1 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(col + (g16 + j + 1) * 16));
+          const float d0 = a0 > 0.f ? __uint_as_float(r[j]) + u : 0.f;   // (padding rows of the image hold a = 0)
+          const float d1 = a1 > 0.f ? __uint_as_float(r[j + 1]) + u : 0.f;
+          const uint32_t pk = convfwd::pack_bf16x2(d0, d1);
+          const float q0 = __uint_as_float(pk << 16), q1 = __uint_as_float(pk & 0xffff0000u);   // dy as stored
+          s0 += q0; s0 += q1;
+          sa = fmaf(q0, a0, sa); sa = fmaf(q1, a1, sa);
+          o[j >> 1] = pk;
+        }
+        // 16 consecutive points of this thread's channel = two 16-byte chunks of the transposed image, straight to global
+        // memory (a warp writes 512 contiguous bytes per store): no shared-memory write, no bulk store
+        uint8_t* dst = gout + (size_t)(g16 >> 3) * kTPlane;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + kTPlane) = make_uint4(o[4], o[5], o[6], o[7]);
+      };
+      {
+        const uint32_t tb = tmem + lane_base + b * 256;
+        uint32_t ra[16], rb[16];
+        if (pbeg < pend) tmem_ld16(tb + pbeg, ra);
+        for (int g16 = pbeg; g16 < pend; g16 += 32) {
+          tmem_ld_wait();
+          if (g16 + 16 < pend) tmem_ld16(tb + g16 + 16, rb);
+          step(ra, g16);
+          if (g16 + 16 < pend) {
+            tmem_ld_wait();
+            if (g16 + 32 < pend) tmem_ld16(tb + g16 + 32, ra);
+            step(rb, g16 + 16);
+          }
         }
       }
       const float s1 = (sa - beta * s0) * ig;
@@ -395,15 +429,9 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
       if (tid == 0) TL(1, li);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->d_empty[b]);
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) {
-        TL(2, li);
-        bulk_copy_s2g(P.dy2_img + (size_t)it * P.img_bytes, smem + (size_t)b * P.img_bytes, P.img_bytes);
-        bulk_wait_read_all();
-        TL(3, li);
-        mbar_arrive(&bars->a2_free[b]);
+      if (lane == 0) {
+        mbar_arrive(&bars->d_empty[b]);
+        mbar_arrive(&bars->a2_free[b]);      // this warp has read all it needs of the tile
       }
     }
     if (n_local > 0) {
@@ -415,6 +443,9 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
     // `team` and the half-chunks hc with hc % 2 == team, so the two buffers are filled concurrently. ----
     const int team = (warp - 8) >> 1;
     const int t = ((warp - 8) & 1) * 32 + lane;      // channel within the 64-channel half-chunk
+    // each warp of a team owns one 32-channel half of the team's S buffer and its own `empty` barrier: the first half is
+    // released as soon as the two MMAs that read it are done, so its refill overlaps the rest of the ring step
+    uint64_t* my_empty = &bars->sd_empty[2 * team + ((warp - 8) & 1)];
     int prev_off = -1;
     uint32_t ph_e = 1;
     constexpr int kMaxHcT = 8;   // half-chunks per team: C3 <= 1024
@@ -447,10 +478,10 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
 #pragma unroll
       for (int h = 0; h < kMaxHcT; ++h) {
         if (h >= nhc_t) break;
-        mbar_wait(&bars->sd_empty[team], ph_e); ph_e ^= 1;
-        if (prev_off >= 0) *reinterpret_cast<__nv_bfloat16*>(sS + prev_off) = __float2bfloat16_rn(0.f);
         const int row = cur_idx[h] - p0;
         const float w = s3r[h] * cur_w[h];
+        mbar_wait(my_empty, ph_e); ph_e ^= 1;
+        if (prev_off >= 0) *reinterpret_cast<__nv_bfloat16*>(sS + prev_off) = __float2bfloat16_rn(0.f);
         if (row >= 0 && row < nvalid && w != 0.f) {
           const int off = (t >> 3) * plane + row * 16 + (t & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(sS + off) = __float2bfloat16_rn(w);
@@ -509,10 +540,12 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
+            for (int ks = 0; ks < 4; ++ks) {
               mma_bf16_raw(d_tmem, desc_advance(a_desc, ks * 2 * kPlaneW), desc_advance(b_desc, ks * 2 * plane), idesc,
                            (r > 0 || ks > 0) ? 1u : 0u);
-            if (scatter_step) mma_commit_raw(&bars->sd_empty[sb]);
+              if (scatter_step && ks == 1) mma_commit_raw(&bars->sd_empty[2 * sb]);
+            }
+            if (scatter_step) mma_commit_raw(&bars->sd_empty[2 * sb + 1]);
             mma_commit_raw(&bars->w_empty[st]);
             if (r == nring - 1) mma_commit_raw(&bars->d_full[b]);
           }
@@ -554,9 +587,8 @@ static __global__ void __launch_bounds__(kDg3Threads, 1) dgrad3_kernel(const Dg3
   if (blockIdx.x == 0 && tid == 0) {
     const long long t0 = g_tl[7][0];
     for (int li = 0; li < min(n_local, 64); ++li)
-      printf("DG3 C3=%d li=%d load_issue=%lld mma_start=%lld gq_wait=%lld a2_full=%lld d_full=%lld epi_end=%lld store_issue=%lld store_read=%lld\n",
-             P.C3, li, g_tl[7][li] - t0, g_tl[4][li] - t0, g_tl[5][li] - t0, g_tl[6][li] - t0, g_tl[0][li] - t0, g_tl[1][li] - t0,
-             g_tl[2][li] - t0, g_tl[3][li] - t0);
+      printf("DG3 C3=%d li=%d load_issue=%lld mma_start=%lld gq_wait=%lld a2_full=%lld d_full=%lld epi_end=%lld\n",
+             P.C3, li, g_tl[7][li] - t0, g_tl[4][li] - t0, g_tl[5][li] - t0, g_tl[6][li] - t0, g_tl[0][li] - t0, g_tl[1][li] - t0);
   }
 #endif
 }
@@ -596,7 +628,7 @@ constexpr uint32_t kL2AccStride = 224;                         // TMEM columns p
 constexpr uint32_t kL2AccWG = 448;                             // wgrad2 accumulator [448, 512)
 
 inline size_t l2_smem_bytes(int PC) {
-  return kL2Groups * (8 + 16) * (size_t)plane_stride(PC) + convfwd::kW2Bytes + 128 * 128 * 2 +
+  return kL2Groups * (8 * (size_t)plane_stride(PC) + dy2_img_bytes(PC)) + convfwd::kW2Bytes + 128 * 128 * 2 +
          kL2Groups * 256 * 4 * 4 + kL2Groups * 4 * 64 * 16 + (192 + 64 + 192 + 64 * 5 + 128 * 6) * 4 + 256;
 }
 
@@ -612,9 +644,10 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
   // (functions of the group index, not pointer arrays: a runtime-indexed array would live in local memory)
+  const uint32_t dz_bytes = dy2_img_bytes(P.PC);          // dy2 / dz2 tile, TRANSPOSED image (see the file header)
   auto sA1b = [&](int g) { return smem + (size_t)g * 8 * plane; };
-  auto sDZb = [&](int g) { return smem + (size_t)(16 + 16 * g) * plane; };
-  uint8_t* sW2T = smem + 48 * plane;
+  auto sDZb = [&](int g) { return smem + (size_t)16 * plane + (size_t)g * dz_bytes; };
+  uint8_t* sW2T = smem + 16 * plane + kL2Groups * dz_bytes;
   uint8_t* sW2P = sW2T + convfwd::kW2Bytes;
   float4* sPtsAll = reinterpret_cast<float4*>(sW2P + 128 * 128 * 2);   // [groups][256] transformed points (x, y, z, -)
   float4* sRedAll = sPtsAll + kL2Groups * 256;                          // [groups][4 parts][64]
@@ -754,29 +787,68 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         const float cA = sL2[256 + k];
         const float cB = -sL2[256 + k] * (sL2[384 + k] + sL2[512 + k] * sL2[k]);
         const float cC = -sL2[256 + k] * sL2[512 + k] * sL2[128 + k];
-        uint8_t* col = sDZ + (k >> 3) * plane + (k & 7) * 2;
+        uint8_t* colT = sDZ + k * 16;            // this channel's chunks: + (pt / 8) * kTPlane
         const int nh = ((NT >> 1) + 15) & ~15;
         const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
+#ifndef AN3D_L2_PIPE8
+        auto step = [&](const uint32_t (&r)[16], int g16, uint8_t* c0, const uint4 v0, const uint4 v1) {
+          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t o[8];
+          const int nreal = nvalid - g16;          // warp-uniform; < 16 only in an item's last group (padding rows -> 0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float z0 = fmaf(__uint_as_float(w[j] << 16), cA, fmaf(__uint_as_float(r[2 * j]), cC, cB));
+            float z1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), cA, fmaf(__uint_as_float(r[2 * j + 1]), cC, cB));
+            if (nreal < 16) {
+              if (2 * j >= nreal) z0 = 0.f;
+              if (2 * j + 1 >= nreal) z1 = 0.f;
+            }
+            o[j] = convfwd::pack_bf16x2(z0, z1);
+          }
+          *reinterpret_cast<uint4*>(c0) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(c0 + kTPlane) = make_uint4(o[4], o[5], o[6], o[7]);
+        };
+        const uint32_t tb = tmem + lane_base + kD;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem + lane_base + kD + g16, r);
+          tmem_ld16(tb + g16, r);
+          uint8_t* c0 = colT + (size_t)(g16 >> 3) * kTPlane;
+          const uint4 v0 = *reinterpret_cast<const uint4*>(c0), v1 = *reinterpret_cast<const uint4*>(c0 + kTPlane);
           tmem_ld_wait();
-          if (g16 + 16 <= nvalid) {              // (warp-uniform; only an item's last group has padding rows)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + (g16 + j) * 16);
-              *ptr = __float2bfloat16_rn(fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int p = g16 + j;
-              __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(col + p * 16);
-              const float dz = p < nvalid ? fmaf(__bfloat162float(*ptr), cA, fmaf(__uint_as_float(r[j]), cC, cB)) : 0.f;
-              *ptr = __float2bfloat16_rn(dz);
-            }
-          }
+          step(r, g16, c0, v0, v1);
         }
+#else
+        // 8 points (one 16-byte chunk) per step; the TMEM load of the next step is in flight while this one is processed
+        auto step8 = [&](const uint32_t (&r)[8], int g8) {
+          uint8_t* c0 = colT + (size_t)(g8 >> 3) * kTPlane;
+          const uint4 v0 = *reinterpret_cast<const uint4*>(c0);
+          const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+          uint32_t o[4];
+          const int nreal = nvalid - g8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float z0 = fmaf(__uint_as_float(w[j] << 16), cA, fmaf(__uint_as_float(r[2 * j]), cC, cB));
+            float z1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), cA, fmaf(__uint_as_float(r[2 * j + 1]), cC, cB));
+            if (nreal < 8) {
+              if (2 * j >= nreal) z0 = 0.f;
+              if (2 * j + 1 >= nreal) z1 = 0.f;
+            }
+            o[j] = convfwd::pack_bf16x2(z0, z1);
+          }
+          *reinterpret_cast<uint4*>(c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        };
+        const uint32_t tb = tmem + lane_base + kD;
+        uint32_t ra[8], rb[8];
+        if (pbeg < pend) tmem_ld8(tb + pbeg, ra);
+        for (int g8 = pbeg; g8 < pend; g8 += 16) {
+          tmem_ld_wait();
+          tmem_ld8(tb + g8 + 8, rb);             // (pend - pbeg is a multiple of 16)
+          step8(ra, g8);
+          tmem_ld_wait();
+          if (g8 + 16 < pend) tmem_ld8(tb + g8 + 16, ra);
+          step8(rb, g8 + 8);
+        }
+#endif
       }
       if (t == 0) TL(4, li);
       tc_fence_before();
@@ -800,9 +872,36 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         // barrier A): one 2-byte load and a sign test instead of re-evaluating the layer and its BN per element.
         // Padding rows hold a1 = 0, so they drop out without a bounds test.
         const uint8_t* a1col = sA1 + (k1 >> 3) * plane + (k1 & 7) * 2;
+#ifdef AN3D_L2_PIPE8
+        auto step8 = [&](const uint32_t (&r)[8], int g8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int p = g8 + j;
+            const short a1bits = *reinterpret_cast<const short*>(a1col + p * 16);
+            const float dy = a1bits > 0 ? __uint_as_float(r[j]) : 0.f;
+            const float4 pt = sPts[p];
+            s0 += dy;
+            sx = fmaf(dy, pt.x, sx);
+            sy = fmaf(dy, pt.y, sy);
+            sz = fmaf(dy, pt.z, sz);
+          }
+        };
+        const uint32_t tb = tmem + lane_base + kD;
+        uint32_t ra[8], rb[8];
+        if (pbeg < pend) tmem_ld8(tb + pbeg, ra);
+        for (int g8 = pbeg; g8 < pend; g8 += 16) {
+          tmem_ld_wait();
+          tmem_ld8(tb + g8 + 8, rb);             // (pend - pbeg is a multiple of 16)
+          step8(ra, g8);
+          tmem_ld_wait();
+          if (g8 + 16 < pend) tmem_ld8(tb + g8 + 16, ra);
+          step8(rb, g8 + 8);
+        }
+#else
+        const uint32_t tb = tmem + lane_base + kD;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem + lane_base + kD + g16, r);
+          tmem_ld16(tb + g16, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -816,6 +915,7 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
             sz = fmaf(dy, pt.z, sz);
           }
         }
+#endif
         sRed[part * 64 + k1] = make_float4(s0, sx, sy, sz);
         // BN1 backward sums: xhat is affine in (x, y, z), so sum dy*xhat follows from the four sums
         r0 += (double)s0;
@@ -862,8 +962,9 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       const uint64_t w2t_desc = make_desc(smem_u32(sW2T), kPlaneW, 128), w2p_desc = make_desc(smem_u32(sW2P), kPlaneW, 128);
       const uint64_t a1k_desc[2] = {make_desc(smem_u32(sA1b(0)), plane, 128), make_desc(smem_u32(sA1b(1)), plane, 128)};
       const uint64_t a1m_desc[2] = {make_desc(smem_u32(sA1b(0)), 128, plane), make_desc(smem_u32(sA1b(1)), 128, plane)};
-      const uint64_t dzk_desc[2] = {make_desc(smem_u32(sDZb(0)), plane, 128), make_desc(smem_u32(sDZb(1)), plane, 128)};
-      const uint64_t dzm_desc[2] = {make_desc(smem_u32(sDZb(0)), 128, plane), make_desc(smem_u32(sDZb(1)), 128, plane)};
+      // dz2 tile (transposed image): K-major A operand of wgrad2 (contraction over points), MN-major B operand of da1
+      const uint64_t dzp_desc[2] = {make_desc(smem_u32(sDZb(0)), kTPlane, 128), make_desc(smem_u32(sDZb(1)), kTPlane, 128)};
+      const uint64_t dzc_desc[2] = {make_desc(smem_u32(sDZb(0)), 128, kTPlane), make_desc(smem_u32(sDZb(1)), 128, kTPlane)};
       // every group of MMAs and its commits is issued from one elected region (see umma.cuh)
       auto issue_d2 = [&](int li) {
         const int g = li & 1;
@@ -883,17 +984,17 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         const int g = li & 1;
         const int NT = nt_of(li);
         tc_fence_after();
-        const uint32_t idesc_w = make_idesc(128, 64, 1, 1);
-        const uint32_t idesc = make_idesc(128, NT, 0, 0);
+        const uint32_t idesc_w = make_idesc(128, 64, 0, 1);
+        const uint32_t idesc = make_idesc(128, NT, 0, 1);
         if (elect_one()) {
-          const uint64_t dzm = g ? dzm_desc[1] : dzm_desc[0], a1m = g ? a1m_desc[1] : a1m_desc[0];
-          const uint64_t dzk = g ? dzk_desc[1] : dzk_desc[0];
+          const uint64_t dzp = g ? dzp_desc[1] : dzp_desc[0], a1m = g ? a1m_desc[1] : a1m_desc[0];
+          const uint64_t dzc = g ? dzc_desc[1] : dzc_desc[0];
           for (int ks = 0; ks < NT / 16; ++ks)
-            mma_bf16_raw(tmem + kL2AccWG, desc_advance(dzm, ks * 256), desc_advance(a1m, ks * 256), idesc_w,
+            mma_bf16_raw(tmem + kL2AccWG, desc_advance(dzp, ks * 2 * kTPlane), desc_advance(a1m, ks * 256), idesc_w,
                          (wg_started || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            mma_bf16_raw(tmem + g * kL2AccStride, desc_advance(w2p_desc, ks * 2 * kPlaneW), desc_advance(dzk, ks * 2 * plane),
+            mma_bf16_raw(tmem + g * kL2AccStride, desc_advance(w2p_desc, ks * 2 * kPlaneW), desc_advance(dzc, ks * 256),
                          idesc, ks > 0);
           mma_commit_raw(&bars->da_full[g]);
           mma_commit_raw(&bars->dz_free[g]);
@@ -920,8 +1021,8 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       for (int li = 0; li < n_local; ++li) {
         const int g = li & 1;
         mbar_wait_relaxed(&bars->dz_free[g], (uint32_t)(((li >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&bars->dz_full[g], P.img_bytes);
-        bulk_copy_g2s(sDZb(g), P.dy2_img + (size_t)(it_begin + li) * P.img_bytes, P.img_bytes, &bars->dz_full[g]);
+        mbar_arrive_expect_tx(&bars->dz_full[g], dz_bytes);
+        bulk_copy_g2s(sDZb(g), P.dy2_img + (size_t)(it_begin + li) * dz_bytes, dz_bytes, &bars->dz_full[g]);
       }
     }
   }
