@@ -18,6 +18,8 @@
 // are bound by shared-memory bandwidth (the MMAs' operand reads alone take ~45 % of it), not by issue slots or the tensor
 // pipe (profiles/r2_timeline_bwd.txt), so the epilogues' access width is what matters.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "conv_fwd_bf16.cuh"
@@ -640,6 +642,11 @@ struct L2Bars {
   float xf[kL2Groups][8];
 };
 
+#ifdef AN3D_L2_SLEEPWAIT
+#define L2_WAIT(bar, ph) mbar_wait_sleep(bar, ph, AN3D_L2_SLEEPWAIT)
+#else
+#define L2_WAIT(bar, ph) mbar_wait_relaxed(bar, ph)
+#endif
 static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t plane = plane_stride(P.PC);
@@ -777,9 +784,9 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full[grp]);
       // ---- dz2 from the raw layer-2 accumulator (xhat2) and dy2 ----
-      mbar_wait_relaxed(&bars->d2_full[grp], ph);
+      L2_WAIT(&bars->d2_full[grp], ph);
       if (t == 0) TL(2, li);
-      mbar_wait_relaxed(&bars->dz_full[grp], ph);
+      L2_WAIT(&bars->dz_full[grp], ph);
       if (t == 0) TL(3, li);
       tc_fence_after();
       {
@@ -790,16 +797,18 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         uint8_t* colT = sDZ + k * 16;            // this channel's chunks: + (pt / 8) * kTPlane
         const int nh = ((NT >> 1) + 15) & ~15;
         const int pbeg = half ? nh : 0, pend = half ? NT : min(nh, NT);
-#ifndef AN3D_L2_PIPE8
-        auto step = [&](const uint32_t (&r)[16], int g16, uint8_t* c0, const uint4 v0, const uint4 v1) {
+        // (the padding test is compiled out of the common path: as a run-time `if` inside one body it became sixteen
+        // predicated selects per step, 9 % of the kernel's instructions)
+        auto step = [&](auto pad_tag, const uint32_t (&r)[16], int g16, uint8_t* c0, const uint4 v0, const uint4 v1) {
+          constexpr bool kPad = decltype(pad_tag)::value;
           const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
           uint32_t o[8];
-          const int nreal = nvalid - g16;          // warp-uniform; < 16 only in an item's last group (padding rows -> 0)
+          const int nreal = nvalid - g16;          // < 16 only in an item's last group (padding rows -> 0)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float z0 = fmaf(__uint_as_float(w[j] << 16), cA, fmaf(__uint_as_float(r[2 * j]), cC, cB));
             float z1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), cA, fmaf(__uint_as_float(r[2 * j + 1]), cC, cB));
-            if (nreal < 16) {
+            if (kPad) {
               if (2 * j >= nreal) z0 = 0.f;
               if (2 * j + 1 >= nreal) z1 = 0.f;
             }
@@ -815,47 +824,16 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
           uint8_t* c0 = colT + (size_t)(g16 >> 3) * kTPlane;
           const uint4 v0 = *reinterpret_cast<const uint4*>(c0), v1 = *reinterpret_cast<const uint4*>(c0 + kTPlane);
           tmem_ld_wait();
-          step(r, g16, c0, v0, v1);
+          if (g16 + 16 <= nvalid) step(std::false_type{}, r, g16, c0, v0, v1);      // (warp-uniform)
+          else step(std::true_type{}, r, g16, c0, v0, v1);
         }
-#else
-        // 8 points (one 16-byte chunk) per step; the TMEM load of the next step is in flight while this one is processed
-        auto step8 = [&](const uint32_t (&r)[8], int g8) {
-          uint8_t* c0 = colT + (size_t)(g8 >> 3) * kTPlane;
-          const uint4 v0 = *reinterpret_cast<const uint4*>(c0);
-          const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
-          uint32_t o[4];
-          const int nreal = nvalid - g8;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float z0 = fmaf(__uint_as_float(w[j] << 16), cA, fmaf(__uint_as_float(r[2 * j]), cC, cB));
-            float z1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), cA, fmaf(__uint_as_float(r[2 * j + 1]), cC, cB));
-            if (nreal < 8) {
-              if (2 * j >= nreal) z0 = 0.f;
-              if (2 * j + 1 >= nreal) z1 = 0.f;
-            }
-            o[j] = convfwd::pack_bf16x2(z0, z1);
-          }
-          *reinterpret_cast<uint4*>(c0) = make_uint4(o[0], o[1], o[2], o[3]);
-        };
-        const uint32_t tb = tmem + lane_base + kD;
-        uint32_t ra[8], rb[8];
-        if (pbeg < pend) tmem_ld8(tb + pbeg, ra);
-        for (int g8 = pbeg; g8 < pend; g8 += 16) {
-          tmem_ld_wait();
-          tmem_ld8(tb + g8 + 8, rb);             // (pend - pbeg is a multiple of 16)
-          step8(ra, g8);
-          tmem_ld_wait();
-          if (g8 + 16 < pend) tmem_ld8(tb + g8 + 16, ra);
-          step8(rb, g8 + 8);
-        }
-#endif
       }
       if (t == 0) TL(4, li);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bars->dz_ready[grp]);
       // ---- dy1 = da1 * [a1 > 0], BN1 backward sums (channels k1 < 64 only) ----
-      mbar_wait_relaxed(&bars->da_full[grp], ph);
+      L2_WAIT(&bars->da_full[grp], ph);
       if (t == 0) TL(5, li);
       tc_fence_after();
       {
@@ -872,32 +850,6 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
         // barrier A): one 2-byte load and a sign test instead of re-evaluating the layer and its BN per element.
         // Padding rows hold a1 = 0, so they drop out without a bounds test.
         const uint8_t* a1col = sA1 + (k1 >> 3) * plane + (k1 & 7) * 2;
-#ifdef AN3D_L2_PIPE8
-        auto step8 = [&](const uint32_t (&r)[8], int g8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int p = g8 + j;
-            const short a1bits = *reinterpret_cast<const short*>(a1col + p * 16);
-            const float dy = a1bits > 0 ? __uint_as_float(r[j]) : 0.f;
-            const float4 pt = sPts[p];
-            s0 += dy;
-            sx = fmaf(dy, pt.x, sx);
-            sy = fmaf(dy, pt.y, sy);
-            sz = fmaf(dy, pt.z, sz);
-          }
-        };
-        const uint32_t tb = tmem + lane_base + kD;
-        uint32_t ra[8], rb[8];
-        if (pbeg < pend) tmem_ld8(tb + pbeg, ra);
-        for (int g8 = pbeg; g8 < pend; g8 += 16) {
-          tmem_ld_wait();
-          tmem_ld8(tb + g8 + 8, rb);             // (pend - pbeg is a multiple of 16)
-          step8(ra, g8);
-          tmem_ld_wait();
-          if (g8 + 16 < pend) tmem_ld8(tb + g8 + 16, ra);
-          step8(rb, g8 + 8);
-        }
-#else
         const uint32_t tb = tmem + lane_base + kD;
         for (int g16 = pbeg; g16 < pend; g16 += 16) {
           uint32_t r[16];
@@ -915,7 +867,6 @@ static __global__ void __launch_bounds__(kL2Threads, 1) bwd_l2_kernel(const L2Pa
             sz = fmaf(dy, pt.z, sz);
           }
         }
-#endif
         sRed[part * 64 + k1] = make_float4(s0, sx, sy, sz);
         // BN1 backward sums: xhat is affine in (x, y, z), so sum dy*xhat follows from the four sums
         r0 += (double)s0;

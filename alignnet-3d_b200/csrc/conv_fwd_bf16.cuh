@@ -370,7 +370,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         for (int h = 0; h < 2; ++h) {
           const int nh = h ? NT - N0 : N0;
           if (nh == 0) continue;
+#ifdef AN3D_FWD_ACCWAIT_SLEEP
+          mbar_wait_sleep(&bars->acc_full[h], (ph_full >> h) & 1u, AN3D_FWD_ACCWAIT_SLEEP); ph_full ^= 1u << h;
+#else
           mbar_wait_relaxed(&bars->acc_full[h], (ph_full >> h) & 1u); ph_full ^= 1u << h;
+#endif
           tc_fence_after();
           const int off = h ? N0 : 0;
           const uint32_t tbase = tmem + lane_base + (h ? kTmemAcc1 : kTmemAcc0);
