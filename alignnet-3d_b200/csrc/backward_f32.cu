@@ -404,7 +404,9 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
   const float* c1o[2] = {out->pred_s1_pc1centers, out->pred_s1_pc2centers};
   const float* c2o[2] = {out->pred_s2_pc1centers, out->pred_s2_pc2centers};
   if (bf16) AN3D_TRY(pack_weights_bf16_bwd(m, p, params, st));
+  prof_mark(PROF_LOSS, true, st);
   AN3D_TRY(run_loss(m, labels, out, B, loss_out, p.loss_scratch, p.dend, st));
+  prof_mark(PROF_LOSS, false, st);
   AN3D_CUDA_CHECK(cudaMemsetAsync(grads, 0, sizeof(float) * m.n_trainable, st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc0, 0, sizeof(double) * m.bn_total_ch(), st));
   AN3D_CUDA_CHECK(cudaMemsetAsync(p.bn.acc1, 0, sizeof(double) * m.bn_total_ch(), st));

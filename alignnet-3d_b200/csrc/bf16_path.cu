@@ -487,7 +487,9 @@ int conv_stack_forward_bf16(const Model& m, const PlanF32& p, int s, int br, con
     const int nparts = (P.n_items + W.items_per_cta - 1) / W.items_per_cta;
     const size_t gsmem = convbwd::gram2_smem_bytes(q.PC);
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(convbwd::gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    prof_mark(PROF_GRAM2, true, st);
     convbwd::gram2_kernel<<<nranges, convbwd::kGram2Threads, gsmem, st>>>(W);
+    prof_mark(PROF_GRAM2, false, st);
     AN3D_LAUNCH_CHECK();
     sum_parts_kernel<<<(128 * 128 + 128 + 31) / 32, 256, 0, st>>>(q.gram_parts[br], nparts, 128, convbwd::kGram2PartCols, 128,
                                                                     q.gram[s][br], q.sa2[s][br]);

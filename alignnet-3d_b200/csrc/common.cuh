@@ -39,7 +39,7 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
 // Optional per-kernel timing (an3d_profile_begin/end): CUDA events recorded on the launch stream
 // around the tagged heavy kernels.
 enum ProfTag { PROF_CONV_STATS2 = 0, PROF_CONV_FULL = 1, PROF_BWD_T1 = 2, PROF_BWD_DGRAD3 = 3, PROF_BWD_L2 = 4,
-               PROF_FC = 5, PROF_NTAGS = 8 };
+               PROF_FC = 5, PROF_LOSS = 6, PROF_GRAM2 = 7, PROF_NTAGS = 8 };
 void prof_mark(int tag, bool begin, cudaStream_t st);
 bool prof_active();
 

@@ -49,6 +49,15 @@ constexpr uint32_t kTmemAcc0 = 0, kTmemAcc1 = 128, kTmemD2 = 256;   // D2: two p
 
 enum Mode { MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
 
+// -DAN3D_TIMELINE: CTA 0 stamps clock64() at the front end's hand-over points and prints one line per item (see
+// conv_bwd_bf16.cuh).  Never defined in the shipped build.
+#ifdef AN3D_TIMELINE
+static __device__ long long g_ftl[8][64];
+#define FTL(slot, li) do { if (blockIdx.x == 0 && (li) < 64) g_ftl[slot][li] = clock64(); } while (0)
+#else
+#define FTL(slot, li) do { } while (0)
+#endif
+
 struct Params {
   const float* pcs;       // [B, N, 3] raw points of this branch
   const float* center;    // [B, 3] subtracted from the points
@@ -277,7 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       const Item I = item_of(P, it);
       const int nvalid = I.nvalid, NT = I.NT;
       const int b = li & 1;
+      if (f == 0) FTL(0, li);
       if (li >= 2) { mbar_wait_sleep(&bars->a2_empty[b], (ph_a2e >> b) & 1u); ph_a2e ^= 1u << b; }   // (a whole item of slack)
+      if (f == 0) FTL(1, li);
       if (save_a2 && f == 0) bulk_wait_read_but1();  // the bulk store of item li-2 no longer reads this buffer
       // A1 aliases the A2 buffer this item will fill after its layer-2 MMA has consumed A1
       uint8_t* sA1 = a2buf(b);
@@ -290,19 +301,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
       // the prefetched raw point of thread f goes to shared memory: layer 1 below is organised by channel group
       if (f < NT) sRaw[b * kMaxPC + f] = f < nvalid ? make_float4(pf_p0, pf_p1, pf_p2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (f == 0) FTL(2, li);
       const float* xfr = bars->xf + (li & 1) * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
       // ---- layer 1: y = relu(W1f^T p' + c1f).  Warp g of the 8 front-end warps owns channels 8g..8g+7 (= plane g
       // of the A1 tile) for ALL points: its 32 folded weights live in registers, lanes walk consecutive points, so
       // the raw-point loads and the 16-byte tile stores are conflict-free.
-      for (int p = lane; p < NT; p += 32)
-        *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) =
-            layer1_chunk(sRaw[b * kMaxPC + p], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+      {
+        // three independent points in flight per lane: with one point per iteration the front-end warps waited on their
+        // own dependency chains (load -> recentre -> rotate -> 3 FMAs -> pack -> store); same-box A/B 1.141 -> 1.113 ms
+        constexpr int kU = 3;
+        int p = lane;
+        for (; p + 32 * (kU - 1) < NT; p += 32 * kU) {
+          float4 raw[kU];
+          uint4 q[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) raw[u] = sRaw[b * kMaxPC + p + 32 * u];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) q[u] = layer1_chunk(raw[u], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+#pragma unroll
+          for (int u = 0; u < kU; ++u) *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + (p + 32 * u) * 16) = q[u];
+        }
+        for (; p < NT; p += 32)
+          *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) =
+              layer1_chunk(sRaw[b * kMaxPC + p], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+      }
+      if (f == 0) FTL(3, li);
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
       // ---- layer-2 epilogue: this thread owns the points  t*128 + 32*quarter + lane  and 64 channels
       mbar_wait_relaxed(&bars->d2_full, ph_d2); ph_d2 ^= 1;
+      if (f == 0) FTL(4, li);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
@@ -338,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           }
         }
       }
+      if (f == 0) FTL(5, li);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bars->a2_full[b]);
@@ -508,6 +539,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+#ifdef AN3D_TIMELINE
+  if (blockIdx.x == 0 && tid == 0) {
+    const long long t0 = g_ftl[0][0];
+    for (int li = 0; li < min(n_local, 64); ++li)
+      printf("FWD nchunk=%d li=%d top=%lld a2_empty=%lld staged=%lld l1_done=%lld d2_full=%lld l2epi_done=%lld\n", P.nchunk, li,
+             g_ftl[0][li] - t0, g_ftl[1][li] - t0, g_ftl[2][li] - t0, g_ftl[3][li] - t0, g_ftl[4][li] - t0, g_ftl[5][li] - t0);
+  }
+#endif
 }
 
 // =============================================================================================================
