@@ -54,8 +54,8 @@ def emb_full_flops_per_pair(N: int) -> float:
 
 
 def measured_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's EMB-stage launch from the committed
-    `ncu --set full` capture (profiles/r2_roofline_traffic.json)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, average over the six launches of one c3 step,
+    from the committed `ncu --set full` capture (profiles/r2_roofline_traffic.json)."""
     path = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
     if os.path.exists(path):
         return json.load(open(path)).get("conv_stack_fwd_kernel<1>")

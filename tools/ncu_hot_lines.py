@@ -1,9 +1,11 @@
 """Per-source-line warp-stall samples of an .ncu-rep (needs -lineinfo + --import-source on): prints the
-hottest CUDA source lines with their share of all samples and of the instructions executed."""
+hottest CUDA source lines with their share of all samples and of the instructions executed.
+    python tools/ncu_hot_lines.py report.ncu-rep [top [launch index]]"""
 import csv, subprocess, sys
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+sel = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []   # one launch of a multi-launch report
+out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass", *sel],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
