@@ -145,6 +145,22 @@ static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2],
     g.C = dX[i]; g.ldc = lddx; g.M = R; g.N = L.cin; g.K = L.cout;
   }
   if (!dz_packed) AN3D_TRY(fc2::pack(pa[0], st, nbr == 2 ? &pa[1] : nullptr));   // (the BN backward wrote the image itself)
+  // wgrad and dgrad of a layer read the same images and write disjoint outputs; neither fills the GPU (a few dozen CTAs
+  // each), so wgrad runs on the side stream next to dgrad -- fork / join with events, legal inside a capture
+#ifndef AN3D_FC_NO_SIDE
+  SideStream* ss = (dX[0] && two_streams_enabled()) ? side_stream() : nullptr;
+#else
+  SideStream* ss = nullptr;
+#endif
+  if (ss) {
+    AN3D_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+    AN3D_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    const int r0 = fc2::launch(w[0], ss->stream, nbr == 2 ? &w[1] : nullptr);
+    const int r1 = fc2::launch(d[0], st, nbr == 2 ? &d[1] : nullptr);
+    AN3D_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
+    AN3D_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
+    return r0 != AN3D_OK ? r0 : r1;
+  }
   AN3D_TRY(fc2::launch(w[0], st, nbr == 2 ? &w[1] : nullptr));
   if (dX[0]) AN3D_TRY(fc2::launch(d[0], st, nbr == 2 ? &d[1] : nullptr));
   return AN3D_OK;
