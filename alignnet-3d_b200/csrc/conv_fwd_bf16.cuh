@@ -210,6 +210,9 @@ __device__ __forceinline__ uint4 layer1_chunk(const float4 raw, float cx, float 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
+#ifdef AN3D_TIMELINE
+  if (threadIdx.x == 0) FTL(6, 0);                    // kernel entry
+#endif
   const uint32_t plane2 = plane_stride(P.PC);         // A2 planes: 16 of them (K = 128)
   const uint32_t plane1 = plane2;                       // A1 uses the same row pitch, 8 planes (K = 64)
   const uint32_t a2_bytes = 16 * plane2;
@@ -248,6 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+#ifdef AN3D_TIMELINE
+  if (threadIdx.x == 0) FTL(6, 1);                    // prologue done
+#endif
 
   if ((warp >= 4 && warp < 8) || (warp >= 14 && warp < 18)) {
     // ================================ front-end ================================
@@ -541,6 +547,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   if (warp == 8) tmem_dealloc(tmem, kTmemCols);
 #ifdef AN3D_TIMELINE
   if (blockIdx.x == 0 && tid == 0) {
+    printf("FWDK nchunk=%d n_local=%d entry->prologue_done=%lld prologue_done->first_top=%lld last_l2epi->exit=%lld total=%lld\n", P.nchunk, n_local,
+           g_ftl[6][1] - g_ftl[6][0], g_ftl[0][0] - g_ftl[6][1], clock64() - g_ftl[5][min(n_local, 64) - 1], clock64() - g_ftl[6][0]);
     const long long t0 = g_ftl[0][0];
     for (int li = 0; li < min(n_local, 64); ++li)
       printf("FWD nchunk=%d li=%d top=%lld a2_empty=%lld staged=%lld l1_done=%lld d2_full=%lld l2epi_done=%lld\n", P.nchunk, li,
