@@ -76,6 +76,10 @@ SIGNATURES = {
     "an3d_decode_angles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "an3d_rigid_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p]),
+    "an3d_transform_pcs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
+    "an3d_loss_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "an3d_launch_count": (C.c_uint64, []),
     "an3d_profile_begin": (C.c_int, []),
     "an3d_profile_end": (C.c_int, [C.POINTER(C.c_float * 8), C.POINTER(C.c_int32 * 8)]),

@@ -62,8 +62,11 @@ __global__ void decode_angles_kernel(const float* logits, float* angles, int B, 
   for (int j = 1; j < nb; ++j)
     if (lg[j] > best) { best = lg[j]; k = j; }
   const float apc = 2.0f * kPi / (float)nb;
-  if (scaled) {  // tf_get_angles, models/tp8.py:294-301
+  if (scaled == 1) {  // tf_get_angles, models/tp8.py:294-301
     const float a = (float)k * apc + lg[nb + k] * (kPi / (float)nb);
+    angles[b] = floor_modf(a + kPi, 2.0f * kPi) - kPi;
+  } else if (scaled == 2) {  // tf_classLogits2angle -> tf_class2angle2, models/tp8.py:213-226,248-251
+    const float a = (float)k * apc + lg[nb + k];
     angles[b] = floor_modf(a + kPi, 2.0f * kPi) - kPi;
   } else {       // classLogits2angle, models/tp8.py:229-244 (quirk Q1: unscaled residual)
     float a = (float)k * apc + lg[nb + k];
@@ -87,6 +90,60 @@ __global__ void rigid_apply_kernel(const float* __restrict__ pts, const float* _
   out[i * 3] = (c * x - s * y) + cx + tx;
   out[i * 3 + 1] = (s * x + c * y) + cy + ty;
   out[i * 3 + 2] = z + cz + tz;
+}
+
+// a21: tf_transform_pcs (models/tp8.py:361-371) as coded.  tf_translate_pcs (:357-358) returns the TILED TRANSLATION (quirk
+// Q6), so each translate step replaces the point; the rotation is a row vector times tf_get_rotation_matrix_z (:26-27).
+__global__ void transform_pcs_q6_kernel(const float* __restrict__ pcs, const float* __restrict__ t,
+                                        const float* __restrict__ ang, const float* __restrict__ ctr,
+                                        float* __restrict__ out, int N, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / N);
+  float x = pcs[i * 3], y = pcs[i * 3 + 1], z = pcs[i * 3 + 2];
+  if (ctr) { x = -ctr[b * 3]; y = -ctr[b * 3 + 1]; z = -ctr[b * 3 + 2]; }
+  if (ang) {
+    float s, c;
+    sincosf(ang[b], &s, &c);
+    const float nx = x * c + y * s, ny = -x * s + y * c;     // [x y z] [[c,-s,0],[s,c,0],[0,0,1]]
+    x = nx; y = ny;
+  }
+  if (t) { x = -t[b * 3]; y = -t[b * 3 + 1]; z = -t[b * 3 + 2]; }
+  if (ctr) { x = ctr[b * 3]; y = ctr[b * 3 + 1]; z = ctr[b * 3 + 2]; }
+  out[i * 3] = x; out[i * 3 + 1] = y; out[i * 3 + 2] = z;
+}
+
+// a21: point_distances = tf.norm(a - g, axis=1) -> [B,3] (the norm runs over the POINT axis, tp8.py:386);
+// acc += sum_d point_distances[b,d]^2.  One block per cloud.
+__global__ void __launch_bounds__(128) p2p_norm_kernel(const float* __restrict__ a, const float* __restrict__ g, int N,
+                                                       double* acc) {
+  __shared__ float sm[3][4];
+  const int b = blockIdx.x;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int64_t i = ((int64_t)b * N + n) * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const float e = a[i + d] - g[i + d]; s[d] = fmaf(e, e, s[d]); }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
+    if ((threadIdx.x & 31) == 0) sm[d][threadIdx.x >> 5] = s[d];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const float nrm = sqrtf(sm[d][0] + sm[d][1] + sm[d][2] + sm[d][3]);
+      tot += (double)(nrm * nrm);
+    }
+    atomicAdd(acc, tot);
+  }
+}
+__global__ void p2p_final_kernel(const double* acc, int B, float* loss_out) {
+  const float loss = (float)(acc[0] / (3.0 * B));       // reduce_mean over [B,3]; min(loss, loss_180) = loss (:388-393)
+  loss_out[0] = loss / (float)B;
+  loss_out[1] = loss;
 }
 
 // t' = -d + Rz(theta) d + t, d = c_new - c_old  (tp_utils/pointcloud.py:309-318)
@@ -407,6 +464,50 @@ int an3d_rigid_apply(const float* pts, const float* translation, const float* an
   if (total == 0) return AN3D_OK;
   rigid_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pts, translation, angle, center,
                                                                                        out, num_points, total);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_transform_pcs(const float* pcs, const float* translations, const float* angles, const float* rotation_centers,
+                       float* out, int32_t batch, int32_t num_points, void* stream) {
+  if (!pcs || !out || batch < 0 || num_points < 0) {
+    set_error("an3d_transform_pcs: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  const int64_t total = (int64_t)batch * num_points;
+  if (total == 0) return AN3D_OK;
+  transform_pcs_q6_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      pcs, translations, angles, rotation_centers, out, num_points, total);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_loss_p2p(const float* pcs1, const float* pred_translations, const float* pred_angles,
+                  const float* pred_s2_pc1centers, const float* translations, const float* rel_angles,
+                  const float* pc1_centers, int32_t batch, int32_t num_points, float* loss_out, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  if (!pcs1 || !pred_translations || !pred_angles || !pred_s2_pc1centers || !translations || !rel_angles || !pc1_centers ||
+      !loss_out || !workspace || batch < 1 || num_points < 1) {
+    set_error("an3d_loss_p2p: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  const int64_t cloud = (int64_t)batch * num_points * 3;
+  if (workspace_bytes < (int64_t)(2 * cloud * sizeof(float) + 16)) {
+    set_error("an3d_loss_p2p: workspace too small: need %lld bytes", (long long)(2 * cloud * sizeof(float) + 16));
+    return AN3D_ERR_WORKSPACE;
+  }
+  AN3D_TRY(check_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = static_cast<double*>(workspace);
+  float* a = reinterpret_cast<float*>(acc + 2);
+  float* g = a + cloud;
+  AN3D_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  AN3D_TRY(an3d_transform_pcs(pcs1, pred_translations, pred_angles, pred_s2_pc1centers, a, batch, num_points, stream));
+  AN3D_TRY(an3d_transform_pcs(pcs1, translations, rel_angles, pc1_centers, g, batch, num_points, stream));
+  p2p_norm_kernel<<<batch, 128, 0, st>>>(a, g, num_points, acc);
+  AN3D_LAUNCH_CHECK();
+  p2p_final_kernel<<<1, 1, 0, st>>>(acc, batch, loss_out);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }

@@ -441,12 +441,29 @@ class Engine:
         return loss
 
     # ---- small utilities on the same ABI ----------------------------------------------------
-    def decode_angles(self, logits: torch.Tensor, scaled: bool) -> torch.Tensor:
+    def decode_angles(self, logits: torch.Tensor, scaled) -> torch.Tensor:
+        """scaled: True / 1 = tf_get_angles, False / 0 = classLogits2angle (host decoder), 2 = tf_classLogits2angle."""
         B = int(logits.shape[0])
         out = torch.empty(B, dtype=torch.float32, device=logits.device)
         stream = torch.cuda.current_stream(logits.device).cuda_stream
         _lib.check(self.lib.an3d_decode_angles(logits.data_ptr(), out.data_ptr(), B, self.num_bins, int(scaled), stream),
                    "an3d_decode_angles")
+        return out
+
+    def loss_p2p(self, pcs1: torch.Tensor, labels: Dict[str, torch.Tensor], end_points: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """a21: `_get_loss_p2p` (models/tp8.py:374-398) as the reference computes it (quirk Q6: the clouds collapse to
+        the tiled rotation centres).  Returns the device vector [per_transform_loss, loss].  Forward value only."""
+        B, N = int(pcs1.shape[0]), int(pcs1.shape[1])
+        dec = lambda k: self.decode_angles(end_points[k], 2)              # tf_classLogits2angle
+        ang = (dec("pred_pc2angle_logits") - dec("pred_pc1angle_logits") + dec("pred_remaining_angle_logits")).contiguous()
+        rel = labels["rel_angles"].reshape(B, -1)[:, 0].contiguous()
+        ws = torch.empty(2 * B * N * 3 + 4, dtype=torch.float32, device=pcs1.device)
+        out = torch.empty(2, dtype=torch.float32, device=pcs1.device)
+        stream = torch.cuda.current_stream(pcs1.device).cuda_stream
+        _lib.check(self.lib.an3d_loss_p2p(pcs1.data_ptr(), end_points["pred_translations"].data_ptr(), ang.data_ptr(),
+                                          end_points["pred_s2_pc1centers"].data_ptr(), labels["translations"].data_ptr(),
+                                          rel.data_ptr(), labels["pc1_centers"].data_ptr(), B, N, out.data_ptr(),
+                                          ws.data_ptr(), ws.numel() * 4, stream), "an3d_loss_p2p")
         return out
 
     def pred_angles(self, end_points: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -466,6 +483,19 @@ def rigid_apply(pts: torch.Tensor, translation=None, angle=None, center=None) ->
     stream = torch.cuda.current_stream(pts.device).cuda_stream
     _lib.check(lib.an3d_rigid_apply(pts.data_ptr(), ptr(translation), ptr(angle), ptr(center), out.data_ptr(), B, N,
                                     stream), "an3d_rigid_apply")
+    return out
+
+
+def transform_pcs(pcs: torch.Tensor, translations=None, angles=None, rotation_centers=None) -> torch.Tensor:
+    """a21: `tf_transform_pcs` (models/tp8.py:361-371) exactly as coded, quirk Q6 included (every translate step REPLACES
+    the cloud by the tiled translation).  The intended transform is `rigid_apply`."""
+    lib = _lib.load()
+    B, N = int(pcs.shape[0]), int(pcs.shape[1])
+    out = torch.empty_like(pcs)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    stream = torch.cuda.current_stream(pcs.device).cuda_stream
+    _lib.check(lib.an3d_transform_pcs(pcs.data_ptr(), ptr(translations), ptr(angles), ptr(rotation_centers),
+                                      out.data_ptr(), B, N, stream), "an3d_transform_pcs")
     return out
 
 

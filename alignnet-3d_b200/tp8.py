@@ -55,12 +55,21 @@ def get_model(pcs1: torch.Tensor, pcs2: torch.Tensor, is_training, bn_decay=None
 
 
 def get_loss(pcs1, pcs2, translations, rel_angles, pc1_centers, pc2_centers, pc1_angles, pc2_angles, end_points):
-    """models/tp8.py:401-407 (`separate` loss): 0-d tensor = per_transform_loss."""
-    if cfg.training.loss.loss != "separate":
-        raise ValueError("only training.loss.loss == 'separate' is implemented")
+    """models/tp8.py:401-407: 0-d tensor = per_transform_loss of the configured loss.  `p2p` (:374-398, selected by no
+    shipped config) is evaluated as the reference computes it (quirk Q6) -- value only, the training step is `separate`."""
     labels = dict(translations=translations, rel_angles=rel_angles, pc1_centers=pc1_centers, pc2_centers=pc2_centers,
                   pc1_angles=pc1_angles, pc2_angles=pc2_angles)
+    if cfg.training.loss.loss == "p2p":
+        return get_engine().loss_p2p(pcs1, labels, end_points)[0]
+    if cfg.training.loss.loss != "separate":
+        raise ValueError(f"training.loss.loss={cfg.training.loss.loss!r}: the reference asserts False here (tp8.py:407)")
     return get_engine().loss(labels, end_points)[0]
+
+
+def tf_transform_pcs(pcs, translations=None, angles=None, rotation_centers=None):
+    """models/tp8.py:361-371 as coded (quirk Q6), on the device."""
+    from . import engine as _engine
+    return _engine.transform_pcs(pcs, translations, angles, rotation_centers)
 
 
 def classLogits2angle(logits: np.ndarray, to_label_format: bool = True) -> np.ndarray:

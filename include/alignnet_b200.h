@@ -172,6 +172,8 @@ int an3d_step_advance(int64_t* step_dev, uint64_t* seed_dev, uint64_t seed_base,
 int an3d_adam_step_dev(float* params, const float* grads, float* m, float* v, int64_t count, float lr,
                        const int64_t* step_dev, float grad_scale, float beta1, float beta2, float eps, void* stream);
 
+/* scaled = 1: tf_get_angles (:294-301); 0: classLogits2angle (:229-244); 2: tf_classLogits2angle / tf_class2angle2
+ * (:213-226, :248-251: unscaled residual, then tf.mod into [-pi, pi)) -- the decoder _get_loss_p2p uses. */
 int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_t num_bins, int32_t scaled,
                        void* stream);
 
@@ -180,6 +182,26 @@ int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_
  * translation / angle / center may be NULL (identity), as in the reference's defaults. */
 int an3d_rigid_apply(const float* pts, const float* translation, const float* angle, const float* center,
                      float* out, int32_t batch, int32_t num_points, void* stream);
+
+/* a21 -- tf_transform_pcs (models/tp8.py:361-371) EXACTLY as the reference codes it, quirk Q6 included: its helper
+ * tf_translate_pcs (:357-358) RETURNS the tiled translation instead of adding it, so every translate step replaces the
+ * cloud:   p = pcs ; if centers: p = -c ; if angles: p = p Rz(a)  (row vector times [[c,-s,0],[s,c,0],[0,0,1]], :26-27) ;
+ *          if translations: p = -t ; if centers: p = c.
+ * translations / angles / rotation_centers may be NULL (the reference's None).  The INTENDED rigid transform is
+ * an3d_rigid_apply above; this entry point exists so that the unselected `p2p` loss is reproduced, not repaired. */
+int an3d_transform_pcs(const float* pcs, const float* translations, const float* angles, const float* rotation_centers,
+                       float* out, int32_t batch, int32_t num_points, void* stream);
+
+/* a21 -- _get_loss_p2p (models/tp8.py:374-398) as the reference computes it: both clouds through an3d_transform_pcs,
+ * tf.norm over the POINT axis (:386), squared, mean over [B,3]; the accept_inverted_angle variant (:388-393) is
+ * identical to the plain one.  pred_angles = tf_classLogits2angle(pc2) - (pc1) + (remaining) (an3d_decode_angles with
+ * scaled = 2).  loss_out[0] = per_transform_loss (= loss / B, what get_loss returns), loss_out[1] = loss.
+ * workspace: at least 2*batch*num_points*3 floats + 16 bytes.  Forward value only: no shipped config selects this loss
+ * (configs/default.json:52) and training with it is not implemented (an3d_loss_backward is the `separate` loss). */
+int an3d_loss_p2p(const float* pcs1, const float* pred_translations, const float* pred_angles,
+                  const float* pred_s2_pc1centers, const float* translations, const float* rel_angles,
+                  const float* pc1_centers, int32_t batch, int32_t num_points, float* loss_out, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* translate_transform_to_new_center_of_rotation (tp_utils/pointcloud.py:309-318):
  * out[i] = -d + Rz(angle[i]) d + t[i],  d = new_center[i] - old_center[i]. */

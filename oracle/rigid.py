@@ -53,3 +53,31 @@ def translate_transform_to_new_center_of_rotation(pred_translations, pred_angles
         shift = np.asarray(c_new, np.float64) - np.asarray(c_old, np.float64)
         out[i] = -shift + get_mat_angle(rotation=float(np.asarray(a).reshape(-1)[0]))[:3, :3] @ shift + t
     return out
+
+
+def tf_transform_pcs(pcs, translations=None, angles=None, rotation_centers=None) -> np.ndarray:
+    """a21: models/tp8.py:361-371 statement by statement, quirk Q6 included: `tf_translate_pcs` (:357-358) returns
+    tile(translation) instead of pcs + translation, so every translate step REPLACES the cloud; the rotation is
+    `tf.matmul(pcs, R)` with R = tf_get_rotation_matrix_z(a) = [[c,-s,0],[s,c,0],[0,0,1]] (:26-27).  [B,N,3] float64."""
+    p = np.asarray(pcs, np.float64).copy()
+    tile = lambda t: np.repeat(np.asarray(t, np.float64)[:, None, :], p.shape[1], axis=1)
+    if rotation_centers is not None:
+        p = tile(-np.asarray(rotation_centers, np.float64))
+    if angles is not None:
+        for b, a in enumerate(np.asarray(angles, np.float64).reshape(-1)):
+            c, s = math.cos(a), math.sin(a)
+            p[b] = p[b] @ np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    if translations is not None:
+        p = tile(-np.asarray(translations, np.float64))
+    if rotation_centers is not None:
+        p = tile(np.asarray(rotation_centers, np.float64))
+    return p
+
+
+def loss_p2p(pcs1, pred_translations, pred_angles, pred_s2_pc1centers, translations, rel_angles, pc1_centers):
+    """a21: models/tp8.py:383-397 statement by statement on top of `tf_transform_pcs`: (per_transform_loss, loss)."""
+    a = tf_transform_pcs(pcs1, pred_translations, pred_angles, pred_s2_pc1centers)
+    g = tf_transform_pcs(pcs1, translations, np.asarray(rel_angles).reshape(len(a), -1)[:, 0], pc1_centers)
+    point_distances = np.linalg.norm(a - g, axis=1)          # tf.norm(..., axis=1): over the POINT axis -> [B,3]
+    loss = float(np.mean(np.square(point_distances)))
+    return loss / a.shape[0], loss

@@ -383,3 +383,40 @@ def test_fp32_edge_shapes_eval_and_train(B, N):
         for k in OUTPUT_KEYS:
             np.testing.assert_allclose(ept[k].cpu().numpy()[ok], ep64[k][ok], atol=5e-4, rtol=0, err_msg=k)
         assert abs(float(loss[0].cpu()) - loss_ref) < 2e-3 * max(1.0, abs(loss_ref))
+
+
+def test_transform_pcs_and_p2p_loss_quirk_q6():
+    """a21: an3d_transform_pcs / an3d_loss_p2p against the oracle's statement-by-statement restatement of
+    models/tp8.py:357-398 (itself pinned to the executed reference code in tests/test_reference_run.py)."""
+    from alignnet_b200 import engine
+    rng = np.random.default_rng(5)
+    B, N = 6, 41
+    pcs = (rng.normal(size=(B, N, 3)) * 4).astype(np.float32)
+    t = rng.normal(size=(B, 3)).astype(np.float32)
+    a = rng.uniform(-3, 3, size=(B,)).astype(np.float32)
+    c = (rng.normal(size=(B, 3)) * 2).astype(np.float32)
+    dev = lambda x: None if x is None else torch.from_numpy(x).cuda()
+    for args in [(t, a, c), (None, a, None), (t, None, None), (None, None, c), (t, a, None), (None, None, None)]:
+        got = engine.transform_pcs(dev(pcs), *[dev(x) for x in args]).cpu().numpy()
+        np.testing.assert_allclose(got, RG.tf_transform_pcs(pcs, *args), atol=1e-5)
+    g, arch, params, state, _, _ = golden_case("tiny_B4_N16")
+    eng = make_engine(arch, params, state)
+    nb = eng.num_bins
+    ep = {k: torch.from_numpy(rng.normal(size=(B, 2 * nb)).astype(np.float32)).cuda()
+          for k in ("pred_pc1angle_logits", "pred_pc2angle_logits", "pred_remaining_angle_logits")}
+    ep["pred_translations"] = dev(t + 0.3)
+    ep["pred_s2_pc1centers"] = dev(c + 0.2 * rng.normal(size=c.shape).astype(np.float32))
+    labels = dict(translations=dev(t), rel_angles=dev(a[:, None].copy()), pc1_centers=dev(c))
+    got = eng.loss_p2p(dev(pcs), labels, ep).cpu().numpy()
+    # tf_classLogits2angle: arg-max bin centre + UNSCALED residual, wrapped into [-pi, pi)
+    def dec(lg):
+        k = lg[:, :nb].argmax(1)
+        ang = k * (2 * math.pi / nb) + lg[np.arange(B), nb + k]
+        return np.mod(ang + math.pi, 2 * math.pi) - math.pi
+    lg = {k: v.cpu().numpy().astype(np.float64) for k, v in ep.items() if k.endswith("logits")}
+    pa = dec(lg["pred_pc2angle_logits"]) - dec(lg["pred_pc1angle_logits"]) + dec(lg["pred_remaining_angle_logits"])
+    np.testing.assert_allclose(eng.decode_angles(ep["pred_pc2angle_logits"], 2).cpu().numpy(),
+                               dec(lg["pred_pc2angle_logits"]), atol=1e-5)
+    per, loss = RG.loss_p2p(pcs, t + 0.3, pa, ep["pred_s2_pc1centers"].cpu().numpy(), t, a[:, None], c)
+    np.testing.assert_allclose(got, [per, loss], rtol=1e-5)
+    assert loss > 0

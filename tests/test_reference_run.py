@@ -172,6 +172,30 @@ def test_p2p_loss_quirk_q6_matches_reference_code():
 
 
 @live
+def test_transform_pcs_quirk_q6_matches_reference_code():
+    """a21: the reference's own tf_transform_pcs (executed on the shim, every None-combination) against the oracle's
+    statement-by-statement restatement; and the p2p loss built on it against the closed form pinned above."""
+    from oracle import rigid as RG
+    tf, tp8, _ = RR.load()
+    RR.configure("SynthCars")
+    rng = np.random.default_rng(3)
+    B, N = 4, 9
+    pcs, t, c = rng.normal(size=(B, N, 3)), rng.normal(size=(B, 3)), rng.normal(size=(B, 3))
+    a = rng.uniform(-3, 3, size=(B,))
+    for args in [(t, a, c), (None, a, None), (t, None, None), (None, None, c), (t, a, None), (None, None, None)]:
+        tf.reset()
+        out = tp8.tf_transform_pcs(tf.constant(pcs), *[None if x is None else tf.constant(x) for x in args])
+        val = np.asarray(out.numpy() if hasattr(out, "numpy") else getattr(out, "value", out), dtype=np.float64)
+        np.testing.assert_allclose(val, RG.tf_transform_pcs(pcs, *args), atol=2e-6)
+    # with rotation centres the cloud collapses to tile(centres): translation and angle drop out (quirk Q6)
+    np.testing.assert_array_equal(RG.tf_transform_pcs(pcs, t, a, c), np.repeat(c[:, None, :], N, axis=1))
+    ep = {"pred_s2_pc1centers": torch.tensor(c + 0.1 * rng.normal(size=c.shape))}
+    per, loss = RG.loss_p2p(pcs, t, a, ep["pred_s2_pc1centers"].numpy(), t, a[:, None], c)
+    closed = float(TR.get_loss_p2p(torch.tensor(pcs), torch.tensor(c), ep))
+    assert abs(per - closed) < 1e-12 and abs(loss - per * B) < 1e-12
+
+
+@live
 def test_shim_scoping_follows_tf1():
     tf, _, _ = RR.load()
     tf.reset()
