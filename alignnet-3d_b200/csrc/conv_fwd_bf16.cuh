@@ -650,12 +650,33 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
       const float* xfr = bars->xf + b * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
-      for (int p = lane; p < NT; p += 32) {
-        const float4 raw = sRaw[b * P.PC + p];
-        *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
-        if (g == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
-          *reinterpret_cast<uint4*>(a1buf(b) + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
-          *reinterpret_cast<uint4*>(a1buf(b) + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+      {
+        // (three independent points in flight per lane, as in the forward kernel: 0.271 -> 0.249 ms per c3 step)
+        constexpr int kU = 3;
+        auto extra_planes = [&](int p, const float4 raw) {
+          if (g == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
+            *reinterpret_cast<uint4*>(a1buf(b) + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a1buf(b) + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
+          }
+        };
+        int p = lane;
+        for (; p + 32 * (kU - 1) < NT; p += 32 * kU) {
+          float4 raw[kU];
+          uint4 q[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) raw[u] = sRaw[b * P.PC + p + 32 * u];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) q[u] = layer1_chunk(raw[u], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + (p + 32 * u) * 16) = q[u];
+            extra_planes(p + 32 * u, raw[u]);
+          }
+        }
+        for (; p < NT; p += 32) {
+          const float4 raw = sRaw[b * P.PC + p];
+          *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
+          extra_planes(p, raw);
         }
       }
       fence_proxy_async_smem();
