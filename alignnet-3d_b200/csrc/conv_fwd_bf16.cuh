@@ -53,6 +53,7 @@ enum Mode { MODE_FULL_TRAIN = 1, MODE_FULL_EVAL = 2 };
 // conv_bwd_bf16.cuh).  Never defined in the shipped build.
 #ifdef AN3D_TIMELINE
 static __device__ long long g_ftl[8][64];
+static __device__ long long g_mtl[4][256];    // MMA warp, per chunk: loop top, weights ready, accumulator half 0 free, half 1 free
 #define FTL(slot, li) do { if (blockIdx.x == 0 && (li) < 64) g_ftl[slot][li] = clock64(); } while (0)
 #else
 #define FTL(slot, li) do { } while (0)
@@ -488,9 +489,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         const uint32_t idesc0 = make_idesc(128, N0, 0, 0), idesc1 = make_idesc(128, N1 > 0 ? N1 : 16, 0, 0);
         bool l2_pending = li + 1 < n_local;
         for (int j = 0; j < P.nchunk; ++j) {
+#ifdef AN3D_TIMELINE
+          const int ci = li * P.nchunk + j;
+          if (blockIdx.x == 0 && lane == 0 && ci < 256) g_mtl[0][ci] = clock64();
+#endif
           mbar_wait(&bars->w3_full[stage], (ph_w3f >> stage) & 1u); ph_w3f ^= 1u << stage;
+#ifdef AN3D_TIMELINE
+          if (blockIdx.x == 0 && lane == 0 && ci < 256) g_mtl[1][ci] = clock64();
+#endif
           const uint64_t a_desc = make_desc(smem_u32(sW3 + (size_t)stage * kW3ChunkBytes), kPlaneW2, 128);
           mbar_wait(&bars->acc_empty[0], ph_acce0); ph_acce0 ^= 1;
+#ifdef AN3D_TIMELINE
+          if (blockIdx.x == 0 && lane == 0 && ci < 256) g_mtl[2][ci] = clock64();
+#endif
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -502,6 +513,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
           __syncwarp();
           if (N1 > 0) {
             mbar_wait(&bars->acc_empty[1], ph_acce1); ph_acce1 ^= 1;
+#ifdef AN3D_TIMELINE
+            if (blockIdx.x == 0 && lane == 0 && ci < 256) g_mtl[3][ci] = clock64();
+#endif
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -549,6 +563,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   if (blockIdx.x == 0 && tid == 0) {
     printf("FWDK nchunk=%d n_local=%d entry->prologue_done=%lld prologue_done->first_top=%lld last_l2epi->exit=%lld total=%lld\n", P.nchunk, n_local,
            g_ftl[6][1] - g_ftl[6][0], g_ftl[0][0] - g_ftl[6][1], clock64() - g_ftl[5][min(n_local, 64) - 1], clock64() - g_ftl[6][0]);
+    {
+      // MMA warp: where each layer-3 chunk's issue time goes (averages over chunks 16.. of the first 256)
+      const int nc = min(n_local * P.nchunk, 256);
+      long long w3 = 0, e0 = 0, e1 = 0, tot = 0;
+      int cnt = 0;
+      for (int c = 16; c + 1 < nc; ++c) {
+        w3 += g_mtl[1][c] - g_mtl[0][c]; e0 += g_mtl[2][c] - g_mtl[1][c]; e1 += g_mtl[3][c] - g_mtl[2][c];
+        tot += g_mtl[0][c + 1] - g_mtl[0][c]; ++cnt;
+      }
+      if (cnt) printf("FWDM nchunk=%d chunks=%d per chunk: total=%lld wait_w3=%lld wait_acc0=%lld issue0+wait_acc1=%lld rest=%lld\n", P.nchunk, cnt,
+                      tot / cnt, w3 / cnt, e0 / cnt, e1 / cnt, (tot - w3 - e0 - e1) / cnt);
+    }
     const long long t0 = g_ftl[0][0];
     for (int li = 0; li < min(n_local, 64); ++li)
       printf("FWD nchunk=%d li=%d top=%lld a2_empty=%lld staged=%lld l1_done=%lld d2_full=%lld l2epi_done=%lld\n", P.nchunk, li,
