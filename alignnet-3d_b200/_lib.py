@@ -20,6 +20,8 @@ ERR_NAMES = {0: "AN3D_OK", -1: "AN3D_ERR_INVALID", -2: "AN3D_ERR_UNSUPPORTED", -
 TRAINING = 1
 PRECISION_FP32 = 0
 PRECISION_BF16 = 2
+PRECISION_BF16X3 = 16
+PRECISION_BF16X6 = 32
 WEIGHTS_PREPARED = 4
 DETERMINISTIC = 8
 
@@ -89,6 +91,9 @@ SIGNATURES = {
     "an3d_selftest_fc_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "an3d_selftest_split_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                           C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "an3d_icp_yaw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "an3d_resample_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -6,6 +6,7 @@
 #include "loss.cuh"
 #include "bf16_path.cuh"
 #include "fc2_gemm.cuh"
+#include "gemm_tc.cuh"
 
 namespace an3d {
 
@@ -170,9 +171,29 @@ static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2],
 //   grads.W += pro(X)^T dZ ; grads.b += colsum(dZ) ; dX = dZ W^T (if dX != nullptr).
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
                     float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
-                    int64_t lddx, double* bias_acc, cudaStream_t st, const FcImages* img = nullptr) {
+                    int64_t lddx, double* bias_acc, cudaStream_t st, const FcImages* img = nullptr,
+                    const PlanF32* tp = nullptr) {
   const bool bf16 = img != nullptr;
   bool wgrad_done = false, dgrad_done = false;
+  if (!bf16 && tp && tcg::use_tensor_cores(*tp, L.cin, L.cout, R)) {
+    // materialised path on the tensor cores (gemm_tc.cuh): the layer's input (BN + ReLU + dropout of the producing layer
+    // applied while packing), the gradient at its output and its weights are packed once and serve wgrad and dgrad
+    tcg::SplitMat x, dz, w;
+    AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_X, X, ldx, R, L.cin, psc, psh, pmask, pmask_scale, &x, st));
+    AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_DZ, dZ, L.cout, R, L.cout, nullptr, nullptr, nullptr, 1.f, &dz, st));
+    tcg::Params f;
+    f.A = x; f.a_mn = 1; f.B = dz; f.b_mn = 1;                                   // contraction over the rows
+    f.C = grads + L.w; f.ldc = L.cout; f.M = L.cin; f.N = L.cout; f.K = R; f.accumulate = 1;
+    AN3D_TRY(tcg::launch(f, st));
+    if (dX) {
+      AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_W, params + L.w, L.cout, L.cin, L.cout, nullptr, nullptr, nullptr, 1.f, &w, st));
+      tcg::Params g;
+      g.A = dz; g.a_mn = 0; g.B = w; g.b_mn = 0;                                 // W image: rows = cin (output index), cols = cout (K)
+      g.C = dX; g.ldc = lddx; g.M = R; g.N = L.cin; g.K = L.cout;
+      AN3D_TRY(tcg::launch(g, st));
+    }
+    wgrad_done = dgrad_done = true;
+  }
   if (bf16) {
     const FcImages im[2] = {*img, FcImages()};
     const float* dz[2] = {dZ, nullptr};
@@ -243,7 +264,7 @@ int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const f
       if (want_input_grad) { dX = p.dpin; lddx = 3; }
     }
     AN3D_TRY(linear_backward(L, X, L.cin, psc, psh, nullptr, 1.f, p.dbuf[cur], (int)M, params, grads, dX, lddx,
-                             p.dbias_acc, st));
+                             p.dbias_acc, st, nullptr, &p));
     cur ^= 1;
   }
   return AN3D_OK;
@@ -291,7 +312,7 @@ int mlp_backward(const Model& m, const PlanF32& p, int s, int br, const float* x
     FcImages im;
     im.x = p.fcx[s][l][br]; im.w = p.fcw[s][l]; im.dz = p.fcdz[0]; im.dz_packed = L.bn >= 0;
     AN3D_TRY(linear_backward(L, X, lx, psc, psh, pm, mask_scale, dZ, p.B, params, grads, dX, lddx, p.dbias_acc, st,
-                             p.bf16 ? &im : nullptr));
+                             p.bf16 ? &im : nullptr, &p));
     dZ = dX;
     cur ^= 1;
   }
@@ -415,7 +436,7 @@ int backward_impl(const Model& m, const float* params, const float* pcs1, const 
     return AN3D_ERR_WORKSPACE;
   }
   const int nb = m.nb;
-  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
+  const bool bf16 = p.bf16;
   const float* pcs[2] = {pcs1, pcs2};
   const float* c1o[2] = {out->pred_s1_pc1centers, out->pred_s1_pc2centers};
   const float* c2o[2] = {out->pred_s2_pc1centers, out->pred_s2_pc2centers};

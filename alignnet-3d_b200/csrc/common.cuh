@@ -171,7 +171,10 @@ struct PlanBf16 {
 // Workspace plan of the fp32 (parity) path: everything the backward needs is materialised.
 struct PlanF32 {
   int B = 0, N = 0;
-  bool bf16 = false;                        // AN3D_PRECISION_BF16: conv stacks and large FC GEMMs on the tensor cores
+  bool bf16 = false;                        // AN3D_PRECISION_BF16 with [64,128,C] conv stacks: the fused tensor-core kernels
+  int tc_split = 0;                         // materialised path: 0 = CUDA-core SGEMM, 1-3 = bf16 images per GEMM operand (gemm_tc.cuh)
+  __nv_bfloat16* tcbuf[3] = {nullptr, nullptr, nullptr};   // image scratch: layer input, output gradient, weights
+  int64_t tcbuf_elems[3] = {0, 0, 0};       // capacity of each (all images of the operand)
   bool deterministic = false;               // AN3D_DETERMINISTIC: no split-K fp32 reductions in inference FC layers
   bool prepared = false;                    // AN3D_WEIGHTS_PREPARED (bf16 inference): folded BN / weight images are reused
   int64_t M = 0;  // rows per branch = B*N

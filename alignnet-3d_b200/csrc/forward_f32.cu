@@ -5,6 +5,7 @@
 #include "kernels_f32.cuh"
 #include "bf16_path.cuh"
 #include "fc2_gemm.cuh"
+#include "gemm_tc.cuh"
 
 namespace an3d {
 
@@ -125,7 +126,7 @@ static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, c
     GemmArgs g;
     g.A = x; g.lda = L.cin; g.B = params + L.w; g.ldb = L.cout; g.C = p.z[s][l][br]; g.ldc = L.cout;
     g.M = (int)M; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
-    AN3D_TRY(launch_gemm(g, false, false, st));
+    AN3D_TRY(gemm_mat(p, g, false, false, st));
     BnView v = bn_view(m, p, params, state, false, br, L.bn);
     AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st));
     x = p.z[s][l][br];
@@ -211,7 +212,7 @@ static int mlp_forward_n(const Model& m, const PlanF32& p, int s, int nbr, int b
         g.pro_mask = mask[0];
         g.pro_mask_scale = 1.0f / m.arch.keep_prob[s];
       }
-      AN3D_TRY(launch_gemm(g, false, false, st));
+      AN3D_TRY(gemm_mat(p, g, false, false, st));
     }
     for (int i = 0; i < nbr; ++i) {
       const int br = br0 + i;
@@ -257,7 +258,7 @@ int forward_impl(const Model& m, const float* params, float* state, const float*
     return AN3D_ERR_WORKSPACE;
   }
   const bool training = (flags & AN3D_TRAINING) != 0;
-  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
+  const bool bf16 = p.bf16;   // the fused kernels; every other mode walks the materialised path below
   p.prepared = bf16 && !training && (flags & AN3D_WEIGHTS_PREPARED) != 0;
   p.deterministic = (flags & AN3D_DETERMINISTIC) != 0;
   if (bf16 && !p.prepared) {

@@ -1,0 +1,343 @@
+// Split-operand tensor-core GEMM of the materialised path (AN3D_PRECISION_BF16X3 / _BF16X6, and AN3D_PRECISION_BF16
+// for conv stacks the fused kernels do not cover): fp32 matrices enter as a SUM of bf16 images
+//
+//     X = X0 + X1 (+ X2),   X0 = bf16(X), X1 = bf16(X - X0), X2 = bf16(X - X0 - X1)
+//
+// and C = A * B is the sum of the bf16 x bf16 -> fp32 tcgen05 products of the image pairs whose weight is above the
+// target precision, all accumulated in ONE TMEM tile:
+//     1 image  (bf16):    A0B0                                     (8 significant bits)
+//     2 images (bf16x3):  A0B0 + A0B1 + A1B0                       (dropped A1B1 ~ 2^-18 |a||b|)
+//     3 images (bf16x6):  A0B0 + A0B1 + A1B0 + A1B1 + A0B2 + A2B0  (~ 2^-24: fp32 grade)
+// Every image is the plane-major block image of fc2_gemm.cuh, so an operand tile is one 32 KB bulk copy and the same
+// image serves as K-major or MN-major operand (forward, wgrad, dgrad of a layer all read the images packed once).
+// The kernel is fc2_gemm_kernel's structure (one TMA-issuing thread, one MMA-issuing warp, four epilogue warps) with the
+// K loop running over (K block, term) pairs, plus a single-stage variant (three CTAs per SM) for the conv layers'
+// forward GEMMs, whose K is one block.  The accumulation length of one TMEM tile is capped (kMaxKBlocksPerCta): the
+// tensor core's fp32 accumulate is not round-to-nearest, and millions of rows per reduction (wgrad over all points)
+// would let that bias grow; the K slices meet in fp32 reductions.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "fc2_gemm.cuh"
+#include "kernels_f32.cuh"
+#include "umma.cuh"
+
+namespace an3d {
+namespace tcg {
+
+using namespace umma;
+using fc2::Image;
+
+constexpr int kMaxSplit = 3;
+constexpr int kMaxTerms = 6;
+constexpr int kMaxKBlocksPerCta = 32;
+
+// one fp32 matrix as 1-3 bf16 images of identical geometry
+struct SplitMat {
+  Image img[kMaxSplit];
+  int n = 0;
+};
+
+__host__ __device__ inline int num_terms(int nsplit) { return nsplit == 1 ? 1 : (nsplit == 2 ? 3 : 6); }
+
+// ---------------------------------------------------------------------------------------------
+// packing: fp32 matrix (+ BN affine + ReLU, + dropout mask of the producing layer) -> nsplit bf16 images
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* src = nullptr; int64_t ld = 0;
+  int rows = 0, cols = 0;
+  const float* scale = nullptr;      // [cols] or nullptr:  relu(x * scale + shift)
+  const float* shift = nullptr;
+  const float* mask = nullptr;       // same layout as src, or nullptr
+  float mask_scale = 1.f;
+  __nv_bfloat16* dst[kMaxSplit] = {nullptr, nullptr, nullptr};
+  int nsplit = 1;
+};
+
+static __global__ void __launch_bounds__(256) pack_split_kernel(const PackArgs a) {
+  const int rows_pad = (a.rows + 127) & ~127, chunks = ((a.cols + 127) & ~127) >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows_pad * chunks) return;
+  // consecutive threads walk the rows of one chunk (fc2::pack_kernel): one 32-byte sector per lane in, 16 contiguous bytes out
+  const int c8 = (int)(i / rows_pad), r = (int)(i - (int64_t)c8 * rows_pad);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (r < a.rows && c8 * 8 < a.cols) {
+    const float* p = a.src + (int64_t)r * a.ld + c8 * 8;
+    const int n = min(8, a.cols - c8 * 8);
+    const bool vec = n == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+    if (vec) {
+      const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < n) v[e] = p[e];
+    }
+    if (a.scale) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < n) v[e] = fmaxf(fmaf(v[e], a.scale[c8 * 8 + e], a.shift[c8 * 8 + e]), 0.f);
+    }
+    if (a.mask) {
+      const float* mp = a.mask + (int64_t)r * a.ld + c8 * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < n) v[e] *= mp[e] * a.mask_scale;
+    }
+  }
+  const int ncb = chunks >> 4;
+  const int64_t off = ((int64_t)(r >> 7) * ncb + (c8 >> 4)) * 16384 + ((c8 & 15) * 128 + (r & 127)) * 8;
+#pragma unroll
+  for (int s = 0; s < kMaxSplit; ++s) {
+    if (s < a.nsplit) {
+      __nv_bfloat162 b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        b[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        // the residual is exact in fp32 (v and its bf16 rounding share the exponent range)
+        v[2 * e] -= __bfloat162float(b[e].x);
+        v[2 * e + 1] -= __bfloat162float(b[e].y);
+      }
+      uint4 out;
+      out.x = *reinterpret_cast<uint32_t*>(&b[0]); out.y = *reinterpret_cast<uint32_t*>(&b[1]);
+      out.z = *reinterpret_cast<uint32_t*>(&b[2]); out.w = *reinterpret_cast<uint32_t*>(&b[3]);
+      *reinterpret_cast<uint4*>(a.dst[s] + off) = out;
+    }
+  }
+}
+
+static int pack(const PackArgs& a, cudaStream_t st, SplitMat* out) {
+  if (a.nsplit < 1 || a.nsplit > kMaxSplit || a.rows < 1 || a.cols < 1) {
+    set_error("tcg::pack: bad arguments (%d x %d, %d images)", a.rows, a.cols, a.nsplit);
+    return AN3D_ERR_INVALID;
+  }
+  const int64_t total = (int64_t)((a.rows + 127) & ~127) * (((a.cols + 127) & ~127) >> 3);
+  pack_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  AN3D_LAUNCH_CHECK();
+  out->n = a.nsplit;
+  for (int s = 0; s < a.nsplit; ++s) { out->img[s].g = a.dst[s]; out->img[s].rows = a.rows; out->img[s].cols = a.cols; }
+  return AN3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM:  C[i, j] (+)= sum_terms sum_k A_t(i,k) * B_t(j,k)  (+ bias[j])
+// ---------------------------------------------------------------------------------------------
+struct Params {
+  SplitMat A; int a_mn = 0;   // a_mn = 0: image rows = i, image cols = k      1: image rows = k, image cols = i
+  SplitMat B; int b_mn = 0;   // b_mn = 0: image rows = j, image cols = k      1: image rows = k, image cols = j
+  float* C = nullptr; int64_t ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;
+  int accumulate = 0;         // reductions into C even with one K slice
+  int ksplit = 1;             // set by launch()
+  int c_vec = 1;              // set by launch()
+  int nterms = 1;             // set by launch()
+};
+
+constexpr int kThreads = 192;                 // warps 0-3 epilogue, 4 TMA issuer, 5 MMA
+constexpr uint32_t kPlane = 128 * 16;
+constexpr uint32_t kTileBytes = 16 * kPlane;  // 32 KB
+constexpr uint32_t kTxBytes = 2 * kTileBytes;
+template <int STAGES> constexpr size_t smem_bytes() { return 2 * STAGES * (size_t)kTileBytes + 1024; }
+
+template <int STAGES>
+struct Bars {
+  uint64_t full[STAGES], empty[STAGES], done;
+  uint32_t tmem_base;
+  float bias[128];
+};
+
+// term t multiplies image ia of A with image ib of B; smallest contributions first.  Six-term order:
+// (2,0) (0,2) (1,1) (1,0) (0,1) (0,0); three terms = the last three, one term = the last.
+__device__ __forceinline__ void term_images(int nterms, int t, int* ia, int* ib) {
+  const int q = 6 - nterms + t;
+  *ia = (0x001102u >> (4 * q)) & 15;
+  *ib = (0x010120u >> (4 * q)) & 15;
+}
+
+template <int STAGES>
+static __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kTileBytes;
+  Bars<STAGES>* bars = reinterpret_cast<Bars<STAGES>*>(smem + 2 * STAGES * kTileBytes);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128, kz = blockIdx.z;
+  const int nkb_total = (P.K + 127) >> 7;
+  const int per = (nkb_total + P.ksplit - 1) / P.ksplit;
+  const int kb0 = kz * per, nkb = max(0, min(nkb_total, kb0 + per) - kb0);
+  const int nit = nkb * P.nterms;
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t ph = (1u << STAGES) - 1u;            // first pass over the ring falls through
+      int st = 0;
+      for (int it = 0; it < nit; ++it) {
+        const int kb = it / P.nterms, t = it - kb * P.nterms;
+        int ia, ib;
+        term_images(P.nterms, t, &ia, &ib);
+        mbar_wait(&bars->empty[st], (ph >> st) & 1u); ph ^= 1u << st;
+        mbar_arrive_expect_tx(&bars->full[st], kTxBytes);
+        const int kblk = kb0 + kb, ibk = i0 >> 7, jbk = j0 >> 7;
+        const Image& A = P.A.img[ia];
+        const Image& B = P.B.img[ib];
+        bulk_copy_g2s(sA + st * kTileBytes, P.a_mn ? A.block(kblk, ibk) : A.block(ibk, kblk), kTileBytes, &bars->full[st]);
+        bulk_copy_g2s(sB + st * kTileBytes, P.b_mn ? B.block(kblk, jbk) : B.block(jbk, kblk), kTileBytes, &bars->full[st]);
+        st = st + 1 == STAGES ? 0 : st + 1;
+      }
+    }
+  } else if (warp == 5) {
+    uint32_t ph = 0;
+    const uint32_t idesc = make_idesc(128, 128, P.a_mn, P.b_mn);
+    int st = 0;
+    for (int it = 0; it < nit; ++it) {
+      mbar_wait(&bars->full[st], (ph >> st) & 1u); ph ^= 1u << st;
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + st * kTileBytes), b_base = smem_u32(sB + st * kTileBytes);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = P.a_mn ? make_desc(a_base + ks * 256, 128, kPlane) : make_desc(a_base + ks * 2 * kPlane, kPlane, 128);
+          const uint64_t bd = P.b_mn ? make_desc(b_base + ks * 256, 128, kPlane) : make_desc(b_base + ks * 2 * kPlane, kPlane, 128);
+          mma_bf16_raw(tmem, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit_raw(&bars->empty[st]);
+        if (it == nit - 1) mma_commit_raw(&bars->done);
+      }
+      __syncwarp();
+      st = st + 1 == STAGES ? 0 : st + 1;
+    }
+  } else if (nit > 0) {
+    bars->bias[tid] = (P.bias && kz == 0 && j0 + tid < P.N) ? P.bias[j0 + tid] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait_relaxed(&bars->done, 0);
+    tc_fence_after();
+    const int i = i0 + tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const bool reduce = P.ksplit > 1 || P.accumulate;
+    for (int g32 = 0; g32 < 128; g32 += 32) {
+      if (j0 + g32 >= P.N) break;
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_base + g32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const int j = j0 + g32 + j4;
+        float v[4] = {__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
+                      __uint_as_float(r[j4 + 3])};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] += bars->bias[g32 + j4 + e];
+        if (i < P.M && j < P.N) {
+          float* dst = P.C + (int64_t)i * P.ldc + j;
+          if (P.c_vec) {
+            if (reduce) red_add_v4(dst, v[0], v[1], v[2], v[3]);
+            else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (j + e < P.N) {
+                if (reduce) atomicAdd(dst + e, v[e]);
+                else dst[e] = v[e];
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 128);
+}
+
+// C must be pre-zeroed by the caller when the launch reduces into it (accumulate, or K longer than one CTA's share:
+// launch() clears it itself in the second case unless `accumulate` says C already holds a value to add to).
+static int launch(Params p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<3>()));
+    AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<1>()));
+    attr_set = true;
+  }
+  const int a_rows = p.a_mn ? p.K : p.M, a_cols = p.a_mn ? p.M : p.K, b_rows = p.b_mn ? p.K : p.N, b_cols = p.b_mn ? p.N : p.K;
+  bool ok = p.M > 0 && p.N > 0 && p.K > 0 && p.C && p.A.n >= 1 && p.A.n == p.B.n && p.A.n <= kMaxSplit;
+  for (int s = 0; ok && s < p.A.n; ++s)
+    ok = p.A.img[s].g && p.B.img[s].g && p.A.img[s].rows == a_rows && p.A.img[s].cols == a_cols && p.B.img[s].rows == b_rows &&
+         p.B.img[s].cols == b_cols;
+  if (!ok) {
+    set_error("tcg::launch: bad operands (shape %d x %d x %d)", p.M, p.N, p.K);
+    return AN3D_ERR_INVALID;
+  }
+  p.nterms = num_terms(p.A.n);
+  p.c_vec = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0 && p.N % 4 == 0;
+  const int nkb = (p.K + 127) >> 7;
+  const int tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
+  int ks = (nkb + kMaxKBlocksPerCta - 1) / kMaxKBlocksPerCta;          // accumulation length cap
+  if (tiles < 148 && nkb > 1) ks = std::max(ks, std::min(nkb, (296 + tiles - 1) / tiles));   // few output tiles: fill the SMs
+  int per = (nkb + ks - 1) / ks;
+  ks = (nkb + per - 1) / per;                                           // no empty slices
+  p.ksplit = ks;
+  if (ks > 1 && !p.accumulate)
+    AN3D_CUDA_CHECK(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)p.N, (size_t)p.M, st));
+  dim3 grid((p.M + 127) / 128, (p.N + 127) / 128, ks);
+  prof_mark(PROF_FC, true, st);
+  if (per * p.nterms <= 6) tc_gemm_kernel<1><<<grid, kThreads, smem_bytes<1>(), st>>>(p);
+  else tc_gemm_kernel<3><<<grid, kThreads, smem_bytes<3>(), st>>>(p);
+  prof_mark(PROF_FC, false, st);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// glue to the materialised path's plan (PlanF32::tc_split images per operand, scratch slots PlanF32::tcbuf)
+// ---------------------------------------------------------------------------------------------
+enum Slot { SLOT_X = 0, SLOT_DZ = 1, SLOT_W = 2 };
+
+// layers with a dimension below 8 (the 3-wide first conv layer, 3-wide outputs) stay on the CUDA cores
+inline bool use_tensor_cores(const PlanF32& p, int M, int N, int K) { return p.tc_split > 0 && std::min(M, std::min(N, K)) >= 8; }
+
+static int pack_slot(const PlanF32& p, int slot, const float* src, int64_t ld, int rows, int cols, const float* scale,
+                     const float* shift, const float* mask, float mask_scale, SplitMat* out, cudaStream_t st) {
+  const int64_t elems = fc_image_elems(rows, cols);
+  if (elems * p.tc_split > p.tcbuf_elems[slot] || !p.tcbuf[slot]) {
+    set_error("tcg::pack_slot: %d x %d does not fit image scratch %d", rows, cols, slot);
+    return AN3D_ERR_WORKSPACE;
+  }
+  PackArgs a;
+  a.src = src; a.ld = ld; a.rows = rows; a.cols = cols; a.scale = scale; a.shift = shift; a.mask = mask; a.mask_scale = mask_scale;
+  a.nsplit = p.tc_split;
+  for (int s = 0; s < p.tc_split; ++s) a.dst[s] = p.tcbuf[slot] + s * elems;
+  return pack(a, st, out);
+}
+
+}  // namespace tcg
+
+// C[M,N] (+)= pro(A) * B (+ bias) with the operand conventions of GemmArgs (kernels_f32.cuh): on the tensor cores when the
+// plan says so, else the CUDA-core SGEMM.  A goes to the input slot, B to the weight slot.
+static int gemm_mat(const PlanF32& p, const GemmArgs& g, bool ta, bool tb, cudaStream_t st) {
+  if (!tcg::use_tensor_cores(p, g.M, g.N, g.K)) return launch_gemm(g, ta, tb, st);
+  tcg::Params q;
+  AN3D_TRY(tcg::pack_slot(p, tcg::SLOT_X, g.A, g.lda, ta ? g.K : g.M, ta ? g.M : g.K, g.pro_scale, g.pro_shift, g.pro_mask,
+                          g.pro_mask_scale, &q.A, st));
+  AN3D_TRY(tcg::pack_slot(p, tcg::SLOT_W, g.B, g.ldb, tb ? g.N : g.K, tb ? g.K : g.N, nullptr, nullptr, nullptr, 1.f, &q.B, st));
+  q.a_mn = ta ? 1 : 0;
+  q.b_mn = tb ? 0 : 1;
+  q.C = g.C; q.ldc = g.ldc; q.M = g.M; q.N = g.N; q.K = g.K; q.bias = g.bias; q.accumulate = g.accumulate;
+  return tcg::launch(q, st);
+}
+
+}  // namespace an3d

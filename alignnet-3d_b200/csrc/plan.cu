@@ -13,8 +13,19 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     return AN3D_ERR_INVALID;
   }
   const bool training = (flags & AN3D_TRAINING) != 0;
-  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0;
-  if (bf16) AN3D_TRY(bf16_supported(m));
+  const int nprec = ((flags & AN3D_PRECISION_BF16) != 0) + ((flags & AN3D_PRECISION_BF16X3) != 0) + ((flags & AN3D_PRECISION_BF16X6) != 0);
+  if (nprec > 1) {
+    set_error("flags name more than one precision mode");
+    return AN3D_ERR_INVALID;
+  }
+  // bf16: the fused conv-stack kernels where the architecture has their shape, else the materialised path with one
+  // bf16 image per GEMM operand; bf16x3 / bf16x6: the materialised path with two / three images
+  const bool bf16 = (flags & AN3D_PRECISION_BF16) != 0 && bf16_supported(m) == AN3D_OK;
+  int tc_split = 0;
+  if ((flags & AN3D_PRECISION_BF16) != 0 && !bf16) tc_split = 1;
+  if (flags & AN3D_PRECISION_BF16X3) tc_split = 2;
+  if (flags & AN3D_PRECISION_BF16X6) tc_split = 3;
+  p->tc_split = tc_split;
   Arena a;
   a.base = static_cast<char*>(workspace);
   p->B = B;
@@ -117,6 +128,25 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     for (int br = 0; br < 2; ++br) p->dc1[br] = p->dc2[br] = p->dang[br] = nullptr;
   }
   if (bf16) plan_bf16(m, B, N, flags, a, &p->bf);
+  if (tc_split > 0) {
+    // image scratch of the split-operand GEMMs (gemm_tc.cuh), reused layer after layer: [0] the layer's input
+    // activations, [1] the gradient at its output (training), [2] its weights.  Layers with a dimension below 8 stay on
+    // the CUDA cores (the 3-wide first conv layer, 3-wide outputs).
+    int64_t e0 = 0, e1 = 0, e2 = 0;
+    auto lin = [&](const Lin& L, int64_t rows) {
+      e0 = std::max(e0, fc_image_elems((int)rows, L.cin));
+      e1 = std::max(e1, fc_image_elems((int)rows, L.cout));
+      e2 = std::max(e2, fc_image_elems(L.cin, L.cout));
+    };
+    for (int s = 0; s < 3; ++s) {
+      for (size_t l = 1; l < m.conv[s].size(); ++l) lin(m.conv[s][l], M);
+      for (size_t l = 0; l < m.fc[s].size(); ++l) lin(m.fc[s][l], B);
+    }
+    p->tcbuf_elems[0] = e0 * tc_split;
+    p->tcbuf_elems[1] = training ? e1 * tc_split : 0;
+    p->tcbuf_elems[2] = e2 * tc_split;
+    for (int i = 0; i < 3; ++i) p->tcbuf[i] = a.take<__nv_bfloat16>(p->tcbuf_elems[i]);
+  }
   p->bytes = (a.off + 255) & ~int64_t(255);
   return AN3D_OK;
 }

@@ -3,6 +3,7 @@
 // checked against autograd without the (discontinuous) rest of the model in between.
 #include "bf16_path.cuh"
 #include "fc2_gemm.cuh"
+#include "gemm_tc.cuh"
 
 using namespace an3d;
 
@@ -69,6 +70,36 @@ extern "C" int an3d_selftest_fc_gemm(const float* a, int64_t lda, int32_t a_mn, 
   f.C = c; f.ldc = ldc; f.M = m; f.N = n; f.K = k; f.bias = bias; f.ksplit = ksplit; f.accumulate = accumulate;
   f.stat_sum = stat_sum; f.stat_sq = stat_sq;
   if (rc == AN3D_OK) rc = fc2::launch(f, st);
+  cudaStreamSynchronize(st);
+  cudaFree(ia); cudaFree(ib);
+  return rc;
+}
+
+extern "C" int an3d_selftest_split_gemm(const float* a, int64_t lda, int32_t a_mn, const float* b, int64_t ldb, int32_t b_mn,
+                                        float* c, int64_t ldc, int32_t m, int32_t n, int32_t k, const float* bias,
+                                        const float* pro_scale, const float* pro_shift, const float* pro_mask,
+                                        float pro_mask_scale, int32_t nsplit, int32_t accumulate, void* stream) {
+  if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || nsplit < 1 || nsplit > tcg::kMaxSplit || (!pro_scale != !pro_shift)) {
+    set_error("an3d_selftest_split_gemm: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  AN3D_TRY(check_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int a_rows = a_mn ? k : m, a_cols = a_mn ? m : k, b_rows = b_mn ? k : n, b_cols = b_mn ? n : k;
+  const int64_t ea = fc_image_elems(a_rows, a_cols), eb = fc_image_elems(b_rows, b_cols);
+  __nv_bfloat16 *ia = nullptr, *ib = nullptr;
+  AN3D_CUDA_CHECK(cudaMalloc(&ia, sizeof(__nv_bfloat16) * ea * nsplit));
+  AN3D_CUDA_CHECK(cudaMalloc(&ib, sizeof(__nv_bfloat16) * eb * nsplit));
+  tcg::PackArgs pa, pb;
+  pa.src = a; pa.ld = lda; pa.rows = a_rows; pa.cols = a_cols; pa.scale = pro_scale; pa.shift = pro_shift; pa.mask = pro_mask;
+  pa.mask_scale = pro_mask_scale; pa.nsplit = nsplit;
+  pb.src = b; pb.ld = ldb; pb.rows = b_rows; pb.cols = b_cols; pb.nsplit = nsplit;
+  for (int s = 0; s < nsplit; ++s) { pa.dst[s] = ia + s * ea; pb.dst[s] = ib + s * eb; }
+  tcg::Params f;
+  int rc = tcg::pack(pa, st, &f.A);
+  if (rc == AN3D_OK) rc = tcg::pack(pb, st, &f.B);
+  f.a_mn = a_mn; f.b_mn = b_mn; f.C = c; f.ldc = ldc; f.M = m; f.N = n; f.K = k; f.bias = bias; f.accumulate = accumulate;
+  if (rc == AN3D_OK) rc = tcg::launch(f, st);
   cudaStreamSynchronize(st);
   cudaFree(ia); cudaFree(ib);
   return rc;

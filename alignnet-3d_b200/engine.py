@@ -128,11 +128,17 @@ class Engine:
             pass
 
     # ---- configuration --------------------------------------------------------------------
+    PRECISIONS = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16, "bf16x3": _lib.PRECISION_BF16X3,
+                  "bf16x6": _lib.PRECISION_BF16X6}
+
     def set_precision(self, precision: str) -> None:
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' (parity mode) or 'bf16' (tcgen05 fast mode)")
+        """'fp32': CUDA-core parity mode.  'bf16': tcgen05 fast mode (fused kernels for [64,128,C] conv stacks, the
+        layer-by-layer tensor-core path for any other stack).  'bf16x3' / 'bf16x6': fp32-grade arithmetic on the tensor
+        cores -- every GEMM operand split into two / three bf16 images (include/alignnet_b200.h)."""
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of %s" % ", ".join(sorted(self.PRECISIONS)))
         self.precision = precision
-        self.pflag = _lib.PRECISION_BF16 if precision == "bf16" else _lib.PRECISION_FP32
+        self.pflag = self.PRECISIONS[precision]
 
     # ---- parameters -----------------------------------------------------------------------
     def init_params(self, seed: int = 0) -> Dict[str, np.ndarray]:

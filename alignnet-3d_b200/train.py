@@ -45,7 +45,8 @@ def parse_args(argv=None):
     p.add_argument("--use_old_results", action="store_true")
     p.add_argument("--refineICPmethod", required=False, default="p2p", choices=["p2p"])
     p.add_argument("--eval_epoch", required=False, default="199", help="Epoch to eval in eval_only mode")
-    p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="bf16 tensor-core mode or fp32 parity mode")
+    p.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "bf16x6"],
+                   help="bf16 tensor-core mode, fp32 CUDA-core parity mode, or fp32-grade split-bf16 tensor-core modes")
     return p.parse_args(argv)
 
 

@@ -418,8 +418,9 @@ def config_entry(r, pk, world):
          "e2e": {"value": r["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d_bytes"],
                  "d2h_bytes_per_step": r["d2h_bytes"]},
          "whole_step_tensor_frac": r["value"] / world * flops_per_pair(r["N"], r["train"]) / (pk["bf16_sustained"] * 1e12)}
-    if r["precision"] != "bf16":
+    if r["precision"] == "fp32":
         e["whole_step_tensor_frac"] = None        # the fp32 parity mode runs on CUDA cores: not held to the bf16 roofline
+    # (bf16x3 / bf16x6: algorithmic FLOPs over the bf16 peak -- the split modes issue 3x / 6x those FLOPs on the tensor pipe)
     return e
 
 
@@ -443,6 +444,9 @@ def run_ours(args, wl):
         short = max(5, args.steps // 2)
         extra["c2"] = measure(ctx, WORKLOADS["c2"], "bf16", short, 3, tags=False)
         extra["c3_fp32"] = measure(ctx, WORKLOADS["c3"], "fp32", 3, 3, tags=False)
+        # the parity tolerance on the tensor cores: every GEMM as six (three) bf16 tcgen05 products of split operands
+        extra["c3_bf16x6"] = measure(ctx, WORKLOADS["c3"], "bf16x6", 3, 3, tags=False)
+        extra["c3_bf16x3"] = measure(ctx, WORKLOADS["c3"], "bf16x3", 3, 3, tags=False)
         if world == 4:
             extra["c4"] = measure(ctx, WORKLOADS["c4"], "bf16", short, 3, tags=False)
         if world == 8:
@@ -494,7 +498,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "bf16x6"])
     ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the `configs` sub-object)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (A/B runs of a kernel switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the stream instead of replaying a CUDA graph")

@@ -64,7 +64,17 @@ typedef struct an3d_ctx an3d_ctx;
 enum {
   AN3D_TRAINING = 1,        /* is_training=True: batch statistics, EMA update, dropout (tf_util.py:476-488,572) */
   AN3D_PRECISION_FP32 = 0,  /* CUDA-core fp32 everywhere: the <=1e-4 parity mode               */
-  AN3D_PRECISION_BF16 = 2,  /* bf16 tcgen05 tensor-core GEMMs with fp32 accumulation (fast mode) */
+  AN3D_PRECISION_BF16 = 2,  /* bf16 tcgen05 tensor-core GEMMs with fp32 accumulation (fast mode).  Conv stacks of the
+                             * form [64, 128, C] run in the fused kernels; any other depth / width (models/tp8.py:49-59,
+                             * e.g. configs/default.json:13-15) runs layer by layer through the split-operand GEMM
+                             * below with ONE bf16 image per operand */
+  /* fp32-grade arithmetic on the tensor cores: every GEMM operand enters as a sum of bf16 images (hi + lo, or
+   * hi + mid + lo) and the tcgen05 products of the significant image pairs accumulate in one fp32 TMEM tile
+   * (3 products: relative error ~2^-18 per product, held to the same tolerances as AN3D_PRECISION_FP32; 6 products:
+   * ~2^-24).  Activations are materialised in fp32 as in the fp32 mode; statistics, pooling, BN and the loss are the
+   * fp32 mode's kernels.  Any conv-stack depth. */
+  AN3D_PRECISION_BF16X3 = 16,
+  AN3D_PRECISION_BF16X6 = 32,
   /* Inference only (ignored with AN3D_TRAINING and in fp32 mode; not part of the workspace size).  The caller
    * asserts that the previous an3d_forward on THIS workspace ran in inference mode with the SAME params and
    * bn_state: the folded BN scales / shifts and the packed weight images it left in the workspace are reused and
@@ -280,6 +290,16 @@ int an3d_selftest_fc_gemm(const float* a, int64_t lda, int32_t a_mn, const float
                           int64_t ldc, int32_t m, int32_t n, int32_t k, const float* bias, const float* pro_scale,
                           const float* pro_shift, const float* pro_mask, float pro_mask_scale, int32_t ksplit,
                           int32_t accumulate, double* stat_sum, double* stat_sq, void* stream);
+
+/* Diagnostic (test-suite only): the split-operand tcgen05 GEMM of the materialised path (AN3D_PRECISION_BF16X3 / _BF16X6,
+ * and AN3D_PRECISION_BF16 for conv stacks the fused kernels do not cover; replaces tf.nn.conv2d of
+ * utils/tf_util.py:157 / tf.matmul of :337 and their gradients).  Same operand conventions as an3d_selftest_fc_gemm;
+ * nsplit = 1, 2 or 3 bf16 images per operand (1, 3 or 6 tensor-core products).  accumulate != 0 adds into C; K slicing
+ * is the library's choice (C is cleared by the call when it slices and accumulate == 0). */
+int an3d_selftest_split_gemm(const float* a, int64_t lda, int32_t a_mn, const float* b, int64_t ldb, int32_t b_mn, float* c,
+                             int64_t ldc, int32_t m, int32_t n, int32_t k, const float* bias, const float* pro_scale,
+                             const float* pro_shift, const float* pro_mask, float pro_mask_scale, int32_t nsplit,
+                             int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

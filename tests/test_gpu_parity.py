@@ -32,6 +32,21 @@ GRAD_REL = 1e-2
 GRAD_ABS = 2e-6
 GRAD_ABS_GLOBAL = 5e-5   # x (largest |grad| of any tensor): cancellation noise of sums that are exactly zero
 NORM_REL = 5e-3
+# shipped_B32_N200 is ill-conditioned in stage 1 of the second branch (batch-statistics BN over 32 samples): the oracle's
+# own torch-CPU fp32 run sits 0.4-0.8 % (relative L2) from its fp64 run on exactly those tensors, norms 0.1-0.3 % off.  The
+# CUDA-core fp32 engine lands 0.17 % from the fp64 norm of the worst tensor, the six-product split mode 1.2 % (measured;
+# at B=1024 / N=512 / N=1024 / the default architecture the two modes are equally close to the oracle:
+# profiles/r2_parity_fullsize.json).  The split modes are therefore held to 2 % on per-tensor norms.
+NORM_REL_SPLIT = 2e-2
+GRAD_REL_SPLIT = 3e-2    # elementwise, of the tensor's max |grad|: the oracle's own fp32-vs-fp64 distance on that case (above)
+
+
+def norm_rel(prec):
+    return NORM_REL if prec == "fp32" else NORM_REL_SPLIT
+
+
+def grad_rel(prec):
+    return GRAD_REL if prec == "fp32" else GRAD_REL_SPLIT
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -39,6 +54,21 @@ def _build():
     import __graft_entry__ as ge
     ge.build()
     assert torch.cuda.is_available()
+
+
+@pytest.fixture(params=["fp32", "bf16x6"])
+def prec(request):
+    """The two modes held to every tolerance of this file: CUDA-core fp32 and the split-operand tensor-core mode
+    AN3D_PRECISION_BF16X6 (every GEMM as six bf16 tcgen05 products of three-way split operands, ~2^-24 per product)."""
+    return request.param
+
+
+@pytest.fixture(params=["fp32", "bf16x3", "bf16x6"])
+def prec_eval(request):
+    """Inference adds AN3D_PRECISION_BF16X3 (two-way split, three products, ~2^-18 per product): it meets the 1e-4
+    output tolerance where BN uses the moving averages; batch-statistics BN over a handful of samples amplifies its
+    error past the training-mode tolerances (measured 4e-4 .. 5e-4 against 2.5e-4 on the golden cases)."""
+    return request.param
 
 
 def make_engine(arch, params, state, precision="fp32"):
@@ -63,9 +93,9 @@ def ambiguous_rows(ep64, arch, margin=1e-3):
 
 
 @pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
-def test_forward_eval_fp32_vs_golden_and_oracle(name):
+def test_forward_eval_fp32_vs_golden_and_oracle(name, prec_eval):
     g, arch, params, state, batch, masks = golden_case(name)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec_eval)
     dev = to_dev(batch)
     ep = e.forward(dev["pcs1"], dev["pcs2"], False)
     torch.cuda.synchronize()
@@ -86,9 +116,9 @@ def test_forward_eval_fp32_vs_golden_and_oracle(name):
 
 
 @pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
-def test_forward_train_fp32_vs_golden(name):
+def test_forward_train_fp32_vs_golden(name, prec):
     g, arch, params, state, batch, masks = golden_case(name)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     dev, dm = to_dev(batch), to_dev(masks)
     ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.5, dm)
     torch.cuda.synchronize()
@@ -101,9 +131,9 @@ def test_forward_train_fp32_vs_golden(name):
 
 
 @pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
-def test_loss_and_gradients_fp32(name):
+def test_loss_and_gradients_fp32(name, prec):
     g, arch, params, state, batch, masks = golden_case(name)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     dev, dm = to_dev(batch), to_dev(masks)
     ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.5, dm)
     loss = e.backward(dev["pcs1"], dev["pcs2"], dev, ep)
@@ -118,7 +148,7 @@ def test_loss_and_gradients_fp32(name):
         got_norm = float(np.sqrt((grads[n].astype(np.float64) ** 2).sum()))
         if n.endswith("/biases") and "/bn" not in n and ref_norm < 1e-6:
             continue   # bias feeding a BN: gradient is exactly zero up to rounding noise
-        assert abs(got_norm - ref_norm) <= NORM_REL * ref_norm + 1e-5, (n, got_norm, ref_norm)
+        assert abs(got_norm - ref_norm) <= norm_rel(prec) * ref_norm + 1e-5, (n, got_norm, ref_norm)
     gmax = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith("grad/"))
     for k in [k for k in g.files if k.startswith("grad/")]:
         n = k[5:]
@@ -126,7 +156,7 @@ def test_loss_and_gradients_fp32(name):
         scale = float(np.abs(ref).max())
         err = float(np.abs(grads[n].reshape(ref.shape) - ref).max())
         worst = max(worst, err / max(scale, 1e-12))
-        assert err <= GRAD_REL * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (n, err, scale)
+        assert err <= grad_rel(prec) * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (n, err, scale)
 
 
 def test_loss_forward_only_and_parts():
@@ -147,7 +177,7 @@ def test_loss_forward_only_and_parts():
 
 
 @pytest.mark.parametrize("accept_inverted", [False, True])
-def test_full_gradient_vs_autograd_small(accept_inverted):
+def test_full_gradient_vs_autograd_small(accept_inverted, prec):
     """Every trainable tensor against fp64 autograd on a small case, both loss selections."""
     from alignnet_b200 import synth
     arch = A.tiny_arch(accept_inverted_angle=accept_inverted, angle_factor=0.5)
@@ -156,7 +186,7 @@ def test_full_gradient_vs_autograd_small(accept_inverted):
     rng = np.random.default_rng(1)
     masks = {k: (rng.uniform(size=(6, 8)) < 0.7).astype(np.float32) for k in MASK_KEYS}
     loss_ref, ep_ref, grads_ref, st_ref = TR.loss_and_grads(batch, arch, params, state, 0.7, masks)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     dev, dm = to_dev(batch), to_dev(masks)
     ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.7, dm)
     loss = e.backward(dev["pcs1"], dev["pcs2"], dev, ep)
@@ -195,12 +225,12 @@ def test_adam_step_matches_tf_formulation():
     assert e.step == 3
 
 
-def test_train_steps_follow_oracle():
+def test_train_steps_follow_oracle(prec):
     """Three optimiser steps (forward, loss, backward, Adam, EMA) track the fp64 oracle."""
     from alignnet_b200 import synth
     arch = A.tiny_arch()
     params, state = A.init_params(arch, 3), A.init_state(arch)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     names = [n for n, _ in A.trainable_specs(arch)]
     p = {k: v.astype(np.float64) for k, v in params.items()}
     s = {k: v.astype(np.float64) for k, v in state.items()}
@@ -286,11 +316,11 @@ def _ref_case(name):
 
 
 @pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
-def test_fp32_engine_vs_reference_run_eval(name):
+def test_fp32_engine_vs_reference_run_eval(name, prec_eval):
     """north_star: pred_translations / pred_angles within 1e-4 abs of the reference path, same inputs."""
     r = _ref_case(name)
     g, arch, params, state, batch, masks = golden_case(name)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec_eval)
     dev = to_dev(batch)
     ep = e.forward(dev["pcs1"], dev["pcs2"], False)
     torch.cuda.synchronize()
@@ -310,10 +340,10 @@ def test_fp32_engine_vs_reference_run_eval(name):
 
 
 @pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
-def test_fp32_engine_vs_reference_run_train(name):
+def test_fp32_engine_vs_reference_run_train(name, prec):
     r = _ref_case(name)
     g, arch, params, state, batch, masks = golden_case(name)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     dev, dm = to_dev(batch), to_dev(masks)
     ep = e.forward(dev["pcs1"], dev["pcs2"], True, 0.5, dm)
     loss = e.backward(dev["pcs1"], dev["pcs2"], dev, ep)
@@ -332,12 +362,12 @@ def test_fp32_engine_vs_reference_run_train(name):
         if n.endswith("/biases") and ref_norm < 1e-6:
             continue
         got_norm = float(np.sqrt((grads[n].astype(np.float64) ** 2).sum()))
-        assert abs(got_norm - ref_norm) <= NORM_REL * ref_norm + 1e-5, (n, got_norm, ref_norm)
+        assert abs(got_norm - ref_norm) <= norm_rel(prec) * ref_norm + 1e-5, (n, got_norm, ref_norm)
     for k in [k for k in r.files if k.startswith("grad/")]:
         ref = r[k]
         scale = float(np.abs(ref).max())
         err = float(np.abs(grads[k[5:]].reshape(ref.shape) - ref).max())
-        assert err <= GRAD_REL * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (k, err, scale)
+        assert err <= grad_rel(prec) * scale + GRAD_ABS + GRAD_ABS_GLOBAL * gmax, (k, err, scale)
 
 
 def test_rigid_kernels_vs_reference_functions():
@@ -354,7 +384,7 @@ def test_rigid_kernels_vs_reference_functions():
 
 
 @pytest.mark.parametrize("B,N", [(1, 1), (1, 7), (2, 3), (3, 300), (65, 17)])
-def test_fp32_edge_shapes_eval_and_train(B, N):
+def test_fp32_edge_shapes_eval_and_train(B, N, prec):
     """Degenerate and ragged shapes: a single pair, a single point per cloud, N not a multiple of anything, a batch
     that is not a multiple of any tile.  Eval mode against the NumPy oracle (1e-4); train mode (batch statistics over as
     little as one row: the variance is zero and BN collapses onto beta, exactly as in the reference) against fp64."""
@@ -362,7 +392,7 @@ def test_fp32_edge_shapes_eval_and_train(B, N):
     arch = A.Arch()
     params, state = A.randomize_for_test(arch, A.init_params(arch, 90), A.init_state(arch), 91)
     batch = synth.make_batch_fast(B, N, seed=100 * B + N)
-    e = make_engine(arch, params, state)
+    e = make_engine(arch, params, state, prec)
     dev = to_dev(batch)
     ref, _ = NF.get_model(batch["pcs1"], batch["pcs2"], arch, params, state, False)
     ep = e.forward(dev["pcs1"], dev["pcs2"], False)
