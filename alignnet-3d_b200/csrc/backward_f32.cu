@@ -117,6 +117,209 @@ int bn_relu_backward(const BnRef& v, const float* Z, int R, const float* dA, int
   return AN3D_OK;
 }
 
+// ---- BN + ReLU backward of a conv layer in the tensor-core modes of the materialised path (gemm_tc.cuh) ----
+// dZ = scale * (dy - sum_dy / R - xhat * sum_dy_xhat / R) goes straight into the split bf16 images the wgrad / dgrad
+// GEMMs read (no fp32 dZ matrix, no pack pass), or -- for a layer whose GEMMs stay on the CUDA cores -- to fp32.
+// dy = ReLU mask * dA with dA either dense [R, C], or (POOLED: the last conv layer, whose output feeds the max-pool)
+// dG[b, c] at row b*N + idx[b, c] and zero elsewhere: the dense [R, C] gradient of the pooled activation -- a memset,
+// a scatter and two reads of R*C floats -- never exists.
+// Thread mapping of the element-wise kernels: a warp covers 8 rows x 4 chunks of 8 columns, so every global access is a
+// full 128-byte line on both sides (row-major fp32: 4 chunks = 128 B per row; image plane: 8 rows x 16 B = 128 B).
+struct SplitBwdArgs {
+  ColArgs c;                    // Z, mean, inv, scale, shift, acc0, acc1 (+ dA / ldd when dense)
+  const float* dG = nullptr;    // POOLED: [B, C] gradient of the pooled features, leading dim ldg
+  int64_t ldg = 0;
+  const int32_t* idx = nullptr; // POOLED: [B, C] arg rows of the pool
+  int N = 0;                    // POOLED: points per cloud
+  const float* cb = nullptr;    // [C]  -scale * sum_dy / R
+  const float* cc = nullptr;    // [C]  -scale * inv * sum_dy_xhat / R
+  __nv_bfloat16* img[3] = {nullptr, nullptr, nullptr};
+  int nsplit = 0;               // 0: fp32 output to dZ
+  float* dZ = nullptr;
+  int64_t ldo = 0;
+  double inv_rows = 0.0;
+};
+
+// sum_dy / sum_dy*xhat of the pooled layer: one thread per (cloud, channel), a block reduces 8 clouds x 32 channels
+static __global__ void __launch_bounds__(256) col_dy_pooled_kernel(SplitBwdArgs a, int B) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  if (c < a.c.C) {
+    const float mean = a.c.mean[c], inv = a.c.inv[c], sc = a.c.scale[c], sh = a.c.shift[c];
+    for (int b = blockIdx.y * 64 + threadIdx.y; b < min(B, (int)blockIdx.y * 64 + 64); b += 8) {
+      const int64_t r = (int64_t)b * a.N + a.idx[(int64_t)b * a.c.C + c];
+      const float z = a.c.Z[r * a.c.ldz + c];
+      const float g = fmaf(z, sc, sh) > 0.f ? a.dG[(int64_t)b * a.ldg + c] : 0.f;
+      s0 += (double)g;
+      s1 += (double)g * (double)((z - mean) * inv);
+    }
+  }
+  __shared__ double sm0[8][33], sm1[8][33];
+  sm0[threadIdx.y][threadIdx.x] = s0;
+  sm1[threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < a.c.C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s0 += sm0[i][threadIdx.x]; s1 += sm1[i][threadIdx.x]; }
+    atomicAdd(a.c.acc0 + c, s0);
+    atomicAdd(a.c.acc1 + c, s1);
+  }
+}
+
+// per-channel constants of dZ = scale * dy + cb + cc * (z - mean)
+static __global__ void bn_bwd_coef_kernel(const double* acc0, const double* acc1, double inv_rows, const float* scale,
+                                          const float* inv, float* cb, float* cc, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m0 = (float)(acc0[c] * inv_rows), m1 = (float)(acc1[c] * inv_rows);
+  cb[c] = -scale[c] * m0;
+  cc[c] = -scale[c] * inv[c] * m1;
+}
+
+__device__ __forceinline__ void load8(const float* p, int n, float (&v)[8]) {
+  if (n == 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = e < n ? p[e] : 0.f;
+  }
+}
+
+template <bool POOLED>
+static __global__ void __launch_bounds__(256) bn_bwd_apply_split_kernel(SplitBwdArgs a) {
+  const int rows_pad = a.nsplit ? (a.c.R + 127) & ~127 : (a.c.R + 7) & ~7;
+  const int chunks = a.nsplit ? ((a.c.C + 127) & ~127) >> 3 : (a.c.C + 7) >> 3;
+  const int cgroups = (chunks + 3) >> 2;                       // groups of 4 chunks (32 columns)
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp: (row group of 8, chunk group), chunk groups fastest
+  const int lane = threadIdx.x & 31;
+  const int64_t rg = w / cgroups;
+  const int r = (int)(rg * 8) + (lane & 7), c8 = (int)(w - rg * cgroups) * 4 + (lane >> 3), c0 = c8 * 8;
+  if (r >= rows_pad || c8 >= chunks) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (r < a.c.R && c0 < a.c.C) {
+    const int n = min(8, a.c.C - c0);
+    float z[8], dy[8], sc[8], sh[8], mean[8], cb[8], cc[8];
+    load8(a.c.Z + (int64_t)r * a.c.ldz + c0, n, z);
+    load8(a.c.scale + c0, n, sc);
+    load8(a.c.shift + c0, n, sh);
+    load8(a.c.mean + c0, n, mean);
+    load8(a.cb + c0, n, cb);
+    load8(a.cc + c0, n, cc);
+    if (POOLED) {
+      const int b = r / a.N, pt = r - b * a.N;
+      const int32_t* ip = a.idx + (int64_t)b * a.c.C + c0;
+      float g[8];
+      load8(a.dG + (int64_t)b * a.ldg + c0, n, g);
+      if (n == 8 && (reinterpret_cast<uintptr_t>(ip) & 15) == 0) {
+        const int4 i0 = *reinterpret_cast<const int4*>(ip), i1 = *reinterpret_cast<const int4*>(ip + 4);
+        const int ix[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dy[e] = ix[e] == pt ? g[e] : 0.f;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dy[e] = (e < n && ip[e] == pt) ? g[e] : 0.f;
+      }
+    } else {
+      load8(a.c.dA + (int64_t)r * a.c.ldd + c0, n, dy);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < n) {
+        const float g = fmaf(z[e], sc[e], sh[e]) > 0.f ? dy[e] : 0.f;
+        v[e] = fmaf(sc[e], g, fmaf(cc[e], z[e] - mean[e], cb[e]));
+      }
+    }
+  }
+  if (a.nsplit == 0) {
+    if (r < a.c.R && c0 < a.c.C) {
+      float* op = a.dZ + (int64_t)r * a.ldo + c0;
+      const int n = min(8, a.c.C - c0);
+      if (n == 8 && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+        *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < n) op[e] = v[e];
+      }
+    }
+    return;
+  }
+  const int64_t off = ((int64_t)(r >> 7) * (chunks >> 4) + (c8 >> 4)) * 16384 + ((c8 & 15) * 128 + (r & 127)) * 8;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s < a.nsplit) {
+      __nv_bfloat162 b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        b[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        v[2 * e] -= __bfloat162float(b[e].x);
+        v[2 * e + 1] -= __bfloat162float(b[e].y);
+      }
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&b[0]); o.y = *reinterpret_cast<uint32_t*>(&b[1]);
+      o.z = *reinterpret_cast<uint32_t*>(&b[2]); o.w = *reinterpret_cast<uint32_t*>(&b[3]);
+      *reinterpret_cast<uint4*>(a.img[s] + off) = o;
+    }
+  }
+}
+
+// One conv layer's BN + ReLU backward in the tensor-core modes.  pooled: dG / idx describe the (sparse) gradient of the
+// layer's activation, else dA [R, C] is dense.  to_img: dZ lands as p.tc_split images in the gradient slot (*dz_img
+// describes them), else as fp32 in dZ (leading dim C; may alias dA).
+static int bn_relu_backward_split(const PlanF32& p, const BnRef& v, const float* Z, int R, bool pooled, const float* dA,
+                                  const float* dG, int64_t ldg, const int32_t* idx, bool to_img, tcg::SplitMat* dz_img,
+                                  float* dZ, cudaStream_t st) {
+  SplitBwdArgs a;
+  a.c.Z = Z; a.c.ldz = v.ch; a.c.R = R; a.c.C = v.ch; a.c.mean = v.mean; a.c.inv = v.inv; a.c.scale = v.scale; a.c.shift = v.shift;
+  a.c.dA = dA; a.c.ldd = v.ch; a.c.acc0 = v.acc0; a.c.acc1 = v.acc1;
+  a.dG = dG; a.ldg = ldg; a.idx = idx; a.N = p.N; a.inv_rows = 1.0 / R;
+  if (pooled) {
+    dim3 grid((v.ch + 31) / 32, (p.B + 63) / 64), block(32, 8);
+    col_dy_pooled_kernel<<<grid, block, 0, st>>>(a, p.B);
+    AN3D_LAUNCH_CHECK();
+  } else {
+    AN3D_TRY(launch_col_reduce(a.c, COL_DY, st));
+  }
+  if (!p.bwd_coef) {
+    set_error("bn_relu_backward_split: no coefficient scratch in this plan");
+    return AN3D_ERR_WORKSPACE;
+  }
+  float* cb = p.bwd_coef;
+  float* cc = p.bwd_coef + ((v.ch + 3) & ~3);
+  bn_bwd_coef_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, 1.0 / R, v.scale, v.inv, cb, cc, v.ch);
+  AN3D_LAUNCH_CHECK();
+  a.cb = cb; a.cc = cc;
+  int64_t warps;
+  if (to_img) {
+    const int64_t elems = fc_image_elems(R, v.ch);
+    if (elems * p.tc_split > p.tcbuf_elems[tcg::SLOT_DZ] || !p.tcbuf[tcg::SLOT_DZ]) {
+      set_error("bn_relu_backward_split: %d x %d does not fit the gradient image scratch", R, v.ch);
+      return AN3D_ERR_WORKSPACE;
+    }
+    a.nsplit = p.tc_split;
+    dz_img->n = p.tc_split;
+    for (int s = 0; s < p.tc_split; ++s) {
+      a.img[s] = p.tcbuf[tcg::SLOT_DZ] + s * elems;
+      dz_img->img[s].g = a.img[s]; dz_img->img[s].rows = R; dz_img->img[s].cols = v.ch;
+    }
+    warps = (int64_t)(((R + 127) & ~127) / 8) * ((((v.ch + 127) & ~127) >> 3) / 4);
+  } else {
+    a.nsplit = 0; a.dZ = dZ; a.ldo = v.ch;
+    warps = (int64_t)((R + 7) / 8) * ((((v.ch + 7) >> 3) + 3) / 4);
+  }
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  if (pooled) bn_bwd_apply_split_kernel<true><<<blocks, 256, 0, st>>>(a);
+  else bn_bwd_apply_split_kernel<false><<<blocks, 256, 0, st>>>(a);
+  AN3D_LAUNCH_CHECK();
+  bn_bwd_params_kernel<<<(v.ch + 127) / 128, 128, 0, st>>>(v.acc0, v.acc1, v.dgamma, v.dbeta, v.ch);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
 // bf16 mode: the operands of an FC layer's backward GEMMs as plane-major bf16 images (fc2_gemm.cuh): the layer's input
 // activations and weights were packed by the forward pass, the gradient image is packed here.
 struct FcImages {
@@ -172,15 +375,18 @@ static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2],
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
                     float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
                     int64_t lddx, double* bias_acc, cudaStream_t st, const FcImages* img = nullptr,
-                    const PlanF32* tp = nullptr) {
+                    const PlanF32* tp = nullptr, const tcg::SplitMat* dz_img = nullptr) {
   const bool bf16 = img != nullptr;
   bool wgrad_done = false, dgrad_done = false;
+  bool skip_bias = bf16 && L.bn >= 0;
   if (!bf16 && tp && tcg::use_tensor_cores(*tp, L.cin, L.cout, R)) {
+    skip_bias = L.bn >= 0 && dz_img != nullptr;   // (no fp32 dZ to reduce; the gradient is identically zero, see below)
     // materialised path on the tensor cores (gemm_tc.cuh): the layer's input (BN + ReLU + dropout of the producing layer
     // applied while packing), the gradient at its output and its weights are packed once and serve wgrad and dgrad
     tcg::SplitMat x, dz, w;
     AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_X, X, ldx, R, L.cin, psc, psh, pmask, pmask_scale, &x, st));
-    AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_DZ, dZ, L.cout, R, L.cout, nullptr, nullptr, nullptr, 1.f, &dz, st));
+    if (dz_img) dz = *dz_img;     // the BN backward wrote the images itself
+    else AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_DZ, dZ, L.cout, R, L.cout, nullptr, nullptr, nullptr, 1.f, &dz, st));
     tcg::Params f;
     f.A = x; f.a_mn = 1; f.B = dz; f.b_mn = 1;                                   // contraction over the rows
     f.C = grads + L.w; f.ldc = L.cout; f.M = L.cin; f.N = L.cout; f.K = R; f.accumulate = 1;
@@ -212,7 +418,7 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
   }
   // bias grad.  A bias that feeds a batch-statistics BN has an identically zero gradient (TF computes rounding
   // noise there); the bf16 path leaves it at zero, as it does for the conv stacks.
-  if (!(bf16 && L.bn >= 0)) {
+  if (!skip_bias) {
     AN3D_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * L.cout, st));
     ColArgs a;
     a.Z = dZ; a.ldz = L.cout; a.R = R; a.C = L.cout; a.acc0 = bias_acc;
@@ -236,7 +442,8 @@ int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const f
   const int64_t M = p.M;
   const int nl = (int)m.conv[s].size();
   int cur = 0;
-  {
+  const bool tc = p.tc_split > 0;
+  if (!tc) {
     const int C = m.conv[s].back().cout;
     AN3D_CUDA_CHECK(cudaMemsetAsync(p.dbuf[cur], 0, sizeof(float) * M * C, st));
     const int64_t total = (int64_t)p.B * C;
@@ -247,7 +454,17 @@ int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const f
   for (int l = nl - 1; l >= 0; --l) {
     const Lin& L = m.conv[s][l];
     BnRef v = bn_ref(m, p, grads, false, br, L.bn);
-    AN3D_TRY(bn_relu_backward(v, p.z[s][l][br], (int)M, p.dbuf[cur], L.cout, nullptr, 1.f, p.dbuf[cur], L.cout, st));
+    tcg::SplitMat dz_img;
+    bool to_img = false;
+    if (tc) {
+      // tensor-core modes: the pooled layer's gradient stays sparse (dG at the arg rows), dZ of a layer whose GEMMs run
+      // on the tensor cores is written as the split images those GEMMs read
+      to_img = tcg::use_tensor_cores(p, L.cin, L.cout, (int)M);
+      AN3D_TRY(bn_relu_backward_split(p, v, p.z[s][l][br], (int)M, l == nl - 1, p.dbuf[cur], dG, ldg, p.gidx[s][br], to_img,
+                                      &dz_img, p.dbuf[cur], st));
+    } else {
+      AN3D_TRY(bn_relu_backward(v, p.z[s][l][br], (int)M, p.dbuf[cur], L.cout, nullptr, 1.f, p.dbuf[cur], L.cout, st));
+    }
     const float *X, *psc = nullptr, *psh = nullptr;
     float* dX = nullptr;
     int64_t lddx = 0;
@@ -264,7 +481,7 @@ int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const f
       if (want_input_grad) { dX = p.dpin; lddx = 3; }
     }
     AN3D_TRY(linear_backward(L, X, L.cin, psc, psh, nullptr, 1.f, p.dbuf[cur], (int)M, params, grads, dX, lddx,
-                             p.dbias_acc, st, nullptr, &p));
+                             p.dbias_acc, st, nullptr, &p, to_img ? &dz_img : nullptr));
     cur ^= 1;
   }
   return AN3D_OK;

@@ -175,6 +175,7 @@ struct PlanF32 {
   int tc_split = 0;                         // materialised path: 0 = CUDA-core SGEMM, 1-3 = bf16 images per GEMM operand (gemm_tc.cuh)
   __nv_bfloat16* tcbuf[3] = {nullptr, nullptr, nullptr};   // image scratch: layer input, output gradient, weights
   int64_t tcbuf_elems[3] = {0, 0, 0};       // capacity of each (all images of the operand)
+  float* bwd_coef = nullptr;                // [2][max conv width]: per-channel constants of the BN backward (tensor-core modes, training)
   bool deterministic = false;               // AN3D_DETERMINISTIC: no split-K fp32 reductions in inference FC layers
   bool prepared = false;                    // AN3D_WEIGHTS_PREPARED (bf16 inference): folded BN / weight images are reused
   int64_t M = 0;  // rows per branch = B*N

@@ -78,24 +78,6 @@ static int conv_stage_two_streams(SideStream* ss, const Model& m, const PlanF32&
   return r0 != AN3D_OK ? r0 : r1;
 }
 
-// batch statistics of Z[R,C] (two-pass, tf.nn.moments) or shadows -> scale/shift; EMA update
-static int bn_forward(const BnView& v, const float* Z, int R, bool training, float decay, cudaStream_t st) {
-  const int C = v.ch;
-  const int tb = 128, nb = (C + tb - 1) / tb;
-  if (training) {
-    ColArgs a;
-    a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1; a.mean = v.mean;
-    AN3D_TRY(launch_col_reduce(a, COL_SUM, st));
-    bn_mean_kernel<<<nb, tb, 0, st>>>(v.acc0, v.mean, C, 1.0 / R);
-    AN3D_LAUNCH_CHECK();
-    AN3D_TRY(launch_col_reduce(a, COL_SQDIFF, st));
-  }
-  bn_finalize_kernel<<<nb, tb, 0, st>>>(v.acc1, 1.0 / R, v.gamma, v.beta, v.state_mean, v.state_var, v.mean, v.inv,
-                                          v.scale, v.shift, C, training ? 1 : 0, decay);
-  AN3D_LAUNCH_CHECK();
-  return AN3D_OK;
-}
-
 // bf16 mode: the producing GEMM's epilogue already accumulated sum z (acc0) and sum z^2 (acc1) per column
 static __global__ void bn_finalize_sums_kernel(const double* acc0, const double* acc1, double inv_rows, const float* gamma,
                                                const float* beta, float* state_mean, float* state_var, float* mean,
@@ -116,6 +98,37 @@ static __global__ void bn_finalize_sums_kernel(const double* acc0, const double*
   shift[c] = beta[c] - mu * sc;
 }
 
+// batch statistics of Z[R,C] (two-pass, tf.nn.moments) or shadows -> scale/shift; EMA update
+// one_pass (tensor-core modes of the materialised path): sum z and sum z^2 in ONE read of Z, both in double -- the
+// variance sum z^2 / R - mean^2 then carries ~1e-16 E[z^2] / var of cancellation error, far below fp32 resolution; the
+// two-pass form is what fp32 arithmetic needs (and what the fp32 mode keeps, as tf.nn.moments does).
+static int bn_forward(const BnView& v, const float* Z, int R, bool training, float decay, cudaStream_t st,
+                      bool one_pass = false) {
+  const int C = v.ch;
+  const int tb = 128, nb = (C + tb - 1) / tb;
+  if (training && one_pass) {
+    ColArgs a;
+    a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1;
+    AN3D_TRY(launch_col_reduce(a, COL_SUMSQ, st));
+    bn_finalize_sums_kernel<<<nb, tb, 0, st>>>(v.acc0, v.acc1, 1.0 / R, v.gamma, v.beta, v.state_mean, v.state_var, v.mean,
+                                               v.inv, v.scale, v.shift, C, decay);
+    AN3D_LAUNCH_CHECK();
+    return AN3D_OK;
+  }
+  if (training) {
+    ColArgs a;
+    a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1; a.mean = v.mean;
+    AN3D_TRY(launch_col_reduce(a, COL_SUM, st));
+    bn_mean_kernel<<<nb, tb, 0, st>>>(v.acc0, v.mean, C, 1.0 / R);
+    AN3D_LAUNCH_CHECK();
+    AN3D_TRY(launch_col_reduce(a, COL_SQDIFF, st));
+  }
+  bn_finalize_kernel<<<nb, tb, 0, st>>>(v.acc1, 1.0 / R, v.gamma, v.beta, v.state_mean, v.state_var, v.mean, v.inv,
+                                          v.scale, v.shift, C, training ? 1 : 0, decay);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
 static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, const float* params, float* state,
                               bool training, float decay, cudaStream_t st) {
   const int64_t M = p.M;
@@ -128,7 +141,7 @@ static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, c
     g.M = (int)M; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
     AN3D_TRY(gemm_mat(p, g, false, false, st));
     BnView v = bn_view(m, p, params, state, false, br, L.bn);
-    AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st));
+    AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st, p.tc_split > 0));
     x = p.z[s][l][br];
     psc = v.scale;
     psh = v.shift;

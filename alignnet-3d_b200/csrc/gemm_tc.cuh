@@ -57,10 +57,15 @@ struct PackArgs {
 
 static __global__ void __launch_bounds__(256) pack_split_kernel(const PackArgs a) {
   const int rows_pad = (a.rows + 127) & ~127, chunks = ((a.cols + 127) & ~127) >> 3;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)rows_pad * chunks) return;
-  // consecutive threads walk the rows of one chunk (fc2::pack_kernel): one 32-byte sector per lane in, 16 contiguous bytes out
-  const int c8 = (int)(i / rows_pad), r = (int)(i - (int64_t)c8 * rows_pad);
+  // a warp covers 8 rows x 4 chunks of 8 columns: 128 contiguous bytes of each of its rows in, 128 contiguous bytes of
+  // each of its 4 image planes out (8 rows x 16 B).  (One chunk per lane along the rows -- fc2::pack_kernel's mapping,
+  // fine for FC-sized matrices -- moved 2.7 TB/s on the [819200, 1024] gradient: 32-byte pieces at a 4 KB stride.)
+  const int cgroups = chunks >> 2;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t rg = w / cgroups;
+  if (rg * 8 >= rows_pad) return;
+  const int r = (int)(rg * 8) + (lane & 7), c8 = (int)(w - rg * cgroups) * 4 + (lane >> 3);
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -114,7 +119,7 @@ static int pack(const PackArgs& a, cudaStream_t st, SplitMat* out) {
     set_error("tcg::pack: bad arguments (%d x %d, %d images)", a.rows, a.cols, a.nsplit);
     return AN3D_ERR_INVALID;
   }
-  const int64_t total = (int64_t)((a.rows + 127) & ~127) * (((a.cols + 127) & ~127) >> 3);
+  const int64_t total = (int64_t)((a.rows + 127) & ~127) * (((a.cols + 127) & ~127) >> 3);   // one thread per (row, chunk)
   pack_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
   AN3D_LAUNCH_CHECK();
   out->n = a.nsplit;
@@ -156,6 +161,28 @@ __device__ __forceinline__ void term_images(int nterms, int t, int* ia, int* ib)
   const int q = 6 - nterms + t;
   *ia = (0x001102u >> (4 * q)) & 15;
   *ib = (0x010120u >> (4 * q)) & 15;
+}
+
+// Epilogue store of one warp's 32 rows x 32 columns: the TMEM load leaves a ROW per lane, so a direct store writes 32
+// rows x 16 B per instruction (32 half-sector transactions at the row stride; the LSU, not HBM, paced the forward conv
+// GEMMs: 9 k cycles per 128 x 128 tile).  Through a per-warp staging tile (32 x 36 floats) every store instruction
+// writes 4 rows x 128 contiguous bytes instead.  `stage` is this warp's 4.5 KB; C must allow 16-byte accesses.
+constexpr int kStageLd = 36;
+constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;
+__device__ __forceinline__ void store_group_coalesced(float* stage, const float (&v)[32], float* C, int64_t ldc, int row0,
+                                                      int col0, int M, int N, int lane) {
+  __syncwarp();                                              // the previous group's reads of the staging tile are done
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    const float4 x = *reinterpret_cast<const float4*>(stage + r * kStageLd + c4);
+    if (row0 + r < M && col0 + c4 < N) *reinterpret_cast<float4*>(C + (int64_t)(row0 + r) * ldc + col0 + c4) = x;
+  }
 }
 
 template <int STAGES>
@@ -229,11 +256,19 @@ static __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const Params P
     const int i = i0 + tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool reduce = P.ksplit > 1 || P.accumulate;
+    float* stage = reinterpret_cast<float*>(sA) + warp * (kStageBytesPerWarp / 4);   // the operand ring is idle once `done` fired
     for (int g32 = 0; g32 < 128; g32 += 32) {
       if (j0 + g32 >= P.N) break;
       uint32_t r[32];
       tmem_ld32(tmem + lane_base + g32, r);
       tmem_ld_wait();
+      if (!reduce && P.c_vec) {
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + bars->bias[g32 + e];
+        store_group_coalesced(stage, v, P.C, P.ldc, i0 + warp * 32, j0 + g32, P.M, P.N, lane);
+        continue;
+      }
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
         const int j = j0 + g32 + j4;
@@ -264,6 +299,147 @@ static __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const Params P
   if (warp == 5) tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// A-stationary variant for the conv layers' forward GEMMs: M = all points of a branch (thousands of row tiles), K one
+// block, N up to 8 column tiles.  The generic kernel above re-reads both operand tiles for every (output tile, term):
+// 6 x 64 KB per 128 x 128 tile in the six-product mode -- 19.7 GB through L2 for one [819200, 128] x [128, 1024] layer,
+// 2.9 ms against 0.6 ms of HBM time for its input and output.  Here a CTA owns a row tile: the NSPLIT images of its A
+// tile are fetched once and stay in shared memory, the B image tiles (weights: L2-resident) stream through a ring --
+// each is fetched once per (row tile, column tile) and meets every A image it pairs with -- and two TMEM accumulators
+// alternate so the epilogue of column tile j runs under the MMAs of j + 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAstatRing = 3;
+constexpr int kAstatMaxN = 2048;
+template <int NSPLIT> constexpr size_t astat_smem_bytes() {
+  return (size_t)(NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp + 256;
+}
+
+struct AstatBars {
+  uint64_t a_full, b_full[kAstatRing], b_empty[kAstatRing], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int NSPLIT>
+static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;                                        // NSPLIT tiles
+  uint8_t* sB = smem + NSPLIT * kTileBytes;                  // ring
+  float* sBias = reinterpret_cast<float*>(smem + (NSPLIT + kAstatRing) * kTileBytes);
+  float* sStage = sBias + kAstatMaxN;                        // 4 warps x 32 x 36 floats
+  AstatBars* bars = reinterpret_cast<AstatBars*>(smem + (NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int ib0 = blockIdx.x, i0 = ib0 * 128;
+  const int ntn = (P.N + 127) >> 7;
+
+  if (tid == 0) {
+    mbar_init(&bars->a_full, 1);
+    for (int i = 0; i < kAstatRing; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 256);
+  for (int j = tid; j < ntn * 128; j += kThreads) sBias[j] = (P.bias && j < P.N) ? P.bias[j] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->a_full, NSPLIT * kTileBytes);
+      for (int s = 0; s < NSPLIT; ++s) bulk_copy_g2s(sA + s * kTileBytes, P.A.img[s].block(ib0, 0), kTileBytes, &bars->a_full);
+      uint32_t ph = (1u << kAstatRing) - 1u;
+      int st = 0;
+      for (int j = 0; j < ntn; ++j)
+        for (int ib = NSPLIT - 1; ib >= 0; --ib) {           // smallest contributions first
+          mbar_wait(&bars->b_empty[st], (ph >> st) & 1u); ph ^= 1u << st;
+          mbar_arrive_expect_tx(&bars->b_full[st], kTileBytes);
+          bulk_copy_g2s(sB + st * kTileBytes, P.B.img[ib].block(0, j), kTileBytes, &bars->b_full[st]);
+          st = st + 1 == kAstatRing ? 0 : st + 1;
+        }
+    }
+  } else if (warp == 5) {
+    const uint32_t idesc = make_idesc(128, 128, 0, 1);
+    mbar_wait(&bars->a_full, 0);
+    uint32_t phb = 0, phe = 3u;                              // accumulators start out free
+    int st = 0;
+    for (int j = 0; j < ntn; ++j) {
+      const int acc = j & 1;
+      mbar_wait(&bars->acc_empty[acc], (phe >> acc) & 1u); phe ^= 1u << acc;
+      tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)acc * 128u;
+      bool first = true;
+      for (int ib = NSPLIT - 1; ib >= 0; --ib) {
+        mbar_wait(&bars->b_full[st], (phb >> st) & 1u); phb ^= 1u << st;
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(sB + st * kTileBytes);
+        if (elect_one()) {
+          for (int ia = NSPLIT - 1 - ib; ia >= 0; --ia) {    // the pairs (ia, ib) with ia + ib < NSPLIT
+            const uint32_t a_base = smem_u32(sA + ia * kTileBytes);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              mma_bf16_raw(d, make_desc(a_base + ks * 2 * kPlane, kPlane, 128), make_desc(b_base + ks * 256, 128, kPlane), idesc,
+                           (first && ks == 0) ? 0u : 1u);
+            }
+            first = false;
+          }
+          mma_commit_raw(&bars->b_empty[st]);
+          if (ib == 0) mma_commit_raw(&bars->acc_full[acc]);
+        }
+        __syncwarp();
+        first = false;
+        st = st + 1 == kAstatRing ? 0 : st + 1;
+      }
+    }
+  } else {
+    const int i = i0 + tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phf = 0;
+    for (int j = 0; j < ntn; ++j) {
+      const int acc = j & 1, j0 = j * 128;
+      mbar_wait_relaxed(&bars->acc_full[acc], (phf >> acc) & 1u); phf ^= 1u << acc;
+      tc_fence_after();
+      for (int g32 = 0; g32 < 128; g32 += 32) {
+        if (j0 + g32 >= P.N) break;
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)acc * 128u + g32, r);
+        tmem_ld_wait();
+        if (P.c_vec) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + sBias[j0 + g32 + e];
+          store_group_coalesced(sStage + warp * (kStageBytesPerWarp / 4), v, P.C, P.ldc, i0 + warp * 32, j0 + g32, P.M, P.N, lane);
+          continue;
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int jj = j0 + g32 + j4;
+          float v[4] = {__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
+                        __uint_as_float(r[j4 + 3])};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] += sBias[jj + e];
+          if (i < P.M && jj < P.N) {
+            float* dst = P.C + (int64_t)i * P.ldc + jj;
+            if (P.c_vec) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (jj + e < P.N) dst[e] = v[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
 // C must be pre-zeroed by the caller when the launch reduces into it (accumulate, or K longer than one CTA's share:
 // launch() clears it itself in the second case unless `accumulate` says C already holds a value to add to).
 static int launch(Params p, cudaStream_t st) {
@@ -284,6 +460,25 @@ static int launch(Params p, cudaStream_t st) {
   }
   p.nterms = num_terms(p.A.n);
   p.c_vec = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0 && p.N % 4 == 0;
+  // the conv layers' forward form: many row tiles, one K block, several column tiles -> A-stationary kernel
+  if (p.a_mn == 0 && p.b_mn == 1 && p.K <= 128 && !p.accumulate && p.N > 128 && p.N <= kAstatMaxN && (p.M + 127) / 128 >= 148) {
+    static bool astat_attr = false;
+    if (!astat_attr) {
+      AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_astat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)astat_smem_bytes<1>()));
+      AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_astat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)astat_smem_bytes<2>()));
+      AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_astat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)astat_smem_bytes<3>()));
+      astat_attr = true;
+    }
+    p.ksplit = 1;
+    const unsigned grid = (unsigned)((p.M + 127) / 128);
+    prof_mark(PROF_FC, true, st);
+    if (p.A.n == 1) tc_gemm_astat_kernel<1><<<grid, kThreads, astat_smem_bytes<1>(), st>>>(p);
+    else if (p.A.n == 2) tc_gemm_astat_kernel<2><<<grid, kThreads, astat_smem_bytes<2>(), st>>>(p);
+    else tc_gemm_astat_kernel<3><<<grid, kThreads, astat_smem_bytes<3>(), st>>>(p);
+    prof_mark(PROF_FC, false, st);
+    AN3D_LAUNCH_CHECK();
+    return AN3D_OK;
+  }
   const int nkb = (p.K + 127) >> 7;
   const int tiles = ((p.M + 127) / 128) * ((p.N + 127) / 128);
   int ks = (nkb + kMaxKBlocksPerCta - 1) / kMaxKBlocksPerCta;          // accumulation length cap

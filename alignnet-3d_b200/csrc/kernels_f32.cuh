@@ -119,7 +119,7 @@ inline int launch_gemm(const GemmArgs& g, bool ta, bool tb, cudaStream_t st) {
 // --------------------------------------------------------------------------------------------
 // Column reductions over Z[R,C] (double accumulation, atomics across row chunks)
 // --------------------------------------------------------------------------------------------
-enum ColMode { COL_SUM = 0, COL_SQDIFF = 1, COL_DY = 2 };
+enum ColMode { COL_SUM = 0, COL_SQDIFF = 1, COL_DY = 2, COL_SUMSQ = 3 };   // SUMSQ: sum z and sum z^2 in one pass (double)
 
 struct ColArgs {
   const float* Z = nullptr;   // [R, C] leading dim ldz
@@ -145,7 +145,7 @@ static __global__ void __launch_bounds__(256) col_reduce_kernel(ColArgs a, int r
   double s0 = 0.0, s1 = 0.0;
   if (c < a.C) {
     float mean = 0.f, inv = 0.f, sc = 0.f, sh = 0.f;
-    if (MODE != COL_SUM) mean = a.mean[c];
+    if (MODE == COL_SQDIFF || MODE == COL_DY) mean = a.mean[c];
     if (MODE == COL_DY) { inv = a.inv[c]; sc = a.scale[c]; sh = a.shift[c]; }
     // four rows per iteration: the loads of a batch are independent and in flight together
     for (int rb = r0 + threadIdx.y; rb < r1; rb += 32) {
@@ -167,6 +167,9 @@ static __global__ void __launch_bounds__(256) col_reduce_kernel(ColArgs a, int r
         if (rb + 8 * u >= r1) continue;
         if (MODE == COL_SUM) {
           s0 += (double)z[u];
+        } else if (MODE == COL_SUMSQ) {
+          s0 += (double)z[u];
+          s1 += (double)z[u] * (double)z[u];
         } else if (MODE == COL_SQDIFF) {
           const float d = z[u] - mean;
           s1 += (double)d * (double)d;
@@ -197,6 +200,7 @@ inline int launch_col_reduce(const ColArgs& a, int mode, cudaStream_t st) {
   dim3 block(32, 8);
   if (mode == COL_SUM) col_reduce_kernel<COL_SUM><<<grid, block, 0, st>>>(a, rows_per_block);
   else if (mode == COL_SQDIFF) col_reduce_kernel<COL_SQDIFF><<<grid, block, 0, st>>>(a, rows_per_block);
+  else if (mode == COL_SUMSQ) col_reduce_kernel<COL_SUMSQ><<<grid, block, 0, st>>>(a, rows_per_block);
   else col_reduce_kernel<COL_DY><<<grid, block, 0, st>>>(a, rows_per_block);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;

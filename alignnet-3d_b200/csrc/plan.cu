@@ -146,6 +146,7 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     p->tcbuf_elems[1] = training ? e1 * tc_split : 0;
     p->tcbuf_elems[2] = e2 * tc_split;
     for (int i = 0; i < 3; ++i) p->tcbuf[i] = a.take<__nv_bfloat16>(p->tcbuf_elems[i]);
+    p->bwd_coef = training ? a.take<float>(2 * ((max_conv_ch + 3) & ~int64_t(3))) : nullptr;
   }
   p->bytes = (a.off + 255) & ~int64_t(255);
   return AN3D_OK;

@@ -41,7 +41,7 @@ def run(lib, A, a_mn, Bm, b_mn, M, N, K, nsplit, bias=None, scale=None, shift=No
 
 @pytest.mark.parametrize("nsplit", [1, 2, 3])
 @pytest.mark.parametrize("M,K,N", [(4096, 256, 512), (200, 512, 256), (48, 2048, 512), (1024, 256, 103), (130, 64, 15),
-                                   (64, 8, 16), (25600, 128, 1024), (1000, 24, 40)])
+                                   (64, 8, 16), (25600, 128, 1024), (1000, 24, 40), (19001, 64, 200), (40000, 128, 256)])
 def test_forward_form(lib, M, K, N, nsplit):
     g = torch.Generator().manual_seed(M + K + N)
     X = torch.randn(M, K, generator=g)
