@@ -370,6 +370,74 @@ static int fc_backward_bf16(const Lin& L, int R, int nbr, const FcImages img[2],
   return AN3D_OK;
 }
 
+// ---- the 3-wide first conv layer (utils/tf_util.py:157 with the [1,3] kernel): its wgrad and dgrad read dZ [R, cout] once.
+// The tiled SGEMM spent 260 / 233 us per launch on them at R = 819,200 (64 x 64 output tiles for a 3-row / 3-column
+// result); these stream dZ at HBM speed.  Used by every mode of the materialised path.
+// wgrad: grads.W[k, c] += sum_r X[r, k] dZ[r, c]   (k < 3).  Block = 256 threads = 4 row lanes x 64 channels... generalised:
+// thread (ry, c) walks rows ry, ry + RY, ... of the block's row range for channel c; fp32 partials per thread, fp64 in the block.
+static __global__ void __launch_bounds__(256) l0_wgrad_kernel(const float* X, const float* dZ, float* gW, int R, int C, int rows_per_block) {
+  const int cpb = min(C, 64);                       // channels per block pass
+  const int ry = threadIdx.x / cpb, ny = 256 / cpb;
+  const int cl = threadIdx.x - ry * cpb;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  __shared__ double red[3][256];
+  for (int cb = blockIdx.y * cpb; cb < C; cb += gridDim.y * cpb) {
+    const int c = cb + cl;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (ry < ny && c < C) {
+      // four independent rows in flight per thread; fp32 partials over the block's short row range, fp64 across blocks' lanes
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      int r = r0 + ry;
+      for (; r + 3 * ny < r1; r += 4 * ny) {
+        float g[4], x[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          g[u] = dZ[(int64_t)(r + u * ny) * C + c];
+          const float* xp = X + (int64_t)(r + u * ny) * 3;
+          x[u][0] = xp[0]; x[u][1] = xp[1]; x[u][2] = xp[2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s0 = fmaf(x[u][0], g[u], s0); s1 = fmaf(x[u][1], g[u], s1); s2 = fmaf(x[u][2], g[u], s2); }
+      }
+      for (; r < r1; r += ny) {
+        const float g = dZ[(int64_t)r * C + c];
+        const float* xp = X + (int64_t)r * 3;
+        s0 = fmaf(xp[0], g, s0); s1 = fmaf(xp[1], g, s1); s2 = fmaf(xp[2], g, s2);
+      }
+      a0 = s0; a1 = s1; a2 = s2;
+    }
+    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      for (int i = 1; i < ny; ++i) { a0 += red[0][i * cpb + cl]; a1 += red[1][i * cpb + cl]; a2 += red[2][i * cpb + cl]; }
+      atomicAdd(gW + c, (float)a0);
+      atomicAdd(gW + C + c, (float)a1);
+      atomicAdd(gW + 2 * C + c, (float)a2);
+    }
+    __syncthreads();
+  }
+}
+
+// dgrad: dX[r, k] = sum_c dZ[r, c] W[k, c]   (k < 3): a warp per row group, lanes across channels (coalesced), shuffle reduce
+static __global__ void __launch_bounds__(256) l0_dgrad_kernel(const float* dZ, const float* W, float* dX, int R, int C) {
+  extern __shared__ float sw[];                     // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += 256) sw[i] = W[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < R; r += (int64_t)gridDim.x * 8) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float g = dZ[r * C + c];
+      s0 = fmaf(g, sw[c], s0); s1 = fmaf(g, sw[C + c], s1); s2 = fmaf(g, sw[2 * C + c], s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { dX[r * 3] = s0; dX[r * 3 + 1] = s1; dX[r * 3 + 2] = s2; }
+  }
+}
+
 // Z = pro(X) W + b.  Given dZ [R,cout] (dense, ld = cout):
 //   grads.W += pro(X)^T dZ ; grads.b += colsum(dZ) ; dX = dZ W^T (if dX != nullptr).
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
@@ -406,6 +474,21 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     float* dx[2] = {dX, nullptr};
     AN3D_TRY(fc_backward_bf16(L, R, 1, im, dz, grads + L.w, dx, lddx, st, img->dz_packed));
     wgrad_done = dgrad_done = true;
+  }
+  // the 3-wide first conv layer at conv-stack row counts: dedicated streaming kernels (no prologue, dense operands)
+  const bool l0 = !bf16 && L.cin == 3 && ldx == 3 && !psc && !pmask && R >= 4096 && L.cout <= 1024;
+  if (!wgrad_done && l0) {
+    const int rpb = 512;
+    dim3 grid((R + rpb - 1) / rpb, 1);
+    l0_wgrad_kernel<<<grid, 256, 0, st>>>(X, dZ, grads + L.w, R, L.cout, rpb);
+    AN3D_LAUNCH_CHECK();
+    wgrad_done = true;
+  }
+  if (dX && !dgrad_done && l0 && lddx == 3) {
+    const unsigned blocks = (unsigned)std::min<int64_t>(((int64_t)R + 7) / 8, 148 * 16);
+    l0_dgrad_kernel<<<blocks, 256, 3 * L.cout * sizeof(float), st>>>(dZ, params + L.w, dX, R, L.cout);
+    AN3D_LAUNCH_CHECK();
+    dgrad_done = true;
   }
   if (!wgrad_done) {  // wgrad: [cin, cout] += X^T [cin, R] * dZ [R, cout]
     GemmArgs g;

@@ -102,14 +102,17 @@ static __global__ void bn_finalize_sums_kernel(const double* acc0, const double*
 // one_pass (tensor-core modes of the materialised path): sum z and sum z^2 in ONE read of Z, both in double -- the
 // variance sum z^2 / R - mean^2 then carries ~1e-16 E[z^2] / var of cancellation error, far below fp32 resolution; the
 // two-pass form is what fp32 arithmetic needs (and what the fp32 mode keeps, as tf.nn.moments does).
+// have_sums: the GEMM that produced Z already left the two sums in acc0 / acc1 (gemm_tc.cuh, A-stationary kernel).
 static int bn_forward(const BnView& v, const float* Z, int R, bool training, float decay, cudaStream_t st,
-                      bool one_pass = false) {
+                      bool one_pass = false, bool have_sums = false) {
   const int C = v.ch;
   const int tb = 128, nb = (C + tb - 1) / tb;
   if (training && one_pass) {
-    ColArgs a;
-    a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1;
-    AN3D_TRY(launch_col_reduce(a, COL_SUMSQ, st));
+    if (!have_sums) {
+      ColArgs a;
+      a.Z = Z; a.ldz = C; a.R = R; a.C = C; a.acc0 = v.acc0; a.acc1 = v.acc1;
+      AN3D_TRY(launch_col_reduce(a, COL_SUMSQ, st));
+    }
     bn_finalize_sums_kernel<<<nb, tb, 0, st>>>(v.acc0, v.acc1, 1.0 / R, v.gamma, v.beta, v.state_mean, v.state_var, v.mean,
                                                v.inv, v.scale, v.shift, C, decay);
     AN3D_LAUNCH_CHECK();
@@ -139,9 +142,11 @@ static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, c
     GemmArgs g;
     g.A = x; g.lda = L.cin; g.B = params + L.w; g.ldb = L.cout; g.C = p.z[s][l][br]; g.ldc = L.cout;
     g.M = (int)M; g.N = L.cout; g.K = L.cin; g.bias = params + L.b; g.pro_scale = psc; g.pro_shift = psh;
-    AN3D_TRY(gemm_mat(p, g, false, false, st));
     BnView v = bn_view(m, p, params, state, false, br, L.bn);
-    AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st, p.tc_split > 0));
+    bool have_sums = false;
+    const bool want_sums = training && p.tc_split > 0;
+    AN3D_TRY(gemm_mat(p, g, false, false, st, want_sums ? v.acc0 : nullptr, want_sums ? v.acc1 : nullptr, &have_sums));
+    AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st, p.tc_split > 0, have_sums));
     x = p.z[s][l][br];
     psc = v.scale;
     psh = v.shift;

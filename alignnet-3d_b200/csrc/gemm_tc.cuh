@@ -137,6 +137,8 @@ struct Params {
   int M = 0, N = 0, K = 0;
   const float* bias = nullptr;
   int accumulate = 0;         // reductions into C even with one K slice
+  double* stat_sum = nullptr; // optional [N] (pre-zeroed): += column sums of C (bias included) ...
+  double* stat_sq = nullptr;  // ... and of C^2.  Honoured by the A-stationary kernel only: launch() reports it in *stats_done
   int ksplit = 1;             // set by launch()
   int c_vec = 1;              // set by launch()
   int nterms = 1;             // set by launch()
@@ -182,6 +184,36 @@ __device__ __forceinline__ void store_group_coalesced(float* stage, const float 
     const int r = it * 4 + rr;
     const float4 x = *reinterpret_cast<const float4*>(stage + r * kStageLd + c4);
     if (row0 + r < M && col0 + c4 < N) *reinterpret_cast<float4*>(C + (int64_t)(row0 + r) * ldc + col0 + c4) = x;
+  }
+}
+
+// The same store, plus the column sums of the 32 x 32 block for the BN statistics of the layer: after the transposed
+// read a lane holds 8 rows of 4 columns; two shuffle rounds fold the 4 lanes that share the columns.  On return lanes
+// 0-7 hold sum / sum of squares of columns col0 + 4 * lane .. + 3 over this warp's (valid) rows, in s / q.
+__device__ __forceinline__ void store_group_coalesced_stats(float* stage, const float (&v)[32], float* C, int64_t ldc, int row0,
+                                                            int col0, int M, int N, int lane, float (&s)[4], float (&q)[4]) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { s[e] = 0.f; q[e] = 0.f; }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    const float4 x = *reinterpret_cast<const float4*>(stage + r * kStageLd + c4);
+    if (row0 + r < M && col0 + c4 < N) {
+      *reinterpret_cast<float4*>(C + (int64_t)(row0 + r) * ldc + col0 + c4) = x;
+      s[0] += x.x; s[1] += x.y; s[2] += x.z; s[3] += x.w;
+      q[0] = fmaf(x.x, x.x, q[0]); q[1] = fmaf(x.y, x.y, q[1]); q[2] = fmaf(x.z, x.z, q[2]); q[3] = fmaf(x.w, x.w, q[3]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);  q[e] += __shfl_xor_sync(0xffffffffu, q[e], 8);
+    s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16); q[e] += __shfl_xor_sync(0xffffffffu, q[e], 16);
   }
 }
 
@@ -310,8 +342,9 @@ static __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const Params P
 // ---------------------------------------------------------------------------------------------
 constexpr int kAstatRing = 3;
 constexpr int kAstatMaxN = 2048;
+constexpr int kAstatStatBytes = 4 * 128 * 2 * 4;             // per epilogue warp: sum / sum of squares of a tile's 128 columns
 template <int NSPLIT> constexpr size_t astat_smem_bytes() {
-  return (size_t)(NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp + 256;
+  return (size_t)(NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp + kAstatStatBytes + 256;
 }
 
 struct AstatBars {
@@ -326,7 +359,9 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
   uint8_t* sB = smem + NSPLIT * kTileBytes;                  // ring
   float* sBias = reinterpret_cast<float*>(smem + (NSPLIT + kAstatRing) * kTileBytes);
   float* sStage = sBias + kAstatMaxN;                        // 4 warps x 32 x 36 floats
-  AstatBars* bars = reinterpret_cast<AstatBars*>(smem + (NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp);
+  float* sStat = sStage + 4 * (kStageBytesPerWarp / 4);      // [4 warps][128 cols][2]
+  AstatBars* bars = reinterpret_cast<AstatBars*>(smem + (NSPLIT + kAstatRing) * kTileBytes + kAstatMaxN * 4 + 4 * kStageBytesPerWarp +
+                                                 kAstatStatBytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int ib0 = blockIdx.x, i0 = ib0 * 128;
   const int ntn = (P.N + 127) >> 7;
@@ -408,7 +443,20 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + sBias[j0 + g32 + e];
-          store_group_coalesced(sStage + warp * (kStageBytesPerWarp / 4), v, P.C, P.ldc, i0 + warp * 32, j0 + g32, P.M, P.N, lane);
+          if (P.stat_sum) {
+            float cs[4], cq[4];
+            store_group_coalesced_stats(sStage + warp * (kStageBytesPerWarp / 4), v, P.C, P.ldc, i0 + warp * 32, j0 + g32, P.M, P.N,
+                                        lane, cs, cq);
+            if (lane < 8) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                sStat[(warp * 128 + g32 + lane * 4 + e) * 2] = cs[e];
+                sStat[(warp * 128 + g32 + lane * 4 + e) * 2 + 1] = cq[e];
+              }
+            }
+          } else {
+            store_group_coalesced(sStage + warp * (kStageBytesPerWarp / 4), v, P.C, P.ldc, i0 + warp * 32, j0 + g32, P.M, P.N, lane);
+          }
           continue;
         }
 #pragma unroll
@@ -433,6 +481,21 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      if (P.stat_sum && P.c_vec) {
+        // fold the four warps' partial sums of this column tile: one thread per column, two fp64 reductions per column
+        // and row tile (fp32 partials over 128 rows; their rounding errors are independent across the thousands of row
+        // tiles, so the totals carry ~1e-9 relative error)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int jj = j0 + tid;
+        if (jj < P.N) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { a0 += sStat[(w4 * 128 + tid) * 2]; a1 += sStat[(w4 * 128 + tid) * 2 + 1]; }
+          atomicAdd(P.stat_sum + jj, (double)a0);
+          atomicAdd(P.stat_sq + jj, (double)a1);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
   }
   tc_fence_before();
@@ -442,7 +505,8 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
 
 // C must be pre-zeroed by the caller when the launch reduces into it (accumulate, or K longer than one CTA's share:
 // launch() clears it itself in the second case unless `accumulate` says C already holds a value to add to).
-static int launch(Params p, cudaStream_t st) {
+static int launch(Params p, cudaStream_t st, bool* stats_done = nullptr) {
+  if (stats_done) *stats_done = false;
   static bool attr_set = false;
   if (!attr_set) {
     AN3D_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<3>()));
@@ -470,6 +534,8 @@ static int launch(Params p, cudaStream_t st) {
       astat_attr = true;
     }
     p.ksplit = 1;
+    if (!p.c_vec || !p.stat_sq) p.stat_sum = p.stat_sq = nullptr;
+    if (stats_done) *stats_done = p.stat_sum != nullptr;
     const unsigned grid = (unsigned)((p.M + 127) / 128);
     prof_mark(PROF_FC, true, st);
     if (p.A.n == 1) tc_gemm_astat_kernel<1><<<grid, kThreads, astat_smem_bytes<1>(), st>>>(p);
@@ -523,7 +589,11 @@ static int pack_slot(const PlanF32& p, int slot, const float* src, int64_t ld, i
 
 // C[M,N] (+)= pro(A) * B (+ bias) with the operand conventions of GemmArgs (kernels_f32.cuh): on the tensor cores when the
 // plan says so, else the CUDA-core SGEMM.  A goes to the input slot, B to the weight slot.
-static int gemm_mat(const PlanF32& p, const GemmArgs& g, bool ta, bool tb, cudaStream_t st) {
+// stat_sum / stat_sq (optional, pre-zeroed [N] doubles): column sums of C and C^2 fused into the GEMM's epilogue where the
+// kernel that runs supports it; *stats_done tells the caller whether they were produced.
+static int gemm_mat(const PlanF32& p, const GemmArgs& g, bool ta, bool tb, cudaStream_t st, double* stat_sum = nullptr,
+                    double* stat_sq = nullptr, bool* stats_done = nullptr) {
+  if (stats_done) *stats_done = false;
   if (!tcg::use_tensor_cores(p, g.M, g.N, g.K)) return launch_gemm(g, ta, tb, st);
   tcg::Params q;
   AN3D_TRY(tcg::pack_slot(p, tcg::SLOT_X, g.A, g.lda, ta ? g.K : g.M, ta ? g.M : g.K, g.pro_scale, g.pro_shift, g.pro_mask,
@@ -532,7 +602,8 @@ static int gemm_mat(const PlanF32& p, const GemmArgs& g, bool ta, bool tb, cudaS
   q.a_mn = ta ? 1 : 0;
   q.b_mn = tb ? 0 : 1;
   q.C = g.C; q.ldc = g.ldc; q.M = g.M; q.N = g.N; q.K = g.K; q.bias = g.bias; q.accumulate = g.accumulate;
-  return tcg::launch(q, st);
+  q.stat_sum = stat_sum; q.stat_sq = stat_sq;
+  return tcg::launch(q, st, stats_done);
 }
 
 }  // namespace an3d

@@ -35,6 +35,13 @@ def shipped_arch(num_bins: int = 50, accept_inverted_angle: bool = True, angle_f
                      (512, 256), 0.7, angle_factor, early_stage_factor, accept_inverted_angle)
 
 
+def default_arch() -> _lib.Arch:
+    """The architecture of the reference's configs/default.json:8-22 (five-layer conv stacks, 36 bins): not of the
+    fused kernels' [64,128,C] form -- the bf16 mode runs it layer by layer on the tensor cores."""
+    return make_arch(36, (128, 128, 256), (512, 256), 0.7, (64, 64, 64, 128, 1024), (512, 256), 0.7,
+                     (64, 64, 64, 128, 1024), (512, 256), 0.7, 1.0, 0.1, False)
+
+
 def make_arch(num_bins, s1_conv, s1_fc, s1_keep, s2_conv, s2_fc, s2_keep, emb_conv, head_fc, head_keep,
               angle_factor=1.0, early_stage_factor=0.5, accept_inverted_angle=True) -> _lib.Arch:
     a = _lib.Arch()

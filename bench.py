@@ -37,6 +37,12 @@ WORKLOADS = {
                B=2048, N=512, train=True, persons=0.0),
     "c5": dict(name="c5: KITTITrackletsCarsHard-shaped synthetic B=2048/GPU N=1024 bf16 fwd+bwd+Adam (+ grad all-reduce)",
                B=2048, N=1024, train=True, persons=0.0),
+    # not a BASELINE config: the reference's own configs/default.json (five-layer conv stacks, N=1024, batch 64) and the
+    # same at a batch that fills the GPU -- the architecture the fused kernels do not cover (layer-by-layer tensor-core path)
+    "cdef": dict(name="configs/default.json of the reference: B=64 N=1024, [128,128,256] + two [64,64,64,128,1024] stacks, training step",
+                 B=64, N=1024, train=True, persons=0.0, arch="default"),
+    "cdef512": dict(name="configs/default.json architecture at B=512 N=1024, training step", B=512, N=1024, train=True,
+                    persons=0.0, arch="default"),
 }
 DEFAULT_WORKLOAD = "c3"
 
@@ -263,7 +269,7 @@ def measure(ctx, wl, precision, steps, warmup, no_graph=False, tags=True):
     from alignnet_b200 import engine, synth
     rank, world, dev, lib, flush = ctx.rank, ctx.world, ctx.dev, ctx.lib, ctx.flush
     B, N, train = wl["B"], wl["N"], wl["train"]
-    eng = engine.Engine(engine.shipped_arch(), str(dev), precision, seed=0)
+    eng = engine.Engine(engine.default_arch() if wl.get("arch") == "default" else engine.shipped_arch(), str(dev), precision, seed=0)
     host = synth.make_batch_fast(B, N, seed=1234 + (2 if train else 1) + rank)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     resident = {k: t.to(dev) for k, t in pinned.items()}
@@ -384,7 +390,7 @@ def measure(ctx, wl, precision, steps, warmup, no_graph=False, tags=True):
     torch.cuda.synchronize()
 
     ms_total = timed(lambda: step(resident), steps)
-    res = dict(B=B, N=N, train=train, precision=precision, steps=steps, ms_per_step=ms_total / steps,
+    res = dict(B=B, N=N, train=train, precision=precision, arch=wl.get("arch", "shipped"), steps=steps, ms_per_step=ms_total / steps,
                value=B * world * steps / (ms_total * 1e-3), h2d_bytes=h2d_bytes, d2h_bytes=80 if train else B * 16,
                allreduce_in_graph=getattr(eng, "_ar_in_graph", None))
     if tags:
@@ -418,8 +424,10 @@ def config_entry(r, pk, world):
          "e2e": {"value": r["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d_bytes"],
                  "d2h_bytes_per_step": r["d2h_bytes"]},
          "whole_step_tensor_frac": r["value"] / world * flops_per_pair(r["N"], r["train"]) / (pk["bf16_sustained"] * 1e12)}
-    if r["precision"] == "fp32":
-        e["whole_step_tensor_frac"] = None        # the fp32 parity mode runs on CUDA cores: not held to the bf16 roofline
+    if r["precision"] == "fp32" or r.get("arch") != "shipped":
+        e["whole_step_tensor_frac"] = None        # fp32 mode: CUDA cores; other architectures: flops_per_pair() does not apply
+    if r.get("arch") != "shipped":
+        e["architecture"] = "reference configs/default.json:8-22 (conv stacks [128,128,256] / [64,64,64,128,1024] x 2, 36 bins)"
     # (bf16x3 / bf16x6: algorithmic FLOPs over the bf16 peak -- the split modes issue 3x / 6x those FLOPs on the tensor pipe)
     return e
 
@@ -447,6 +455,10 @@ def run_ours(args, wl):
         # the parity tolerance on the tensor cores: every GEMM as six (three) bf16 tcgen05 products of split operands
         extra["c3_bf16x6"] = measure(ctx, WORKLOADS["c3"], "bf16x6", 3, 3, tags=False)
         extra["c3_bf16x3"] = measure(ctx, WORKLOADS["c3"], "bf16x3", 3, 3, tags=False)
+        # the reference's default architecture (not [64,128,C]): bf16 layer by layer on the tensor cores vs the fp32 mode
+        extra["default_arch_bf16"] = measure(ctx, WORKLOADS["cdef"], "bf16", short, 3, tags=False)
+        extra["default_arch_b512_bf16"] = measure(ctx, WORKLOADS["cdef512"], "bf16", 3, 3, tags=False)
+        extra["default_arch_b512_fp32"] = measure(ctx, WORKLOADS["cdef512"], "fp32", 3, 3, tags=False)
         if world == 4:
             extra["c4"] = measure(ctx, WORKLOADS["c4"], "bf16", short, 3, tags=False)
         if world == 8:

@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_split_gemm.py tests/test_gpu_parity.py -q -m gpu > gpurun_out/r2_s61_parity.log 2>&1; echo "gemm+parity rc=$?"
+tail -4 gpurun_out/r2_s61_parity.log
+timeout 1200 python -m pytest tests/test_zz_fullsize_oracle.py -q -s -m gpu > gpurun_out/r2_s61_full.log 2>&1; echo "fullsize rc=$?"
+tail -4 gpurun_out/r2_s61_full.log | cut -c1-300
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_s61_bench.json 2> gpurun_out/r2_s61_bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_s61_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'])
+for k,v in d.get('configs',{}).items(): print(k, v['ms_per_step'], v['value'])
+PY
+tail -3 gpurun_out/r2_s61_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_s61_launches_x6.csv python tools/prof_step.py --workload c3 --steps 1 --precision bf16x6 > gpurun_out/r2_s61.log 2>&1; echo rc=$?
+python tools/launch_summary.py gpurun_out/r2_s61_launches_x6.csv 1 2>/dev/null | head -16
