@@ -21,6 +21,7 @@ extern "C" int an3d_selftest_conv_stack(const an3d_ctx* ctx, const float* params
   const Model& m = ctx->impl.model;
   cudaStream_t st = (cudaStream_t)stream;
   const int flags = AN3D_TRAINING | AN3D_PRECISION_BF16;
+  AN3D_TRY(bf16_supported(m));           // this entry exercises the FUSED kernels: [64, 128, C] stacks only
   PlanF32 p;
   AN3D_TRY(plan_f32(m, batch, num_points, flags, workspace, &p));
   if (p.bytes > workspace_bytes) {

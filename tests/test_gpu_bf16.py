@@ -179,14 +179,27 @@ def test_bf16_matches_rounding_model(name, training):
                 np.testing.assert_allclose(st[k], v.numpy(), atol=tol, rtol=tol, err_msg=k)
 
 
-def test_bf16_rejects_unsupported_arch():
+def test_bf16_other_architectures_take_the_layer_by_layer_path():
+    """A conv stack that is not [64, 128, C] used to be refused in bf16 mode; it now runs layer by layer through the
+    split-operand tensor-core GEMM with one bf16 image per operand (csrc/gemm_tc.cuh).  The fused kernels' diagnostic
+    entry still refuses it."""
     from alignnet_b200 import _lib
     arch = A.tiny_arch()
-    with pytest.raises(_lib.An3dError) as ei:
-        e = make_engine(arch, A.init_params(arch, 0), A.init_state(arch))
-        x = torch.zeros(2, 16, 3, device="cuda")
-        e.forward(x, x, False)
-    assert "UNSUPPORTED" in str(ei.value)
+    params, state = A.randomize_for_test(arch, A.init_params(arch, 0), A.init_state(arch), 1)
+    e16 = make_engine(arch, params, state)
+    e32 = make_engine(arch, params, state, "fp32")
+    g = torch.Generator().manual_seed(5)
+    x1, x2 = torch.randn(8, 40, 3, generator=g).cuda(), torch.randn(8, 40, 3, generator=g).cuda()
+    a, b = e16.forward(x1, x2, False), e32.forward(x1, x2, False)
+    torch.cuda.synchronize()
+    for k in ("pred_s1_pc1centers", "pred_s2_pc2centers", "pred_pc1angle_logits"):      # upstream of the arg-max canonicalisation
+        d = (a[k] - b[k]).abs().max().item()
+        assert np.isfinite(a[k].cpu().numpy()).all() and d < MAX_ABS, (k, d)
+    lib = _lib.load()
+    z = torch.zeros(8, 3, device="cuda")
+    rc = lib.an3d_selftest_conv_stack(e16.ctx, e16.params.data_ptr(), e16.bn_state.data_ptr(), 0, 0, x1.data_ptr(), z.data_ptr(), None,
+                                      8, 40, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, z.data_ptr(), 0, None)
+    assert rc == -2, rc                                                                    # AN3D_ERR_UNSUPPORTED
 
 
 def _rel_l2(a, b):
