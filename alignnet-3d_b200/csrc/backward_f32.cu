@@ -443,7 +443,7 @@ static __global__ void __launch_bounds__(256) l0_dgrad_kernel(const float* dZ, c
 int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc, const float* psh, const float* pmask,
                     float pmask_scale, const float* dZ, int R, const float* params, float* grads, float* dX,
                     int64_t lddx, double* bias_acc, cudaStream_t st, const FcImages* img = nullptr,
-                    const PlanF32* tp = nullptr, const tcg::SplitMat* dz_img = nullptr) {
+                    const PlanF32* tp = nullptr, const tcg::SplitMat* dz_img = nullptr, const __nv_bfloat16* x_kept = nullptr) {
   const bool bf16 = img != nullptr;
   bool wgrad_done = false, dgrad_done = false;
   bool skip_bias = bf16 && L.bn >= 0;
@@ -452,7 +452,8 @@ int linear_backward(const Lin& L, const float* X, int64_t ldx, const float* psc,
     // materialised path on the tensor cores (gemm_tc.cuh): the layer's input (BN + ReLU + dropout of the producing layer
     // applied while packing), the gradient at its output and its weights are packed once and serve wgrad and dgrad
     tcg::SplitMat x, dz, w;
-    AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_X, X, ldx, R, L.cin, psc, psh, pmask, pmask_scale, &x, st));
+    if (x_kept) x = tcg::kept_images(*tp, x_kept, R, L.cin);     // the forward kept them
+    else AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_X, X, ldx, R, L.cin, psc, psh, pmask, pmask_scale, &x, st));
     if (dz_img) dz = *dz_img;     // the BN backward wrote the images itself
     else AN3D_TRY(tcg::pack_slot(*tp, tcg::SLOT_DZ, dZ, L.cout, R, L.cout, nullptr, nullptr, nullptr, 1.f, &dz, st));
     tcg::Params f;
@@ -564,7 +565,7 @@ int conv_stack_backward(const Model& m, const PlanF32& p, int s, int br, const f
       if (want_input_grad) { dX = p.dpin; lddx = 3; }
     }
     AN3D_TRY(linear_backward(L, X, L.cin, psc, psh, nullptr, 1.f, p.dbuf[cur], (int)M, params, grads, dX, lddx,
-                             p.dbias_acc, st, nullptr, &p, to_img ? &dz_img : nullptr));
+                             p.dbias_acc, st, nullptr, &p, to_img ? &dz_img : nullptr, p.tcx[s][l][br]));
     cur ^= 1;
   }
   return AN3D_OK;

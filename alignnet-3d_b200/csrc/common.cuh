@@ -175,6 +175,7 @@ struct PlanF32 {
   int tc_split = 0;                         // materialised path: 0 = CUDA-core SGEMM, 1-3 = bf16 images per GEMM operand (gemm_tc.cuh)
   __nv_bfloat16* tcbuf[3] = {nullptr, nullptr, nullptr};   // image scratch: layer input, output gradient, weights
   int64_t tcbuf_elems[3] = {0, 0, 0};       // capacity of each (all images of the operand)
+  __nv_bfloat16* tcx[3][AN3D_MAX_LAYERS][2];  // training: input images of conv layer l >= 1 of (stage, branch), kept for the backward (else null)
   float* bwd_coef = nullptr;                // [2][max conv width]: per-channel constants of the BN backward (tensor-core modes, training)
   bool deterministic = false;               // AN3D_DETERMINISTIC: no split-K fp32 reductions in inference FC layers
   bool prepared = false;                    // AN3D_WEIGHTS_PREPARED (bf16 inference): folded BN / weight images are reused

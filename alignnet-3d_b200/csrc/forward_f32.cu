@@ -145,7 +145,8 @@ static int conv_stack_forward(const Model& m, const PlanF32& p, int s, int br, c
     BnView v = bn_view(m, p, params, state, false, br, L.bn);
     bool have_sums = false;
     const bool want_sums = training && p.tc_split > 0;
-    AN3D_TRY(gemm_mat(p, g, false, false, st, want_sums ? v.acc0 : nullptr, want_sums ? v.acc1 : nullptr, &have_sums));
+    AN3D_TRY(gemm_mat(p, g, false, false, st, want_sums ? v.acc0 : nullptr, want_sums ? v.acc1 : nullptr, &have_sums,
+                      training ? p.tcx[s][l][br] : nullptr));
     AN3D_TRY(bn_forward(v, p.z[s][l][br], (int)M, training, decay, st, p.tc_split > 0, have_sums));
     x = p.z[s][l][br];
     psc = v.scale;

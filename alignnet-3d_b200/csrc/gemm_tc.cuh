@@ -267,12 +267,16 @@ static __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const Params P
       mbar_wait(&bars->full[st], (ph >> st) & 1u); ph ^= 1u << st;
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA + st * kTileBytes), b_base = smem_u32(sB + st * kTileBytes);
+      // K steps of this block that hold data (the image pads K to 128 with zeros: a 64-wide layer needs 4 of the 8)
+      const int nks = min(8, (P.K - (kb0 + it / P.nterms) * 128 + 15) >> 4);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = P.a_mn ? make_desc(a_base + ks * 256, 128, kPlane) : make_desc(a_base + ks * 2 * kPlane, kPlane, 128);
-          const uint64_t bd = P.b_mn ? make_desc(b_base + ks * 256, 128, kPlane) : make_desc(b_base + ks * 2 * kPlane, kPlane, 128);
-          mma_bf16_raw(tmem, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (ks < nks) {
+            const uint64_t ad = P.a_mn ? make_desc(a_base + ks * 256, 128, kPlane) : make_desc(a_base + ks * 2 * kPlane, kPlane, 128);
+            const uint64_t bd = P.b_mn ? make_desc(b_base + ks * 256, 128, kPlane) : make_desc(b_base + ks * 2 * kPlane, kPlane, 128);
+            mma_bf16_raw(tmem, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         mma_commit_raw(&bars->empty[st]);
         if (it == nit - 1) mma_commit_raw(&bars->done);
@@ -395,6 +399,7 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
     }
   } else if (warp == 5) {
     const uint32_t idesc = make_idesc(128, 128, 0, 1);
+    const int nks = min(8, (P.K + 15) >> 4);                 // K steps that hold data (K <= 128 here)
     mbar_wait(&bars->a_full, 0);
     uint32_t phb = 0, phe = 3u;                              // accumulators start out free
     int st = 0;
@@ -413,8 +418,9 @@ static __global__ void __launch_bounds__(kThreads, 1) tc_gemm_astat_kernel(const
             const uint32_t a_base = smem_u32(sA + ia * kTileBytes);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              mma_bf16_raw(d, make_desc(a_base + ks * 2 * kPlane, kPlane, 128), make_desc(b_base + ks * 256, 128, kPlane), idesc,
-                           (first && ks == 0) ? 0u : 1u);
+              if (ks < nks)
+                mma_bf16_raw(d, make_desc(a_base + ks * 2 * kPlane, kPlane, 128), make_desc(b_base + ks * 256, 128, kPlane), idesc,
+                             (first && ks == 0) ? 0u : 1u);
             }
             first = false;
           }
@@ -578,18 +584,30 @@ enum Slot { SLOT_X = 0, SLOT_DZ = 1, SLOT_W = 2 };
 // layers with a dimension below 8 (the 3-wide first conv layer, 3-wide outputs) stay on the CUDA cores
 inline bool use_tensor_cores(const PlanF32& p, int M, int N, int K) { return p.tc_split > 0 && std::min(M, std::min(N, K)) >= 8; }
 
+// `keep`: pack into this buffer (p.tc_split images of fc_image_elems(rows, cols) elements) instead of the scratch slot --
+// the training forward keeps the conv layers' input images for the backward pass
 static int pack_slot(const PlanF32& p, int slot, const float* src, int64_t ld, int rows, int cols, const float* scale,
-                     const float* shift, const float* mask, float mask_scale, SplitMat* out, cudaStream_t st) {
+                     const float* shift, const float* mask, float mask_scale, SplitMat* out, cudaStream_t st,
+                     __nv_bfloat16* keep = nullptr) {
   const int64_t elems = fc_image_elems(rows, cols);
-  if (elems * p.tc_split > p.tcbuf_elems[slot] || !p.tcbuf[slot]) {
+  if (!keep && (elems * p.tc_split > p.tcbuf_elems[slot] || !p.tcbuf[slot])) {
     set_error("tcg::pack_slot: %d x %d does not fit image scratch %d", rows, cols, slot);
     return AN3D_ERR_WORKSPACE;
   }
   PackArgs a;
   a.src = src; a.ld = ld; a.rows = rows; a.cols = cols; a.scale = scale; a.shift = shift; a.mask = mask; a.mask_scale = mask_scale;
   a.nsplit = p.tc_split;
-  for (int s = 0; s < p.tc_split; ++s) a.dst[s] = p.tcbuf[slot] + s * elems;
+  for (int s = 0; s < p.tc_split; ++s) a.dst[s] = (keep ? keep : p.tcbuf[slot]) + s * elems;
   return pack(a, st, out);
+}
+
+// the images pack_slot(..., keep) left in `buf`
+inline SplitMat kept_images(const PlanF32& p, const __nv_bfloat16* buf, int rows, int cols) {
+  SplitMat m;
+  m.n = p.tc_split;
+  const int64_t elems = fc_image_elems(rows, cols);
+  for (int s = 0; s < p.tc_split; ++s) { m.img[s].g = buf + s * elems; m.img[s].rows = rows; m.img[s].cols = cols; }
+  return m;
 }
 
 }  // namespace tcg
@@ -599,12 +617,12 @@ static int pack_slot(const PlanF32& p, int slot, const float* src, int64_t ld, i
 // stat_sum / stat_sq (optional, pre-zeroed [N] doubles): column sums of C and C^2 fused into the GEMM's epilogue where the
 // kernel that runs supports it; *stats_done tells the caller whether they were produced.
 static int gemm_mat(const PlanF32& p, const GemmArgs& g, bool ta, bool tb, cudaStream_t st, double* stat_sum = nullptr,
-                    double* stat_sq = nullptr, bool* stats_done = nullptr) {
+                    double* stat_sq = nullptr, bool* stats_done = nullptr, __nv_bfloat16* keep_a = nullptr) {
   if (stats_done) *stats_done = false;
   if (!tcg::use_tensor_cores(p, g.M, g.N, g.K)) return launch_gemm(g, ta, tb, st);
   tcg::Params q;
   AN3D_TRY(tcg::pack_slot(p, tcg::SLOT_X, g.A, g.lda, ta ? g.K : g.M, ta ? g.M : g.K, g.pro_scale, g.pro_shift, g.pro_mask,
-                          g.pro_mask_scale, &q.A, st));
+                          g.pro_mask_scale, &q.A, st, keep_a));
   AN3D_TRY(tcg::pack_slot(p, tcg::SLOT_W, g.B, g.ldb, tb ? g.N : g.K, tb ? g.K : g.N, nullptr, nullptr, nullptr, 1.f, &q.B, st));
   q.a_mn = ta ? 1 : 0;
   q.b_mn = tb ? 0 : 1;

@@ -128,6 +128,8 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     for (int br = 0; br < 2; ++br) p->dc1[br] = p->dc2[br] = p->dang[br] = nullptr;
   }
   if (bf16) plan_bf16(m, B, N, flags, a, &p->bf);
+  for (int s = 0; s < 3; ++s)
+    for (int l = 0; l < AN3D_MAX_LAYERS; ++l) p->tcx[s][l][0] = p->tcx[s][l][1] = nullptr;
   if (tc_split > 0) {
     // image scratch of the split-operand GEMMs (gemm_tc.cuh), reused layer after layer: [0] the layer's input
     // activations, [1] the gradient at its output (training), [2] its weights.  Layers with a dimension below 8 stay on
@@ -147,6 +149,15 @@ int plan_f32(const Model& m, int B, int N, int flags, void* workspace, PlanF32* 
     p->tcbuf_elems[2] = e2 * tc_split;
     for (int i = 0; i < 3; ++i) p->tcbuf[i] = a.take<__nv_bfloat16>(p->tcbuf_elems[i]);
     p->bwd_coef = training ? a.take<float>(2 * ((max_conv_ch + 3) & ~int64_t(3))) : nullptr;
+    // the conv layers' input images stay for the backward's wgrad (the pack applies BN + ReLU of the producing layer:
+    // re-packing them read every activation a second time)
+    if (training)
+      for (int s = 0; s < 3; ++s)
+        for (size_t l = 1; l < m.conv[s].size(); ++l) {
+          const Lin& L = m.conv[s][l];
+          if (std::min(std::min<int64_t>(L.cin, L.cout), M) < 8) continue;        // (tcg::use_tensor_cores)
+          for (int br = 0; br < 2; ++br) p->tcx[s][l][br] = a.take<__nv_bfloat16>(fc_image_elems((int)M, L.cin) * tc_split);
+        }
   }
   p->bytes = (a.off + 255) & ~int64_t(255);
   return AN3D_OK;
