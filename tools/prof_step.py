@@ -23,7 +23,7 @@ from alignnet_b200 import engine, synth
 from bench import WORKLOADS
 
 wl = WORKLOADS[a.workload]
-eng = engine.Engine(engine.shipped_arch(), "cuda:0", a.precision, seed=0)
+eng = engine.Engine(engine.default_arch() if wl.get("arch") == "default" else engine.shipped_arch(), "cuda:0", a.precision, seed=0)
 batch = {k: torch.from_numpy(v).cuda() for k, v in synth.make_batch_fast(wl["B"], wl["N"], seed=1236).items()}
 if not wl["train"]:
     for i in range(3):
