@@ -12,9 +12,14 @@ its specification:
                    (tensorflow/core/protobuf/tensor_bundle.proto).
   <prefix>.data-*  the tensors' raw little-endian bytes at the recorded offsets.
 
-PARITY UNPINNED for this row: no TensorFlow-written checkpoint is available offline (the reference ships none; its
-released weights are an external download, README.md:92), so reader and writer are validated against each other and
-against hand-built blocks (tests/test_tf_checkpoint.py), not against a file produced by TensorFlow.  The reader
+PARITY PARTLY PINNED for this row: no TensorFlow-written checkpoint is available offline (the reference ships none; its
+released weights are an external download, README.md:92).  What can be pinned to third-party code is
+(tests/test_tf_checkpoint.py::test_proto_layer_and_crc_against_tensorflows_own_definitions): the entry / header records
+parse under Google's protobuf runtime over TensorFlow's own generated TensorShapeProto / DataType / VersionDef (shipped
+with TensorBoard) and that runtime serialises the same values to identical bytes; crc32c and its mask equal TensorBoard's
+implementation for TensorFlow record files; DataType numbers map to the same numpy dtypes.  The LevelDB table container
+around the records stays UNPINNED (no independent reader of that format is installed): reader and writer are validated
+against each other and against hand-built blocks, not against a file produced by TensorFlow.  The reader
 accepts what a real Saver emits beyond what the writer produces: several data blocks, shared key prefixes, snappy-
 compressed blocks, unknown proto fields, and the EMA shadow names TF's slot creator produces
 (`<variable scope>/bn/<op name>/ExponentialMovingAverage`, see `tf_ema_key`: the second siamese branch reads

@@ -129,3 +129,74 @@ def test_engine_export_import_round_trip(tmp_path):
     ea, eb = a.forward(batch["pcs1"], batch["pcs2"], False), b.forward(batch["pcs1"], batch["pcs2"], False)
     for k in ea:
         torch.testing.assert_close(eb[k], ea[k], rtol=0, atol=1e-6)
+
+
+def test_proto_layer_and_crc_against_tensorflows_own_definitions():
+    """Third-party pin of the parts of the checkpoint format that CAN be pinned offline.  TensorBoard (installed here) ships
+    TensorFlow's own generated protos for the sub-messages of a bundle entry (TensorShapeProto, DataType, VersionDef) and its
+    own crc32c / crc mask used for TensorFlow record files.  The two bundle messages themselves
+    (tensorflow/core/protobuf/tensor_bundle.proto) are declared here over those definitions and run through Google's protobuf
+    runtime: what this module writes must parse into them field for field, and the runtime's serialisation of the same
+    values must be byte-identical to this module's encoder.  (The LevelDB table container around the entries stays
+    unpinned: no independent reader of that format is installed.)"""
+    pytest.importorskip("tensorboard")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from tensorboard.compat.proto import tensor_shape_pb2, types_pb2, versions_pb2
+    from tensorboard.compat.tensorflow_stub import dtypes as tb_dtypes, pywrap_tensorflow as pw
+    from alignnet_b200 import tf_checkpoint as T
+
+    # crc32c and the LevelDB / TensorFlow mask
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 64, 4097, 300000):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert T.crc32c(data) == pw.crc32c(data), n
+        assert T.mask_crc(T.crc32c(data)) == pw.masked_crc32c(data), n
+
+    # DataType numbers -> numpy dtypes
+    for num, np_t in T.DT.items():
+        assert tb_dtypes.as_dtype(num).as_numpy_dtype == np_t, num
+    assert T.DT_INV[np.dtype(np.float32).str] == types_pb2.DT_FLOAT and T.DT_INV[np.dtype(np.int64).str] == types_pb2.DT_INT64
+
+    # tensor_bundle.proto over TensorFlow's own sub-message definitions
+    pkg = tensor_shape_pb2.DESCRIPTOR.package
+    fd = descriptor_pb2.FileDescriptorProto(name="an3d_test/tensor_bundle.proto", package="an3d_test", syntax="proto3")
+    fd.dependency.extend([tensor_shape_pb2.DESCRIPTOR.name, types_pb2.DESCRIPTOR.name, versions_pb2.DESCRIPTOR.name])
+    F = descriptor_pb2.FieldDescriptorProto
+    hdr = fd.message_type.add(name="BundleHeaderProto")
+    hdr.field.add(name="num_shards", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    hdr.field.add(name="endianness", number=2, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)      # enum {LITTLE = 0, BIG = 1}
+    hdr.field.add(name="version", number=3, type=F.TYPE_MESSAGE, type_name=f".{pkg}.VersionDef", label=F.LABEL_OPTIONAL)
+    ent = fd.message_type.add(name="BundleEntryProto")
+    ent.field.add(name="dtype", number=1, type=F.TYPE_ENUM, type_name=f".{pkg}.DataType", label=F.LABEL_OPTIONAL)
+    ent.field.add(name="shape", number=2, type=F.TYPE_MESSAGE, type_name=f".{pkg}.TensorShapeProto", label=F.LABEL_OPTIONAL)
+    ent.field.add(name="shard_id", number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="offset", number=4, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="size", number=5, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="crc32c", number=6, type=F.TYPE_FIXED32, label=F.LABEL_OPTIONAL)
+    pool = descriptor_pool.Default()
+    try:
+        file_desc = pool.Add(fd) if hasattr(pool, "Add") else pool.AddSerializedFile(fd.SerializeToString())
+    except TypeError:
+        file_desc = pool.AddSerializedFile(fd.SerializeToString())
+    file_desc = pool.FindFileByName("an3d_test/tensor_bundle.proto")
+    Header = message_factory.GetMessageClass(file_desc.message_types_by_name["BundleHeaderProto"])
+    Entry = message_factory.GetMessageClass(file_desc.message_types_by_name["BundleEntryProto"])
+
+    cases = [(types_pb2.DT_FLOAT, (1, 3, 1, 64), 0, 768, 0xDEADBEEF), (types_pb2.DT_FLOAT, (2048, 512), 123456789012, 4194304, 1),
+             (types_pb2.DT_INT64, (), 17, 8, 0x80000000), (types_pb2.DT_INT32, (0,), 5, 0, 0), (types_pb2.DT_FLOAT, (1024,), 4096, 4096, 77)]
+    for dtype, shape, offset, size, crc in cases:
+        mine = T._encode_entry(dtype, shape, offset, size, crc)
+        e = Entry()
+        e.ParseFromString(mine)                                    # Google's runtime reads what this module writes ...
+        assert e.dtype == dtype and tuple(d.size for d in e.shape.dim) == tuple(shape)
+        assert (e.shard_id, e.offset, e.size, e.crc32c) == (0, offset, size, crc)
+        theirs = Entry(dtype=dtype, shape=tensor_shape_pb2.TensorShapeProto(dim=[tensor_shape_pb2.TensorShapeProto.Dim(size=s) for s in shape]),
+                       offset=offset, size=size, crc32c=crc).SerializeToString(deterministic=True)
+        if size and crc:
+            assert theirs == mine, (shape, theirs.hex(), mine.hex())    # ... and writes the same bytes (proto3 skips zero fields)
+        d = T._decode_entry(theirs)                                # and this module reads what the runtime writes
+        assert (d["dtype"], tuple(d["shape"]), d["offset"], d["size"], d["crc32c"]) == (dtype, tuple(shape), offset, size, crc)
+    h = Header()
+    h.ParseFromString(b"\x08\x01" + b"\x1a\x02\x08\x01")           # the header record write_checkpoint emits
+    assert h.num_shards == 1 and h.endianness == 0 and h.version.producer == 1
+    assert Header(num_shards=1, version=versions_pb2.VersionDef(producer=1)).SerializeToString(deterministic=True) == b"\x08\x01\x1a\x02\x08\x01"
