@@ -200,3 +200,16 @@ def test_proto_layer_and_crc_against_tensorflows_own_definitions():
     h.ParseFromString(b"\x08\x01" + b"\x1a\x02\x08\x01")           # the header record write_checkpoint emits
     assert h.num_shards == 1 and h.endianness == 0 and h.version.producer == 1
     assert Header(num_shards=1, version=versions_pb2.VersionDef(producer=1)).SerializeToString(deterministic=True) == b"\x08\x01\x1a\x02\x08\x01"
+
+
+def test_snappy_decoder_against_pyarrows_snappy():
+    """The block decompressor (LevelDB tables may carry snappy-compressed blocks) against the snappy library bundled
+    with pyarrow: literals, short and long copies, incompressible input."""
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("snappy"):
+        pytest.skip("pyarrow built without snappy")
+    from alignnet_b200 import tf_checkpoint as T
+    rng = np.random.default_rng(0)
+    for data in (b"", b"a", b"abcabcabcabc" * 100, rng.integers(0, 4, 100000, dtype=np.uint8).tobytes(),
+                 rng.integers(0, 256, 70000, dtype=np.uint8).tobytes(), b"siamese/transformer1/embedding/conv1/weights" * 50):
+        assert T.snappy_decompress(pa.compress(data, codec="snappy", asbytes=True)) == data
