@@ -57,6 +57,16 @@ def tiny_arch(**kw) -> Arch:
     return Arch(**base)
 
 
+def default_arch(**kw) -> Arch:
+    """The architecture of the reference's configs/default.json:8-22: [128,128,256] for stage 1, five-layer conv stacks
+    for stage 2 and the embedding (models/tp8.py:49-59 builds any depth), 36 bins, no inverted-angle acceptance."""
+    base = dict(num_bins=36, s1_conv=(128, 128, 256), s1_fc=(512, 256), s1_keep=0.7, s2_conv=(64, 64, 64, 128, 1024),
+                s2_fc=(512, 256), s2_keep=0.7, emb_conv=(64, 64, 64, 128, 1024), head_fc=(512, 256), head_keep=0.7,
+                angle_factor=1.0, early_stage_factor=0.1, accept_inverted_angle=False)
+    base.update(kw)
+    return Arch(**base)
+
+
 @dataclass
 class LinearSpec:
     scope: str          # TF scope below the branch prefix, e.g. "transformer1/embedding/conv1"

@@ -61,3 +61,4 @@ if __name__ == "__main__":
     case("tiny_B4_N16", A.tiny_arch(), 4, 16, seed=11)
     case("shipped_B4_N16", A.Arch(), 4, 16, seed=21)
     case("shipped_B32_N200", A.Arch(), 32, 200, seed=31)
+    case("default_B32_N64", A.default_arch(), 32, 64, seed=41)      # configs/default.json: five-layer conv stacks

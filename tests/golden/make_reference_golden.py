@@ -30,6 +30,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def case(name, accept_inverted=True):
     g, arch, params, state, batch, masks = golden_case(name)
+    if accept_inverted is None:
+        accept_inverted = arch.accept_inverted_angle      # the architecture's own setting
     arch.accept_inverted_angle = accept_inverted
     out = {"source": "reference models/tp8.py executed on oracle/tf1_shim", "case": name,
            "accept_inverted_angle": accept_inverted}
@@ -55,7 +57,7 @@ def case(name, accept_inverted=True):
             out["var_shapes"] = np.array([" ".join(map(str, tr["var_shapes"][n])) for n in tr["var_names"]])
             out["trainable"] = np.array(tr["trainable"])
             out["shadow_names"] = np.array(sorted(tr["new_state"].keys()))
-    suffix = "" if accept_inverted else "_noinv"
+    suffix = "" if (accept_inverted or name.startswith("default")) else "_noinv"
     np.savez_compressed(os.path.join(HERE, f"reference_{name}{suffix}.npz"), **out)
     print(name, suffix, "loss", out["f64/train/loss"])
 
@@ -86,4 +88,5 @@ if __name__ == "__main__":
     case("tiny_B4_N16", accept_inverted=False)
     case("shipped_B4_N16")
     case("shipped_B32_N200")
+    case("default_B32_N64", accept_inverted=None)                   # configs/default.json's architecture (five-layer stacks)
     rigid()

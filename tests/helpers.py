@@ -14,7 +14,7 @@ OUTPUT_KEYS = ("pred_s1_pc1centers", "pred_s1_pc2centers", "pred_s2_pc1centers",
 
 def golden_case(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    arch = A.tiny_arch() if name.startswith("tiny") else A.Arch()
+    arch = A.tiny_arch() if name.startswith("tiny") else (A.default_arch() if name.startswith("default") else A.Arch())
     seed = int(g["seed"])
     params = A.init_params(arch, seed)
     state = A.init_state(arch)

@@ -52,7 +52,7 @@ def test_rigid_apply_matches_composition():
     assert np.allclose(RG.rigid_apply(pts, t2, th, new_c), out)
 
 
-@pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"])
+@pytest.mark.parametrize("name", ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200", "default_B32_N64"])
 def test_golden_reproduced(name):
     g, arch, params, state, batch, masks = golden_case(name)
     ep, _ = NF.get_model(batch["pcs1"], batch["pcs2"], arch, params, state, False)

@@ -18,7 +18,7 @@ import torch
 from oracle import arch as A, np_forward as NF, reference_run as RR, rigid as RG, torch_ref as TR
 from helpers import GOLDEN, OUTPUT_KEYS, golden_case
 
-CASES = ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200"]
+CASES = ["tiny_B4_N16", "shipped_B4_N16", "shipped_B32_N200", "default_B32_N64"]
 live = pytest.mark.skipif(not RR.available(), reason="/root/reference not present on this box")
 
 
@@ -30,7 +30,7 @@ def ref_case(name, suffix=""):
 def test_reference_graph_creates_the_variables_the_layout_assumes(name):
     """Names, shapes and trainability of every variable the reference graph creates."""
     r = ref_case(name)
-    arch = A.tiny_arch() if name.startswith("tiny") else A.Arch()
+    arch = A.tiny_arch() if name.startswith("tiny") else (A.default_arch() if name.startswith("default") else A.Arch())
     specs = dict(A.trainable_specs(arch))
     assert set(r["trainable"].tolist()) == set(specs)
     assert sorted(r["var_names"].tolist()) == sorted(specs)          # no non-trainable tf variables besides the shadows
