@@ -47,6 +47,14 @@ def _bn(z, spec, branch, params, state, new_state, training, bn_decay, axes):
 
 
 SIM_BF16 = False   # model the rounding points of the engine's bf16 fast mode (tests only)
+# With SIM_BF16: layers with a dimension (rows, inputs, outputs) below this stay exact.  0 = the fused kernels' FC path
+# (every FC layer on the tensor cores); 8 = the engine's layer-by-layer tensor-core path, which keeps 3-wide layers on
+# the CUDA cores in fp32 (csrc/gemm_tc.cuh: use_tensor_cores).
+SIM_BF16_MIN_DIM = 0
+
+
+def _sim_round(x, w):
+    return SIM_BF16 and min(x.reshape(-1, x.shape[-1]).shape[0], w.shape[0], w.shape[1]) >= SIM_BF16_MIN_DIM
 
 
 def _r16(t):
@@ -60,7 +68,7 @@ def _conv_stack(p, specs, branch, params, state, new_state, training, bn_decay):
     for i, s in enumerate(specs):
         n = weight_names(s)
         w = params[n["weights"]]
-        if SIM_BF16 and i > 0:
+        if i > 0 and _sim_round(x, w):
             x, w = _r16(x), _r16(w)
         z = x @ w + params[n["biases"]]
         x = torch.relu(_bn(z, s, branch, params, state, new_state, training, bn_decay, (0, 1)))
@@ -74,7 +82,7 @@ def _mlp(g, specs, branch, params, state, new_state, training, bn_decay, keep, m
     for s in specs[:-1]:
         n = weight_names(s)
         w = params[n["weights"]]
-        if SIM_BF16:
+        if _sim_round(x, w):
             x, w = _r16(x), _r16(w)
         z = x @ w + params[n["biases"]]
         x = torch.relu(_bn(z, s, branch, params, state, new_state, training, bn_decay, (0,)))
@@ -82,7 +90,7 @@ def _mlp(g, specs, branch, params, state, new_state, training, bn_decay, keep, m
         x = x / keep * mask
     n = weight_names(specs[-1])
     w = params[n["weights"]]
-    if SIM_BF16:
+    if _sim_round(x, w):
         x, w = _r16(x), _r16(w)
     return x @ w + params[n["biases"]]
 
