@@ -152,27 +152,29 @@ __global__ void bn_bwd_coeff_kernel(const double* red, int C, double count, floa
 //   A   = sum_p dz1     = s1 (S0 - n m0 - m1 sum_p xhat)
 //   B_d = sum_p dz1 q_d = s1 (S_d - m0 P_d - m1 sum_p xhat q_d),   d in {x, y, z}
 // give wgrad1 (sum of B over items) and the gradient of the stage input reduced per cloud to d(center) and
-// d(angle).  One block per item, 256 threads: point moments by block reduction, then 64 channel threads.
+// d(angle).  One WARP per item (a block's eight warps walk its items side by side; the one-block-per-item version spent its
+// 22 us per launch in three block-wide barriers per item): point moments by warp shuffles, then each lane finishes two of
+// the 64 channels.
 __global__ void __launch_bounds__(256) bwd_l1_finish_kernel(const float* pcs, const float* center, const float* angle,
                                                             const float* l1sums, int N, int PC, int npc, int n_items,
                                                             int items_per_block, const float* W1, const float* b1,
                                                             const float* mean1, const float* inv1, const float* scale1,
                                                             const float* coef1, float* gW1, float* dcenter, float* dangle,
                                                             int want_input_grad) {
-  __shared__ float wred[8][9];
-  __shared__ float mom[9];
-  __shared__ float fin[64][4];
-  const int c = threadIdx.x;
-  float wx = 0.f, wy = 0.f, wz = 0.f, s1 = 0.f, m0 = 0.f, m1 = 0.f, ax = 0.f, ay = 0.f, az = 0.f, a0 = 0.f;
-  if (c < 64) {
-    wx = W1[c]; wy = W1[64 + c]; wz = W1[128 + c];
+  __shared__ float gsum[8][64][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float wx[2], wy[2], wz[2], s1[2], m0[2], m1[2], ax[2], ay[2], az[2], a0[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = lane + 32 * h;
+    wx[h] = W1[c]; wy[h] = W1[64 + c]; wz[h] = W1[128 + c];
     const float iv = inv1[c];
-    s1 = scale1[c]; m0 = coef1[2 * c]; m1 = coef1[2 * c + 1];
-    ax = iv * wx; ay = iv * wy; az = iv * wz; a0 = iv * (b1[c] - mean1[c]);
+    s1[h] = scale1[c]; m0[h] = coef1[2 * c]; m1[h] = coef1[2 * c + 1];
+    ax[h] = iv * wx[h]; ay[h] = iv * wy[h]; az[h] = iv * wz[h]; a0[h] = iv * (b1[c] - mean1[c]);
   }
-  float gwx = 0.f, gwy = 0.f, gwz = 0.f;     // wgrad1 partial sums over this block's items (one atomic each at the end)
+  float gwx[2] = {0.f, 0.f}, gwy[2] = {0.f, 0.f}, gwz[2] = {0.f, 0.f};   // wgrad1 partial sums over this warp's items
   const int it_end = min(n_items, (int)(blockIdx.x + 1) * items_per_block);
-  for (int it = blockIdx.x * items_per_block; it < it_end; ++it) {
+  for (int it = blockIdx.x * items_per_block + warp; it < it_end; it += 8) {
     const int cloud = it / npc, pchunk = it - cloud * npc;
     const int p0 = pchunk * PC;
     const int nvalid = min(PC, N - p0);
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256) bwd_l1_finish_kernel(const float* pcs, co
     if (angle) sincosf(angle[cloud], &sn, &cs);
     const float cx = center[cloud * 3], cy = center[cloud * 3 + 1], cz = center[cloud * 3 + 2];
     float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // Px Py Pz Pxx Pxy Pxz Pyy Pyz Pzz
-    for (int p = threadIdx.x; p < nvalid; p += 256) {
+    for (int p = lane; p < nvalid; p += 32) {
       const float* src = pcs + (row0 + p) * 3;
       const float x0 = src[0] - cx, y0 = src[1] - cy;
       const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs, z = src[2] - cz;
@@ -192,56 +194,49 @@ __global__ void __launch_bounds__(256) bwd_l1_finish_kernel(const float* pcs, co
 #pragma unroll
     for (int q = 0; q < 9; ++q)
       for (int o = 16; o > 0; o >>= 1) m[q] += __shfl_xor_sync(0xffffffffu, m[q], o);
-    __syncthreads();     // previous item's readers of wred / mom / fin are done
-    if ((threadIdx.x & 31) == 0)
-      for (int q = 0; q < 9; ++q) wred[threadIdx.x >> 5][q] = m[q];
-    __syncthreads();
-    if (threadIdx.x < 9) {
-      float t = 0.f;
-      for (int w = 0; w < 8; ++w) t += wred[w][threadIdx.x];
-      mom[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (c < 64) {
-      const float n = (float)nvalid;
-      const float4 S = reinterpret_cast<const float4*>(l1sums)[(size_t)it * 64 + c];
-      const float sxh = ax * mom[0] + ay * mom[1] + az * mom[2] + n * a0;
-      const float sxh_x = ax * mom[3] + ay * mom[4] + az * mom[5] + a0 * mom[0];
-      const float sxh_y = ax * mom[4] + ay * mom[6] + az * mom[7] + a0 * mom[1];
-      const float sxh_z = ax * mom[5] + ay * mom[7] + az * mom[8] + a0 * mom[2];
-      const float A = s1 * (S.x - n * m0 - m1 * sxh);
-      const float Bx = s1 * (S.y - m0 * mom[0] - m1 * sxh_x);
-      const float By = s1 * (S.z - m0 * mom[1] - m1 * sxh_y);
-      const float Bz = s1 * (S.w - m0 * mom[2] - m1 * sxh_z);
-      gwx += Bx; gwy += By; gwz += Bz;
+    const float n = (float)nvalid;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 S = reinterpret_cast<const float4*>(l1sums)[(size_t)it * 64 + lane + 32 * h];
+      const float sxh = ax[h] * m[0] + ay[h] * m[1] + az[h] * m[2] + n * a0[h];
+      const float sxh_x = ax[h] * m[3] + ay[h] * m[4] + az[h] * m[5] + a0[h] * m[0];
+      const float sxh_y = ax[h] * m[4] + ay[h] * m[6] + az[h] * m[7] + a0[h] * m[1];
+      const float sxh_z = ax[h] * m[5] + ay[h] * m[7] + az[h] * m[8] + a0[h] * m[2];
+      const float A = s1[h] * (S.x - n * m0[h] - m1[h] * sxh);
+      const float Bx = s1[h] * (S.y - m0[h] * m[0] - m1[h] * sxh_x);
+      const float By = s1[h] * (S.z - m0[h] * m[1] - m1[h] * sxh_y);
+      const float Bz = s1[h] * (S.w - m0[h] * m[2] - m1[h] * sxh_z);
+      gwx[h] += Bx; gwy[h] += By; gwz[h] += Bz;
       // d(sum_p dq_d) = sum_c W1[d,c] A_c ; d(angle) = sum_c (-W1[x,c] By_c + W1[y,c] Bx_c)
-      fin[c][0] = wx * A; fin[c][1] = wy * A; fin[c][2] = wz * A; fin[c][3] = -wx * By + wy * Bx;
+      f0 = fmaf(wx[h], A, f0); f1 = fmaf(wy[h], A, f1); f2 = fmaf(wz[h], A, f2); f3 += -wx[h] * By + wy[h] * Bx;
     }
     if (want_input_grad) {
-      __syncthreads();
-      if (threadIdx.x < 4) {
-        float s = 0.f;
-        for (int i = 0; i < 64; ++i) s += fin[i][threadIdx.x];
-        // one writer per (cloud, component) when a cloud is one item; atomics keep multi-item clouds correct
-        if (threadIdx.x == 3) {
-          if (dangle) atomicAdd(dangle + cloud, s);
-        } else {
-          wred[0][threadIdx.x] = s;
-        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+        f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const float gx = wred[0][0], gy = wred[0][1], gz = wred[0][2];
-        atomicAdd(dcenter + cloud * 3, -(gx * cs + gy * sn));
-        atomicAdd(dcenter + cloud * 3 + 1, -(-gx * sn + gy * cs));
-        atomicAdd(dcenter + cloud * 3 + 2, -gz);
+      if (lane == 0) {
+        // one writer per (cloud, component) when a cloud is one item; atomics keep multi-item clouds correct
+        if (dangle) atomicAdd(dangle + cloud, f3);
+        atomicAdd(dcenter + cloud * 3, -(f0 * cs + f1 * sn));
+        atomicAdd(dcenter + cloud * 3 + 1, -(-f0 * sn + f1 * cs));
+        atomicAdd(dcenter + cloud * 3 + 2, -f2);
       }
     }
   }
-  if (c < 64) {
-    atomicAdd(gW1 + c, gwx);
-    atomicAdd(gW1 + 64 + c, gwy);
-    atomicAdd(gW1 + 128 + c, gwz);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    gsum[warp][lane + 32 * h][0] = gwx[h]; gsum[warp][lane + 32 * h][1] = gwy[h]; gsum[warp][lane + 32 * h][2] = gwz[h];
+  }
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    const int d = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += gsum[w][c][d];
+    atomicAdd(gW1 + d * 64 + c, t);
   }
 }
 
