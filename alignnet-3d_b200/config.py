@@ -187,14 +187,35 @@ def validate(cfg: NameSpace) -> None:
         raise ValueError("training.loss.options.soft_angle_classes=true is not implemented")
     if cfg.data.num_channels != 3:
         raise ValueError("data.num_channels must be 3")
+    if cfg.training.has("optimizer") and cfg.training.optimizer.has("optimizer"):
+        name = cfg.training.optimizer.optimizer
+        if name not in ("adam", "momentum"):
+            raise ValueError(f"training.optimizer.optimizer={name!r}: Invalid optimizer (train.py:215)")
+        if name == "momentum" and not cfg.training.optimizer.has("momentum"):
+            raise ValueError("training.optimizer.optimizer='momentum' needs training.optimizer.momentum (train.py:212; "
+                             "configs/default.json does not define it)")
+    if cfg.evaluation.has("special"):
+        mode = cfg.evaluation.special.mode
+        if mode == "icp":                                        # train.py:548-551 -> icp.py:150
+            sp = cfg.evaluation.special.icp if cfg.evaluation.special.has("icp") else None
+            if sp is None or not sp.has("variant") or sp.variant != "p2point" or not sp.has("with_constraint") \
+                    or not sp.with_constraint or sp.has("refine"):
+                raise ValueError("evaluation.special.mode='icp': only icp.variant='p2point' with icp.with_constraint=true and "
+                                 "no icp.refine is implemented (the yaw-constrained point-to-point ICP of row N4, the "
+                                 "reference's icp_<dataset>_o3_p2p.json configs); the global-registration variants of the "
+                                 "Open3D fork (icp.py:84-143) are outside the hot path")
+        elif mode != "timings":
+            raise ValueError(f"evaluation.special.mode={mode!r} is not implemented: 'held' (evaluate_held, evaluation.py:49) "
+                             "is outside the hot path; 'timings' (train.py:553-559) and 'icp' (variant p2point) are")
+
+
+def optimizer_from_config(cfg: NameSpace):
+    """train.py:211-216 -> (name, momentum) for Engine.set_optimizer."""
+    validate(cfg)
     if cfg.training.has("optimizer") and cfg.training.optimizer.has("optimizer") \
-            and cfg.training.optimizer.optimizer != "adam":
-        raise ValueError(f"training.optimizer.optimizer={cfg.training.optimizer.optimizer!r} is not implemented (only "
-                         "'adam'; the reference's momentum branch, train.py:211-212, is selected by no shipped config)")
-    if cfg.evaluation.has("special") and cfg.evaluation.special.mode != "timings":
-        raise ValueError(f"evaluation.special.mode={cfg.evaluation.special.mode!r} is not implemented: 'icp' (the Open3D "
-                         "baselines, icp.py:150) and 'held' (evaluate_held, evaluation.py:49) are outside the hot path; "
-                         "'timings' (train.py:553-559) is")
+            and cfg.training.optimizer.optimizer == "momentum":
+        return "momentum", float(cfg.training.optimizer.momentum)
+    return "adam", None
 
 
 def arch_from_config(cfg: NameSpace) -> "_lib.Arch":

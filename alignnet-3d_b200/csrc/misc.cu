@@ -47,6 +47,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// tf.train.MomentumOptimizer(lr, momentum) [TF-sem, ApplyMomentum with use_nesterov = false]: accum <- momentum accum + g ;
+// p <- p - lr accum  (train.py:211-212)
+__global__ void momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ acc, int64_t n,
+                                float lr, float momentum, float grad_scale) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 aa = *reinterpret_cast<float4*>(acc + i4), pp = *reinterpret_cast<float4*>(p + i4);
+    aa.x = momentum * aa.x + gg.x * grad_scale; pp.x = pp.x - lr * aa.x;
+    aa.y = momentum * aa.y + gg.y * grad_scale; pp.y = pp.y - lr * aa.y;
+    aa.z = momentum * aa.z + gg.z * grad_scale; pp.z = pp.z - lr * aa.z;
+    aa.w = momentum * aa.w + gg.w * grad_scale; pp.w = pp.w - lr * aa.w;
+    *reinterpret_cast<float4*>(acc + i4) = aa;
+    *reinterpret_cast<float4*>(p + i4) = pp;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float ai = momentum * acc[i] + g[i] * grad_scale;
+      acc[i] = ai;
+      p[i] = p[i] - lr * ai;
+    }
+  }
+}
+
 __device__ __forceinline__ float floor_modf(float x, float y) {
   float r = fmodf(x, y);
   if (r != 0.f && ((y < 0.f) != (r < 0.f))) r += y;
@@ -436,6 +459,25 @@ int an3d_adam_step_dev(float* params, const float* grads, float* m, float* v, in
   adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, count, 0.f,
                                                                                    grad_scale, beta1, beta2, eps, step_dev,
                                                                                    lr);
+  AN3D_LAUNCH_CHECK();
+  return AN3D_OK;
+}
+
+int an3d_momentum_step(float* params, const float* grads, float* accum, int64_t count, float lr, float momentum,
+                       float grad_scale, void* stream) {
+  if (!params || !grads || !accum || count < 0) {
+    set_error("an3d_momentum_step: bad argument");
+    return AN3D_ERR_INVALID;
+  }
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)accum) & 15) {
+    set_error("an3d_momentum_step: buffers must be 16-byte aligned");
+    return AN3D_ERR_ALIGN;
+  }
+  AN3D_TRY(check_device());
+  const int64_t nthreads = (count + 3) / 4;
+  if (nthreads == 0) return AN3D_OK;
+  momentum_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, accum, count, lr,
+                                                                                       momentum, grad_scale);
   AN3D_LAUNCH_CHECK();
   return AN3D_OK;
 }

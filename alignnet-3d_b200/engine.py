@@ -124,6 +124,9 @@ class Engine:
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
             self._graphs: Dict[tuple, tuple] = {}
             self._ar_in_graph = None                  # None: untried, True / False: the collective can(not) be captured
+            self.optimizer = "adam"                   # train.py:211-216: 'adam' | 'momentum' (set_optimizer)
+            self.momentum = 0.0
+            self.mom_accum = None                     # MomentumOptimizer's slot (`<var>/Momentum`), allocated on demand
             self.set_params(self.init_params(seed))
 
     def __del__(self):
@@ -336,16 +339,51 @@ class Engine:
                                            self.adam_v.data_ptr(), self.params.numel(), lr, self.step, grad_scale,
                                            beta1, beta2, eps, stream), "an3d_adam_step")
 
+    def set_optimizer(self, optimizer: str = "adam", momentum: Optional[float] = None) -> None:
+        """cfg.training.optimizer.optimizer (train.py:211-216): 'adam' (tf.train.AdamOptimizer(lr)) or 'momentum'
+        (tf.train.MomentumOptimizer(lr, momentum=cfg.training.optimizer.momentum)); anything else is the reference's
+        `assert False, "Invalid optimizer"`."""
+        if optimizer == "adam":
+            self.optimizer = "adam"
+            return
+        if optimizer != "momentum":
+            raise ValueError(f"Invalid optimizer {optimizer!r} (train.py:215)")
+        if momentum is None:
+            raise ValueError("the momentum optimiser needs cfg.training.optimizer.momentum (train.py:212)")
+        self.optimizer, self.momentum = "momentum", float(momentum)
+        if self.mom_accum is None:
+            self.mom_accum = torch.zeros_like(self.params)
+
+    def momentum_step(self, lr: float, grad_scale: float = 1.0, count_step: bool = True) -> None:
+        """tf.train.MomentumOptimizer(lr, momentum).minimize(..., global_step) (train.py:211-212, 217)."""
+        if self.mom_accum is None:
+            raise RuntimeError("momentum_step before set_optimizer('momentum', momentum=...)")
+        if count_step:
+            self.step += 1
+        self._pversion += 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.an3d_momentum_step(self.params.data_ptr(), self.grads.data_ptr(), self.mom_accum.data_ptr(),
+                                               self.params.numel(), lr, self.momentum, grad_scale, stream),
+                   "an3d_momentum_step")
+
+    def optimizer_step(self, lr: float, grad_scale: float = 1.0) -> None:
+        """train_op = optimizer.minimize(loss, global_step=batch) (train.py:217) with the configured optimiser."""
+        if self.optimizer == "momentum":
+            self.momentum_step(lr, grad_scale)
+        else:
+            self.adam_step(lr, grad_scale=grad_scale)
+
     def train_step(self, batch: Dict[str, torch.Tensor], lr: float, bn_decay: float, seed: Optional[int] = None,
                    masks=None, allreduce=None) -> torch.Tensor:
         """One `sess.run([train_op, loss, ...])` (train.py:368): forward, loss, backward,
-        optional gradient all-reduce (callable), Adam.  Returns the device loss vector."""
+        optional gradient all-reduce (callable), optimiser update (Adam unless set_optimizer chose momentum).  Returns the
+        device loss vector."""
         ep = self.forward(batch["pcs1"], batch["pcs2"], True, bn_decay, masks, self.step if seed is None else seed)
         loss = self.backward(batch["pcs1"], batch["pcs2"], batch, ep)
         scale = 1.0
         if allreduce is not None:
             scale = allreduce(self.grads)
-        self.adam_step(lr, grad_scale=scale)
+        self.optimizer_step(lr, grad_scale=scale)
         return loss
 
     # ---- CUDA-graph replay ----------------------------------------------------------------------
@@ -393,6 +431,14 @@ class Engine:
         _lib.check(self.lib.an3d_step_advance(self.step_dev.data_ptr(), self.seed_dev.data_ptr(), int(seed_base), stream),
                    "an3d_step_advance")
 
+    def _optimizer_step_dev(self, lr: float, grad_scale: float) -> None:
+        """The update inside a captured step: Adam reads its step count from device memory; the momentum update carries
+        none, so its ordinary entry point is captured as it is (the host counter is advanced by train_step_graph)."""
+        if self.optimizer == "momentum":
+            self.momentum_step(lr, grad_scale, count_step=False)
+        else:
+            self._adam_step_dev(lr, grad_scale)
+
     def _adam_step_dev(self, lr: float, grad_scale: float, beta1=0.9, beta2=0.999, eps=1e-8) -> None:
         self._pversion += 1
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -425,9 +471,10 @@ class Engine:
             def whole():
                 loss = fwd_bwd()
                 scale = 1.0 if allreduce is None else float(allreduce(self.grads))
-                self._adam_step_dev(lr, scale)
+                self._optimizer_step_dev(lr, scale)
                 return loss
-            key = ("train" if allreduce is None else "train-ar", ptrs, shape, float(lr), float(bn_decay), self.pflag, salt)
+            opt = (self.optimizer, self.momentum if self.optimizer == "momentum" else None)
+            key = ("train" if allreduce is None else "train-ar", ptrs, shape, float(lr), float(bn_decay), self.pflag, salt, opt)
             try:
                 g, loss, fresh = self._capture(key, whole)
                 if allreduce is not None:
@@ -445,7 +492,8 @@ class Engine:
             if not fresh:
                 g1.replay()
             scale = float(allreduce(self.grads))
-            g2, _, fresh2 = self._capture(("train-b", float(lr), scale), lambda: self._adam_step_dev(lr, scale))
+            g2, _, fresh2 = self._capture(("train-b", float(lr), scale, self.optimizer, self.momentum),
+                                          lambda: self._optimizer_step_dev(lr, scale))
             if not fresh2:
                 g2.replay()
         self.step += 1

@@ -34,6 +34,36 @@ def str_to_np(s: str) -> np.ndarray:
     return np.loadtxt(io.BytesIO(s.encode("ascii")))
 
 
+def np_to_str(arr) -> str:
+    """pointcloud.py:247-252 (plaintext branch): the text np.savetxt writes; `str_to_np` reads it back exactly (%.18e)."""
+    out = io.BytesIO()
+    np.savetxt(out, np.asarray(arr, np.float64))
+    return out.getvalue().decode("ascii")
+
+
+def save_example(basepath: str, idx: int, cloud1: np.ndarray, cloud2: np.ndarray, start_position, start_angle: float,
+                 end_position, end_angle: float, translation, rel_angle: float, additional_meta: Optional[dict] = None) -> None:
+    """The writer half of the on-disk format (Scene.save_pointclouds / save_meta, pointcloud.py:979-997):
+    `pointcloud{1,2}/%08d.npy` and `meta/%08d.json` with the text-encoded arrays.  Creates the directories."""
+    for d in ("meta", "pointcloud1", "pointcloud2", "split"):
+        os.makedirs(os.path.join(basepath, d), exist_ok=True)
+    name = str(idx).zfill(8)
+    np.save(f"{basepath}/pointcloud1/{name}", np.asarray(cloud1))
+    np.save(f"{basepath}/pointcloud2/{name}", np.asarray(cloud2))
+    data = {"start_position": np_to_str(start_position), "start_angle": float(start_angle),
+            "end_position": np_to_str(end_position), "end_angle": float(end_angle),
+            "translation": np_to_str(translation), "rel_angle": float(rel_angle), **(additional_meta or {})}
+    with open(f"{basepath}/meta/{name}.json", "w") as fh:
+        json.dump(data, fh)
+
+
+def save_split(basepath: str, name: str, indices: Sequence[int]) -> None:
+    """`split/{train,val}.txt`: one example index per line (read by get_data_files, provider.py:74-75)."""
+    os.makedirs(os.path.join(basepath, "split"), exist_ok=True)
+    with open(f"{basepath}/split/{name}.txt", "w") as fh:
+        fh.write("".join(f"{int(i)}\n" for i in indices))
+
+
 def get_data_files(list_filename: str) -> List[int]:
     """provider.py:74-75."""
     return [int(line.rstrip()) for line in open(list_filename)]

@@ -121,3 +121,38 @@ def make_batch_fast(batch_size: int, num_points: int, seed: int = 1234, dtype=np
         "pc1_centers": start, "pc2_centers": end, "pc1_angles": a1[:, None], "pc2_angles": a2[:, None],
     }
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in out.items()}
+
+
+def write_dataset(basepath: str, num_examples: int, seed: int = 1234, points_range=(150, 600), persons_prob: float = 0.0,
+                  val_fraction: float = 0.2, max_rel_angle: float = np.pi / 2, max_speed: float = 1.0) -> None:
+    """Writes `num_examples` synthetic pairs in the reference's on-disk format (provider.save_example: the layout
+    `Scene.save_pointclouds` / `save_meta` produce, pointcloud.py:979-997), with RAGGED full clouds of
+    `points_range` points each (the provider resamples them to cfg.model.num_points, provider.py:97), a fourth column
+    like the reference's clouds carry, and `split/{train,val}.txt`.  The same distributions as `make_batch`;
+    `max_rel_angle` / `max_speed` narrow the motion (e.g. for ICP tests, whose basin of convergence is small)."""
+    from . import provider
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for i in range(num_examples):
+        if rng.uniform() < persons_prob:
+            height = rng.uniform(1.6, 2.0)
+            length, width = 0.3 * height, 0.3 * height
+        else:
+            length = 6.0
+            width = length * rng.uniform(0.35, 0.45)
+            height = length * rng.uniform(0.25, 0.35)
+        start_angle = rng.uniform(-np.pi, np.pi)
+        r, phi = rng.uniform(4.0, 20.0), rng.uniform(-np.pi, np.pi)
+        start = np.array([r * np.sin(phi), r * np.cos(phi), 0.0])
+        v, psi = rng.uniform(0.0, max_speed), rng.uniform(-np.pi, np.pi)
+        trans = np.array([v * np.sin(psi), v * np.cos(psi), 0.0])
+        rel = rng.uniform(-1.0, 1.0) * max_rel_angle
+        end, end_angle = start + trans, start_angle + rel
+        sigma = max(0.005, 0.05 * r / 80.0)
+        n1, n2 = (int(rng.integers(points_range[0], points_range[1] + 1)) for _ in range(2))
+        clouds = [_box_partial_view(rng, n, length, width, height, c, a, sigma)
+                  for n, c, a in ((n1, start, start_angle), (n2, end, end_angle))]
+        clouds = [np.concatenate([c, np.ones((len(c), 1))], axis=1).astype(np.float32) for c in clouds]
+        provider.save_example(basepath, i, clouds[0], clouds[1], start, start_angle, end, end_angle, trans, rel)
+    n_val = max(1, int(round(num_examples * val_fraction)))
+    provider.save_split(basepath, "train", range(num_examples - n_val))
+    provider.save_split(basepath, "val", range(num_examples - n_val, num_examples))

@@ -475,16 +475,26 @@ def load_into_engine(engine, prefix: str, strict: bool = True) -> Dict[str, List
     if have_adam:
         engine.adam_m.copy_(torch.from_numpy(engine._flatten(engine.params_layout, m)))
         engine.adam_v.copy_(torch.from_numpy(engine._flatten(engine.params_layout, v)))
+    if getattr(engine, "mom_accum", None) is not None:       # MomentumOptimizer's slot, `<var>/Momentum` (train.py:211-212)
+        acc = engine._unflatten(engine.params_layout, engine.mom_accum.cpu().numpy())
+        have_mom = False
+        for name in list(acc):
+            a = ckpt.get(name + "/Momentum")
+            if a is not None:
+                acc[name], have_mom = np.asarray(a, np.float32).reshape(acc[name].shape), True
+        if have_mom:
+            engine.mom_accum.copy_(torch.from_numpy(engine._flatten(engine.params_layout, acc)))
     if "Variable" in ckpt:                                   # global step (train.py:195)
         engine.step = int(ckpt["Variable"])
     used = set(params) | set(state) | {tf_ema_key(k) for k in state}
-    return dict(missing=missing, unused=[k for k in ckpt if k not in used and not k.endswith(("/Adam", "/Adam_1"))
+    return dict(missing=missing, unused=[k for k in ckpt if k not in used and not k.endswith(("/Adam", "/Adam_1", "/Momentum"))
                                          and k not in ("Variable", "beta1_power", "beta2_power")])
 
 
 def save_from_engine(engine, prefix: str, beta1: float = 0.9, beta2: float = 0.999) -> None:
     """saver.save (train.py:316-322): the engine's variables under the reference graph's names, conv kernels in
-    TF's [1, kw, Cin, Cout] shape, Adam slots, `beta{1,2}_power` and the global step."""
+    TF's [1, kw, Cin, Cout] shape, the optimiser's slots (Adam: `<var>/Adam`, `<var>/Adam_1`, `beta{1,2}_power`; momentum:
+    `<var>/Momentum`) and the global step."""
     tensors: Dict[str, np.ndarray] = {}
     for name, a in engine.get_params().items():
         if "/conv" in name and name.endswith("/weights"):
@@ -493,12 +503,17 @@ def save_from_engine(engine, prefix: str, beta1: float = 0.9, beta2: float = 0.9
             a = a.reshape(1, kw, cin // kw, cout)
         tensors[name] = a.astype(np.float32)
     tensors.update({tf_ema_key(k): v.astype(np.float32) for k, v in engine.get_state().items()})
-    m = engine._unflatten(engine.params_layout, engine.adam_m.cpu().numpy())
-    v = engine._unflatten(engine.params_layout, engine.adam_v.cpu().numpy())
-    for name in m:
-        shape = tensors[name].shape
-        tensors[name + "/Adam"], tensors[name + "/Adam_1"] = m[name].reshape(shape), v[name].reshape(shape)
     tensors["Variable"] = np.array(engine.step, np.int32)
-    tensors["beta1_power"] = np.array(beta1 ** max(engine.step, 0) * beta1, np.float32)
-    tensors["beta2_power"] = np.array(beta2 ** max(engine.step, 0) * beta2, np.float32)
+    if getattr(engine, "optimizer", "adam") == "momentum":   # a MomentumOptimizer graph holds one slot per variable
+        acc = engine._unflatten(engine.params_layout, engine.mom_accum.cpu().numpy())
+        for name in acc:
+            tensors[name + "/Momentum"] = acc[name].reshape(tensors[name].shape)
+    else:
+        m = engine._unflatten(engine.params_layout, engine.adam_m.cpu().numpy())
+        v = engine._unflatten(engine.params_layout, engine.adam_v.cpu().numpy())
+        for name in m:
+            shape = tensors[name].shape
+            tensors[name + "/Adam"], tensors[name + "/Adam_1"] = m[name].reshape(shape), v[name].reshape(shape)
+        tensors["beta1_power"] = np.array(beta1 ** max(engine.step, 0) * beta1, np.float32)
+        tensors["beta2_power"] = np.array(beta2 ** max(engine.step, 0) * beta2, np.float32)
     write_checkpoint(prefix, tensors)

@@ -12,7 +12,9 @@ Differences, all deliberate: there is no TensorBoard writer, `--refineICP` runs 
 authors' Open3D fork (row N4, parity unpinned), and the
 val/test split of the synthetic sets (evaluation.py:161-162: idx >= 1000) is computed here and passed to the device
 evaluation.  `evaluation.special.mode == "timings"` is the reference's own benchmark harness (train.py:553-559): batch 32,
-no restore, ten evaluation passes, `Timing bs=32: <seconds per pair>`.  `training.pretraining.model` is restored like the
+no restore, ten evaluation passes, `Timing bs=32: <seconds per pair>`; `"icp"` with `icp.variant == "p2point"` runs the ICP
+baseline over the validation split (train.py:548-551, icp.py:150-225) on the same device kernel.  `training.optimizer.optimizer`
+selects Adam or the momentum optimiser (train.py:211-216).  `training.pretraining.model` is restored like the
 reference does (all variables except the global step, then an initial evaluation, train.py:276-293).  One process per GPU;
 under torchrun every rank reads only its shard of each batch and the gradient all-reduce is the only collective."""
 from __future__ import annotations
@@ -213,6 +215,9 @@ def main(argv=None) -> Dict:
         C.save_config(copy)
         logging.basicConfig(level=logging.INFO, handlers=[logging.FileHandler(f"{cfg.logging.logdir}/out.log"),
                                                           logging.StreamHandler()])
+    if cfg.evaluation.has("special") and cfg.evaluation.special.mode == "icp":          # train.py:548-551: no model at all
+        torch.cuda.set_device(local)
+        return icp.evaluate(cfg, bool(flags.use_old_results), f"cuda:{local}") if rank == 0 else {}
     train_idxs = provider.get_data_files(f"{cfg.data.basepath}/split/train.txt")
     val_idxs = provider.get_data_files(f"{cfg.data.basepath}/split/val.txt")
     device = f"cuda:{local}"
@@ -221,6 +226,7 @@ def main(argv=None) -> Dict:
     if timings:                                                  # train.py:553-559
         cfg.training.__dict__["batch_size"] = 32
     eng = E.Engine(C.arch_from_config(cfg), device, flags.precision, seed=0)
+    eng.set_optimizer(*C.optimizer_from_config(cfg))             # train.py:211-216
     start_epoch = 0
     ckpt = f"{cfg.logging.logdir}/model.ckpt"
     eval_only = flags.operation == "eval_only" or timings

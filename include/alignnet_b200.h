@@ -182,6 +182,13 @@ int an3d_step_advance(int64_t* step_dev, uint64_t* seed_dev, uint64_t seed_base,
 int an3d_adam_step_dev(float* params, const float* grads, float* m, float* v, int64_t count, float lr,
                        const int64_t* step_dev, float grad_scale, float beta1, float beta2, float eps, void* stream);
 
+/* tf.train.MomentumOptimizer(lr, momentum=cfg.training.optimizer.momentum).apply_gradients (train.py:211-212; TF's
+ * ApplyMomentum, use_nesterov = false): g = grads*grad_scale; accum = momentum*accum + g; p -= lr*accum.  `accum` is the
+ * optimiser's one slot per variable (TF name `<var>/Momentum`), same flat layout as params.  Carries no step count, so the
+ * same entry point serves eager steps and CUDA-graph replay. */
+int an3d_momentum_step(float* params, const float* grads, float* accum, int64_t count, float lr, float momentum,
+                       float grad_scale, void* stream);
+
 /* scaled = 1: tf_get_angles (:294-301); 0: classLogits2angle (:229-244); 2: tf_classLogits2angle / tf_class2angle2
  * (:213-226, :248-251: unscaled residual, then tf.mod into [-pi, pi)) -- the decoder _get_loss_p2p uses. */
 int an3d_decode_angles(const float* logits, float* angles, int32_t batch, int32_t num_bins, int32_t scaled,

@@ -268,6 +268,15 @@ def adam_step(params, grads, m, v, lr: float, t: int, beta1=0.9, beta2=0.999, ep
     return params, m, v
 
 
+def momentum_step(params, grads, accum, lr: float, momentum: float):
+    """tf.train.MomentumOptimizer(lr, momentum) (train.py:211-212) [TF-sem: ApplyMomentum, use_nesterov = False]:
+    accum = momentum * accum + g ; theta -= lr * accum.  In place on numpy / torch arrays."""
+    for k in params:
+        accum[k] = momentum * accum[k] + grads[k]
+        params[k] = params[k] - lr * accum[k]
+    return params, accum
+
+
 # --------------------------------------------------------------------------------------
 # convenience: one full train-mode evaluation with gradients
 # --------------------------------------------------------------------------------------

@@ -3,6 +3,7 @@ reference's on-disk format, written with the reference's own `np_to_str`; tests/
 the reference's OWN `provider.load_batch` + `jitter_point_cloud` return for it with `np.random.seed(77)`
 (generator: tests/golden/make_reference_provider_golden.py).  With the same seed the host half here must draw the
 same points, and the device half must assemble the same batch."""
+import json
 import os
 
 import numpy as np
@@ -76,3 +77,34 @@ def test_prefetcher_feeds_the_engine():
         assert torch.isfinite(loss[0]).item()
         n += 1
     assert n == 3
+
+
+def test_writer_round_trip(tmp_path):
+    """The writer half of the format (pointcloud.py:247-258, 979-997): what `save_example` / `synth.write_dataset` write is
+    what `load_meta` / `read_host_batch` read, bit for bit (np.savetxt's %.18e is exact for float64)."""
+    from alignnet_b200 import provider, synth
+    rng = np.random.default_rng(0)
+    c1, c2 = rng.normal(size=(7, 4)).astype(np.float32), rng.normal(size=(0, 4)).astype(np.float32)
+    start, end, tr = rng.normal(size=3), rng.normal(size=3), rng.normal(size=3)
+    provider.save_example(str(tmp_path), 12, c1, c2, start, 0.25, end, -1.5, tr, 1 / 3, additional_meta={"trackids": [2]})
+    t, ra, s0, s1, a0, a1 = provider.load_meta(str(tmp_path), 12)
+    assert np.array_equal(t, tr) and np.array_equal(s0, start) and np.array_equal(s1, end)
+    assert (ra, a0, a1) == (1 / 3, 0.25, -1.5)
+    assert np.array_equal(np.load(tmp_path / "pointcloud1" / "00000012.npy"), c1)
+    assert np.load(tmp_path / "pointcloud2" / "00000012.npy").shape == (0, 4)
+    assert json.load(open(tmp_path / "meta" / "00000012.json"))["trackids"] == [2]
+    assert provider.str_to_np(provider.np_to_str(tr)).tolist() == tr.tolist()
+    base = tmp_path / "ds"
+    synth.write_dataset(str(base), 10, seed=3, points_range=(20, 40), persons_prob=0.5)
+    train, val = (provider.get_data_files(str(base / "split" / f"{k}.txt")) for k in ("train", "val"))
+    assert train == list(range(8)) and val == [8, 9]
+    np.random.seed(1)
+    host = provider.read_host_batch(str(base), val, 16)
+    assert host["translations"].shape == (2, 3) and np.isfinite(host["translations"]).all()
+    for i in val:
+        for w in (1, 2):
+            c = np.load(base / f"pointcloud{w}" / f"{i:08d}.npy")
+            assert c.ndim == 2 and c.shape[1] == 4 and 20 <= len(c) <= 40 and c.dtype == np.float32
+        t, ra, s0, s1, a0, a1 = provider.load_meta(str(base), i)
+        np.testing.assert_allclose(s1, s0 + t, atol=1e-12)                     # end = start + translation
+        assert abs(a1 - (a0 + ra)) < 1e-12 and abs(ra) <= np.pi / 2

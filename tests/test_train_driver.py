@@ -129,7 +129,9 @@ def test_train_then_eval_only_round_trip(tmp_path):
     res16 = train.main(["eval_only", "--config", str(t_path), "--eval_epoch", "1", "--precision", "bf16"])
     assert res16["mean_time"] > 0
     # what the engine does not implement is rejected, not ignored
-    for bad in ({"evaluation": {"special": {"mode": "icp"}}}, {"training": {"optimizer": {"optimizer": "momentum"}}}):
+    for bad in ({"evaluation": {"special": {"mode": "icp"}}}, {"evaluation": {"special": {"mode": "held"}}},
+                {"evaluation": {"special": {"mode": "icp", "icp": {"variant": "o3_gicp", "with_constraint": True}}}},
+                {"training": {"optimizer": {"optimizer": "momentum"}}}, {"training": {"optimizer": {"optimizer": "sgd"}}}):
         cfg = json.load(open(cfg_path))
         for k, v in bad.items():
             cfg.setdefault(k, {}).update(v)
@@ -138,6 +140,90 @@ def test_train_then_eval_only_round_trip(tmp_path):
         C.reset_config()
         with pytest.raises(ValueError):
             train.main(["train", "--config", str(b_path), "--precision", "fp32"])
+    C.reset_config()
+
+
+@pytest.mark.gpu
+def test_momentum_optimizer_run(tmp_path):
+    """`training.optimizer.optimizer == 'momentum'` (train.py:211-212): the driver trains with the momentum update, the
+    checkpoint carries `<var>/Momentum` slots (no Adam slots) and resuming restores them."""
+    import __graft_entry__ as ge
+    ge.build()
+    from alignnet_b200 import config as C, tf_checkpoint, train
+    cfg_path, logdir = _make_run(tmp_path)
+    cfg = json.load(open(cfg_path))
+    cfg["training"]["optimizer"] = {"optimizer": "momentum", "momentum": 0.9}
+    cfg["training"]["learning_rate"] = 1e-4
+    open(cfg_path, "w").write(json.dumps(cfg))
+    C.reset_config()
+    np.random.seed(3)
+    last = train.main(["train", "--config", cfg_path, "--precision", "fp32"])
+    assert last["eval"]["num"] == 6
+    ck = tf_checkpoint.read_checkpoint(str(logdir / "model-1"))
+    assert int(ck["Variable"]) == 6
+    slots = [k for k in ck if k.endswith("/Momentum")]
+    assert "siamese/embedding/conv3/weights/Momentum" in slots and len(slots) == len([k for k in ck if k + "/Momentum" in ck])
+    assert not any(k.endswith(("/Adam", "/Adam_1")) for k in ck) and "beta1_power" not in ck
+    acc = ck["siamese/embedding/conv3/weights/Momentum"]
+    assert acc.shape == ck["siamese/embedding/conv3/weights"].shape and np.isfinite(acc).all() and np.abs(acc).max() > 0
+    # resume (train.py:267-275): one more epoch from model.ckpt continues at step 6 with the stored accumulators
+    cfg["training"]["num_epochs"] = 3
+    open(cfg_path, "w").write(json.dumps(cfg))
+    C.reset_config()
+    np.random.seed(4)
+    train.main(["train", "--config", cfg_path, "--precision", "fp32"])
+    assert int(tf_checkpoint.read_checkpoint(str(logdir / "model-2"))["Variable"]) == 9
+    C.reset_config()
+
+
+@pytest.mark.gpu
+def test_icp_special_mode(tmp_path):
+    """`evaluation.special.mode == 'icp'`, variant p2point with the yaw constraint (the reference's icp_<dataset>_o3_p2p.json,
+    train.py:548-551 -> icp.py:150-225): ICP from the centroid initialisation over the validation split, results and
+    eval files where the reference writes them, equal to the restated algorithm run pair by pair."""
+    import __graft_entry__ as ge
+    ge.build()
+    from alignnet_b200 import config as C, train
+    from alignnet_b200 import synth
+    from oracle import icp_ref as I
+    base = tmp_path / "SynthTiny"
+    # 30 box-shaped pairs with small motion (ICP from the centroid initialisation has a small basin), the last six = val
+    synth.write_dataset(str(base), 30, seed=5, points_range=(300, 500), max_rel_angle=0.05, max_speed=0.15)
+    cfg = {"data": {"basepath": str(base)}, "logging": {"basedir": str(tmp_path / "logs")},
+           "evaluation": {"special": {"mode": "icp", "icp": {"variant": "p2point", "with_constraint": True}}}}
+    path = tmp_path / "icp_SynthTiny_o3_p2p.json"
+    path.write_text(json.dumps(cfg))
+    C.reset_config()
+    res = train.main(["eval_only", "--config", str(path)])
+    edir = tmp_path / "logs" / "icp_SynthTiny" / "icp_SynthTiny_o3_p2p" / "val" / "eval000000"        # config.py:104-105
+    for rel in ("pred_translations.npy", "pred_angles.npy", "pred_s1_pc1centers.npy", "eval.json", "eval_180.json"):
+        assert (edir / rel).exists(), rel
+    t, a, c = (np.load(edir / f"{k}.npy") for k in ("pred_translations", "pred_angles", "pred_s1_pc1centers"))
+    assert t.shape == (6, 3) and a.shape == (6, 1) and c.shape == (6, 3) and not c.any()                # icp.py:207
+    assert t.dtype == np.float32 and a.dtype == np.float32
+    assert res["eval"]["num"] == 6 and res["eval_180"]["num"] == 6 and res["eval"]["mean_time"] > 0
+    val = [int(x) for x in open(base / "split" / "val.txt")]
+    gt = np.array([json.load(open(base / "meta" / f"{i:08d}.json"))["rel_angle"] for i in val])
+    compared = 0
+    for k, idx in enumerate(val):
+        p1 = np.load(base / "pointcloud1" / f"{idx:08d}.npy")[:, :3]
+        p2 = np.load(base / "pointcloud2" / f"{idx:08d}.npy")[:, :3]
+        init = np.eye(4)
+        init[:3, 3] = p2.mean(0) - p1.mean(0)                                                           # icp.py:62-66
+        T, _, _, _ = I.icp_yaw(p1, p2, init, radius=0.1, its=30)
+        if abs(np.arctan2(T[1, 0], T[0, 0]) - gt[k]) > 0.02:
+            continue            # the algorithm itself left the basin (a box seen from one side): its path is not reproducible
+        compared += 1
+        moved = p1 @ T[:3, :3].T + T[:3, 3]
+        cs, sn = np.cos(a[k, 0]), np.sin(a[k, 0])
+        R = np.array([[cs, -sn, 0], [sn, cs, 0], [0, 0, 1.0]])
+        assert np.abs(p1 @ R.T + t[k] - moved).max() < 5e-3, k          # fp32 distances may pick another neighbour here and there
+    assert compared >= 4
+    assert np.median(np.abs(a[:, 0] - gt)) < 0.02                       # and the refinement finds the motion
+    # --use_old_results re-evaluates the stored predictions (icp.py:177-180)
+    C.reset_config()
+    again = train.main(["eval_only", "--config", str(path), "--use_old_results"])
+    assert again["eval"]["corr_levels"] == res["eval"]["corr_levels"]
     C.reset_config()
 
 
