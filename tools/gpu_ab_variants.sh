@@ -16,5 +16,5 @@ done
 for v in "$@"; do
   case $v in bwd*) export ALIGNNET_B200_LIB=$PWD/tools/bin/libvar_$v.so; echo "=== tests $v"; timeout 600 python -m pytest tests/test_gpu_conv_stack.py tests/test_gpu_bf16.py tests/test_gpu_determinism.py -q -m gpu -x 2>&1 | tail -3;; esac
 done
-} > gpurun_out/r2_s21.log 2>&1
-cat gpurun_out/r2_s21.log | cut -c1-300
+} > gpurun_out/r2_ab_variants.log 2>&1
+cat gpurun_out/r2_ab_variants.log | cut -c1-300
