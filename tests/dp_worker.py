@@ -121,6 +121,54 @@ def main():
         report["dp_vs_replicas_params_max_abs"], report["dp_vs_replicas_update_cos"] = d, cos
         report["params_moved_max_abs"] = float(u_solo.abs().max())
         assert d <= 2 * K * 1e-3 * 1.05 and cos >= 0.8 and float(u_solo.abs().max()) > 1e-3, (d, cos)
+
+    # ---- 4. the momentum optimiser (train.py:211-212) under data parallelism: identical parameters / accumulators on every
+    #         rank through the graph path, and -- the update being LINEAR in the gradient, unlike Adam's -- the data-parallel
+    #         run equals single-GPU replicas with averaged gradients tightly
+    e = fresh()
+    e.set_optimizer("momentum", momentum=0.9)
+    for t in range(K):
+        e.train_step_graph(shard, lr=1e-4, bn_decay=0.5, allreduce=D.allreduce_grads)
+    torch.cuda.synchronize()
+    for name, buf in (("params", e.params), ("mom_accum", e.mom_accum)):
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        flag = torch.tensor([1 if torch.equal(ref, buf) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        report[f"momentum_graph_{name}_identical"] = bool(flag.item())
+        assert flag.item() == 1, name
+    assert not bool(e.adam_m.any()) and e.step == K
+    e = fresh()
+    e.set_optimizer("momentum", momentum=0.9)
+    p_dp = []
+    for t in range(K):
+        e.train_step(shard, lr=1e-4, bn_decay=0.5, seed=100 + t, allreduce=D.allreduce_grads)
+        p_dp.append(e.params.clone())
+    if rank == 0:
+        solo = fresh()
+        solo.set_optimizer("momentum", momentum=0.9)
+        replicas = [fresh() for _ in range(world)]
+        p0 = fresh().params
+        for t in range(K):
+            gs = []
+            for r, rep in enumerate(replicas):
+                rep.params.copy_(solo.params)
+                rep.params_changed()
+                gs.append(local_grad(rep, shards[r], seed=100 + t))
+            solo.grads.copy_(torch.stack(gs).sum(0))
+            solo.momentum_step(1e-4, grad_scale=1.0 / world)
+            u_solo, u_dp = (solo.params - p0).double(), (p_dp[t] - p0).double()
+            cos = float(torch.dot(u_solo, u_dp) / (u_solo.norm() * u_dp.norm()))
+            rel = float((u_solo - u_dp).norm() / u_solo.norm())
+            report[f"momentum_dp_vs_replicas_step{t + 1}_update_cos"], report[f"momentum_dp_vs_replicas_step{t + 1}_rel_l2"] = cos, rel
+            if t == 0:
+                # one step: the update is -lr * (mean shard gradient), so the two computations agree as tightly as the
+                # gradients do (check 1).  Later steps are reported, not bounded: the parameters of the two runs then differ
+                # in the last bits, and this loss is discontinuous in them at a fresh initialisation (the batch-level choice
+                # between the angle loss and its 180-degree twin, quirk Q5, is a near-tie; arg-max bins) -- measured cos
+                # 0.94 after three steps on 2 GPUs, the same spread the Adam comparison above shows
+                assert cos >= 0.9999 and rel <= 2e-2 and float(u_solo.abs().max()) > 0, (cos, rel)
+    if rank == 0:
         print(json.dumps(report))
     dist.barrier()
     dist.destroy_process_group()
