@@ -89,8 +89,7 @@ __host__ __device__ inline uint32_t plane_stride(int rows) { return (uint32_t)ro
 
 inline size_t smem_bytes(int PC, int nstages) {
   const size_t a2 = 16 * (size_t)plane_stride(PC);
-  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,bn2*/ + 2 * kMaxPC * 16 /*raw points*/ +
-         256 /*barriers*/ + 128;
+  return 2 * a2 + kW2Bytes + (size_t)nstages * kW3ChunkBytes + 2048 /*w1f,c1f,bn2*/ + 256 /*barriers*/ + 128;
 }
 
 __device__ __forceinline__ uint32_t to_ordered(uint32_t bits) {
@@ -191,21 +190,37 @@ __device__ __forceinline__ Item item_of(const Params& P, int it) {
   return I;
 }
 
-// 8 channels of layer 1 for one point -> one 16-byte chunk of the A1 tile
-__device__ __forceinline__ uint4 layer1_chunk(const float4 raw, float cx, float cy, float cz, float cs, float sn,
-                                              const float (&w1x)[8], const float (&w1y)[8], const float (&w1z)[8],
-                                              const float (&c1r)[8]) {
-  uint4 q = make_uint4(0, 0, 0, 0);
-  if (raw.w != 0.f) {
-    const float x0 = raw.x - cx, y0 = raw.y - cy, z = raw.z - cz;
-    const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
-    float v[8];
+// Layer 1 for ONE point and all 64 channels: the thread that prefetched the point keeps it in registers, recentres /
+// rotates it once and walks the 8 channel groups (= planes of the A1 tile) with the folded weights read as broadcast
+// 16-byte shared-memory loads.  `row` = this point's 16-byte slot in plane 0 of the tile.  (Until the third session of
+// round 2 a WARP owned a channel group for all points, weights in registers, three points in flight per lane: every warp
+// then repeated the recentre / rotate of every point and the raw points went through a shared-memory staging buffer --
+// ~570 warp instructions per front-end warp and cloud against ~310 now, the same arithmetic in the same order, so the
+// A1 tile is the same bit for bit.  Same-box A/B: forward kernels 1.061 -> 0.974 ms per c3 step, statistics pass
+// 0.249 -> 0.240, step 4.596 -> 4.465 ms; profiles/r2_ab_variants.txt (14).)
+__device__ __forceinline__ void layer1_point(float px, float py, float pz, bool real, float cx, float cy, float cz, float cs,
+                                             float sn, const float* __restrict__ sW1f, const float* __restrict__ sC1f,
+                                             uint8_t* row, uint32_t plane) {
+  if (!real) {                       // padding rows of the tile (only the cloud's last warp diverges)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(x, w1x[j], fmaf(y, w1y[j], fmaf(z, w1z[j], c1r[j])));
-    q.x = pack_bf16x2_relu(v[0], v[1]); q.y = pack_bf16x2_relu(v[2], v[3]);
-    q.z = pack_bf16x2_relu(v[4], v[5]); q.w = pack_bf16x2_relu(v[6], v[7]);
+    for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(row + (size_t)g * plane) = make_uint4(0u, 0u, 0u, 0u);
+    return;
   }
-  return q;
+  const float x0 = px - cx, y0 = py - cy, z = pz - cz;
+  const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 xa = *reinterpret_cast<const float4*>(sW1f + g * 8), xb = *reinterpret_cast<const float4*>(sW1f + g * 8 + 4);
+    const float4 ya = *reinterpret_cast<const float4*>(sW1f + 64 + g * 8), yb = *reinterpret_cast<const float4*>(sW1f + 64 + g * 8 + 4);
+    const float4 za = *reinterpret_cast<const float4*>(sW1f + 128 + g * 8), zb = *reinterpret_cast<const float4*>(sW1f + 128 + g * 8 + 4);
+    const float4 ca = *reinterpret_cast<const float4*>(sC1f + g * 8), cb = *reinterpret_cast<const float4*>(sC1f + g * 8 + 4);
+    const float v0 = fmaf(x, xa.x, fmaf(y, ya.x, fmaf(z, za.x, ca.x))), v1 = fmaf(x, xa.y, fmaf(y, ya.y, fmaf(z, za.y, ca.y)));
+    const float v2 = fmaf(x, xa.z, fmaf(y, ya.z, fmaf(z, za.z, ca.z))), v3 = fmaf(x, xa.w, fmaf(y, ya.w, fmaf(z, za.w, ca.w)));
+    const float v4 = fmaf(x, xb.x, fmaf(y, yb.x, fmaf(z, zb.x, cb.x))), v5 = fmaf(x, xb.y, fmaf(y, yb.y, fmaf(z, zb.y, cb.y)));
+    const float v6 = fmaf(x, xb.z, fmaf(y, yb.z, fmaf(z, zb.z, cb.z))), v7 = fmaf(x, xb.w, fmaf(y, yb.w, fmaf(z, zb.w, cb.w)));
+    *reinterpret_cast<uint4*>(row + (size_t)g * plane) =
+        make_uint4(pack_bf16x2_relu(v0, v1), pack_bf16x2_relu(v2, v3), pack_bf16x2_relu(v4, v5), pack_bf16x2_relu(v6, v7));
+  }
 }
 
 template <int MODE>
@@ -223,8 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
   float* sW1f = reinterpret_cast<float*>(sW3 + (size_t)P.nstages * kW3ChunkBytes);  // [3][64]
   float* sC1f = sW1f + 192;
   float4* sBn2 = reinterpret_cast<float4*>(sC1f + 64);       // [64] channel pairs: (scale, shift) of 2c, (scale, shift) of 2c+1
-  float4* sRaw = sBn2 + 64;                                  // [2][kMaxPC] raw points (w = 1 for real points)
-  Barriers* bars = reinterpret_cast<Barriers*>(sRaw + 2 * kMaxPC);
+  Barriers* bars = reinterpret_cast<Barriers*>(sBn2 + 64);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
@@ -258,11 +272,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
 
   if ((warp >= 4 && warp < 8) || (warp >= 14 && warp < 18)) {
     // ================================ front-end ================================
-    // 8 warps.  Layer 1: warp g owns channels 8g..8g+7 for all points.  Layer-2 epilogue: warp (quarter, half)
+    // 8 warps.  Layer 1: thread f owns point f.  Layer-2 epilogue: warp (quarter, half)
     // reads TMEM lanes [32 quarter, +32) = points of a 128-point tile, and 64 of the 128 channel columns.
     const int fgroup = warp >= 14 ? 1 : 0;
     const int quarter = warp & 3;
-    const int f = fgroup * 128 + quarter * 32 + lane;   // 0..255: point slot of the raw-point staging
+    const int f = fgroup * 128 + quarter * 32 + lane;   // 0..255: the point this thread prefetches and runs layer 1 for
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t ph_d2 = 0, ph_a2e = 0;     // (phase bits in one scalar: an array indexed by li & 1 would live in local memory)
     const bool save_a2 = MODE == MODE_FULL_TRAIN && P.a2_img != nullptr;
@@ -281,12 +295,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         pf_p0 = src[0]; pf_p1 = src[1]; pf_p2 = src[2];
       }
     };
-    const int fg8 = fgroup * 4 + quarter;          // channel group (A1 plane) of this warp in layer 1
-    float w1x[8], w1y[8], w1z[8], c1r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      w1x[j] = sW1f[fg8 * 8 + j]; w1y[j] = sW1f[64 + fg8 * 8 + j]; w1z[j] = sW1f[128 + fg8 * 8 + j]; c1r[j] = sC1f[fg8 * 8 + j];
-    }
     if (n_local > 0) prefetch(0);
     for (int li = 0; li < n_local; ++li) {
       const int it = it_begin + li;
@@ -305,35 +313,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_stack_fwd_kernel(const Param
         float* xf = bars->xf + (li & 1) * 8;
         xf[0] = pf_c0; xf[1] = pf_c1; xf[2] = pf_c2; xf[3] = cs; xf[4] = sn;
       }
-      // the prefetched raw point of thread f goes to shared memory: layer 1 below is organised by channel group
-      if (f < NT) sRaw[b * kMaxPC + f] = f < nvalid ? make_float4(pf_p0, pf_p1, pf_p2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float my_x = pf_p0, my_y = pf_p1, my_z = pf_p2;     // thread f keeps its own point (prefetch() below reloads pf_*)
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // the transform thread 0 just wrote is visible to all
       if (f == 0) FTL(2, li);
       const float* xfr = bars->xf + (li & 1) * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
-      // ---- layer 1: y = relu(W1f^T p' + c1f).  Warp g of the 8 front-end warps owns channels 8g..8g+7 (= plane g
-      // of the A1 tile) for ALL points: its 32 folded weights live in registers, lanes walk consecutive points, so
-      // the raw-point loads and the 16-byte tile stores are conflict-free.
-      {
-        // three independent points in flight per lane: with one point per iteration the front-end warps waited on their
-        // own dependency chains (load -> recentre -> rotate -> 3 FMAs -> pack -> store); same-box A/B 1.141 -> 1.113 ms
-        constexpr int kU = 3;
-        int p = lane;
-        for (; p + 32 * (kU - 1) < NT; p += 32 * kU) {
-          float4 raw[kU];
-          uint4 q[kU];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) raw[u] = sRaw[b * kMaxPC + p + 32 * u];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) q[u] = layer1_chunk(raw[u], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
-#pragma unroll
-          for (int u = 0; u < kU; ++u) *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + (p + 32 * u) * 16) = q[u];
-        }
-        for (; p < NT; p += 32)
-          *reinterpret_cast<uint4*>(sA1 + fg8 * plane1 + p * 16) =
-              layer1_chunk(sRaw[b * kMaxPC + p], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
-      }
+      // ---- layer 1: y = relu(W1f^T p' + c1f), thread f computes all 64 channels of point f (consecutive lanes write
+      // consecutive 16-byte rows of each plane: conflict-free)
+      if (f < NT) layer1_point(my_x, my_y, my_z, f < nvalid, cx, cy, cz, cs, sn, sW1f, sC1f, sA1 + f * 16, plane1);
       if (f == 0) FTL(3, li);
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full);
@@ -599,7 +587,7 @@ constexpr uint32_t kStatsTmemCols = 128;
 // tile has 10 (channels 80..127 are don't-care accumulator lanes).  The bytes it reads there must merely EXIST inside
 // the CTA's allocation -- the second tile plus 6 more planes' worth, which also hold the small arrays.
 inline size_t stats2_smem_bytes(int PC) {
-  const size_t tail = 1024 + 2 * (size_t)PC * 16 + 128;
+  const size_t tail = 1024 + 256;                        // folded layer-1 weights + barriers
   return 20 * (size_t)plane_stride(PC) + std::max(tail, 6 * (size_t)plane_stride(PC));
 }
 
@@ -616,8 +604,7 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
   auto a1buf = [&](int b) { return smem + (size_t)b * a1_bytes; };
   float* sW1f = reinterpret_cast<float*>(smem + 2 * a1_bytes);   // [3][64]
   float* sC1f = sW1f + 192;
-  float4* sRaw = reinterpret_cast<float4*>(sC1f + 64);           // [2][PC]
-  StatsBars* bars = reinterpret_cast<StatsBars*>(sRaw + 2 * P.PC);
+  StatsBars* bars = reinterpret_cast<StatsBars*>(sC1f + 64);
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int it_begin = min(P.n_items, (int)blockIdx.x * P.item_begin_stride);
@@ -638,13 +625,7 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
   const uint32_t tmem = bars->tmem_base;
 
   if (warp < 8) {
-    const int f = tid;                              // 0..255: point slot of the raw-point staging
-    const int g = warp;                             // channel group (A1 plane) of this warp
-    float w1x[8], w1y[8], w1z[8], c1r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      w1x[j] = sW1f[g * 8 + j]; w1y[j] = sW1f[64 + g * 8 + j]; w1z[j] = sW1f[128 + g * 8 + j]; c1r[j] = sC1f[g * 8 + j];
-    }
+    const int f = tid;                              // 0..255: the point this thread prefetches and runs layer 1 for
     float pf_c0 = 0.f, pf_c1 = 0.f, pf_c2 = 0.f, pf_ang = 0.f, pf_p0 = 0.f, pf_p1 = 0.f, pf_p2 = 0.f;
     auto prefetch = [&](int li) {
       const Item I = item_of(P, it_begin + li);
@@ -671,39 +652,18 @@ static __global__ void __launch_bounds__(kStatsThreads) conv_stats2_kernel(const
         float* xf = bars->xf + b * 8;
         xf[0] = pf_c0; xf[1] = pf_c1; xf[2] = pf_c2; xf[3] = cs; xf[4] = sn;
       }
-      if (f < NT) sRaw[b * P.PC + f] = f < nvalid ? make_float4(pf_p0, pf_p1, pf_p2, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float my_x = pf_p0, my_y = pf_p1, my_z = pf_p2;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* xfr = bars->xf + b * 8;
       const float cx = xfr[0], cy = xfr[1], cz = xfr[2], cs = xfr[3], sn = xfr[4];
       if (li + 1 < n_local) prefetch(li + 1);
-      {
-        // (three independent points in flight per lane, as in the forward kernel: 0.271 -> 0.249 ms per c3 step)
-        constexpr int kU = 3;
-        auto extra_planes = [&](int p, const float4 raw) {
-          if (g == 0) {   // channel 64 = 1 for real points (column sums), channels 65..79 = 0
-            *reinterpret_cast<uint4*>(a1buf(b) + 8 * plane1 + p * 16) = make_uint4(raw.w != 0.f ? 0x00003f80u : 0u, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a1buf(b) + 9 * plane1 + p * 16) = make_uint4(0, 0, 0, 0);
-          }
-        };
-        int p = lane;
-        for (; p + 32 * (kU - 1) < NT; p += 32 * kU) {
-          float4 raw[kU];
-          uint4 q[kU];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) raw[u] = sRaw[b * P.PC + p + 32 * u];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) q[u] = layer1_chunk(raw[u], cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
-#pragma unroll
-          for (int u = 0; u < kU; ++u) {
-            *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + (p + 32 * u) * 16) = q[u];
-            extra_planes(p + 32 * u, raw[u]);
-          }
-        }
-        for (; p < NT; p += 32) {
-          const float4 raw = sRaw[b * P.PC + p];
-          *reinterpret_cast<uint4*>(a1buf(b) + g * plane1 + p * 16) = layer1_chunk(raw, cx, cy, cz, cs, sn, w1x, w1y, w1z, c1r);
-          extra_planes(p, raw);
-        }
+      if (f < NT) {
+        // thread f owns point f: 64 channels, then its entries of the 'ones' plane (channel 64 = 1 for real points: the column
+        // sums) and of the zero plane (channels 72..79)
+        uint8_t* row = a1buf(b) + f * 16;
+        layer1_point(my_x, my_y, my_z, f < nvalid, cx, cy, cz, cs, sn, sW1f, sC1f, row, plane1);
+        *reinterpret_cast<uint4*>(row + 8 * (size_t)plane1) = make_uint4(f < nvalid ? 0x00003f80u : 0u, 0, 0, 0);
+        *reinterpret_cast<uint4*>(row + 9 * (size_t)plane1) = make_uint4(0, 0, 0, 0);
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars->a1_full[b]);
