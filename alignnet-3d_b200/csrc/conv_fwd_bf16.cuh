@@ -208,6 +208,10 @@ __device__ __forceinline__ void layer1_point(float px, float py, float pz, bool 
   }
   const float x0 = px - cx, y0 = py - cy, z = pz - cz;
   const float x = x0 * cs - y0 * sn, y = x0 * sn + y0 * cs;
+  // (Loading the weights of group g + 1 before group g's tile store -- the compiler keeps loads written after a store it
+  // cannot disambiguate behind it -- made both kernels ~1.5 % faster in isolation and the STEP 0.4 % slower: at 94 instead
+  // of 75 registers per thread the forward CTAs leave no room for the other branch's small kernels to co-reside.
+  // profiles/r2_ab_variants.txt (15): rejected.)
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const float4 xa = *reinterpret_cast<const float4*>(sW1f + g * 8), xb = *reinterpret_cast<const float4*>(sW1f + g * 8 + 4);
